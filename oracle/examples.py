@@ -1,0 +1,98 @@
+"""Trace tables for the BASELINE configs (oracle; test infrastructure only).
+
+``simple_pie`` follows examples/simple/src/main.rs:15-22 + the row emitters in
+crates/graph/src/op/prim.rs (LuminairAdd::process_trace :967-1013, LuminairMul,
+CopyToStwo :72-84) with the node ids of ui/demo/public/graph.dot.
+``synthetic_pie`` builds satisfiable Mul-shaped tables of any size (BASELINE cfg 3).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .fields import P, U64
+
+SCALE = 4096  # Fixed<12>
+
+
+def _m(v):
+    return v % P
+
+
+def add_rows(node, lid, rid, l, r, o, lm, rm, om):
+    n = len(l)
+    return [[node, lid, rid, i, 1 if i == n - 1 else 0, node, lid, rid, i + 1,
+             _m(l[i]), _m(r[i]), _m(o[i]), _m(lm), _m(rm), _m(om)] for i in range(n)]
+
+
+def mul_rows(node, lid, rid, l, r, o, rem, lm, rm, om):
+    n = len(l)
+    return [[node, lid, rid, i, 1 if i == n - 1 else 0, node, lid, rid, i + 1,
+             _m(l[i]), _m(r[i]), _m(o[i]), _m(rem[i]), _m(lm), _m(rm), _m(om)] for i in range(n)]
+
+
+def inputs_rows(node, vals, mult):
+    n = len(vals)
+    return [[node, i, 1 if i == n - 1 else 0, node, i + 1, _m(vals[i]), _m(mult)] for i in range(n)]
+
+
+def fixed_mul(x, y):
+    """numerair Fixed<12> mul -> (q, r) with x*y = q*4096 + r, floor division (r >= 0)."""
+    p = x * y
+    return p // SCALE, p % SCALE
+
+
+def simple_values():
+    a = [1, 2, 3, 4]
+    b = [10, 20, 30, 40]
+    w = [-1] * 4
+    fa, fb, fw = ([x * SCALE for x in v] for v in (a, b, w))
+    c, crem = zip(*[fixed_mul(x, y) for x, y in zip(fa, fb)])
+    d = [x + y for x, y in zip(c, fw)]
+    e, erem = zip(*[fixed_mul(x, y) for x, y in zip(c, d)])
+    return fa, fb, fw, list(c), list(crem), d, list(e), list(erem)
+
+
+def simple_pie(era: str = "current"):
+    """era="artifact": schema of the committed UI proof (no Inputs component; inputs that
+    come from initializers carry multiplicity 0).  era="current": schema of the tree at
+    /root/reference (Inputs component yields every CopyToStwo value)."""
+    fa, fb, fw, c, crem, d, e, erem = simple_values()
+    if era == "artifact":
+        add = add_rows(4, 3, 8, c, fw, d, -1, 0, 1)
+        mul = mul_rows(3, 6, 7, fa, fb, c, crem, 0, 0, 2) + mul_rows(5, 3, 4, c, d, e, erem, -1, -1, 0)
+        return [("add", np.array(add, dtype=U64)), ("mul", np.array(mul, dtype=U64))]
+    add = add_rows(4, 3, 8, c, fw, d, -1, -1, 1)
+    mul = mul_rows(3, 6, 7, fa, fb, c, crem, -1, -1, 2) + mul_rows(5, 3, 4, c, d, e, erem, -1, -1, 0)
+    inp = inputs_rows(6, fa, 1) + inputs_rows(7, fb, 1) + inputs_rows(8, fw, 1)
+    return [("add", np.array(add, dtype=U64)), ("mul", np.array(mul, dtype=U64)), ("inputs", np.array(inp, dtype=U64))]
+
+
+def synthetic_mul_table(log_rows: int, seed: int, node_id: int = 3) -> np.ndarray:
+    """One Mul node over 2^log_rows elements with random Fixed<12> operands in (-0.5, 0.5);
+    every multiplicity 0 except a self-cancelling pair so the LogUp sum is zero:
+    lhs consumed once (-1) and yielded once by `out` of the same value?  No - to keep the
+    table self-contained we set lhs == out-of-previous semantics aside and simply use
+    lhs_mult = rhs_mult = out_mult = 0 (constraints hold; claimed sum 0)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = 1 << log_rows
+    x = np.round(rng.uniform(-0.5, 0.5, n) * SCALE).astype(np.int64)
+    y = np.round(rng.uniform(-0.5, 0.5, n) * SCALE).astype(np.int64)
+    p = x * y
+    q = p // SCALE
+    r = p - q * SCALE
+    rows = np.zeros((n, 16), dtype=np.int64)
+    idx = np.arange(n)
+    rows[:, 0] = node_id
+    rows[:, 1] = node_id + 3
+    rows[:, 2] = node_id + 4
+    rows[:, 3] = idx
+    rows[:, 4] = (idx == n - 1)
+    rows[:, 5] = node_id
+    rows[:, 6] = node_id + 3
+    rows[:, 7] = node_id + 4
+    rows[:, 8] = idx + 1
+    rows[:, 9] = x
+    rows[:, 10] = y
+    rows[:, 11] = q
+    rows[:, 12] = r
+    return (rows % P).astype(U64)
