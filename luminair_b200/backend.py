@@ -1,0 +1,147 @@
+"""CudaBackend: host mirror of the stwo backend traits LuminAIR names as ``SimdBackend``
+(crates/prover/src/prover.rs:22,38,312; crates/air/src/utils.rs:112-128).
+
+Every method is a thin call into the C ABI (include/luminair_b200.h); arrays that cross
+the boundary are numpy uint32 host buffers or ``DeviceBuffer`` handles.  There is no CPU
+path: constructing a backend without the CUDA library / a GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import LuminairB200Error, check, load_library
+
+
+class DeviceBuffer:
+    """Owned device allocation of ``n`` u32 (stwo ``Column<M31>`` storage)."""
+
+    def __init__(self, backend: "CudaBackend", n: int):
+        self.backend = backend
+        self.n = int(n)
+        p = C.c_void_p()
+        check(backend.ctx, backend.lib.lb_alloc(backend.ctx, self.n, C.byref(p)), "lb_alloc")
+        self.ptr = p.value or 0
+
+    def free(self):
+        if self.ptr and self.backend.ctx:
+            self.backend.lib.lb_free(self.backend.ctx, C.c_void_p(self.ptr))
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def at(self, offset_u32: int) -> int:
+        return self.ptr + 4 * int(offset_u32)
+
+
+class ColumnBatch:
+    """n_cols columns of 2^log_size u32 at a fixed stride inside one DeviceBuffer."""
+
+    def __init__(self, buf: DeviceBuffer, n_cols: int, log_size: int, stride: int | None = None, offset: int = 0):
+        self.buf, self.n_cols, self.log_size = buf, n_cols, log_size
+        self.stride = stride if stride is not None else (1 << log_size)
+        self.offset = offset
+
+    @property
+    def ptr(self):
+        return self.buf.at(self.offset)
+
+    def col_ptr(self, c: int) -> int:
+        return self.buf.at(self.offset + c * self.stride)
+
+    def col_ptrs(self):
+        return [self.col_ptr(c) for c in range(self.n_cols)]
+
+
+class CudaBackend:
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        ctx = C.c_void_p()
+        rc = self.lib.lb_ctx_create(device, C.byref(ctx))
+        if rc != 0:
+            raise LuminairB200Error(f"lb_ctx_create(device={device}) failed ({rc}): no usable CUDA device; "
+                                    "luminair_b200 has no CPU fallback")
+        self.ctx = ctx
+        sm = C.c_int()
+        mem = C.c_size_t()
+        self.lib.lb_device_info(self.ctx, C.byref(sm), C.byref(mem))
+        self.sm_count, self.total_mem = sm.value, mem.value
+
+    def close(self):
+        if self.ctx:
+            self.lib.lb_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    # ---- memory -------------------------------------------------------------------
+    def alloc(self, n: int) -> DeviceBuffer:
+        return DeviceBuffer(self, n)
+
+    def upload(self, arr: np.ndarray, buf: DeviceBuffer | None = None, offset: int = 0) -> DeviceBuffer:
+        arr = np.ascontiguousarray(arr, dtype=np.uint32)
+        if buf is None:
+            buf = self.alloc(arr.size)
+        check(self.ctx, self.lib.lb_upload(self.ctx, C.c_void_p(buf.at(offset)), arr.ctypes.data_as(C.c_void_p), arr.size), "lb_upload")
+        return buf
+
+    def download(self, buf: DeviceBuffer, n: int | None = None, offset: int = 0) -> np.ndarray:
+        n = buf.n - offset if n is None else n
+        out = np.empty(n, dtype=np.uint32)
+        check(self.ctx, self.lib.lb_download(self.ctx, out.ctypes.data_as(C.c_void_p), C.c_void_p(buf.at(offset)), n), "lb_download")
+        return out
+
+    def download_ptr(self, ptr: int, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.uint32)
+        check(self.ctx, self.lib.lb_download(self.ctx, out.ctypes.data_as(C.c_void_p), C.c_void_p(ptr), n), "lb_download")
+        return out
+
+    def sync(self):
+        check(self.ctx, self.lib.lb_sync(self.ctx), "lb_sync")
+
+    def timer_start(self):
+        check(self.ctx, self.lib.lb_timer_start(self.ctx), "lb_timer_start")
+
+    def timer_stop_ms(self) -> float:
+        ms = C.c_float()
+        check(self.ctx, self.lib.lb_timer_stop_ms(self.ctx, C.byref(ms)), "lb_timer_stop_ms")
+        return float(ms.value)
+
+    # ---- PolyOps --------------------------------------------------------------------
+    def precompute_twiddles(self, max_log: int):
+        check(self.ctx, self.lib.lb_twiddles_ensure(self.ctx, max_log), "lb_twiddles_ensure")
+
+    def export_twiddles(self, root_log: int) -> np.ndarray:
+        self.precompute_twiddles(root_log + 1)
+        buf = self.alloc(1 << root_log)
+        check(self.ctx, self.lib.lb_twiddles_export(self.ctx, root_log, C.c_void_p(buf.ptr)), "lb_twiddles_export")
+        out = self.download(buf)
+        buf.free()
+        return out
+
+    def interpolate(self, cols: ColumnBatch):
+        check(self.ctx, self.lib.lb_interpolate_batch(self.ctx, C.c_void_p(cols.ptr), cols.stride, cols.n_cols, cols.log_size), "lb_interpolate_batch")
+
+    def evaluate(self, coeffs: ColumnBatch, out: ColumnBatch):
+        assert coeffs.n_cols == out.n_cols
+        check(self.ctx, self.lib.lb_evaluate_batch(self.ctx, C.c_void_p(coeffs.ptr), coeffs.stride, coeffs.log_size,
+                                                    C.c_void_p(out.ptr), out.stride, out.log_size, out.n_cols), "lb_evaluate_batch")
+
+    # ---- MerkleOps -------------------------------------------------------------------
+    def merkle_commit_layer(self, log_size: int, prev_ptr: int | None, col_ptrs, out_ptr: int):
+        n = len(col_ptrs)
+        arr = (C.c_void_p * max(n, 1))(*col_ptrs)
+        check(self.ctx, self.lib.lb_merkle_commit_layer(self.ctx, log_size, C.c_void_p(prev_ptr or 0), arr, n, C.c_void_p(out_ptr)), "lb_merkle_commit_layer")
+
+    def gather_rows(self, col_ptrs, idx) -> np.ndarray:
+        n = len(col_ptrs)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        out = np.empty((len(idx), n), dtype=np.uint32)
+        if n == 0 or len(idx) == 0:
+            return out
+        arr = (C.c_void_p * n)(*col_ptrs)
+        check(self.ctx, self.lib.lb_gather_rows(self.ctx, arr, n, idx.ctypes.data_as(C.c_void_p), len(idx), out.ctypes.data_as(C.c_void_p)), "lb_gather_rows")
+        return out
