@@ -164,7 +164,8 @@ int lb_device_info(lb_ctx* ctx, int* sm_count, size_t* total_mem_bytes) {
 }
 
 int lb_twiddles_ensure(lb_ctx* ctx, int max_log) {
-    if (!ctx || max_log < 2 || max_log > 28) return fail(ctx, LB_ERR_BAD_ARG, "twiddles: max_log out of range");
+    if (!ctx || max_log < 1 || max_log > 28) return fail(ctx, LB_ERR_BAD_ARG, "twiddles: max_log out of range");
+    if (max_log < 2) max_log = 2;
     if (ctx->tw.max_log >= max_log) return LB_OK;
     cudaSetDevice(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream), "twiddles/sync");

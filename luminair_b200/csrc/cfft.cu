@@ -74,7 +74,7 @@ static void host_gen_pow2(Pt* out) {
 }
 
 cudaError_t twiddles_create(Twiddles* tw, int max_log, cudaStream_t stream) {
-    // supports domains of log size <= max_log:  X[1..max_log-1], Y[1..max_log-1]
+    // supports domains of log size <= max_log:  X[1..max_log-1], Y[0..max_log-1]
     tw->max_log = max_log;
     Pt hp[31];
     host_gen_pow2(hp);
@@ -83,19 +83,21 @@ cudaError_t twiddles_create(Twiddles* tw, int max_log, cudaStream_t stream) {
     int K = max_log - 1;
     if (K < 1) K = 1;
     size_t nx = ((size_t)1 << K);      // sum_{k=1..K} 2^(k-1) = 2^K - 1
-    size_t ny = ((size_t)2 << K);      // sum_{k=1..K} 2^k = 2^(K+1) - 2
+    size_t ny = ((size_t)2 << K);      // sum_{k=0..K} 2^k = 2^(K+1) - 1
     size_t total = nx + ny;
     e = cudaMalloc(&tw->fwd, total * sizeof(uint2));
     if (e != cudaSuccess) return e;
     e = cudaMalloc(&tw->inv, total * sizeof(uint2));
     if (e != cudaSuccess) return e;
     tw->y_off = nx;
-    for (int k = 1; k <= K; ++k) {
-        size_t xo = ((size_t)1 << (k - 1)) - 1;
-        size_t yo = nx + ((size_t)1 << k) - 2;
-        uint32_t cx = 1u << (k - 1), cy = 1u << k;
-        gen_twiddles_kernel<<<(cx + 255) / 256, 256, 0, stream>>>(tw->fwd + xo, tw->inv + xo, k, 0);
+    for (int k = 0; k <= K; ++k) {
+        size_t yo = nx + ((size_t)1 << k) - 1;
+        uint32_t cy = 1u << k;
         gen_twiddles_kernel<<<(cy + 255) / 256, 256, 0, stream>>>(tw->fwd + yo, tw->inv + yo, k, 1);
+        if (k == 0) continue;
+        size_t xo = ((size_t)1 << (k - 1)) - 1;
+        uint32_t cx = 1u << (k - 1);
+        gen_twiddles_kernel<<<(cx + 255) / 256, 256, 0, stream>>>(tw->fwd + xo, tw->inv + xo, k, 0);
     }
     return cudaGetLastError();
 }
@@ -111,23 +113,25 @@ static inline const uint2* layer_tw(const Twiddles* tw, bool inverse, int n, int
     const uint2* base = inverse ? tw->inv : tw->fwd;
     if (i == 0) {
         int k = n - 1;  // Y[n-1]
-        return base + tw->y_off + ((size_t)1 << k) - 2;
+        return base + tw->y_off + ((size_t)1 << k) - 1;
     }
     int k = n - i;  // X[n-i]
     return base + ((size_t)1 << (k - 1)) - 1;
 }
 
 // ------------------------------------------------------------------------------------
-// Butterflies (lazy; any u32 <= 3P in, <= 3P out)
+// Butterflies.  P = 2^31-1 leaves no headroom in 32 bits (2P+1 = 2^32-1), so values are kept
+// as arbitrary u32 representatives and folded with red() right where a sum could overflow.
+// Both butterflies are closed on the full u32 range.
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ void bfly_fwd(uint32_t& v0, uint32_t& v1, uint2 w) {
-    uint32_t a = red(v0);              // [0, P+1]
-    uint32_t t = mul_shoup(v1, w);     // [0, 2P)
-    v0 = a + t;                        // <= 3P
-    v1 = a + 2u * P - t;               // <= 3P + 1 < 2^32
+    uint32_t a = red(v0);                 // [0, P+1]
+    uint32_t t = red(mul_shoup(v1, w));   // [0, P]
+    v0 = a + t;                           // <= 2P+1
+    v1 = a + P - t;                       // <= 2P+1
 }
 __device__ __forceinline__ void bfly_inv(uint32_t& v0, uint32_t& v1, uint2 w) {
-    uint32_t a = red(v0), b = red(v1);  // [0, P] for inputs <= 3P
+    uint32_t a = red(v0), b = red(v1);  // [0, P] for inputs <= 2P
     v0 = a + b;                         // [0, 2P]
     v1 = mul_shoup(a + P - b, w);       // [0, 2P)
 }

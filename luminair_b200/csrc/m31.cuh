@@ -4,7 +4,8 @@
 // /root/reference, Cargo.toml:21-28).  The instruction selection is B200-specific:
 //   * twiddle multiplications use Shoup's precomputed-quotient form: 3 IMAD-class
 //     instructions on the FMA pipe, zero ALU-pipe work, any u32 multiplicand, result in [0,2P)
-//   * additions stay lazy in [0, 2^32) and are folded with (x & P) + (x >> 31)
+//   * sums stay lazy u32 representatives, folded with (x & P) + (x >> 31) only where the
+//     next add could overflow (2P+1 = 2^32-1: Mersenne-31 has no spare bit)
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -14,11 +15,11 @@ namespace lb {
 constexpr uint32_t P = 0x7FFFFFFFu;
 
 // ---- lazy helpers -----------------------------------------------------------------
-// any u32 -> [0, P+1]  (<= P when x <= 3P)
+// any u32 -> [0, P+1]  (<= P when x <= 2P)
 __device__ __forceinline__ uint32_t red(uint32_t x) { return (x & P) + (x >> 31); }
 // [0, 2P) -> [0, P)
 __device__ __forceinline__ uint32_t canon2(uint32_t x) { return min(x, x - P); }
-// any u32 <= 3P -> [0, P)
+// any u32 -> [0, P)
 __device__ __forceinline__ uint32_t canon(uint32_t x) {
     x = red(x);
     return min(x, x - P);

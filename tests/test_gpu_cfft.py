@@ -131,3 +131,14 @@ def test_gather_rows(be):
     buf = be.upload(a.reshape(-1))
     got = be.gather_rows([buf.at(c * 64) for c in range(5)], [3, 17, 63])
     assert np.array_equal(got, a[:, [3, 17, 63]].T)
+
+
+def test_evaluate_in_place(be):
+    from luminair_b200.backend import ColumnBatch
+    log, ncols = 14, 3
+    rng = np.random.Generator(np.random.PCG64(99))
+    vals = rng.integers(0, P, size=(ncols, 1 << log), dtype=np.uint64).astype(np.uint32)
+    cb = _batch(be, vals, log)
+    be.interpolate(cb)
+    be.evaluate(cb, cb)
+    assert np.array_equal(be.download(cb.buf).reshape(ncols, -1), vals)
