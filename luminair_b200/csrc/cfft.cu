@@ -82,8 +82,10 @@ cudaError_t twiddles_create(Twiddles* tw, int max_log, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     int K = max_log - 1;
     if (K < 1) K = 1;
-    size_t nx = ((size_t)1 << K);      // sum_{k=1..K} 2^(k-1) = 2^K - 1
-    size_t ny = ((size_t)2 << K);      // sum_{k=0..K} 2^k = 2^(K+1) - 1
+    // X[k] lives at entry offset 2^(k-1), Y[k] at y_off + 2^k: every table is aligned to its own
+    // size, so the per-thread twiddle vectors of the fast kernels are 16-byte aligned.
+    size_t nx = ((size_t)1 << K);
+    size_t ny = ((size_t)2 << K);
     size_t total = nx + ny;
     e = cudaMalloc(&tw->fwd, total * sizeof(uint2));
     if (e != cudaSuccess) return e;
@@ -91,11 +93,11 @@ cudaError_t twiddles_create(Twiddles* tw, int max_log, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     tw->y_off = nx;
     for (int k = 0; k <= K; ++k) {
-        size_t yo = nx + ((size_t)1 << k) - 1;
+        size_t yo = nx + ((size_t)1 << k);
         uint32_t cy = 1u << k;
         gen_twiddles_kernel<<<(cy + 255) / 256, 256, 0, stream>>>(tw->fwd + yo, tw->inv + yo, k, 1);
         if (k == 0) continue;
-        size_t xo = ((size_t)1 << (k - 1)) - 1;
+        size_t xo = ((size_t)1 << (k - 1));
         uint32_t cx = 1u << (k - 1);
         gen_twiddles_kernel<<<(cx + 255) / 256, 256, 0, stream>>>(tw->fwd + xo, tw->inv + xo, k, 0);
     }
@@ -113,10 +115,10 @@ static inline const uint2* layer_tw(const Twiddles* tw, bool inverse, int n, int
     const uint2* base = inverse ? tw->inv : tw->fwd;
     if (i == 0) {
         int k = n - 1;  // Y[n-1]
-        return base + tw->y_off + ((size_t)1 << k) - 1;
+        return base + tw->y_off + ((size_t)1 << k);
     }
     int k = n - i;  // X[n-i]
-    return base + ((size_t)1 << (k - 1)) - 1;
+    return base + ((size_t)1 << (k - 1));
 }
 
 // ------------------------------------------------------------------------------------
@@ -272,33 +274,286 @@ __global__ void __launch_bounds__(256) cfft_pass_kernel(PassParams p, int cols_p
 }
 
 // ------------------------------------------------------------------------------------
+// Fast path (log_n >= 12): fully unrolled rounds, one 16-element group per thread, every
+// shared-memory offset a compile-time constant, first/last round of a pass straight from/to
+// global memory (no staging), vectorised twiddle loads.
+//
+//   low  pass <M>: 4096 contiguous elements, layers 0..M-1 (8 <= M <= 12), 256 threads
+//   high pass <M>: 2^M elements at stride 2^i_lo x W adjacent offsets (4 <= M <= 10),
+//                  W = 2^(12-M) for M <= 8 (256 threads), W = 16 for M = 9, 10
+// Round r of a pass works on the 4-bit index field at bit A = min(4r, M-4) and executes the
+// layers of that field not done yet: field bits [4r - A, 4).
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ int low_pad(int e) { return e + ((e >> 5) << 2) + ((e >> 8) << 4); }
+constexpr int LOW_SMEM_WORDS = 4096 + 512 + 256;
+
+template <int W>
+__device__ __forceinline__ int high_word(int e, int w) {
+    return e * W + w + (W == 16 ? ((e >> 4) << 4) : 0);
+}
+template <int M, int W>
+constexpr int high_smem_words() {
+    return (1 << M) * W + (W == 16 ? (1 << M) : 0);
+}
+
+template <int CNT>
+__device__ __forceinline__ void load_tw(uint2 (&w)[8], const uint2* p) {
+    if (CNT == 1) {
+        w[0] = __ldg(p);
+    } else {
+#pragma unroll
+        for (int q = 0; q < CNT / 2; ++q) {
+            uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + q);
+            w[2 * q] = make_uint2(v.x, v.y);
+            w[2 * q + 1] = make_uint2(v.z, v.w);
+        }
+    }
+}
+
+// layers of one index field: field bits [BLO, 4); A = bit position of the field in the tile
+// index; twiddle pointer for field bit b: tw[A+b] + (tile_h << (TS-1-A-b)) + (e0_hi << (3-b))
+template <bool FWD, int A, int BLO, int TS>
+__device__ __forceinline__ void field_layers(uint32_t (&v)[16], const PassParams& p, uint32_t tile_h, int e0_hi) {
+#pragma unroll
+    for (int bb = 0; bb < 4 - BLO; ++bb) {
+        const int b = FWD ? (3 - bb) : (BLO + bb);
+        const int bl = A + b;
+        const uint2* twp = p.tw[bl] + ((size_t)tile_h << (TS - 1 - bl)) + ((size_t)e0_hi << (3 - b));
+        uint2 w[8];
+        if (b == 0) load_tw<8>(w, twp);
+        if (b == 1) load_tw<4>(w, twp);
+        if (b == 2) load_tw<2>(w, twp);
+        if (b == 3) load_tw<1>(w, twp);
+#pragma unroll
+        for (int pr = 0; pr < 8; ++pr) {
+            const int j0 = ((pr >> b) << (b + 1)) | (pr & ((1 << b) - 1));
+            const int j1 = j0 | (1 << b);
+            if (FWD)
+                bfly_fwd(v[j0], v[j1], w[pr >> b]);
+            else
+                bfly_inv(v[j0], v[j1], w[pr >> b]);
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t finalize(uint32_t x, int mode, uint2 scale) {
+    if (mode == 1) return canon(x);
+    if (mode == 2) return canon2(mul_shoup(x, scale));
+    return x;
+}
+
+template <int M, int R>
+struct RoundGeom {
+    static constexpr int A = (4 * R < M - 4) ? 4 * R : (M - 4);
+    static constexpr int BLO = 4 * R - A;
+};
+
+// ---- low pass ---------------------------------------------------------------------------
+template <bool FWD, int M, int R>
+__device__ __forceinline__ void low_round(uint32_t* sm, const PassParams& p, uint32_t tile, const uint32_t* src,
+                                          uint32_t* dst, bool first, bool last) {
+    constexpr int A = RoundGeom<M, R>::A;
+    constexpr int BLO = RoundGeom<M, R>::BLO;
+    const int g = threadIdx.x;
+    const int e0_hi = g >> A;
+    const int e0 = (e0_hi << (A + 4)) | (g & ((1 << A) - 1));
+    const size_t gbase = ((size_t)tile << 12) + e0;
+    uint32_t v[16];
+    if (first) {
+        if (A == 0) {
+            const size_t n_src = (size_t)1 << p.log_src;  // zero extension beyond n_src
+            if (gbase + 16 <= n_src) {
+                const uint4* s4 = reinterpret_cast<const uint4*>(src + gbase);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint4 t = s4[q];
+                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = gbase + j < n_src ? src[gbase + j] : 0u;
+            }
+        } else {
+            const size_t n_src = (size_t)1 << p.log_src;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                size_t gi = gbase + ((size_t)j << A);
+                v[j] = gi < n_src ? src[gi] : 0u;
+            }
+        }
+    } else {
+        const int sb = low_pad(e0);
+        if (A == 0) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(sm + sb);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint4 t = s4[q];
+                v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = sm[sb + low_pad(j << A)];
+        }
+    }
+    field_layers<FWD, A, BLO, 12>(v, p, tile, e0_hi);
+    if (last) {
+        if (A == 0) {
+            uint4* d4 = reinterpret_cast<uint4*>(dst + gbase);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                d4[q] = make_uint4(finalize(v[4 * q], p.final_mode, p.scale), finalize(v[4 * q + 1], p.final_mode, p.scale),
+                                   finalize(v[4 * q + 2], p.final_mode, p.scale), finalize(v[4 * q + 3], p.final_mode, p.scale));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dst[gbase + ((size_t)j << A)] = finalize(v[j], p.final_mode, p.scale);
+        }
+    } else {
+        const int sb = low_pad(e0);
+        if (A == 0) {
+            uint4* d4 = reinterpret_cast<uint4*>(sm + sb);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) d4[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sm[sb + low_pad(j << A)] = v[j];
+        }
+    }
+}
+
+template <bool FWD, int M>
+__global__ void __launch_bounds__(256, 3) cfft_low_fast(PassParams p, int cols_per_block) {
+    __shared__ __align__(16) uint32_t sm[LOW_SMEM_WORDS];
+    constexpr int NR = (M + 3) / 4;
+    const uint32_t tile = blockIdx.x;
+    const int c0 = blockIdx.y * cols_per_block;
+    const int c1 = min(p.n_cols, c0 + cols_per_block);
+    for (int c = c0; c < c1; ++c) {
+        const uint32_t* src = p.src + (size_t)c * p.src_stride;
+        uint32_t* dst = p.dst + (size_t)c * p.dst_stride;
+        if (FWD) {
+            if constexpr (NR == 3) { low_round<FWD, M, 2>(sm, p, tile, src, dst, true, false); __syncthreads(); }
+            low_round<FWD, M, 1>(sm, p, tile, src, dst, NR == 2, false);
+            __syncthreads();
+            low_round<FWD, M, 0>(sm, p, tile, src, dst, false, true);
+        } else {
+            low_round<FWD, M, 0>(sm, p, tile, src, dst, true, false);
+            __syncthreads();
+            low_round<FWD, M, 1>(sm, p, tile, src, dst, false, NR == 2);
+            if constexpr (NR == 3) { __syncthreads(); low_round<FWD, M, 2>(sm, p, tile, src, dst, false, true); }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- high pass --------------------------------------------------------------------------
+template <bool FWD, int M, int W, int R>
+__device__ __forceinline__ void high_round(uint32_t* sm, const PassParams& p, uint32_t tile_h, size_t g_base,
+                                           const uint32_t* src, uint32_t* dst, bool first, bool last) {
+    constexpr int A = RoundGeom<M, R>::A;
+    constexpr int BLO = RoundGeom<M, R>::BLO;
+    const int w = threadIdx.x % W;
+    const int g = threadIdx.x / W;
+    const int e0_hi = g >> A;
+    const int e0 = (e0_hi << (A + 4)) | (g & ((1 << A) - 1));
+    const size_t gb = g_base + ((size_t)e0 << p.i_lo) + w;
+    const int sb = high_word<W>(e0, w);
+    uint32_t v[16];
+    if (first) {
+        const size_t n_src = (size_t)1 << p.log_src;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            size_t gi = gb + ((size_t)(j << A) << p.i_lo);
+            v[j] = gi < n_src ? src[gi] : 0u;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = sm[sb + high_word<W>(j << A, 0)];
+    }
+    field_layers<FWD, A, BLO, M>(v, p, tile_h, e0_hi);
+    if (last) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dst[gb + ((size_t)(j << A) << p.i_lo)] = finalize(v[j], p.final_mode, p.scale);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sm[sb + high_word<W>(j << A, 0)] = v[j];
+    }
+}
+
+template <int M>
+struct HighGeom {
+    static constexpr int W = (M <= 8) ? (1 << (12 - M)) : 16;
+    static constexpr int THREADS = (1 << (M - 4)) * W;
+};
+
+template <bool FWD, int M>
+__global__ void __launch_bounds__(HighGeom<M>::THREADS) cfft_high_fast(PassParams p, int cols_per_block) {
+    constexpr int W = HighGeom<M>::W;
+    constexpr int NR = (M + 3) / 4;
+    extern __shared__ __align__(16) uint32_t smh[];
+    const uint32_t l_tiles = (1u << p.i_lo) / W;
+    const uint32_t tile_h = blockIdx.x / l_tiles, lt = blockIdx.x % l_tiles;
+    const size_t g_base = ((size_t)tile_h << (p.i_lo + M)) + (size_t)lt * W;
+    const int c0 = blockIdx.y * cols_per_block;
+    const int c1 = min(p.n_cols, c0 + cols_per_block);
+    for (int c = c0; c < c1; ++c) {
+        const uint32_t* src = p.src + (size_t)c * p.src_stride;
+        uint32_t* dst = p.dst + (size_t)c * p.dst_stride;
+        if constexpr (NR == 1) {
+            high_round<FWD, M, W, 0>(smh, p, tile_h, g_base, src, dst, true, true);
+        } else if constexpr (FWD) {
+            if constexpr (NR == 3) { high_round<FWD, M, W, 2>(smh, p, tile_h, g_base, src, dst, true, false); __syncthreads(); }
+            high_round<FWD, M, W, (NR >= 2 ? 1 : 0)>(smh, p, tile_h, g_base, src, dst, NR == 2, false);
+            __syncthreads();
+            high_round<FWD, M, W, 0>(smh, p, tile_h, g_base, src, dst, false, true);
+            __syncthreads();
+        } else {
+            high_round<FWD, M, W, 0>(smh, p, tile_h, g_base, src, dst, true, false);
+            __syncthreads();
+            high_round<FWD, M, W, (NR >= 2 ? 1 : 0)>(smh, p, tile_h, g_base, src, dst, false, NR == 2);
+            if constexpr (NR == 3) { __syncthreads(); high_round<FWD, M, W, 2>(smh, p, tile_h, g_base, src, dst, false, true); }
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // Host-side pass planning
 // ------------------------------------------------------------------------------------
 static constexpr int LOW_TS_MAX = 12;
-static constexpr int HIGH_M_MAX = 10;
-static constexpr int HIGH_W = 16;
 
 struct Plan {
     int n_pass;
     int i_lo[8], m[8];
+    bool fast;
 };
 
 static Plan make_plan(int n) {
     Plan pl{};
-    if (n <= LOW_TS_MAX) {
+    pl.i_lo[0] = 0;
+    if (n < LOW_TS_MAX) {  // small transforms: one generic tile covers the column
         pl.n_pass = 1;
-        pl.i_lo[0] = 0;
         pl.m[0] = n;
+        pl.fast = false;
         return pl;
     }
-    // low pass takes at least half of the layers (high tiles need i_lo >= 4), at most 12
-    int low = std::min(LOW_TS_MAX, std::max(n - HIGH_M_MAX, (n + 1) / 2));
-    int rem = n - low;
-    int n_high = (rem + HIGH_M_MAX - 1) / HIGH_M_MAX;
+    pl.fast = true;
+    if (n == 12) {
+        pl.n_pass = 1;
+        pl.m[0] = 12;
+        return pl;
+    }
+    if (n <= 15) {  // low n-4 (9..11) + high 4
+        pl.n_pass = 2;
+        pl.m[0] = n - 4;
+        pl.i_lo[1] = n - 4;
+        pl.m[1] = 4;
+        return pl;
+    }
+    int rem = n - 12;
+    int n_high = (rem + 9) / 10;
     pl.n_pass = 1 + n_high;
-    pl.i_lo[0] = 0;
-    pl.m[0] = low;
-    int at = low;
+    pl.m[0] = 12;
+    int at = 12;
     for (int k = 0; k < n_high; ++k) {
         int mk = rem / n_high + (k < rem % n_high ? 1 : 0);
         pl.i_lo[1 + k] = at;
@@ -308,42 +563,83 @@ static Plan make_plan(int n) {
     return pl;
 }
 
+static int pick_cols_per_block(size_t tiles, int n_cols, int sm_count) {
+    int cpb = 1;
+    size_t target_blocks = (size_t)sm_count * 16;
+    while (cpb < n_cols && cpb < 8 && tiles * ((n_cols + cpb - 1) / cpb) > target_blocks) cpb *= 2;
+    return cpb;
+}
+
 template <bool FWD>
-static cudaError_t launch_pass(const PassParams& p, bool low, int sm_count, cudaStream_t stream) {
-    size_t tiles, smem;
-    if (low) {
-        tiles = (size_t)1 << (p.log_n - p.ts);
-        size_t el = (size_t)1 << p.ts;
-        smem = (el + (el >> 4) + 1) * sizeof(uint32_t);
-    } else {
-        tiles = ((size_t)1 << (p.log_n - p.i_lo - p.m)) * (((size_t)1 << p.i_lo) / HIGH_W);
-        smem = ((size_t)1 << p.ts) * HIGH_W * sizeof(uint32_t);
-    }
-    // choose columns per block so that the grid has a few waves of blocks
-    int cols_per_block = 1;
-    size_t target_blocks = (size_t)sm_count * 8;
-    while (cols_per_block < p.n_cols && tiles * ((p.n_cols + cols_per_block - 1) / cols_per_block) > 2 * target_blocks &&
-           cols_per_block < 8)
-        cols_per_block *= 2;
-    dim3 grid((unsigned)tiles, (unsigned)((p.n_cols + cols_per_block - 1) / cols_per_block));
+static cudaError_t launch_generic(const PassParams& p, int sm_count, cudaStream_t stream) {
+    size_t tiles = (size_t)1 << (p.log_n - p.ts);
+    size_t el = (size_t)1 << p.ts;
+    size_t smem = (el + (el >> 4) + 1) * sizeof(uint32_t);
+    int cpb = pick_cols_per_block(tiles, p.n_cols, sm_count);
+    dim3 grid((unsigned)tiles, (unsigned)((p.n_cols + cpb - 1) / cpb));
     if (grid.y > 65535) return cudaErrorInvalidValue;
-    cudaError_t e;
-    if (low) {
-        auto k = cfft_pass_kernel<FWD, 1>;
-        if (smem > 48 * 1024) {
-            e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-        }
-        k<<<grid, 256, smem, stream>>>(p, cols_per_block);
-    } else {
-        auto k = cfft_pass_kernel<FWD, HIGH_W>;
-        if (smem > 48 * 1024) {
-            e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-        }
-        k<<<grid, 256, smem, stream>>>(p, cols_per_block);
-    }
+    cfft_pass_kernel<FWD, 1><<<grid, 256, smem, stream>>>(p, cpb);
     return cudaGetLastError();
+}
+
+template <bool FWD, int M>
+static cudaError_t launch_low_m(const PassParams& p, int sm_count, cudaStream_t stream) {
+    size_t tiles = (size_t)1 << (p.log_n - 12);
+    int cpb = pick_cols_per_block(tiles, p.n_cols, sm_count);
+    dim3 grid((unsigned)tiles, (unsigned)((p.n_cols + cpb - 1) / cpb));
+    if (grid.y > 65535) return cudaErrorInvalidValue;
+    cfft_low_fast<FWD, M><<<grid, 256, 0, stream>>>(p, cpb);
+    return cudaGetLastError();
+}
+
+template <bool FWD>
+static cudaError_t launch_low(const PassParams& p, int sm_count, cudaStream_t stream) {
+    switch (p.m) {
+        case 8: return launch_low_m<FWD, 8>(p, sm_count, stream);
+        case 9: return launch_low_m<FWD, 9>(p, sm_count, stream);
+        case 10: return launch_low_m<FWD, 10>(p, sm_count, stream);
+        case 11: return launch_low_m<FWD, 11>(p, sm_count, stream);
+        case 12: return launch_low_m<FWD, 12>(p, sm_count, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <bool FWD, int M>
+static cudaError_t launch_high_m(const PassParams& p, int sm_count, cudaStream_t stream) {
+    constexpr int W = HighGeom<M>::W;
+    if (((size_t)1 << p.i_lo) < (size_t)W) return cudaErrorInvalidValue;
+    size_t tiles = ((size_t)1 << (p.log_n - p.i_lo - M)) * (((size_t)1 << p.i_lo) / W);
+    size_t smem = (size_t)high_smem_words<M, W>() * sizeof(uint32_t);
+    int cpb = pick_cols_per_block(tiles, p.n_cols, sm_count);
+    dim3 grid((unsigned)tiles, (unsigned)((p.n_cols + cpb - 1) / cpb));
+    if (grid.y > 65535) return cudaErrorInvalidValue;
+    auto k = cfft_high_fast<FWD, M>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k<<<grid, HighGeom<M>::THREADS, smem, stream>>>(p, cpb);
+    return cudaGetLastError();
+}
+
+template <bool FWD>
+static cudaError_t launch_high(const PassParams& p, int sm_count, cudaStream_t stream) {
+    switch (p.m) {
+        case 4: return launch_high_m<FWD, 4>(p, sm_count, stream);
+        case 5: return launch_high_m<FWD, 5>(p, sm_count, stream);
+        case 6: return launch_high_m<FWD, 6>(p, sm_count, stream);
+        case 7: return launch_high_m<FWD, 7>(p, sm_count, stream);
+        case 8: return launch_high_m<FWD, 8>(p, sm_count, stream);
+        case 9: return launch_high_m<FWD, 9>(p, sm_count, stream);
+        case 10: return launch_high_m<FWD, 10>(p, sm_count, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <bool FWD>
+static cudaError_t launch_pass(const PassParams& p, const Plan& pl, int k, int sm_count, cudaStream_t stream) {
+    if (!pl.fast) return launch_generic<FWD>(p, sm_count, stream);
+    return k == 0 ? launch_low<FWD>(p, sm_count, stream) : launch_high<FWD>(p, sm_count, stream);
 }
 
 cudaError_t cfft_interpolate(const Twiddles* tw, uint32_t* data, size_t stride, int n_cols, int log_n, int sm_count,
@@ -362,13 +658,11 @@ cudaError_t cfft_interpolate(const Twiddles* tw, uint32_t* data, size_t stride, 
         p.log_src = log_n;
         p.i_lo = pl.i_lo[k];
         p.m = pl.m[k];
-        bool low = (k == 0);
-        p.ts = low ? std::min(log_n, std::max(p.m, LOW_TS_MAX)) : p.m;
-        if (low && p.ts > log_n) p.ts = log_n;
+        p.ts = (k == 0) ? std::min(log_n, LOW_TS_MAX) : p.m;
         p.final_mode = (k == pl.n_pass - 1) ? 2 : 0;
         p.scale = make_uint2(inv_n, shoup_companion(inv_n));
         for (int b = 0; b < p.m; ++b) p.tw[b] = layer_tw(tw, true, log_n, p.i_lo + b);
-        cudaError_t e = launch_pass<false>(p, low, sm_count, stream);
+        cudaError_t e = launch_pass<false>(p, pl, k, sm_count, stream);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
@@ -391,11 +685,10 @@ cudaError_t cfft_evaluate(const Twiddles* tw, const uint32_t* coeffs, size_t src
         p.log_src = first ? log_in : log_out;
         p.i_lo = pl.i_lo[k];
         p.m = pl.m[k];
-        bool low = (k == 0);
-        p.ts = low ? std::min(log_out, std::max(p.m, LOW_TS_MAX)) : p.m;
+        p.ts = (k == 0) ? std::min(log_out, LOW_TS_MAX) : p.m;
         p.final_mode = (k == 0) ? 1 : 0;
         for (int b = 0; b < p.m; ++b) p.tw[b] = layer_tw(tw, false, log_out, p.i_lo + b);
-        cudaError_t e = launch_pass<true>(p, low, sm_count, stream);
+        cudaError_t e = launch_pass<true>(p, pl, k, sm_count, stream);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
@@ -417,7 +710,7 @@ __global__ void export_stwo_twiddles_kernel(const uint2* fwd_x_base, uint32_t* o
     int lg = 63 - __clzll((long long)rem);   // rem in [2^lg, 2^(lg+1))
     int kx = lg + 1;                         // X[kx] has 2^(kx-1) = 2^lg entries
     size_t off_in_layer = ((size_t)2 << lg) - 1 - rem;  // position inside the layer
-    const uint2* x = fwd_x_base + (((size_t)1 << (kx - 1)) - 1);
+    const uint2* x = fwd_x_base + ((size_t)1 << (kx - 1));
     out[t] = x[off_in_layer].x;
 }
 

@@ -24,10 +24,10 @@ def _batch(be, arr, log):
     return ColumnBatch(buf, arr.shape[0], log)
 
 
-@pytest.mark.parametrize("log", [1, 2, 3, 4, 5, 7, 10, 12, 13, 14, 16, 18])
+@pytest.mark.parametrize("log", [1, 2, 3, 4, 5, 7, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22])
 def test_interpolate_evaluate_vs_oracle(be, log):
     rng = np.random.Generator(np.random.PCG64(log))
-    ncols = 3 if log > 12 else 5
+    ncols = 5 if log <= 12 else (3 if log <= 18 else 2)
     vals = rng.integers(0, P, size=(ncols, 1 << log), dtype=np.uint64).astype(np.uint32)
     dom = CanonicCoset(log).circle_domain()
     cb = _batch(be, vals, log)
