@@ -312,11 +312,11 @@ __device__ __forceinline__ void load_tw(uint2 (&w)[8], const uint2* p) {
 
 // layers of one index field: field bits [BLO, 4); A = bit position of the field in the tile
 // index; twiddle pointer for field bit b: tw[A+b] + (tile_h << (TS-1-A-b)) + (e0_hi << (3-b))
-template <bool FWD, int A, int BLO, int TS>
-__device__ __forceinline__ void field_layers(uint32_t (&v)[16], const PassParams& p, uint32_t tile_h, int e0_hi) {
+template <bool FWD, int A, int BLO, int BHI, int TS>
+__device__ __forceinline__ void field_layers_range(uint32_t (&v)[16], const PassParams& p, uint32_t tile_h, int e0_hi) {
 #pragma unroll
-    for (int bb = 0; bb < 4 - BLO; ++bb) {
-        const int b = FWD ? (3 - bb) : (BLO + bb);
+    for (int bb = 0; bb < BHI - BLO; ++bb) {
+        const int b = FWD ? (BHI - 1 - bb) : (BLO + bb);
         const int bl = A + b;
         const uint2* twp = p.tw[bl] + ((size_t)tile_h << (TS - 1 - bl)) + ((size_t)e0_hi << (3 - b));
         uint2 w[8];
@@ -395,7 +395,7 @@ __device__ __forceinline__ void low_round(uint32_t* sm, const PassParams& p, uin
             for (int j = 0; j < 16; ++j) v[j] = sm[sb + low_pad(j << A)];
         }
     }
-    field_layers<FWD, A, BLO, 12>(v, p, tile, e0_hi);
+    field_layers_range<FWD, A, BLO, 4, 12>(v, p, tile, e0_hi);
     if (last) {
         if (A == 0) {
             uint4* d4 = reinterpret_cast<uint4*>(dst + gbase);
@@ -421,7 +421,7 @@ __device__ __forceinline__ void low_round(uint32_t* sm, const PassParams& p, uin
 }
 
 template <bool FWD, int M>
-__global__ void __launch_bounds__(256, 3) cfft_low_fast(PassParams p, int cols_per_block) {
+__global__ void __launch_bounds__(256, 4) cfft_low_fast(PassParams p, int cols_per_block) {
     __shared__ __align__(16) uint32_t sm[LOW_SMEM_WORDS];
     constexpr int NR = (M + 3) / 4;
     const uint32_t tile = blockIdx.x;
@@ -446,33 +446,62 @@ __global__ void __launch_bounds__(256, 3) cfft_low_fast(PassParams p, int cols_p
 }
 
 // ---- high pass --------------------------------------------------------------------------
-template <bool FWD, int M, int W, int R>
+// ILO: compile-time i_lo (0 = runtime) so the 16 strided global offsets become immediates.
+// ZEXT (forward first pass only): 0 = source is full size; 1 = source is the lower half
+// (blow-up 2: the upper half is zero, the top layer degenerates to a copy); 2 = generic bound check.
+template <bool FWD, int M, int W, int R, int ILO, int ZEXT>
 __device__ __forceinline__ void high_round(uint32_t* sm, const PassParams& p, uint32_t tile_h, size_t g_base,
                                            const uint32_t* src, uint32_t* dst, bool first, bool last) {
     constexpr int A = RoundGeom<M, R>::A;
     constexpr int BLO = RoundGeom<M, R>::BLO;
+    constexpr bool TOP = (A + 4 == M);
+    const int ilo = ILO ? ILO : p.i_lo;
     const int w = threadIdx.x % W;
     const int g = threadIdx.x / W;
     const int e0_hi = g >> A;
     const int e0 = (e0_hi << (A + 4)) | (g & ((1 << A) - 1));
-    const size_t gb = g_base + ((size_t)e0 << p.i_lo) + w;
+    const size_t gb = g_base + ((size_t)e0 << ilo) + w;
     const int sb = high_word<W>(e0, w);
     uint32_t v[16];
+    bool half_zero = false;
     if (first) {
-        const size_t n_src = (size_t)1 << p.log_src;
+        const uint32_t* sp = src + gb;
+        if (ZEXT == 2) {
+            const size_t n_src = (size_t)1 << p.log_src;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            size_t gi = gb + ((size_t)(j << A) << p.i_lo);
-            v[j] = gi < n_src ? src[gi] : 0u;
+            for (int j = 0; j < 16; ++j) {
+                size_t off = (size_t)(j << A) << ilo;
+                v[j] = gb + off < n_src ? sp[off] : 0u;
+            }
+        } else if (ZEXT == 1 && TOP) {
+            // tile covers the top layers (tile_h == 0): elements with the top index bit set are zero
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = sp[(size_t)(j << A) << ilo];
+#pragma unroll
+            for (int j = 8; j < 16; ++j) v[j] = v[j - 8];
+            half_zero = true;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = sp[(size_t)(j << A) << ilo];
         }
     } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = sm[sb + high_word<W>(j << A, 0)];
     }
-    field_layers<FWD, A, BLO, M>(v, p, tile_h, e0_hi);
+    if (ZEXT == 1 && TOP && FWD && BLO < 4) {
+        // top layer on (v, 0) pairs is the identity copy done above; run the remaining layers
+        if (half_zero) {
+            field_layers_range<FWD, A, BLO, 3, M>(v, p, tile_h, e0_hi);
+        } else {
+            field_layers_range<FWD, A, BLO, 4, M>(v, p, tile_h, e0_hi);
+        }
+    } else {
+        field_layers_range<FWD, A, BLO, 4, M>(v, p, tile_h, e0_hi);
+    }
     if (last) {
+        uint32_t* dp = dst + gb;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) dst[gb + ((size_t)(j << A) << p.i_lo)] = finalize(v[j], p.final_mode, p.scale);
+        for (int j = 0; j < 16; ++j) dp[(size_t)(j << A) << ilo] = finalize(v[j], p.final_mode, p.scale);
     } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) sm[sb + high_word<W>(j << A, 0)] = v[j];
@@ -483,34 +512,36 @@ template <int M>
 struct HighGeom {
     static constexpr int W = (M <= 8) ? (1 << (12 - M)) : 16;
     static constexpr int THREADS = (1 << (M - 4)) * W;
+    static constexpr int MIN_BLOCKS = (M <= 8) ? 3 : 1;
 };
 
-template <bool FWD, int M>
-__global__ void __launch_bounds__(HighGeom<M>::THREADS) cfft_high_fast(PassParams p, int cols_per_block) {
+template <bool FWD, int M, int ILO, int ZEXT>
+__global__ void __launch_bounds__(HighGeom<M>::THREADS, HighGeom<M>::MIN_BLOCKS) cfft_high_fast(PassParams p, int cols_per_block) {
     constexpr int W = HighGeom<M>::W;
     constexpr int NR = (M + 3) / 4;
     extern __shared__ __align__(16) uint32_t smh[];
-    const uint32_t l_tiles = (1u << p.i_lo) / W;
+    const int ilo = ILO ? ILO : p.i_lo;
+    const uint32_t l_tiles = (1u << ilo) / W;
     const uint32_t tile_h = blockIdx.x / l_tiles, lt = blockIdx.x % l_tiles;
-    const size_t g_base = ((size_t)tile_h << (p.i_lo + M)) + (size_t)lt * W;
+    const size_t g_base = ((size_t)tile_h << (ilo + M)) + (size_t)lt * W;
     const int c0 = blockIdx.y * cols_per_block;
     const int c1 = min(p.n_cols, c0 + cols_per_block);
     for (int c = c0; c < c1; ++c) {
         const uint32_t* src = p.src + (size_t)c * p.src_stride;
         uint32_t* dst = p.dst + (size_t)c * p.dst_stride;
         if constexpr (NR == 1) {
-            high_round<FWD, M, W, 0>(smh, p, tile_h, g_base, src, dst, true, true);
+            high_round<FWD, M, W, 0, ILO, ZEXT>(smh, p, tile_h, g_base, src, dst, true, true);
         } else if constexpr (FWD) {
-            if constexpr (NR == 3) { high_round<FWD, M, W, 2>(smh, p, tile_h, g_base, src, dst, true, false); __syncthreads(); }
-            high_round<FWD, M, W, (NR >= 2 ? 1 : 0)>(smh, p, tile_h, g_base, src, dst, NR == 2, false);
+            if constexpr (NR == 3) { high_round<FWD, M, W, 2, ILO, ZEXT>(smh, p, tile_h, g_base, src, dst, true, false); __syncthreads(); }
+            high_round<FWD, M, W, 1, ILO, ZEXT>(smh, p, tile_h, g_base, src, dst, NR == 2, false);
             __syncthreads();
-            high_round<FWD, M, W, 0>(smh, p, tile_h, g_base, src, dst, false, true);
+            high_round<FWD, M, W, 0, ILO, ZEXT>(smh, p, tile_h, g_base, src, dst, false, true);
             __syncthreads();
         } else {
-            high_round<FWD, M, W, 0>(smh, p, tile_h, g_base, src, dst, true, false);
+            high_round<FWD, M, W, 0, ILO, 0>(smh, p, tile_h, g_base, src, dst, true, false);
             __syncthreads();
-            high_round<FWD, M, W, (NR >= 2 ? 1 : 0)>(smh, p, tile_h, g_base, src, dst, false, NR == 2);
-            if constexpr (NR == 3) { __syncthreads(); high_round<FWD, M, W, 2>(smh, p, tile_h, g_base, src, dst, false, true); }
+            high_round<FWD, M, W, 1, ILO, 0>(smh, p, tile_h, g_base, src, dst, false, NR == 2);
+            if constexpr (NR == 3) { __syncthreads(); high_round<FWD, M, W, 2, ILO, 0>(smh, p, tile_h, g_base, src, dst, false, true); }
             __syncthreads();
         }
     }
@@ -604,8 +635,8 @@ static cudaError_t launch_low(const PassParams& p, int sm_count, cudaStream_t st
     return cudaErrorInvalidValue;
 }
 
-template <bool FWD, int M>
-static cudaError_t launch_high_m(const PassParams& p, int sm_count, cudaStream_t stream) {
+template <bool FWD, int M, int ILO, int ZEXT>
+static cudaError_t launch_high_k(const PassParams& p, int sm_count, cudaStream_t stream) {
     constexpr int W = HighGeom<M>::W;
     if (((size_t)1 << p.i_lo) < (size_t)W) return cudaErrorInvalidValue;
     size_t tiles = ((size_t)1 << (p.log_n - p.i_lo - M)) * (((size_t)1 << p.i_lo) / W);
@@ -613,13 +644,35 @@ static cudaError_t launch_high_m(const PassParams& p, int sm_count, cudaStream_t
     int cpb = pick_cols_per_block(tiles, p.n_cols, sm_count);
     dim3 grid((unsigned)tiles, (unsigned)((p.n_cols + cpb - 1) / cpb));
     if (grid.y > 65535) return cudaErrorInvalidValue;
-    auto k = cfft_high_fast<FWD, M>;
+    auto k = cfft_high_fast<FWD, M, ILO, ZEXT>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     k<<<grid, HighGeom<M>::THREADS, smem, stream>>>(p, cpb);
     return cudaGetLastError();
+}
+
+template <bool FWD, int M>
+static cudaError_t launch_high_m(const PassParams& p, int sm_count, cudaStream_t stream) {
+    // zero extension only matters for the forward pass that reads the coefficients
+    int zext = 0;
+    if (FWD && p.log_src < p.log_n) {
+        bool top = (p.i_lo + M == p.log_n);
+        zext = (top && p.log_src == p.log_n - 1 && M >= 4) ? 1 : 2;
+    }
+    if constexpr (FWD) {
+        if (p.i_lo == 12) {
+            if (zext == 1) return launch_high_k<FWD, M, 12, 1>(p, sm_count, stream);
+            if (zext == 2) return launch_high_k<FWD, M, 0, 2>(p, sm_count, stream);
+            return launch_high_k<FWD, M, 12, 0>(p, sm_count, stream);
+        }
+        if (zext) return launch_high_k<FWD, M, 0, 2>(p, sm_count, stream);
+        return launch_high_k<FWD, M, 0, 0>(p, sm_count, stream);
+    } else {
+        if (p.i_lo == 12) return launch_high_k<FWD, M, 12, 0>(p, sm_count, stream);
+        return launch_high_k<FWD, M, 0, 0>(p, sm_count, stream);
+    }
 }
 
 template <bool FWD>
