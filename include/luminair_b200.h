@@ -31,6 +31,7 @@ extern "C" {
 #define LB_ERR_OOM (-2)
 #define LB_ERR_BAD_ARG (-3)
 #define LB_ERR_NCCL (-4)
+#define LB_ERR_CONSTRAINTS (-5) /* ProvingError::ConstraintsNotSatisfied (prover.rs:312) */
 
 typedef struct lb_ctx lb_ctx;
 
@@ -72,6 +73,85 @@ int lb_merkle_commit_layer(lb_ctx* ctx, int log_size, const uint32_t* d_prev, co
 /* h_out[k*n_cols + c] = cols[c][h_idx[k]]  (decommitment gathers) */
 int lb_gather_rows(lb_ctx* ctx, const uint32_t* const* h_cols, int n_cols, const uint32_t* h_idx, int n_idx,
                    uint32_t* h_out);
+
+/* ---- PolyOps::eval_at_point (OODS sampling inside stwo::prover::prove, prover.rs:311-312) ---- */
+/* h_cols: HOST array of n_cols DEVICE coefficient columns (2^log_size each); point = x (4 u32) then y (4 u32),
+ * QM31 coordinates; h_out: HOST, 4 u32 per column */
+int lb_eval_at_point(lb_ctx* ctx, const uint32_t* const* h_cols, int n_cols, int log_size, const uint32_t point[8],
+                     uint32_t* h_out);
+
+/* ---- QuotientOps::accumulate_quotients (DEEP quotients) --------------------------------------- */
+/* one ColumnSampleBatch: a sample point and the (column index, sampled value) pairs taken there */
+typedef struct {
+    uint32_t point[8];      /* x (4 u32), y (4 u32) */
+    int n_cols;
+    const int* col_idx;     /* indices into h_cols */
+    const uint32_t* values; /* 4 u32 per column */
+} lb_sample_batch;
+/* h_cols: HOST array of DEVICE LDE columns of 2^log_size; d_out: 4 DEVICE coordinate columns of 2^log_size */
+int lb_accumulate_quotients(lb_ctx* ctx, int log_size, const uint32_t* const* h_cols, int n_cols,
+                            const lb_sample_batch* batches, int n_batches, const uint32_t random_coeff[4],
+                            uint32_t* const d_out[4]);
+
+/* ---- FriOps ------------------------------------------------------------------------------------- */
+/* dst (4 coords of 2^(log_size-1)) = dst * alpha^2 + fold(src (4 coords of 2^log_size on CanonicCoset(log_size))) */
+int lb_fold_circle_into_line(lb_ctx* ctx, uint32_t* const d_dst[4], const uint32_t* const d_src[4], int log_size,
+                             const uint32_t alpha[4]);
+/* dst (4 coords of 2^(log_size-1)) = fold(src on LineDomain(half_odds(log_size))) */
+int lb_fold_line(lb_ctx* ctx, uint32_t* const d_dst[4], const uint32_t* const d_src[4], int log_size,
+                 const uint32_t alpha[4]);
+
+/* ---- GrindOps<Blake2sChannel>::grind -------------------------------------------------------------- */
+/* smallest nonce whose mix_u64 into `digest` leaves >= pow_bits trailing zero bits; channel_variant as in lb_prove_config */
+int lb_grind(lb_ctx* ctx, const uint32_t digest[8], int channel_variant, uint32_t pow_bits, uint64_t* nonce_out);
+
+/* ---- AIR kernels (crates/air): component ids ------------------------------------------------------- */
+#define LB_COMP_ADD 0    /* components/add    (component.rs:38-116, witness.rs:126-167) */
+#define LB_COMP_MUL 1    /* components/mul    */
+#define LB_COMP_INPUTS 2 /* components/inputs */
+#define LB_COMP_MUL_ARTIFACT 3 /* Mul AIR of the revision that produced ui/demo/public/proof (KAT only) */
+/* InteractionClaimGenerator::write_interaction_trace: LogUp columns from the main trace (values, not
+ * coefficients).  d_inter receives 4*k columns of 2^log_size; claimed_out = claimed sum (4 u32, HOST). */
+int lb_logup_interaction_trace(lb_ctx* ctx, int component, const uint32_t* d_main, size_t main_stride, uint32_t* d_inter,
+                               size_t inter_stride, int log_size, const uint32_t z[4], const uint32_t alpha[4],
+                               uint32_t claimed_out[4]);
+/* ComponentProver::evaluate_constraint_quotients_on_domain for FrameworkComponent<XEval>
+ * (crates/air/src/components/mod.rs:530-601): d_main / d_inter are the LDE columns on CanonicCoset(log_size+1);
+ * pows = this component's random-coefficient powers, first constraint first (4 u32 each);
+ * d_acc = 4 coordinate columns of 2^(log_size+1), overwritten (accumulate = 0) or added to (1). */
+int lb_constraint_quotients(lb_ctx* ctx, int component, const uint32_t* d_main, size_t main_stride, const uint32_t* d_inter,
+                            size_t inter_stride, int log_size, const uint32_t z[4], const uint32_t alpha[4],
+                            const uint32_t claimed_sum[4], const uint32_t* pows, int n_pows, uint32_t* const d_acc[4],
+                            int accumulate);
+
+/* ---- luminair_prover::prover::prove (crates/prover/src/prover.rs:28-319) ---------------------------- */
+/* one `TraceTable` of the LuminairPie (crates/air/src/pie.rs:143-148): row-major rows of the component's
+ * main-trace columns, canonical M31 values */
+typedef struct {
+    int slot;             /* field index in LuminairClaim (crates/air/src/lib.rs:30-48): add 0, mul 1, inputs 15 */
+    int n_cols;
+    uint64_t n_rows;      /* unpadded */
+    const uint32_t* rows; /* n_rows x n_cols, HOST (or DEVICE when rows_on_device != 0) */
+    int rows_on_device;
+} lb_trace_table;
+typedef struct {
+    uint32_t pow_bits, log_blowup_factor, log_last_layer_degree_bound; /* PcsConfig::default(): 5, 1, 0 */
+    uint64_t n_queries;                                                  /* 3 */
+    int channel_variant; /* 0: Blake2sChannel as pinned by the reference's committed proof; 1: "v2" mixing */
+    int n_slots;         /* Option fields in LuminairClaim: 17 */
+    int air_era;         /* 0: AIRs of the tree at /root/reference; 1: the revision that produced ui/demo/public/proof
+                            (8 claim slots, Mul AIR with one extra, identically-zero constraint) - known-answer test only */
+    int draw_lookup_elements; /* 1: LuminairInteractionElements::draw also draws the 4 LUT relations (components/mod.rs:227-235) */
+} lb_prove_config;
+/* Tables in pie order.  On success *proof_out is a malloc'd bincode `LuminairProof` (free with lb_free_host).
+ * cfg == NULL: the reference's defaults.  Errors: LB_ERR_BAD_ARG ("TraceError::EmptyTrace", unsupported
+ * component), LB_ERR_CONSTRAINTS (ProvingError::ConstraintsNotSatisfied). */
+int lb_prove(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_prove_config* cfg, uint8_t** proof_out,
+             size_t* proof_len);
+void lb_free_host(void* p);
+/* diagnostics of the last lb_prove: channel digest after every mix (32 B each) and per-stage wall-clock ms */
+int lb_prove_transcript(lb_ctx* ctx, uint8_t* out, size_t cap_hashes, size_t* n_hashes);
+int lb_prove_stage_ms(lb_ctx* ctx, float* out, int cap, int* n);
 
 #ifdef __cplusplus
 }

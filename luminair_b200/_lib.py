@@ -45,6 +45,44 @@ SIGNATURES = {
 }
 
 
+class TraceTable(C.Structure):
+    """lb_trace_table"""
+    _fields_ = [("slot", C.c_int), ("n_cols", C.c_int), ("n_rows", C.c_uint64), ("rows", C.c_void_p),
+                ("rows_on_device", C.c_int)]
+
+
+class ProveConfig(C.Structure):
+    """lb_prove_config"""
+    _fields_ = [("pow_bits", C.c_uint32), ("log_blowup_factor", C.c_uint32), ("log_last_layer_degree_bound", C.c_uint32),
+                ("n_queries", C.c_uint64), ("channel_variant", C.c_int), ("n_slots", C.c_int), ("air_era", C.c_int),
+                ("draw_lookup_elements", C.c_int)]
+
+
+class SampleBatch(C.Structure):
+    """lb_sample_batch"""
+    _fields_ = [("point", C.c_uint32 * 8), ("n_cols", C.c_int), ("col_idx", C.POINTER(C.c_int)),
+                ("values", C.POINTER(C.c_uint32))]
+
+
+SIGNATURES.update({
+    "lb_eval_at_point": (C.c_int, [ctxp, C.POINTER(C.c_void_p), C.c_int, C.c_int, u32p, u32p]),
+    "lb_accumulate_quotients": (C.c_int, [ctxp, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(SampleBatch), C.c_int,
+                                          u32p, C.POINTER(C.c_void_p)]),
+    "lb_fold_circle_into_line": (C.c_int, [ctxp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, u32p]),
+    "lb_fold_line": (C.c_int, [ctxp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, u32p]),
+    "lb_grind": (C.c_int, [ctxp, u32p, C.c_int, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "lb_logup_interaction_trace": (C.c_int, [ctxp, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, u32p,
+                                             u32p, u32p]),
+    "lb_constraint_quotients": (C.c_int, [ctxp, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, u32p, u32p,
+                                          u32p, u32p, C.c_int, C.POINTER(C.c_void_p), C.c_int]),
+    "lb_prove": (C.c_int, [ctxp, C.POINTER(TraceTable), C.c_int, C.POINTER(ProveConfig), C.POINTER(C.c_void_p),
+                           C.POINTER(C.c_size_t)]),
+    "lb_free_host": (None, [C.c_void_p]),
+    "lb_prove_transcript": (C.c_int, [ctxp, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "lb_prove_stage_ms": (C.c_int, [ctxp, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]),
+})
+
+
 def load_library():
     """Load libluminair_b200.so; fail loudly when it is missing (no CPU fallback exists)."""
     global _lib

@@ -145,3 +145,78 @@ class CudaBackend:
         arr = (C.c_void_p * n)(*col_ptrs)
         check(self.ctx, self.lib.lb_gather_rows(self.ctx, arr, n, idx.ctypes.data_as(C.c_void_p), len(idx), out.ctypes.data_as(C.c_void_p)), "lb_gather_rows")
         return out
+
+    # ---- PolyOps::eval_at_point ---------------------------------------------------------
+    def eval_at_point(self, col_ptrs, log_size: int, point) -> np.ndarray:
+        """point = 8 u32 (x then y, QM31 coordinates) -> [n_cols, 4] u32."""
+        n = len(col_ptrs)
+        arr = (C.c_void_p * max(n, 1))(*col_ptrs)
+        pt = (C.c_uint32 * 8)(*[int(v) for v in point])
+        out = np.zeros((n, 4), dtype=np.uint32)
+        check(self.ctx, self.lib.lb_eval_at_point(self.ctx, arr, n, log_size, pt, out.ctypes.data_as(C.POINTER(C.c_uint32))),
+              "lb_eval_at_point")
+        return out
+
+    # ---- QuotientOps ---------------------------------------------------------------------
+    def accumulate_quotients(self, log_size: int, col_ptrs, batches, random_coeff, out_ptrs):
+        """batches: list of (point[8], [(col_idx, value[4])...]); out_ptrs: 4 device coordinate columns."""
+        from ._lib import SampleBatch
+        n = len(col_ptrs)
+        arr = (C.c_void_p * n)(*col_ptrs)
+        keep = []
+        sb = (SampleBatch * len(batches))()
+        for i, (pt, cols) in enumerate(batches):
+            idx = (C.c_int * len(cols))(*[int(c) for c, _ in cols])
+            vals = (C.c_uint32 * (4 * len(cols)))(*[int(x) for _, v in cols for x in v])
+            keep += [idx, vals]
+            sb[i].point = (C.c_uint32 * 8)(*[int(v) for v in pt])
+            sb[i].n_cols = len(cols)
+            sb[i].col_idx = idx
+            sb[i].values = vals
+        rc = (C.c_uint32 * 4)(*[int(v) for v in random_coeff])
+        outs = (C.c_void_p * 4)(*out_ptrs)
+        check(self.ctx, self.lib.lb_accumulate_quotients(self.ctx, log_size, arr, n, sb, len(batches), rc, outs),
+              "lb_accumulate_quotients")
+
+    # ---- FriOps ----------------------------------------------------------------------------
+    def fold_circle_into_line(self, dst_ptrs, src_ptrs, log_size: int, alpha):
+        d = (C.c_void_p * 4)(*dst_ptrs)
+        s = (C.c_void_p * 4)(*src_ptrs)
+        a = (C.c_uint32 * 4)(*[int(v) for v in alpha])
+        check(self.ctx, self.lib.lb_fold_circle_into_line(self.ctx, d, s, log_size, a), "lb_fold_circle_into_line")
+
+    def fold_line(self, dst_ptrs, src_ptrs, log_size: int, alpha):
+        d = (C.c_void_p * 4)(*dst_ptrs)
+        s = (C.c_void_p * 4)(*src_ptrs)
+        a = (C.c_uint32 * 4)(*[int(v) for v in alpha])
+        check(self.ctx, self.lib.lb_fold_line(self.ctx, d, s, log_size, a), "lb_fold_line")
+
+    # ---- GrindOps ---------------------------------------------------------------------------
+    def grind(self, digest: bytes, pow_bits: int, channel_variant: int = 0) -> int:
+        dg = (C.c_uint32 * 8).from_buffer_copy(digest)
+        nonce = C.c_uint64()
+        check(self.ctx, self.lib.lb_grind(self.ctx, dg, channel_variant, pow_bits, C.byref(nonce)), "lb_grind")
+        return int(nonce.value)
+
+    # ---- AIR kernels -------------------------------------------------------------------------
+    def logup_interaction_trace(self, component: int, main: ColumnBatch, inter: ColumnBatch, z, alpha) -> np.ndarray:
+        zz = (C.c_uint32 * 4)(*[int(v) for v in z])
+        aa = (C.c_uint32 * 4)(*[int(v) for v in alpha])
+        claimed = (C.c_uint32 * 4)()
+        check(self.ctx, self.lib.lb_logup_interaction_trace(self.ctx, component, C.c_void_p(main.ptr), main.stride,
+                                                             C.c_void_p(inter.ptr), inter.stride, main.log_size, zz, aa, claimed),
+              "lb_logup_interaction_trace")
+        return np.array(list(claimed), dtype=np.uint32)
+
+    def constraint_quotients(self, component: int, main_lde: ColumnBatch, inter_lde: ColumnBatch, log_size: int, z, alpha,
+                             claimed_sum, pows, acc_ptrs, accumulate: bool = False):
+        zz = (C.c_uint32 * 4)(*[int(v) for v in z])
+        aa = (C.c_uint32 * 4)(*[int(v) for v in alpha])
+        cs = (C.c_uint32 * 4)(*[int(v) for v in claimed_sum])
+        flat = [int(x) for p in pows for x in p]
+        pw = (C.c_uint32 * len(flat))(*flat)
+        acc = (C.c_void_p * 4)(*acc_ptrs)
+        check(self.ctx, self.lib.lb_constraint_quotients(self.ctx, component, C.c_void_p(main_lde.ptr), main_lde.stride,
+                                                          C.c_void_p(inter_lde.ptr), inter_lde.stride, log_size, zz, aa, cs, pw,
+                                                          len(pows), acc, 1 if accumulate else 0),
+              "lb_constraint_quotients")

@@ -1,0 +1,256 @@
+// AIR-side kernels for sm_100a: LogUp interaction-trace generation and batched constraint-quotient
+// evaluation over the evaluation domain.
+//
+//   logup_interaction_trace  replaces `InteractionClaimGenerator::write_interaction_trace`
+//       (/root/reference/crates/air/src/components/add/witness.rs:126-167 and siblings), i.e. stwo's
+//       LogupTraceGenerator::{new_col, write_frac, finalize_col, finalize_last}   
+//   constraint_quotients     replaces ComponentProver::evaluate_constraint_quotients_on_domain for
+//       FrameworkComponent<XEval> (crates/air/src/components/mod.rs:530-601)      
+//
+// Both are one thread per row over column-major data (coalesced 128-byte warp reads, each input
+// byte read once); the LogUp prefix sum runs in canonic-coset order over the bit-reversed
+// storage as a three-phase scan.
+#include "kernels.cuh"
+
+namespace lb {
+
+// ------------------------------------------------------------------------------------
+// LogUp fractions.  Column k (QM31, 4 coordinate columns) = sum_{k' <= k} mult_k' / denom_k',
+// denom = alpha * id + val - z.  The n_fracs inversions of a row share one QM31 inversion.
+// ------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) logup_fracs_kernel(const uint32_t* __restrict__ main, size_t main_stride,
+                                                          uint32_t* __restrict__ inter, size_t inter_stride, uint32_t n,
+                                                          Relation2 node) {
+    constexpr int NF = component_shape(KIND).n_fracs;
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    QM31 den[NF], pre[NF];
+    uint32_t mult[NF];
+    QM31 run = q_from_m(1);
+#pragma unroll
+    for (int k = 0; k < NF; ++k) {
+        const LookupTerm t = lookup_term(KIND, k);
+        uint32_t val = main[(size_t)t.val * main_stride + j];
+        uint32_t id = main[(size_t)t.id * main_stride + j];
+        mult[k] = main[(size_t)t.mult * main_stride + j];
+        QM31 d = q_mul_m(node.alpha, id);
+        d.a.a = m_add(d.a.a, val);
+        d = q_sub(d, node.z);
+        den[k] = d;
+        pre[k] = run;
+        run = q_mul(run, d);
+    }
+    QM31 inv = q_inv(run);
+    QM31 dinv[NF];
+#pragma unroll
+    for (int k = NF - 1; k >= 0; --k) {
+        dinv[k] = q_mul(inv, pre[k]);
+        inv = q_mul(inv, den[k]);
+    }
+    QM31 acc = q_zero();
+#pragma unroll
+    for (int k = 0; k < NF; ++k) {
+        acc = q_add(acc, q_mul_m(dinv[k], mult[k]));
+        uint32_t* o = inter + (size_t)(4 * k) * inter_stride + j;
+        o[0] = acc.a.a;
+        o[inter_stride] = acc.a.b;
+        o[2 * inter_stride] = acc.b.a;
+        o[3 * inter_stride] = acc.b.b;
+    }
+}
+
+// storage index of canonic-coset point k (CanonicCoset(log).coset order):
+//   circle-domain index = k/2 (k even) | n - (k+1)/2 (k odd);  storage = bitrev(domain index)
+__device__ __forceinline__ uint32_t coset_to_storage(uint32_t k, int log) {
+    uint32_t n = 1u << log;
+    uint32_t d = (k & 1) ? (n - ((k + 1) >> 1)) : (k >> 1);
+    return log ? (__brev(d) >> (32 - log)) : 0;
+}
+
+constexpr int SCAN_BLOCK = 1024;  // elements per CTA (256 threads x 4)
+
+// phase 1: per-CTA inclusive scan of the last column in coset order (gathered), mod P
+__global__ void __launch_bounds__(256) logup_scan_local_kernel(const uint32_t* __restrict__ col, size_t coord_stride,
+                                                               uint32_t* __restrict__ tmp, uint32_t* __restrict__ block_sums,
+                                                               int log) {
+    __shared__ uint32_t s_warp[8];
+    const uint32_t n = 1u << log;
+    const int coord = blockIdx.y;
+    const uint32_t* src = col + (size_t)coord * coord_stride;
+    uint32_t* dst = tmp + (size_t)coord * n;
+    const uint32_t k0 = blockIdx.x * SCAN_BLOCK + threadIdx.x * 4;
+    uint32_t v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = (k0 + i < n) ? src[coset_to_storage(k0 + i, log)] : 0u;
+    v[1] = m_add(v[1], v[0]);
+    v[2] = m_add(v[2], v[1]);
+    v[3] = m_add(v[3], v[2]);
+    uint32_t tot = v[3];
+    // warp inclusive scan of the per-thread totals
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t s = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, s, o);
+        if (lane >= o) s = m_add(s, t);
+    }
+    if (lane == 31) s_warp[w] = s;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int i = 0; i < w; ++i) woff = m_add(woff, s_warp[i]);
+    uint32_t excl = m_add(woff, m_sub(s, tot));
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (k0 + i < n) dst[k0 + i] = m_add(v[i], excl);
+    if (threadIdx.x == 255) block_sums[(size_t)coord * gridDim.x + blockIdx.x] = m_add(s, woff);
+}
+
+// phase 2: exclusive scan of the CTA totals (<= 2^21 / 1024 entries per coordinate); total -> claimed
+__global__ void logup_scan_sums_kernel(uint32_t* block_sums, uint32_t n_blocks, uint32_t* claimed) {
+    int coord = threadIdx.x;
+    if (coord >= 4) return;
+    uint32_t* s = block_sums + (size_t)coord * n_blocks;
+    uint32_t run = 0;
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        uint32_t t = s[b];
+        s[b] = run;
+        run = m_add(run, t);
+    }
+    claimed[coord] = run;
+}
+
+// phase 3: out[storage(k)] = local[k] + offset[block] - (k + 1) * claimed / n
+__global__ void __launch_bounds__(256) logup_scan_apply_kernel(uint32_t* __restrict__ col, size_t coord_stride,
+                                                               const uint32_t* __restrict__ tmp,
+                                                               const uint32_t* __restrict__ block_sums,
+                                                               const uint32_t* __restrict__ claimed, int log, uint32_t inv_n) {
+    const uint32_t n = 1u << log;
+    const int coord = blockIdx.y;
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t n_blocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    uint32_t shift = m_mul(claimed[coord], inv_n);
+    uint32_t v = m_add(tmp[(size_t)coord * n + k], block_sums[(size_t)coord * n_blocks + k / SCAN_BLOCK]);
+    v = m_sub(v, m_mul(shift, (k + 1) % P));
+    col[(size_t)coord * coord_stride + coset_to_storage(k, log)] = v;
+}
+
+cudaError_t logup_interaction_trace(int kind, const uint32_t* main, size_t main_stride, uint32_t* inter,
+                                    size_t inter_stride, int log, const Relation2& node, uint32_t* d_scan_tmp,
+                                    uint32_t* d_block_sums, uint32_t* d_claimed, cudaStream_t stream) {
+    uint32_t n = 1u << log;
+    unsigned blocks = (n + 255) / 256;
+    int nf = component_shape(kind).n_fracs;
+    switch (kind) {
+        case COMP_ADD: logup_fracs_kernel<COMP_ADD><<<blocks, 256, 0, stream>>>(main, main_stride, inter, inter_stride, n, node); break;
+        case COMP_MUL:
+        case COMP_MUL_ARTIFACT: logup_fracs_kernel<COMP_MUL><<<blocks, 256, 0, stream>>>(main, main_stride, inter, inter_stride, n, node); break;
+        case COMP_INPUTS: logup_fracs_kernel<COMP_INPUTS><<<blocks, 256, 0, stream>>>(main, main_stride, inter, inter_stride, n, node); break;
+        default: return cudaErrorInvalidValue;
+    }
+    uint32_t* last = inter + (size_t)(4 * (nf - 1)) * inter_stride;
+    uint32_t n_blocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    logup_scan_local_kernel<<<dim3(n_blocks, 4), 256, 0, stream>>>(last, inter_stride, d_scan_tmp, d_block_sums, log);
+    logup_scan_sums_kernel<<<1, 32, 0, stream>>>(d_block_sums, n_blocks, d_claimed);
+    uint32_t inv_n = m_inv(n % P);
+    logup_scan_apply_kernel<<<dim3(blocks, 4), 256, 0, stream>>>(last, inter_stride, d_scan_tmp, d_block_sums, d_claimed, log,
+                                                                 inv_n);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
+// Constraint quotients: one thread per evaluation-domain row.
+// ------------------------------------------------------------------------------------
+struct DomainEval : LogupMixin<DomainEval, FM, FQ> {
+    typedef FM F;
+    typedef FQ EF;
+    const ConstraintParams& p;
+    uint32_t row, row_prev;
+    int mc = 0, ic = 0, ci = 0;
+    QM31 res;
+    QM31 cumsum_shift;
+
+    __device__ __forceinline__ DomainEval(const ConstraintParams& p_, uint32_t row_, uint32_t row_prev_)
+        : p(p_), row(row_), row_prev(row_prev_), res(q_zero()), cumsum_shift(p_.cumsum_shift) {}
+
+    __device__ __forceinline__ FM constant(uint32_t c) const { return {c}; }
+    __device__ __forceinline__ FM next_trace_mask() {
+        FM v = {p.main[(size_t)mc * p.main_stride + row]};
+        ++mc;
+        return v;
+    }
+    __device__ __forceinline__ FQ read_ext(uint32_t r) const {
+        const uint32_t* b = p.inter + (size_t)ic * p.inter_stride + r;
+        return {q_make(b[0], b[p.inter_stride], b[2 * p.inter_stride], b[3 * p.inter_stride])};
+    }
+    __device__ __forceinline__ FQ next_ext_mask_cur() {
+        FQ v = read_ext(row);
+        ic += 4;
+        return v;
+    }
+    __device__ __forceinline__ void next_ext_mask_prev_cur(FQ& prev, FQ& cur) {
+        prev = read_ext(row_prev);
+        cur = read_ext(row);
+        ic += 4;
+    }
+    __device__ __forceinline__ void add_constraint(FM c) {
+        res = q_add(res, q_mul_m(p.pows[ci], c.v));
+        ++ci;
+    }
+    __device__ __forceinline__ void add_constraint_ef(FQ c) {
+        res = q_add(res, q_mul(p.pows[ci], c.v));
+        ++ci;
+    }
+};
+
+// offset_bit_reversed_circle_domain_index(row, domain_log, eval_log, -1)
+__device__ __forceinline__ uint32_t prev_row_index(uint32_t j, int domain_log, int eval_log) {
+    uint32_t n = 1u << eval_log, half = n >> 1;
+    uint32_t nat = __brev(j) >> (32 - eval_log);
+    uint32_t step = 1u << (eval_log - domain_log - 1);  // |offset| = 1
+    uint32_t r;
+    if (nat < half)
+        r = (nat + half - step) & (half - 1);
+    else
+        r = ((nat - half + step) & (half - 1)) + half;
+    return __brev(r) >> (32 - eval_log);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) constraint_quotients_kernel(const __grid_constant__ ConstraintParams p) {
+    uint32_t n = 1u << p.eval_log;
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    DomainEval ev(p, j, prev_row_index(j, p.log_size, p.eval_log));
+    if (KIND == COMP_ADD)
+        eval_add(ev, p.node);
+    else if (KIND == COMP_MUL)
+        eval_mul<DomainEval, false>(ev, p.node);
+    else if (KIND == COMP_MUL_ARTIFACT)
+        eval_mul<DomainEval, true>(ev, p.node);
+    else
+        eval_inputs(ev, p.node);
+    QM31 r = q_mul_m(ev.res, p.denom_inv[j >> p.log_size]);
+    if (p.accumulate) r = q_add(r, q_make(p.acc[0][j], p.acc[1][j], p.acc[2][j], p.acc[3][j]));
+    p.acc[0][j] = r.a.a;
+    p.acc[1][j] = r.a.b;
+    p.acc[2][j] = r.b.a;
+    p.acc[3][j] = r.b.b;
+}
+
+cudaError_t constraint_quotients(int kind, const ConstraintParams& p, cudaStream_t stream) {
+    if (p.eval_log - p.log_size < 1 || p.eval_log - p.log_size > 2) return cudaErrorInvalidValue;
+    uint32_t n = 1u << p.eval_log;
+    unsigned blocks = (n + 255) / 256;
+    switch (kind) {
+        case COMP_ADD: constraint_quotients_kernel<COMP_ADD><<<blocks, 256, 0, stream>>>(p); break;
+        case COMP_MUL: constraint_quotients_kernel<COMP_MUL><<<blocks, 256, 0, stream>>>(p); break;
+        case COMP_MUL_ARTIFACT: constraint_quotients_kernel<COMP_MUL_ARTIFACT><<<blocks, 256, 0, stream>>>(p); break;
+        case COMP_INPUTS: constraint_quotients_kernel<COMP_INPUTS><<<blocks, 256, 0, stream>>>(p); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace lb

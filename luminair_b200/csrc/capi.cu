@@ -1,38 +1,15 @@
 // extern "C" boundary of libluminair_b200.so — see include/luminair_b200.h.
-#include "../../include/luminair_b200.h"
-
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
-#include "cfft.cuh"
+#include "ctx.h"
 #include "merkle.cuh"
 
-struct lb_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int sm_count = 0;
-    size_t total_mem = 0;
-    lb::Twiddles tw;
-    std::string err;
-    // scratch for pointer tables / index lists
-    void* d_scratch = nullptr;
-    size_t scratch_bytes = 0;
-};
-
 namespace {
-int fail(lb_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
-    if (ctx) {
-        ctx->err = what;
-        if (e != cudaSuccess) {
-            ctx->err += ": ";
-            ctx->err += cudaGetErrorString(e);
-        }
-    }
-    return code;
-}
+int fail(lb_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess) { return lb::ctx_fail(ctx, code, what, e); }
 #define CK(call, what)                                                          \
     do {                                                                        \
         cudaError_t _e = (call);                                                \
@@ -54,7 +31,7 @@ int ensure_scratch(lb_ctx* ctx, size_t bytes) {
 
 extern "C" {
 
-int lb_version(void) { return 1; }
+int lb_version(void) { return 2; }
 
 int lb_ctx_create(int device, lb_ctx** out) {
     if (!out) return LB_ERR_BAD_ARG;
@@ -72,6 +49,14 @@ int lb_ctx_create(int device, lb_ctx** out) {
     if (e != cudaSuccess) {
         delete ctx;
         return LB_ERR_CUDA;
+    }
+    {
+        // keep stream-ordered allocations cached between prove() calls
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
     }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->total_mem = prop.totalGlobalMem;
@@ -238,6 +223,90 @@ int lb_gather_rows(lb_ctx* ctx, const uint32_t* const* h_cols, int n_cols, const
        "gather");
     CK(cudaMemcpyAsync(h_out, d_out, ob, cudaMemcpyDeviceToHost, ctx->stream), "gather/out");
     CK(cudaStreamSynchronize(ctx->stream), "gather/sync2");
+    return LB_OK;
+}
+
+int lb_eval_at_point(lb_ctx* ctx, const uint32_t* const* h_cols, int n_cols, int log_size, const uint32_t point[8],
+                     uint32_t* h_out) {
+    if (!ctx || n_cols < 0 || log_size < 0 || log_size > 30 || (n_cols && (!h_cols || !h_out)) || !point)
+        return fail(ctx, LB_ERR_BAD_ARG, "eval_at_point: bad args");
+    if (n_cols == 0) return LB_OK;
+    return lb::eval_at_point_impl(ctx, h_cols, n_cols, log_size, point, h_out);
+}
+
+int lb_accumulate_quotients(lb_ctx* ctx, int log_size, const uint32_t* const* h_cols, int n_cols,
+                            const lb_sample_batch* batches, int n_batches, const uint32_t random_coeff[4],
+                            uint32_t* const d_out[4]) {
+    if (!ctx || log_size < 1 || log_size > 30 || n_cols < 1 || !h_cols || !batches || n_batches < 1 || !random_coeff || !d_out)
+        return fail(ctx, LB_ERR_BAD_ARG, "accumulate_quotients: bad args");
+    return lb::accumulate_quotients_impl(ctx, log_size, h_cols, n_cols, batches, n_batches, random_coeff, d_out);
+}
+
+int lb_fold_circle_into_line(lb_ctx* ctx, uint32_t* const d_dst[4], const uint32_t* const d_src[4], int log_size,
+                             const uint32_t alpha[4]) {
+    if (!ctx || !d_dst || !d_src || !alpha) return fail(ctx, LB_ERR_BAD_ARG, "fold_circle_into_line: bad args");
+    return lb::fold_impl(ctx, 1, d_dst, d_src, log_size, alpha);
+}
+
+int lb_fold_line(lb_ctx* ctx, uint32_t* const d_dst[4], const uint32_t* const d_src[4], int log_size, const uint32_t alpha[4]) {
+    if (!ctx || !d_dst || !d_src || !alpha) return fail(ctx, LB_ERR_BAD_ARG, "fold_line: bad args");
+    return lb::fold_impl(ctx, 0, d_dst, d_src, log_size, alpha);
+}
+
+int lb_grind(lb_ctx* ctx, const uint32_t digest[8], int channel_variant, uint32_t pow_bits, uint64_t* nonce_out) {
+    if (!ctx || !digest || !nonce_out || channel_variant < 0 || channel_variant > 1)
+        return fail(ctx, LB_ERR_BAD_ARG, "grind: bad args");
+    return lb::grind_impl(ctx, digest, channel_variant, pow_bits, nonce_out);
+}
+
+int lb_logup_interaction_trace(lb_ctx* ctx, int component, const uint32_t* d_main, size_t main_stride, uint32_t* d_inter,
+                               size_t inter_stride, int log_size, const uint32_t z[4], const uint32_t alpha[4],
+                               uint32_t claimed_out[4]) {
+    if (!ctx || !d_main || !d_inter || !z || !alpha || !claimed_out || log_size < 1 || log_size > 30)
+        return fail(ctx, LB_ERR_BAD_ARG, "logup: bad args");
+    return lb::logup_impl(ctx, component, d_main, main_stride, d_inter, inter_stride, log_size, z, alpha, claimed_out);
+}
+
+int lb_constraint_quotients(lb_ctx* ctx, int component, const uint32_t* d_main, size_t main_stride, const uint32_t* d_inter,
+                            size_t inter_stride, int log_size, const uint32_t z[4], const uint32_t alpha[4],
+                            const uint32_t claimed_sum[4], const uint32_t* pows, int n_pows, uint32_t* const d_acc[4],
+                            int accumulate) {
+    if (!ctx || !d_main || !d_inter || !z || !alpha || !claimed_sum || !pows || !d_acc || log_size < 1 || log_size > 29)
+        return fail(ctx, LB_ERR_BAD_ARG, "constraint_quotients: bad args");
+    return lb::constraint_quotients_impl(ctx, component, d_main, main_stride, d_inter, inter_stride, log_size, z, alpha,
+                                         claimed_sum, pows, n_pows, d_acc, accumulate);
+}
+
+int lb_prove(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_prove_config* cfg, uint8_t** proof_out,
+             size_t* proof_len) {
+    if (!ctx || !proof_out || !proof_len) return fail(ctx, LB_ERR_BAD_ARG, "prove: bad args");
+    *proof_out = nullptr;
+    *proof_len = 0;
+    std::vector<uint8_t> bytes;
+    int r = lb::prove_impl(ctx, tables, n_tables, cfg, bytes);
+    if (r) return r;
+    uint8_t* p = (uint8_t*)std::malloc(bytes.size() ? bytes.size() : 1);
+    if (!p) return fail(ctx, LB_ERR_OOM, "prove: host malloc");
+    std::memcpy(p, bytes.data(), bytes.size());
+    *proof_out = p;
+    *proof_len = bytes.size();
+    return LB_OK;
+}
+
+void lb_free_host(void* p) { std::free(p); }
+
+int lb_prove_transcript(lb_ctx* ctx, uint8_t* out, size_t cap_hashes, size_t* n_hashes) {
+    if (!ctx || !n_hashes) return LB_ERR_BAD_ARG;
+    *n_hashes = ctx->transcript.size();
+    size_t n = ctx->transcript.size() < cap_hashes ? ctx->transcript.size() : cap_hashes;
+    for (size_t i = 0; i < n && out; ++i) std::memcpy(out + 32 * i, ctx->transcript[i].b, 32);
+    return LB_OK;
+}
+
+int lb_prove_stage_ms(lb_ctx* ctx, float* out, int cap, int* n) {
+    if (!ctx || !n) return LB_ERR_BAD_ARG;
+    *n = (int)ctx->stage_ms.size();
+    for (int i = 0; i < cap && i < *n && out; ++i) out[i] = ctx->stage_ms[i];
     return LB_OK;
 }
 

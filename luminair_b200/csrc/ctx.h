@@ -1,0 +1,55 @@
+// lb_ctx: one per device; owns the stream, the twiddle tables, scratch and the last error text.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/luminair_b200.h"
+#include "blake2s.cuh"
+#include "cfft.cuh"
+
+struct lb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0;
+    size_t total_mem = 0;
+    lb::Twiddles tw;
+    std::string err;
+    // scratch for pointer tables / index lists
+    void* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    bool kernels_ready = false;
+    // diagnostics of the last lb_prove call
+    std::vector<lb::Hash32> transcript;  // channel digest after every mix
+    std::vector<float> stage_ms;         // wall-clock per stage (stream-synchronised)
+};
+
+namespace lb {
+inline int ctx_fail(lb_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
+    if (ctx) {
+        ctx->err = what;
+        if (e != cudaSuccess) {
+            ctx->err += ": ";
+            ctx->err += cudaGetErrorString(e);
+        }
+    }
+    return code;
+}
+// the prover proper (prover.cu)
+int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_prove_config* cfg,
+               std::vector<uint8_t>& out);
+int eval_at_point_impl(lb_ctx* ctx, const uint32_t* const* h_cols, int n_cols, int log, const uint32_t point[8],
+                       uint32_t* h_out);
+int accumulate_quotients_impl(lb_ctx* ctx, int log, const uint32_t* const* h_cols, int n_cols,
+                              const lb_sample_batch* batches, int n_batches, const uint32_t random_coeff[4],
+                              uint32_t* const d_out[4]);
+int fold_impl(lb_ctx* ctx, int circle, uint32_t* const d_dst[4], const uint32_t* const d_src[4], int log,
+              const uint32_t alpha[4]);
+int grind_impl(lb_ctx* ctx, const uint32_t digest[8], int variant, uint32_t pow_bits, uint64_t* nonce_out);
+int logup_impl(lb_ctx* ctx, int kind, const uint32_t* d_main, size_t main_stride, uint32_t* d_inter, size_t inter_stride,
+               int log, const uint32_t z[4], const uint32_t alpha[4], uint32_t claimed_out[4]);
+int constraint_quotients_impl(lb_ctx* ctx, int kind, const uint32_t* d_main, size_t main_stride, const uint32_t* d_inter,
+                              size_t inter_stride, int log_size, const uint32_t z[4], const uint32_t alpha[4],
+                              const uint32_t claimed_sum[4], const uint32_t* pows, int n_pows, uint32_t* const d_acc[4],
+                              int accumulate);
+}  // namespace lb

@@ -1,0 +1,84 @@
+// Launchers of the streaming kernels behind the PCS / FRI / AIR stages (pcs_kernels.cu,
+// air_kernels.cu).  Everything takes device pointers and a stream; nothing synchronises.
+#pragma once
+#include "air.cuh"
+#include "cfft.cuh"
+
+namespace lb {
+
+cudaError_t kernels_init(cudaStream_t stream);  // constant tables (call once per context)
+
+// (x, y) of CanonicCoset(log).circle_domain() at storage index 2h, h < 2^(log-1); index 2h+1 is (x, -y)
+cudaError_t domain_points(uint2* d_pts, int log, cudaStream_t stream);
+
+// ---- PolyOps::eval_at_point ------------------------------------------------------------------
+// d_cols: device table of n_cols coefficient columns (2^log each).  d_mappings: log QM31 fold
+// factors [y, x, pi(x), ...] (host computes them).  d_basis: scratch of 2^min(log,12) QM31.
+// d_partials: scratch of n_cols * 2^(log - min(log,12)) QM31.  d_out: n_cols QM31.
+cudaError_t eval_at_point(const uint32_t* const* d_cols, int n_cols, int log, const QM31* d_mappings, QM31* d_basis,
+                          QM31* d_partials, QM31* d_out, cudaStream_t stream);
+
+// ---- QuotientOps::accumulate_quotients ---------------------------------------------------------
+constexpr int MAX_QUOTIENT_BATCHES = 8;
+struct QuotientBatch {
+    CM31 prx, pry, pix, piy;  // sample point: real / imaginary CM31 halves of x and y
+    QM31 sum_a, sum_b;        // sum_j alpha^j a_j, sum_j alpha^j b_j  (line coefficients, folded on host)
+    QM31 rc_pow;              // random_coeff ^ |batch|
+    int first, count;         // entries [first, first+count) of the entry table
+};
+struct QuotientEntry {
+    QM31 c;   // alpha^j * c_j
+    int col;  // index into d_cols
+    int pad[3];
+};
+struct QuotientParams {
+    int n_batches;
+    QuotientBatch b[MAX_QUOTIENT_BATCHES];
+};
+cudaError_t accumulate_quotients(uint32_t* const out[4], const uint32_t* const* d_cols, const QuotientEntry* d_entries,
+                                 const QuotientParams& qp, const uint2* d_pts, int log, cudaStream_t stream);
+
+// ---- FriOps -------------------------------------------------------------------------------------
+// dst (4 coords, n/2) = dst * alpha^2 + fold(src (4 coords, n = 2^log));  itw = inverse y twiddles of the domain
+cudaError_t fold_circle_into_line(uint32_t* const dst[4], const uint32_t* const src[4], const uint2* itw, int log,
+                                  QM31 alpha, cudaStream_t stream);
+// dst (4 coords, n/2) = fold(src (4 coords, n = 2^log)); itw = inverse x twiddles of the line domain
+cudaError_t fold_line(uint32_t* const dst[4], const uint32_t* const src[4], const uint2* itw, int log, QM31 alpha,
+                      cudaStream_t stream);
+
+// ---- GrindOps ------------------------------------------------------------------------------------
+// tests nonces [base, base + count); *d_found = min nonce that works (or UINT64_MAX)
+cudaError_t grind_range(const uint32_t digest[8], int variant, uint32_t pow_bits, uint64_t base, uint64_t count,
+                        unsigned long long* d_found, cudaStream_t stream);
+
+// ---- small column utilities -----------------------------------------------------------------------
+cudaError_t add_inplace(uint32_t* dst, const uint32_t* src, size_t n, cudaStream_t stream);  // dst += src (M31)
+cudaError_t gather_words(uint32_t* d_out, const uint32_t* const* d_addrs, int n, cudaStream_t stream);
+// rows (row-major n_rows x n_cols) -> n_cols columns of 2^log at `stride`, padded with the row
+// (0,..,1 at pad_one_col,..,0) (write_trace, e.g. add/witness.rs:43-46)
+cudaError_t transpose_pad(uint32_t* d_cols, size_t stride, const uint32_t* d_rows, uint64_t n_rows, int n_cols, int log,
+                          int pad_one_col, cudaStream_t stream);
+
+// ---- AIR: LogUp interaction trace + constraint quotients -----------------------------------------
+// main: component's n_main trace columns (2^log at main_stride) ; inter: 4*n_fracs columns out.
+// d_scan_tmp: 4 * 2^log u32 ; d_block_sums: 4 * (2^log / 1024 + 1) u32 ; d_claimed: 4 u32 out.
+cudaError_t logup_interaction_trace(int kind, const uint32_t* main, size_t main_stride, uint32_t* inter,
+                                    size_t inter_stride, int log, const Relation2& node, uint32_t* d_scan_tmp,
+                                    uint32_t* d_block_sums, uint32_t* d_claimed, cudaStream_t stream);
+
+struct ConstraintParams {
+    const uint32_t* main;
+    size_t main_stride;  // LDE columns on CanonicCoset(eval_log)
+    const uint32_t* inter;
+    size_t inter_stride;
+    uint32_t* acc[4];
+    int accumulate;  // 0: store, 1: add to acc
+    int log_size, eval_log;
+    Relation2 node;
+    QM31 cumsum_shift;
+    QM31 pows[16];          // this component's random-coefficient powers, first constraint first
+    uint32_t denom_inv[4];  // 1 / Z_H at eval_domain.at(bitrev(i)), i < 2^(eval_log - log_size)
+};
+cudaError_t constraint_quotients(int kind, const ConstraintParams& p, cudaStream_t stream);
+
+}  // namespace lb

@@ -1,0 +1,404 @@
+// Streaming kernels of the polynomial-commitment / FRI stages for sm_100a.
+//
+// Each replaces one stwo SimdBackend trait method reached from stwo::prover::prove, which
+// /root/reference calls at crates/prover/src/prover.rs:311-312:
+//   eval_at_point          PolyOps::eval_at_point           (OODS sampling)
+//   accumulate_quotients   QuotientOps::accumulate_quotients (DEEP quotients, a11)
+//   fold_circle_into_line / fold_line   FriOps               (a12)
+//   grind_range            GrindOps<Blake2sChannel>::grind   (a13)
+// All of them are one-pass, HBM-bound kernels over column-major u32 data: a warp reads 128
+// contiguous bytes per column, every input byte is read once, no shared-memory staging is
+// needed except for the block reductions of eval_at_point.
+#include "kernels.cuh"
+
+#include "blake2s.cuh"
+
+namespace lb {
+
+__constant__ Pt k_gen_pow2[31];  // G * 2^j, G = (2, 1268011823)
+
+cudaError_t kernels_init(cudaStream_t stream) {
+    Pt hp[31];
+    Pt p = {2, 1268011823u};
+    for (int j = 0; j < 31; ++j) {
+        hp[j] = p;
+        p = pt_add(p, p);
+    }
+    cudaError_t e = cudaMemcpyToSymbolAsync(k_gen_pow2, hp, sizeof(hp), 0, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(stream);  // hp is a stack buffer
+}
+
+__device__ __forceinline__ Pt k_point_of_index(uint32_t idx) {
+    Pt r = {1, 0};
+#pragma unroll 1
+    for (int j = 0; j < 31; ++j)
+        if ((idx >> j) & 1) r = pt_add(r, k_gen_pow2[j]);
+    return r;
+}
+
+// half_odds(log-1).at(bitrev(h, log-1)): initial = 2^(30-log), step = 2^(32-log)
+__global__ void domain_points_kernel(uint2* pts, int log) {
+    uint32_t bits = log - 1;
+    uint32_t n = 1u << bits;
+    uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n) return;
+    uint32_t i = bits ? (__brev(h) >> (32 - bits)) : 0;
+    uint32_t init = 1u << (30 - log);
+    uint32_t step = (log >= 1 && log <= 31) ? (uint32_t)(((uint64_t)1 << (32 - log)) & 0x7FFFFFFFu) : 0;
+    uint32_t idx = (init + i * step) & 0x7FFFFFFFu;
+    Pt p = k_point_of_index(idx);
+    pts[h] = make_uint2(p.x, p.y);
+}
+
+cudaError_t domain_points(uint2* d_pts, int log, cudaStream_t stream) {
+    uint32_t n = 1u << (log - 1);
+    domain_points_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_pts, log);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
+// eval_at_point:  f(P) = sum_k c_k * prod_{bit b of k} mappings[b]
+// The index is split k = (chunk << m) | e.  basis[e] covers the low m bits and is shared by all
+// columns and chunks; each CTA reduces one chunk of one column against it, multiplies by the
+// chunk's high-bit factor and stores one QM31 partial; a second kernel sums the partials.
+// Traffic: 4 B per coefficient (+ the 64 KiB basis table, L1/L2 resident).
+// ------------------------------------------------------------------------------------
+__global__ void eval_basis_kernel(QM31* basis, const QM31* mappings, int m) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (1u << m)) return;
+    QM31 r = q_from_m(1);
+    for (int b = 0; b < m; ++b)
+        if ((k >> b) & 1) r = q_mul(r, mappings[b]);
+    basis[k] = r;
+}
+
+__device__ __forceinline__ uint32_t fold64(uint64_t x) {
+    // any u64 -> canonical M31
+    uint64_t y = (x & P) + (x >> 31);  // < 2^34
+    return m_reduce64(y);
+}
+
+__device__ __forceinline__ QM31 warp_sum_q(QM31 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        QM31 w;
+        w.a.a = __shfl_xor_sync(0xFFFFFFFFu, v.a.a, o);
+        w.a.b = __shfl_xor_sync(0xFFFFFFFFu, v.a.b, o);
+        w.b.a = __shfl_xor_sync(0xFFFFFFFFu, v.b.a, o);
+        w.b.b = __shfl_xor_sync(0xFFFFFFFFu, v.b.b, o);
+        v = q_add(v, w);
+    }
+    return v;
+}
+
+// block-wide QM31 sum (blockDim.x == 256); result valid in thread 0
+__device__ __forceinline__ QM31 block_sum_q(QM31 v) {
+    __shared__ QM31 s_w[8];
+    v = warp_sum_q(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) s_w[w] = v;
+    __syncthreads();
+    QM31 r = q_zero();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r = q_add(r, s_w[i]);
+    }
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(256) eval_partial_kernel(const uint32_t* const* __restrict__ cols, int log, int m,
+                                                           const QM31* __restrict__ basis,
+                                                           const QM31* __restrict__ mappings, QM31* __restrict__ partials) {
+    const uint32_t chunk = blockIdx.x;
+    const uint32_t n_chunks = gridDim.x;
+    const uint32_t* col = cols[blockIdx.y] + ((size_t)chunk << m);
+    const uint32_t elems = 1u << m;
+    uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    int pending = 0;
+    for (uint32_t e = threadIdx.x; e < elems; e += 256) {
+        uint64_t c = col[e];
+        uint4 b = *reinterpret_cast<const uint4*>(&basis[e]);
+        a0 += c * b.x;
+        a1 += c * b.y;
+        a2 += c * b.z;
+        a3 += c * b.w;
+        if (++pending == 2) {  // products < 2^62: fold before a third could overflow
+            a0 = (a0 & P) + (a0 >> 31);
+            a1 = (a1 & P) + (a1 >> 31);
+            a2 = (a2 & P) + (a2 >> 31);
+            a3 = (a3 & P) + (a3 >> 31);
+            pending = 0;
+        }
+    }
+    QM31 v = q_make(fold64(a0), fold64(a1), fold64(a2), fold64(a3));
+    v = block_sum_q(v);
+    if (threadIdx.x == 0) {
+        for (int b = 0; m + b < log; ++b)
+            if ((chunk >> b) & 1) v = q_mul(v, mappings[m + b]);
+        partials[(size_t)blockIdx.y * n_chunks + chunk] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) eval_sum_kernel(const QM31* __restrict__ partials, uint32_t n_chunks, QM31* out) {
+    const QM31* p = partials + (size_t)blockIdx.x * n_chunks;
+    QM31 v = q_zero();
+    for (uint32_t i = threadIdx.x; i < n_chunks; i += 256) v = q_add(v, p[i]);
+    v = block_sum_q(v);
+    if (threadIdx.x == 0) out[blockIdx.x] = v;
+}
+
+cudaError_t eval_at_point(const uint32_t* const* d_cols, int n_cols, int log, const QM31* d_mappings, QM31* d_basis,
+                          QM31* d_partials, QM31* d_out, cudaStream_t stream) {
+    if (n_cols == 0) return cudaSuccess;
+    int m = log < 12 ? log : 12;
+    uint32_t n_chunks = 1u << (log - m);
+    uint32_t nb = 1u << m;
+    eval_basis_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(d_basis, d_mappings, m);
+    dim3 grid(n_chunks, n_cols);
+    eval_partial_kernel<<<grid, 256, 0, stream>>>(d_cols, log, m, d_basis, d_mappings, d_partials);
+    eval_sum_kernel<<<n_cols, 256, 0, stream>>>(d_partials, n_chunks, d_out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
+// DEEP quotients.  Per row:  acc = sum over batches (Horner in rc_pow) of
+//     ( sum_j c_j * f_j(row) - (A * y + B) ) * 1 / ((Pr.x - x) Pi.y - (Pr.y - y) Pi.x)
+// One thread per row; every column value is read once per batch it belongs to (4 B per
+// column per row + 16 B written).  The per-row CM31 inversions of all batches share one
+// field inversion (Montgomery's trick across the batches).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) quotients_kernel(uint32_t* __restrict__ o0, uint32_t* __restrict__ o1,
+                                                        uint32_t* __restrict__ o2, uint32_t* __restrict__ o3,
+                                                        const uint32_t* const* __restrict__ cols,
+                                                        const QuotientEntry* __restrict__ entries, QuotientParams qp,
+                                                        const uint2* __restrict__ pts, uint32_t n) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint2 pt = pts[j >> 1];
+    uint32_t x = pt.x, y = (j & 1) ? m_neg(pt.y) : pt.y;
+    CM31 den[MAX_QUOTIENT_BATCHES];
+    CM31 pre[MAX_QUOTIENT_BATCHES];
+    CM31 run = {1, 0};
+    for (int b = 0; b < qp.n_batches; ++b) {
+        const QuotientBatch& B = qp.b[b];
+        CM31 dx = {m_sub(B.prx.a, x), B.prx.b};
+        CM31 dy = {m_sub(B.pry.a, y), B.pry.b};
+        CM31 d = c_sub(c_mul(dx, B.piy), c_mul(dy, B.pix));
+        den[b] = d;
+        pre[b] = run;
+        run = c_mul(run, d);
+    }
+    CM31 inv = c_inv(run);
+    QM31 acc = q_zero();
+    // inverses come out last-to-first; the Horner accumulation runs first-to-last, so keep them
+    CM31 dinv[MAX_QUOTIENT_BATCHES];
+    for (int b = qp.n_batches - 1; b >= 0; --b) {
+        dinv[b] = c_mul(inv, pre[b]);
+        inv = c_mul(inv, den[b]);
+    }
+    for (int b = 0; b < qp.n_batches; ++b) {
+        const QuotientBatch& B = qp.b[b];
+        QM31 num = q_zero();
+        for (int k = 0; k < B.count; ++k) {
+            const QuotientEntry& e = entries[B.first + k];
+            uint32_t v = cols[e.col][j];
+            num = q_add(num, q_mul_m(e.c, v));
+        }
+        QM31 lin = q_add(q_mul_m(B.sum_a, y), B.sum_b);
+        num = q_sub(num, lin);
+        QM31 q = q_mul_c(num, dinv[b]);
+        acc = (b == 0) ? q : q_add(q_mul(acc, B.rc_pow), q);
+    }
+    o0[j] = acc.a.a;
+    o1[j] = acc.a.b;
+    o2[j] = acc.b.a;
+    o3[j] = acc.b.b;
+}
+
+cudaError_t accumulate_quotients(uint32_t* const out[4], const uint32_t* const* d_cols, const QuotientEntry* d_entries,
+                                 const QuotientParams& qp, const uint2* d_pts, int log, cudaStream_t stream) {
+    if (qp.n_batches < 1 || qp.n_batches > MAX_QUOTIENT_BATCHES) return cudaErrorInvalidValue;
+    uint32_t n = 1u << log;
+    quotients_kernel<<<(n + 255) / 256, 256, 0, stream>>>(out[0], out[1], out[2], out[3], d_cols, d_entries, qp, d_pts, n);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
+// FRI folds (48 B per output element: 32 read + 16 written, + dst read for the circle fold)
+// ------------------------------------------------------------------------------------
+struct Coords4 {
+    uint32_t* p[4];
+};
+struct CCoords4 {
+    const uint32_t* p[4];
+};
+
+template <bool CIRCLE>
+__global__ void __launch_bounds__(256) fold_kernel(Coords4 dst, CCoords4 src, const uint2* __restrict__ itw, uint32_t n_out,
+                                                   QM31 alpha, QM31 alpha_sq) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    uint32_t a[4], b[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint2 v = *reinterpret_cast<const uint2*>(src.p[c] + 2 * (size_t)i);
+        a[c] = v.x;
+        b[c] = v.y;
+    }
+    uint32_t tinv = itw[i].x;
+    QM31 f_p = q_make(a[0], a[1], a[2], a[3]), f_n = q_make(b[0], b[1], b[2], b[3]);
+    QM31 f0 = q_add(f_p, f_n);
+    QM31 f1 = q_mul_m(q_sub(f_p, f_n), tinv);
+    QM31 r = q_add(q_mul(alpha, f1), f0);
+    if (CIRCLE) {
+        QM31 d = q_make(dst.p[0][i], dst.p[1][i], dst.p[2][i], dst.p[3][i]);
+        r = q_add(q_mul(d, alpha_sq), r);
+    }
+    dst.p[0][i] = r.a.a;
+    dst.p[1][i] = r.a.b;
+    dst.p[2][i] = r.b.a;
+    dst.p[3][i] = r.b.b;
+}
+
+cudaError_t fold_circle_into_line(uint32_t* const dst[4], const uint32_t* const src[4], const uint2* itw, int log,
+                                  QM31 alpha, cudaStream_t stream) {
+    Coords4 d;
+    CCoords4 s;
+    for (int c = 0; c < 4; ++c) {
+        d.p[c] = dst[c];
+        s.p[c] = src[c];
+    }
+    uint32_t n_out = 1u << (log - 1);
+    fold_kernel<true><<<(n_out + 255) / 256, 256, 0, stream>>>(d, s, itw, n_out, alpha, q_mul(alpha, alpha));
+    return cudaGetLastError();
+}
+
+cudaError_t fold_line(uint32_t* const dst[4], const uint32_t* const src[4], const uint2* itw, int log, QM31 alpha,
+                      cudaStream_t stream) {
+    Coords4 d;
+    CCoords4 s;
+    for (int c = 0; c < 4; ++c) {
+        d.p[c] = dst[c];
+        s.p[c] = src[c];
+    }
+    uint32_t n_out = 1u << (log - 1);
+    fold_kernel<false><<<(n_out + 255) / 256, 256, 0, stream>>>(d, s, itw, n_out, alpha, q_zero());
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
+// Proof of work
+// ------------------------------------------------------------------------------------
+struct Digest8 {
+    uint32_t w[8];
+};
+
+__global__ void __launch_bounds__(256) grind_kernel(Digest8 dg, int variant, uint32_t pow_bits, uint64_t base,
+                                                    uint64_t count, unsigned long long* found) {
+    uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    uint64_t nonce = base + t;
+    uint32_t h[8], m[16];
+    uint32_t w0, w1;
+    if (variant == 0) {
+        // legacy mix_u64: raw compress(h = digest, m = [lo, hi, 0..], t = 0, f = 0)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = dg.w[i];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) m[i] = 0;
+        m[0] = (uint32_t)nonce;
+        m[1] = (uint32_t)(nonce >> 32);
+        blake2s_compress(h, m, 0, 0, 0);
+    } else {
+        // Blake2s(digest || nonce LE): one 40-byte final block
+        blake2s_init(h);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = dg.w[i];
+        m[8] = (uint32_t)nonce;
+        m[9] = (uint32_t)(nonce >> 32);
+#pragma unroll
+        for (int i = 10; i < 16; ++i) m[i] = 0;
+        blake2s_compress(h, m, 40, 0, 0xFFFFFFFFu);
+    }
+    w0 = h[0];
+    w1 = h[1];
+    bool ok;
+    if (pow_bits <= 32)
+        ok = pow_bits == 32 ? (w0 == 0) : ((w0 & ((1u << pow_bits) - 1)) == 0);
+    else
+        ok = (w0 == 0) && ((w1 & ((pow_bits >= 64) ? 0xFFFFFFFFu : ((1u << (pow_bits - 32)) - 1))) == 0);
+    if (ok) atomicMin(found, (unsigned long long)nonce);
+}
+
+cudaError_t grind_range(const uint32_t digest[8], int variant, uint32_t pow_bits, uint64_t base, uint64_t count,
+                        unsigned long long* d_found, cudaStream_t stream) {
+    Digest8 dg;
+    for (int i = 0; i < 8; ++i) dg.w[i] = digest[i];
+    uint64_t blocks = (count + 255) / 256;
+    grind_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dg, variant, pow_bits, base, count, d_found);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
+// column utilities
+// ------------------------------------------------------------------------------------
+__global__ void add_inplace_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = m_add(dst[i], src[i]);
+}
+cudaError_t add_inplace(uint32_t* dst, const uint32_t* src, size_t n, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    add_inplace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dst, src, n);
+    return cudaGetLastError();
+}
+
+__global__ void gather_words_kernel(uint32_t* out, const uint32_t* const* addrs, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = *addrs[i];
+}
+cudaError_t gather_words(uint32_t* d_out, const uint32_t* const* d_addrs, int n, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    gather_words_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_out, d_addrs, n);
+    return cudaGetLastError();
+}
+
+// 32 x 32 tile transpose through shared memory: coalesced reads of the row-major table and
+// coalesced writes of the columns.
+__global__ void transpose_pad_kernel(uint32_t* __restrict__ cols, size_t stride, const uint32_t* __restrict__ rows,
+                                     uint64_t n_rows, int n_cols, uint64_t n_padded, int pad_one_col) {
+    __shared__ uint32_t tile[32][33];
+    uint64_t r0 = (uint64_t)blockIdx.x * 32;
+    int c0 = blockIdx.y * 32;
+    // read: thread (ty, tx) reads row r0+ty.., col c0+tx
+    for (int ty = threadIdx.y; ty < 32; ty += blockDim.y) {
+        uint64_t r = r0 + ty;
+        int c = c0 + threadIdx.x;
+        uint32_t v = 0;
+        if (c < n_cols) {
+            if (r < n_rows)
+                v = rows[r * n_cols + c];
+            else
+                v = (c == pad_one_col) ? 1u : 0u;
+        }
+        tile[ty][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int ty = threadIdx.y; ty < 32; ty += blockDim.y) {
+        int c = c0 + ty;
+        uint64_t r = r0 + threadIdx.x;
+        if (c < n_cols && r < n_padded) cols[(size_t)c * stride + r] = tile[threadIdx.x][ty];
+    }
+}
+
+cudaError_t transpose_pad(uint32_t* d_cols, size_t stride, const uint32_t* d_rows, uint64_t n_rows, int n_cols, int log,
+                          int pad_one_col, cudaStream_t stream) {
+    uint64_t n = (uint64_t)1 << log;
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((n_cols + 31) / 32));
+    dim3 block(32, 8);
+    transpose_pad_kernel<<<grid, block, 0, stream>>>(d_cols, stride, d_rows, n_rows, n_cols, n, pad_one_col);
+    return cudaGetLastError();
+}
+
+}  // namespace lb

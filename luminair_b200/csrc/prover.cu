@@ -1,0 +1,1346 @@
+// Device-resident prover: the host orchestration of `luminair_prover::prover::prove`
+// (/root/reference/crates/prover/src/prover.rs:28-319) and of what it calls in stwo @0790eba
+// (CommitmentSchemeProver / TreeBuilder, prover::prove, FriProver, MerkleProver::decommit,
+// Blake2sChannel; un-vendored, Cargo.toml:21-28).  Every O(N) step is a CUDA kernel on the
+// context's stream; the host keeps only the Fiat-Shamir channel, the sampled values, the query
+// bookkeeping and the proof bytes.  Columns are uploaded once (row-major trace tables) and
+// never leave HBM until the decommitment gathers.
+//
+// The reference's host side is compiled Rust; no Rust toolchain exists in this image, so this
+// file is the host side in C++ above the same kernels a Rust `CudaBackend` shim would bind
+// one by one.
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "ctx.h"
+#include "host_util.h"
+#include "kernels.cuh"
+#include "merkle.cuh"
+
+namespace lb {
+namespace {
+
+// ------------------------------------------------------------------------------------
+// host field / circle helpers
+// ------------------------------------------------------------------------------------
+inline QM31 q_one() { return q_from_m(1); }
+inline QM31 q_conj(QM31 x) { return {x.a, c_neg(x.b)}; }  // a - b u
+inline bool q_is_zero(QM31 x) { return q_eq(x, q_zero()); }
+inline QM31 q_double_x(QM31 x) {
+    QM31 s = q_mul(x, x);
+    return q_sub(q_add(s, s), q_one());
+}
+// SecureField::from_partial_evals: e0 + e1 i + e2 u + e3 iu
+inline QM31 q_from_partial_evals(const QM31 e[4]) {
+    QM31 r = e[0];
+    r = q_add(r, q_mul(e[1], q_make(0, 1, 0, 0)));
+    r = q_add(r, q_mul(e[2], q_make(0, 0, 1, 0)));
+    r = q_add(r, q_mul(e[3], q_make(0, 0, 0, 1)));
+    return r;
+}
+
+constexpr uint32_t CIRCLE_ORDER_MASK = 0x7FFFFFFFu;  // indices live in Z / 2^31
+
+Pt host_index_to_point(uint32_t idx) {
+    static Pt pow2[31];
+    static bool init = false;
+    if (!init) {
+        Pt p = {2, 1268011823u};
+        for (int j = 0; j < 31; ++j) {
+            pow2[j] = p;
+            p = pt_add(p, p);
+        }
+        init = true;
+    }
+    idx &= CIRCLE_ORDER_MASK;
+    Pt r = {1, 0};
+    for (int j = 0; j < 31; ++j)
+        if ((idx >> j) & 1) r = pt_add(r, pow2[j]);
+    return r;
+}
+
+struct QPt {
+    QM31 x, y;
+};
+inline QPt qpt_add(QPt p, QPt q) {
+    return {q_sub(q_mul(p.x, q.x), q_mul(p.y, q.y)), q_add(q_mul(p.x, q.y), q_mul(p.y, q.x))};
+}
+inline QPt qpt_lift(Pt p) { return {q_from_m(p.x), q_from_m(p.y)}; }
+inline bool qpt_eq(const QPt& a, const QPt& b) { return q_eq(a.x, b.x) && q_eq(a.y, b.y); }
+inline bool qpt_less(const QPt& a, const QPt& b) {
+    // BTreeMap order of CirclePoint<SecureField>: x then y, each by its 4 u32 coordinates
+    uint32_t ka[8] = {a.x.a.a, a.x.a.b, a.x.b.a, a.x.b.b, a.y.a.a, a.y.a.b, a.y.b.a, a.y.b.b};
+    uint32_t kb[8] = {b.x.a.a, b.x.a.b, b.x.b.a, b.x.b.b, b.y.a.a, b.y.a.b, b.y.b.a, b.y.b.b};
+    for (int i = 0; i < 8; ++i)
+        if (ka[i] != kb[i]) return ka[i] < kb[i];
+    return false;
+}
+
+inline uint32_t subgroup_gen(int log) { return (uint32_t)(((uint64_t)1 << (31 - log)) & CIRCLE_ORDER_MASK); }
+
+// core/constraints.rs coset_vanishing for CanonicCoset(log).coset = odds(log)
+QM31 coset_vanishing_q(int log, QPt p) {
+    uint32_t initial = subgroup_gen(log + 1), step = subgroup_gen(log);
+    QPt q = qpt_add(qpt_add(p, qpt_lift(host_index_to_point((0u - initial) & CIRCLE_ORDER_MASK))),
+                    qpt_lift(host_index_to_point(step >> 1)));
+    QM31 x = q.x;
+    for (int i = 1; i < log; ++i) x = q_double_x(x);
+    return x;
+}
+uint32_t coset_vanishing_m(int log, Pt p) {
+    uint32_t initial = subgroup_gen(log + 1), step = subgroup_gen(log);
+    Pt q = pt_add(pt_add(p, host_index_to_point((0u - initial) & CIRCLE_ORDER_MASK)), host_index_to_point(step >> 1));
+    uint32_t x = q.x;
+    for (int i = 1; i < log; ++i) x = m_sub(m_mul(2, m_mul(x, x)), 1);
+    return x;
+}
+inline uint32_t bit_reverse(uint32_t i, int log) {
+    uint32_t r = 0;
+    for (int b = 0; b < log; ++b) r |= ((i >> b) & 1u) << (log - 1 - b);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------
+// Blake2sChannel (core/channel/blake2s.rs; call sites prover.rs:44,177,296)
+//   variant 0 "legacy": mix_u64 = raw compress(h = digest, m = [lo, hi, 0..]);
+//                       draw = Blake2s(digest || counter as 32 LE bytes)      [artifact-verified]
+//   variant 1 "v2":     mix_u64 = Blake2s(digest || lo || hi); draw appends one 0x00 byte
+// ------------------------------------------------------------------------------------
+class Channel {
+   public:
+    explicit Channel(int variant, std::vector<Hash32>* log) : variant_(variant), log_(log) { std::memset(digest_.b, 0, 32); }
+    const Hash32& digest() const { return digest_; }
+    void digest_words(uint32_t w[8]) const { std::memcpy(w, digest_.b, 32); }
+
+    void mix_root(const Hash32& root) {
+        uint8_t buf[64];
+        std::memcpy(buf, digest_.b, 32);
+        std::memcpy(buf + 32, root.b, 32);
+        update(blake2s_hash(buf, 64));
+    }
+    void mix_felts(const std::vector<QM31>& felts) {
+        std::vector<uint8_t> buf(32 + 16 * felts.size());
+        std::memcpy(buf.data(), digest_.b, 32);
+        for (size_t i = 0; i < felts.size(); ++i) {
+            uint32_t w[4] = {felts[i].a.a, felts[i].a.b, felts[i].b.a, felts[i].b.b};
+            std::memcpy(buf.data() + 32 + 16 * i, w, 16);
+        }
+        update(blake2s_hash(buf.data(), buf.size()));
+    }
+    void mix_u64(uint64_t v) {
+        uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+        if (variant_ == 0) {
+            uint32_t h[8], m[16] = {0};
+            std::memcpy(h, digest_.b, 32);
+            m[0] = lo;
+            m[1] = hi;
+            blake2s_compress(h, m, 0, 0, 0);
+            Hash32 d;
+            std::memcpy(d.b, h, 32);
+            update(d);
+        } else {
+            uint8_t buf[40];
+            std::memcpy(buf, digest_.b, 32);
+            std::memcpy(buf + 32, &lo, 4);
+            std::memcpy(buf + 36, &hi, 4);
+            update(blake2s_hash(buf, 40));
+        }
+    }
+    Hash32 draw_random_bytes() {
+        uint8_t buf[65];
+        std::memset(buf, 0, sizeof(buf));
+        std::memcpy(buf, digest_.b, 32);
+        uint32_t c = n_sent_;
+        std::memcpy(buf + 32, &c, 4);
+        ++n_sent_;
+        return blake2s_hash(buf, variant_ == 0 ? 64 : 65);
+    }
+    void draw_base_felts(uint32_t out[8]) {
+        for (;;) {
+            Hash32 h = draw_random_bytes();
+            uint32_t u[8];
+            std::memcpy(u, h.b, 32);
+            bool ok = true;
+            for (int i = 0; i < 8; ++i) ok = ok && (u[i] < 2 * P);
+            if (!ok) continue;
+            for (int i = 0; i < 8; ++i) out[i] = u[i] >= P ? u[i] - P : u[i];
+            return;
+        }
+    }
+    QM31 draw_secure_felt() {
+        uint32_t f[8];
+        draw_base_felts(f);
+        return q_make(f[0], f[1], f[2], f[3]);
+    }
+    std::vector<QM31> draw_secure_felts(int n) {
+        std::vector<QM31> out;
+        std::vector<uint32_t> pool;
+        while ((int)out.size() < n) {
+            if (pool.size() < 4) {
+                uint32_t f[8];
+                draw_base_felts(f);
+                pool.insert(pool.end(), f, f + 8);
+            }
+            out.push_back(q_make(pool[0], pool[1], pool[2], pool[3]));
+            pool.erase(pool.begin(), pool.begin() + 4);
+        }
+        return out;
+    }
+
+   private:
+    void update(const Hash32& d) {
+        digest_ = d;
+        n_sent_ = 0;
+        if (log_) log_->push_back(d);
+    }
+    int variant_;
+    Hash32 digest_;
+    uint32_t n_sent_ = 0;
+    std::vector<Hash32>* log_;
+};
+
+// ------------------------------------------------------------------------------------
+// Merkle trees over mixed-height column sets (prover/vcs/prover.rs MerkleProver)
+// ------------------------------------------------------------------------------------
+struct ColRef {
+    const uint32_t* ptr;
+    int log;
+};
+
+struct MerkleTree {
+    int max_log = 0;
+    bool empty = true;
+    std::vector<uint32_t*> layers;  // layers[k]: 2^k digests (8 u32 each), device
+    std::vector<ColRef> sorted;     // stable sort by size, descending
+    Hash32 root;
+};
+
+// collects device word addresses; one gather kernel + one D2H serves the whole decommitment
+struct Gatherer {
+    std::vector<const uint32_t*> addrs;
+    std::vector<uint32_t> values;
+    size_t add(const uint32_t* a) {
+        addrs.push_back(a);
+        return addrs.size() - 1;
+    }
+};
+
+inline size_t add_hash(Gatherer& g, const uint32_t* h) {
+    size_t first = g.add(h);
+    for (int i = 1; i < 8; ++i) g.add(h + i);
+    return first;
+}
+
+struct DecommitIdx {
+    std::vector<size_t> hash_witness;    // index of the first of 8 words
+    std::vector<size_t> column_witness;  // word index
+    std::vector<size_t> queried_values;  // word index
+};
+
+void merkle_commit(lb_ctx* ctx, Arena& arena, const std::vector<ColRef>& cols, MerkleTree& t) {
+    if (cols.empty()) {
+        t.empty = true;
+        t.max_log = 0;
+        t.root = blake2s_hash(nullptr, 0);
+        return;
+    }
+    t.empty = false;
+    t.sorted = cols;
+    std::stable_sort(t.sorted.begin(), t.sorted.end(), [](const ColRef& a, const ColRef& b) { return a.log > b.log; });
+    t.max_log = t.sorted[0].log;
+    t.layers.assign(t.max_log + 1, nullptr);
+    // one pointer table for all layers
+    std::vector<const uint32_t*> table;
+    std::vector<int> first(t.max_log + 2, 0), count(t.max_log + 1, 0);
+    for (int log = t.max_log; log >= 0; --log) {
+        first[log] = (int)table.size();
+        for (const ColRef& c : t.sorted)
+            if (c.log == log) table.push_back(c.ptr);
+        count[log] = (int)table.size() - first[log];
+    }
+    const uint32_t** d_table = arena.upload(table);
+    const uint32_t* prev = nullptr;
+    for (int log = t.max_log; log >= 0; --log) {
+        t.layers[log] = arena.alloc<uint32_t>((size_t)8 << log);
+        ck(merkle_commit_layer(t.layers[log], prev, d_table + first[log], count[log], log, ctx->stream), "merkle layer");
+        prev = t.layers[log];
+    }
+    ck(cudaMemcpyAsync(t.root.b, t.layers[0], 32, cudaMemcpyDeviceToHost, ctx->stream), "root d2h");
+    ck(cudaStreamSynchronize(ctx->stream), "root sync");
+}
+
+// MerkleProver::decommit: emits, in proof order, what must be gathered
+void merkle_decommit_plan(const MerkleTree& t, const std::map<int, std::vector<uint32_t>>& queries_per_log, Gatherer& g,
+                          DecommitIdx& out) {
+    std::vector<uint32_t> last;
+    for (int log = t.max_log; log >= 0; --log) {
+        const uint32_t* prev_hashes = (!t.empty && log + 1 <= t.max_log) ? t.layers[log + 1] : nullptr;
+        std::vector<uint32_t> col_q;
+        auto it = queries_per_log.find(log);
+        if (it != queries_per_log.end()) col_q = it->second;
+        const std::vector<uint32_t>& prev_q = last;
+        size_t pi = 0, ci = 0;
+        std::vector<uint32_t> total;
+        while (pi < prev_q.size() || ci < col_q.size()) {
+            uint32_t node = 0xFFFFFFFFu;
+            if (pi < prev_q.size()) node = std::min(node, prev_q[pi] / 2);
+            if (ci < col_q.size()) node = std::min(node, col_q[ci]);
+            if (prev_hashes) {
+                if (pi < prev_q.size() && prev_q[pi] == 2 * node)
+                    ++pi;
+                else
+                    out.hash_witness.push_back(add_hash(g, prev_hashes + (size_t)(2 * node) * 8));
+                if (pi < prev_q.size() && prev_q[pi] == 2 * node + 1)
+                    ++pi;
+                else
+                    out.hash_witness.push_back(add_hash(g, prev_hashes + (size_t)(2 * node + 1) * 8));
+            }
+            bool queried = ci < col_q.size() && col_q[ci] == node;
+            if (queried) ++ci;
+            for (const ColRef& c : t.sorted) {
+                if (c.log != log) continue;
+                size_t idx = g.add(c.ptr + node);
+                (queried ? out.queried_values : out.column_witness).push_back(idx);
+            }
+            total.push_back(node);
+        }
+        last.swap(total);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------
+// proof structures (indices into the Gatherer until the final D2H) + bincode 1.3 writer
+// layout: crates/prover/src/lib.rs:15-32, crates/air/src/lib.rs:29-48,189-207 + stwo serde derives
+// ------------------------------------------------------------------------------------
+struct FriLayerOut {
+    std::vector<size_t> witness;  // per QM31: index of coordinate 0..3 are consecutive gather slots
+    DecommitIdx decommit;
+    Hash32 commitment;
+};
+
+struct Writer {
+    std::vector<uint8_t>& o;
+    void u8(uint8_t v) { o.push_back(v); }
+    void u32(uint32_t v) { raw(&v, 4); }
+    void u64(uint64_t v) { raw(&v, 8); }
+    void raw(const void* p, size_t n) { o.insert(o.end(), (const uint8_t*)p, (const uint8_t*)p + n); }
+    void qm31(QM31 q) {
+        uint32_t w[4] = {q.a.a, q.a.b, q.b.a, q.b.b};
+        raw(w, 16);
+    }
+    void hash(const Hash32& h) { raw(h.b, 32); }
+};
+
+void write_decommit(Writer& w, const DecommitIdx& d, const Gatherer& g) {
+    w.u64(d.hash_witness.size());
+    for (size_t i : d.hash_witness) w.raw(&g.values[i], 32);
+    w.u64(d.column_witness.size());
+    for (size_t i : d.column_witness) w.u32(g.values[i]);
+}
+void write_fri_layer(Writer& w, const FriLayerOut& l, const Gatherer& g) {
+    w.u64(l.witness.size());
+    for (size_t i : l.witness) w.raw(&g.values[i], 16);
+    write_decommit(w, l.decommit, g);
+    w.hash(l.commitment);
+}
+
+// ------------------------------------------------------------------------------------
+// queries (core/queries.rs, core/fri.rs)
+// ------------------------------------------------------------------------------------
+std::vector<uint32_t> generate_queries(Channel& ch, int log_domain_size, size_t n_queries) {
+    std::vector<uint32_t> qs;
+    size_t cnt = 0;
+    uint32_t mask = (log_domain_size >= 32) ? 0xFFFFFFFFu : ((1u << log_domain_size) - 1);
+    while (cnt < n_queries) {
+        Hash32 rb = ch.draw_random_bytes();
+        uint32_t w[8];
+        std::memcpy(w, rb.b, 32);
+        for (int i = 0; i < 8 && cnt < n_queries; ++i) {
+            qs.push_back(w[i] & mask);
+            ++cnt;
+        }
+    }
+    std::sort(qs.begin(), qs.end());
+    qs.erase(std::unique(qs.begin(), qs.end()), qs.end());
+    return qs;
+}
+
+std::vector<uint32_t> fold_queries(const std::vector<uint32_t>& pos, int n_folds) {
+    std::vector<uint32_t> out;
+    for (uint32_t q : pos) {
+        uint32_t f = q >> n_folds;
+        if (out.empty() || out.back() != f) out.push_back(f);
+    }
+    return out;
+}
+
+// compute_decommitment_positions_and_witness_evals with fold_step = 1
+void fri_positions_and_witness(uint32_t* const coords[4], const std::vector<uint32_t>& queries, Gatherer& g,
+                               std::vector<uint32_t>& positions, std::vector<size_t>& witness) {
+    size_t i = 0;
+    while (i < queries.size()) {
+        size_t j = i;
+        while (j < queries.size() && (queries[j] >> 1) == (queries[i] >> 1)) ++j;
+        uint32_t start = (queries[i] >> 1) << 1;
+        size_t k = i;
+        for (uint32_t pos = start; pos < start + 2; ++pos) {
+            positions.push_back(pos);
+            if (k < j && queries[k] == pos) {
+                ++k;
+                continue;
+            }
+            size_t first = g.add(coords[0] + pos);
+            for (int c = 1; c < 4; ++c) g.add(coords[c] + pos);
+            witness.push_back(first);
+        }
+        i = j;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// host evaluators over the component templates (air.cuh)
+// ------------------------------------------------------------------------------------
+struct InfoEval : LogupMixin<InfoEval, FQ, FQ> {
+    typedef FQ F;
+    typedef FQ EF;
+    int n_main = 0, n_inter = 0, n_constraints = 0;
+    QM31 cumsum_shift = q_zero();
+    FQ constant(uint32_t c) const { return {q_from_m(c)}; }
+    FQ next_trace_mask() {
+        ++n_main;
+        return {q_zero()};
+    }
+    FQ next_ext_mask_cur() {
+        n_inter += 4;
+        return {q_zero()};
+    }
+    void next_ext_mask_prev_cur(FQ& prev, FQ& cur) {
+        n_inter += 4;
+        prev = cur = FQ{q_zero()};
+    }
+    void add_constraint(FQ) { ++n_constraints; }
+    void add_constraint_ef(FQ) { ++n_constraints; }
+};
+
+// constraint-framework PointEvaluator: F = EF = SecureField, mask values from the sampled values
+struct PointEval : LogupMixin<PointEval, FQ, FQ> {
+    typedef FQ F;
+    typedef FQ EF;
+    const std::vector<std::vector<QM31>>* main;   // sampled_values[1] (global column index)
+    const std::vector<std::vector<QM31>>* inter;  // sampled_values[2]
+    size_t mc, ic;
+    QM31 denom_inverse, random_coeff;
+    QM31* acc;
+    QM31 cumsum_shift;
+
+    FQ constant(uint32_t c) const { return {q_from_m(c)}; }
+    FQ next_trace_mask() { return {(*main)[mc++][0]}; }
+    FQ ext_at(size_t k) const {
+        QM31 e[4] = {(*inter)[ic][k], (*inter)[ic + 1][k], (*inter)[ic + 2][k], (*inter)[ic + 3][k]};
+        return {q_from_partial_evals(e)};
+    }
+    FQ next_ext_mask_cur() {
+        FQ v = ext_at(0);
+        ic += 4;
+        return v;
+    }
+    void next_ext_mask_prev_cur(FQ& prev, FQ& cur) {
+        prev = ext_at(0);
+        cur = ext_at(1);
+        ic += 4;
+    }
+    void add_constraint(FQ c) { *acc = q_add(q_mul(*acc, random_coeff), q_mul(denom_inverse, c.v)); }
+    void add_constraint_ef(FQ c) { add_constraint(c); }
+};
+
+// ------------------------------------------------------------------------------------
+// shared launch helpers (used by prove_impl and by the trait-level C ABI)
+// ------------------------------------------------------------------------------------
+struct HostBatch {  // ColumnSampleBatch: one sample point and the (column, value) pairs sampled there
+    QPt pt;
+    std::vector<std::pair<int, QM31>> cols;
+};
+
+// PolyOps::eval_at_point for a set of equally sized coefficient columns
+void launch_eval_at_point(lb_ctx* ctx, Arena& arena, const std::vector<const uint32_t*>& cols, int log, const QPt& pt,
+                          QM31* d_out) {
+    std::vector<QM31> mappings;
+    mappings.push_back(pt.y);
+    QM31 x = pt.x;
+    for (int i = 1; i < log; ++i) {
+        mappings.push_back(x);
+        x = q_double_x(x);
+    }
+    int m = std::min(log, 12);
+    QM31* d_map = arena.upload(mappings);
+    const uint32_t** d_cols = arena.upload(cols);
+    QM31* d_basis = arena.alloc<QM31>((size_t)1 << m);
+    QM31* d_part = arena.alloc<QM31>(cols.size() << (log - m));
+    ck(eval_at_point(d_cols, (int)cols.size(), log, d_map, d_basis, d_part, d_out, ctx->stream), "eval_at_point");
+}
+
+// QuotientOps::accumulate_quotients: quotient_constants (core/pcs/quotients.rs) on the host,
+// the row loop on the device
+void launch_quotients(lb_ctx* ctx, Arena& arena, int lg, const std::vector<const uint32_t*>& colptrs,
+                      std::vector<HostBatch>& batches, QM31 rc_q, uint32_t* const out[4]) {
+    std::sort(batches.begin(), batches.end(), [](const HostBatch& a, const HostBatch& b) { return qpt_less(a.pt, b.pt); });
+    if (batches.empty() || batches.size() > (size_t)MAX_QUOTIENT_BATCHES) fail(LB_ERR_BAD_ARG, "quotients: bad number of sample batches");
+    QuotientParams qp{};
+    qp.n_batches = (int)batches.size();
+    std::vector<QuotientEntry> entries;
+    for (size_t bi = 0; bi < batches.size(); ++bi) {
+        const HostBatch& b = batches[bi];
+        QuotientBatch& o = qp.b[bi];
+        o.prx = b.pt.x.a;
+        o.pix = b.pt.x.b;
+        o.pry = b.pt.y.a;
+        o.piy = b.pt.y.b;
+        o.first = (int)entries.size();
+        o.count = (int)b.cols.size();
+        o.sum_a = q_zero();
+        o.sum_b = q_zero();
+        QM31 alpha = q_one();
+        QM31 cc = q_sub(q_conj(b.pt.y), b.pt.y);
+        for (auto& cv : b.cols) {
+            if (cv.first < 0 || cv.first >= (int)colptrs.size()) fail(LB_ERR_BAD_ARG, "quotients: column index out of range");
+            alpha = q_mul(alpha, rc_q);
+            QM31 a = q_sub(q_conj(cv.second), cv.second);
+            QM31 bcoef = q_sub(q_mul(cv.second, cc), q_mul(a, b.pt.y));
+            o.sum_a = q_add(o.sum_a, q_mul(alpha, a));
+            o.sum_b = q_add(o.sum_b, q_mul(alpha, bcoef));
+            QuotientEntry e{};
+            e.c = q_mul(alpha, cc);
+            e.col = cv.first;
+            entries.push_back(e);
+        }
+        o.rc_pow = q_pow(rc_q, b.cols.size());
+    }
+    const uint32_t** d_cols = arena.upload(colptrs);
+    QuotientEntry* d_entries = arena.upload(entries);
+    uint2* d_pts = arena.alloc<uint2>((size_t)1 << (lg - 1));
+    ck(domain_points(d_pts, lg, ctx->stream), "domain points");
+    ck(accumulate_quotients(out, d_cols, d_entries, qp, d_pts, lg, ctx->stream), "accumulate quotients");
+}
+
+// ------------------------------------------------------------------------------------
+// commitment scheme state
+// ------------------------------------------------------------------------------------
+struct PolyCol {
+    uint32_t* coeffs;  // 2^log
+    uint32_t* lde;     // 2^(log + blowup), filled by commit
+    int log;
+};
+struct CommitTree {
+    std::vector<PolyCol> cols;
+    MerkleTree merkle;
+};
+
+struct Component {
+    int kind, slot, log;
+    size_t main_loc, inter_loc;  // first column in tree 1 / tree 2
+    uint32_t* main_evals;        // trace values (n_main x 2^log), kept for the LogUp pass
+    QM31 claimed_sum;
+};
+
+int kind_of_slot(int slot, int n_slots, int air_era) {
+    // LuminairClaim field order, crates/air/src/lib.rs:30-48 (17 slots): add, mul, ..., inputs (15), contiguous
+    if (slot == 0) return COMP_ADD;
+    if (slot == 1) return air_era == 1 ? COMP_MUL_ARTIFACT : COMP_MUL;
+    if (n_slots == 17 && slot == 15) return COMP_INPUTS;
+    return -1;
+}
+
+const uint2* inv_y_twiddles(const Twiddles& tw, int domain_log) { return tw.inv + tw.y_off + ((size_t)1 << (domain_log - 1)); }
+const uint2* inv_x_twiddles(const Twiddles& tw, int line_log) { return tw.inv + ((size_t)1 << (line_log - 1)); }
+
+struct StageTimer {
+    lb_ctx* ctx;
+    std::chrono::steady_clock::time_point t0;
+    explicit StageTimer(lb_ctx* c) : ctx(c), t0(std::chrono::steady_clock::now()) {}
+    void lap() {
+        cudaStreamSynchronize(ctx->stream);
+        auto t1 = std::chrono::steady_clock::now();
+        ctx->stage_ms.push_back(std::chrono::duration<float, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
+}  // namespace
+
+// ======================================================================================
+int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_prove_config* cfg_in,
+               std::vector<uint8_t>& out) {
+    try {
+        lb_prove_config cfg;
+        if (cfg_in)
+            cfg = *cfg_in;
+        else {
+            cfg.pow_bits = 5;  // PcsConfig::default() (prover.rs:36)
+            cfg.log_blowup_factor = 1;
+            cfg.log_last_layer_degree_bound = 0;
+            cfg.n_queries = 3;
+            cfg.channel_variant = 0;
+            cfg.n_slots = 17;
+            cfg.air_era = 0;
+            cfg.draw_lookup_elements = 1;
+        }
+        if (n_tables < 1 || !tables) fail(LB_ERR_BAD_ARG, "prove: no trace tables");
+        if (cfg.n_slots < 2 || cfg.n_slots > 64) fail(LB_ERR_BAD_ARG, "prove: bad n_slots");
+        if (cfg.log_blowup_factor < 1 || cfg.log_blowup_factor > 4) fail(LB_ERR_BAD_ARG, "prove: bad blow-up");
+        const int blowup = (int)cfg.log_blowup_factor;
+        cudaStream_t st = ctx->stream;
+        ck(cudaSetDevice(ctx->device), "set device");
+        if (!ctx->kernels_ready) {
+            ck(kernels_init(st), "kernels init");
+            ctx->kernels_ready = true;
+        }
+        ctx->transcript.clear();
+        ctx->stage_ms.clear();
+        StageTimer timer(ctx);
+        Arena arena(st);
+        Channel channel(cfg.channel_variant, &ctx->transcript);
+        std::vector<CommitTree> trees(4);
+
+        // ---- sizes, twiddles -------------------------------------------------------------
+        int max_log = 0;
+        for (int t = 0; t < n_tables; ++t) {
+            if (tables[t].n_rows == 0) fail(LB_ERR_BAD_ARG, "TraceError::EmptyTrace");
+            int lg = 0;
+            while (((uint64_t)1 << lg) < tables[t].n_rows) ++lg;
+            if (lg < 4) lg = 4;  // N_LANES = 16, crates/air/src/utils.rs:22-27
+            if (lg > 24) fail(LB_ERR_BAD_ARG, "prove: table too large");
+            max_log = std::max(max_log, lg);
+        }
+        {
+            int r = lb_twiddles_ensure(ctx, max_log + 1 + blowup);
+            if (r) return r;
+        }
+        const Twiddles& tw = ctx->tw;
+
+        auto commit_tree = [&](CommitTree& tree) {
+            // evaluate every polynomial on CanonicCoset(log + blowup), Merkle-commit, mix the root
+            std::vector<ColRef> refs;
+            size_t i = 0;
+            while (i < tree.cols.size()) {
+                // consecutive columns allocated as one batch share stride: detect runs
+                size_t j = i;
+                int lg = tree.cols[i].log;
+                size_t stride = (size_t)1 << lg;
+                while (j + 1 < tree.cols.size() && tree.cols[j + 1].log == lg &&
+                       tree.cols[j + 1].coeffs == tree.cols[j].coeffs + stride)
+                    ++j;
+                int n = (int)(j - i + 1);
+                size_t out_stride = (size_t)1 << (lg + blowup);
+                uint32_t* lde = arena.alloc<uint32_t>(out_stride * n);
+                ck(cfft_evaluate(&tw, tree.cols[i].coeffs, stride, lg, lde, out_stride, lg + blowup, n, ctx->sm_count, st),
+                   "LDE evaluate");
+                for (int k = 0; k < n; ++k) {
+                    tree.cols[i + k].lde = lde + (size_t)k * out_stride;
+                    refs.push_back({tree.cols[i + k].lde, lg + blowup});
+                }
+                i = j + 1;
+            }
+            merkle_commit(ctx, arena, refs, tree.merkle);
+            channel.mix_root(tree.merkle.root);
+        };
+
+        // ---- phase 0: preprocessed trace (no LUT columns for Add/Mul/Inputs graphs) ----------
+        commit_tree(trees[0]);
+
+        // ---- phase 1: main trace (prover.rs:66-179) ------------------------------------------
+        std::vector<int> claim(cfg.n_slots, -1);
+        std::vector<Component> by_slot(cfg.n_slots);
+        for (int t = 0; t < n_tables; ++t) {
+            const lb_trace_table& tb = tables[t];
+            if (tb.slot < 0 || tb.slot >= cfg.n_slots) fail(LB_ERR_BAD_ARG, "prove: slot out of range");
+            int kind = kind_of_slot(tb.slot, cfg.n_slots, cfg.air_era);
+            if (kind < 0) fail(LB_ERR_BAD_ARG, "prove: component not supported by this backend yet");
+            ComponentShape sh = component_shape(kind);
+            if (tb.n_cols != sh.n_main) fail(LB_ERR_BAD_ARG, "prove: wrong column count for component");
+            if (claim[tb.slot] >= 0) fail(LB_ERR_BAD_ARG, "prove: duplicate table for slot");
+            // LuminairGraph::gen_trace emits tables in claim-slot order (graph.rs:502-593); the column spans the
+            // components read (TraceLocationAllocator) only line up with the committed order in that case
+            if (t > 0 && tables[t - 1].slot > tb.slot) fail(LB_ERR_BAD_ARG, "prove: trace tables must come in claim-slot order");
+            int lg = 0;
+            while (((uint64_t)1 << lg) < tb.n_rows) ++lg;
+            if (lg < 4) lg = 4;
+            size_t n = (size_t)1 << lg;
+            const uint32_t* d_rows;
+            uint32_t* staged = nullptr;
+            if (tb.rows_on_device) {
+                d_rows = tb.rows;
+            } else {
+                staged = arena.alloc<uint32_t>(tb.n_rows * tb.n_cols);
+                ck(cudaMemcpyAsync(staged, tb.rows, tb.n_rows * tb.n_cols * sizeof(uint32_t), cudaMemcpyHostToDevice, st),
+                   "trace upload");
+                d_rows = staged;
+            }
+            uint32_t* evals = arena.alloc<uint32_t>(n * sh.n_main);
+            ck(transpose_pad(evals, n, d_rows, tb.n_rows, sh.n_main, lg, sh.padding_one_col, st), "transpose");
+            uint32_t* coeffs = arena.alloc<uint32_t>(n * sh.n_main);
+            ck(cudaMemcpyAsync(coeffs, evals, n * sh.n_main * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st), "copy");
+            ck(cfft_interpolate(&tw, coeffs, n, sh.n_main, lg, ctx->sm_count, st), "interpolate");
+            if (staged) {
+                ck(cudaStreamSynchronize(st), "upload sync");  // host rows may be pageable
+                arena.release(staged);
+            }
+            Component c{};
+            c.kind = kind;
+            c.slot = tb.slot;
+            c.log = lg;
+            c.main_evals = evals;
+            c.main_loc = trees[1].cols.size();  // location by pie order; components use slot order (see below)
+            for (int k = 0; k < sh.n_main; ++k) trees[1].cols.push_back({coeffs + (size_t)k * n, nullptr, lg});
+            claim[tb.slot] = lg;
+            by_slot[tb.slot] = c;
+        }
+        for (int s = 0; s < cfg.n_slots; ++s)
+            if (claim[s] >= 0) channel.mix_u64((uint64_t)claim[s]);  // LuminairClaim::mix_into
+        commit_tree(trees[1]);
+        timer.lap();  // stage 0: upload + interpolate + LDE + Merkle of the main trace
+
+        // ---- phase 2: interaction trace (prover.rs:181-298) -----------------------------------
+        // LuminairInteractionElements::draw (components/mod.rs:227-235): node, then sin, exp2, log2, range_check
+        std::vector<QM31> node_el = channel.draw_secure_felts(2);
+        if (cfg.draw_lookup_elements)
+            for (int k = 0; k < 4; ++k) (void)channel.draw_secure_felts(2);
+        Relation2 node{node_el[0], node_el[1]};
+
+        std::vector<Component> comps;  // slot order = LuminairComponents order
+        {
+            // TraceLocationAllocator hands out spans in component (slot) order
+            size_t main_next = 0;
+            for (int s = 0; s < cfg.n_slots; ++s) {
+                if (claim[s] < 0) continue;
+                Component c = by_slot[s];
+                ComponentShape sh = component_shape(c.kind);
+                size_t n = (size_t)1 << c.log;
+                int n_ic = 4 * sh.n_fracs;
+                uint32_t* inter = arena.alloc<uint32_t>(n * n_ic);
+                uint32_t* scan_tmp = arena.alloc<uint32_t>(4 * n);
+                uint32_t* block_sums = arena.alloc<uint32_t>(4 * (n / 1024 + 1));
+                uint32_t* d_claimed = arena.alloc<uint32_t>(4);
+                ck(logup_interaction_trace(c.kind, c.main_evals, n, inter, n, c.log, node, scan_tmp, block_sums, d_claimed, st),
+                   "logup");
+                uint32_t cl[4];
+                ck(cudaMemcpyAsync(cl, d_claimed, 16, cudaMemcpyDeviceToHost, st), "claimed d2h");
+                ck(cfft_interpolate(&tw, inter, n, n_ic, c.log, ctx->sm_count, st), "interpolate interaction");
+                ck(cudaStreamSynchronize(st), "claimed sync");
+                c.claimed_sum = q_make(cl[0], cl[1], cl[2], cl[3]);
+                arena.release(scan_tmp);
+                arena.release(c.main_evals);
+                c.main_evals = nullptr;
+                c.inter_loc = trees[2].cols.size();
+                for (int k = 0; k < n_ic; ++k) trees[2].cols.push_back({inter + (size_t)k * n, nullptr, c.log});
+                c.main_loc = main_next;  // span in slot order (equals the pie-order location when the pie is slot-ordered)
+                main_next += sh.n_main;
+                comps.push_back(c);
+            }
+        }
+        for (const Component& c : comps) channel.mix_felts({c.claimed_sum});  // LuminairInteractionClaim::mix_into
+        commit_tree(trees[2]);
+        timer.lap();  // stage 1: LogUp + interpolate + LDE + Merkle of the interaction trace
+
+        // ---- stwo::prover::prove -------------------------------------------------------------
+        QM31 random_coeff = channel.draw_secure_felt();
+        // constraint counts from the AIR itself
+        std::vector<int> n_constraints;
+        int total_constraints = 0;
+        for (const Component& c : comps) {
+            InfoEval info;
+            eval_component(c.kind, info, node);
+            ComponentShape sh = component_shape(c.kind);
+            if (info.n_main != sh.n_main || info.n_inter != 4 * sh.n_fracs || info.n_constraints != sh.n_constraints)
+                fail(LB_ERR_BAD_ARG, "internal: component shape table out of date");
+            n_constraints.push_back(info.n_constraints);
+            total_constraints += info.n_constraints;
+        }
+        std::vector<QM31> powers(total_constraints);
+        {
+            QM31 cur = q_one();
+            for (int i = 0; i < total_constraints; ++i) {
+                powers[i] = cur;
+                cur = q_mul(cur, random_coeff);
+            }
+        }
+        // per evaluation-domain size accumulators (DomainEvaluationAccumulator)
+        std::map<int, uint32_t*> acc;  // eval_log -> 4 coordinate columns (stride 2^eval_log)
+        {
+            int remaining = total_constraints;
+            for (size_t ci = 0; ci < comps.size(); ++ci) {
+                const Component& c = comps[ci];
+                int nc = n_constraints[ci];
+                int eval_log = c.log + 1;  // max_constraint_log_degree_bound (add/component.rs:33-35)
+                if (eval_log != c.log + blowup) fail(LB_ERR_BAD_ARG, "prove: blow-up != 1 needs a separate evaluation domain");
+                ConstraintParams p{};
+                p.main = trees[1].cols[c.main_loc].lde;
+                p.main_stride = (size_t)1 << eval_log;
+                p.inter = trees[2].cols[c.inter_loc].lde;
+                p.inter_stride = (size_t)1 << eval_log;
+                bool fresh = acc.find(eval_log) == acc.end();
+                if (fresh) acc[eval_log] = arena.alloc<uint32_t>((size_t)4 << eval_log);
+                for (int k = 0; k < 4; ++k) p.acc[k] = acc[eval_log] + ((size_t)k << eval_log);
+                p.accumulate = fresh ? 0 : 1;
+                p.log_size = c.log;
+                p.eval_log = eval_log;
+                p.node = node;
+                p.cumsum_shift = q_mul_m(c.claimed_sum, m_inv((uint32_t)(((uint64_t)1 << c.log) % P)));
+                // this component owns the last `nc` of the remaining powers, highest first
+                for (int k = 0; k < nc; ++k) p.pows[k] = powers[remaining - 1 - k];
+                remaining -= nc;
+                // 1 / Z_H on the 2^(eval_log - log) cosets of the evaluation domain
+                int log_expand = eval_log - c.log;
+                uint32_t init = subgroup_gen(eval_log + 1), step = subgroup_gen(eval_log - 1);
+                for (uint32_t i = 0; i < (1u << log_expand); ++i) {
+                    Pt pt = host_index_to_point(init + step * bit_reverse(i, log_expand));
+                    p.denom_inv[i] = m_inv(coset_vanishing_m(c.log, pt));
+                }
+                ck(constraint_quotients(c.kind, p, st), "constraint quotients");
+            }
+        }
+        // finalize: lift smaller accumulators into larger ones, interpolate -> composition coefficients
+        uint32_t* comp_coeffs = nullptr;
+        int comp_log = 0;
+        for (auto& kv : acc) {  // ascending eval_log
+            int lg = kv.first;
+            uint32_t* vals = kv.second;
+            size_t n = (size_t)1 << lg;
+            if (comp_coeffs) {
+                uint32_t* lifted = arena.alloc<uint32_t>(4 * n);
+                ck(cfft_evaluate(&tw, comp_coeffs, (size_t)1 << comp_log, comp_log, lifted, n, lg, 4, ctx->sm_count, st),
+                   "lift composition");
+                ck(add_inplace(vals, lifted, 4 * n, st), "accumulate");
+            }
+            ck(cfft_interpolate(&tw, vals, n, 4, lg, ctx->sm_count, st), "interpolate composition");
+            comp_coeffs = vals;
+            comp_log = lg;
+        }
+        for (int k = 0; k < 4; ++k) trees[3].cols.push_back({comp_coeffs + ((size_t)k << comp_log), nullptr, comp_log});
+        commit_tree(trees[3]);
+        timer.lap();  // stage 2: constraint quotients + composition commit
+
+        // ---- OODS point and mask points ---------------------------------------------------------
+        QPt oods;
+        {
+            QM31 t = channel.draw_secure_felt();
+            QM31 t2 = q_mul(t, t);
+            QM31 inv = q_inv(q_add(t2, q_one()));
+            oods.x = q_mul(q_sub(q_one(), t2), inv);
+            oods.y = q_mul(q_add(t, t), inv);
+        }
+        // sample_points[tree][col] = list of points
+        std::vector<std::vector<std::vector<QPt>>> sample_points(4);
+        sample_points[1].resize(trees[1].cols.size());
+        sample_points[2].resize(trees[2].cols.size());
+        for (const Component& c : comps) {
+            ComponentShape sh = component_shape(c.kind);
+            for (int k = 0; k < sh.n_main; ++k) sample_points[1][c.main_loc + k] = {oods};
+            int n_ic = 4 * sh.n_fracs;
+            QPt prev = qpt_add(oods, qpt_lift(host_index_to_point((0u - subgroup_gen(c.log)) & CIRCLE_ORDER_MASK)));
+            for (int k = 0; k < n_ic; ++k) {
+                if (k >= n_ic - 4)
+                    sample_points[2][c.inter_loc + k] = {prev, oods};  // mask offsets [-1, 0]
+                else
+                    sample_points[2][c.inter_loc + k] = {oods};
+            }
+        }
+        sample_points[3].assign(4, {oods});
+
+        // ---- prove_values: sample every polynomial -----------------------------------------------
+        std::vector<std::vector<std::vector<QM31>>> sampled(4);
+        for (int t = 0; t < 4; ++t) {
+            sampled[t].resize(trees[t].cols.size());
+            for (size_t c = 0; c < trees[t].cols.size(); ++c) sampled[t][c].resize(sample_points[t][c].size());
+        }
+        {
+            struct Job {
+                int log;
+                QPt pt;
+                std::vector<const uint32_t*> cols;
+                std::vector<QM31*> dst;
+            };
+            std::vector<Job> jobs;
+            for (int t = 0; t < 4; ++t)
+                for (size_t c = 0; c < trees[t].cols.size(); ++c)
+                    for (size_t s = 0; s < sample_points[t][c].size(); ++s) {
+                        const QPt& pt = sample_points[t][c][s];
+                        int lg = trees[t].cols[c].log;
+                        Job* job = nullptr;
+                        for (Job& j : jobs)
+                            if (j.log == lg && qpt_eq(j.pt, pt)) job = &j;
+                        if (!job) {
+                            jobs.push_back({lg, pt, {}, {}});
+                            job = &jobs.back();
+                        }
+                        job->cols.push_back(trees[t].cols[c].coeffs);
+                        job->dst.push_back(&sampled[t][c][s]);
+                    }
+            std::vector<std::vector<QM31>> results(jobs.size());
+            std::vector<QM31*> d_results(jobs.size());
+            for (size_t ji = 0; ji < jobs.size(); ++ji) {
+                Job& j = jobs[ji];
+                d_results[ji] = arena.alloc<QM31>(j.cols.size());
+                launch_eval_at_point(ctx, arena, j.cols, j.log, j.pt, d_results[ji]);
+            }
+            for (size_t ji = 0; ji < jobs.size(); ++ji) {
+                results[ji].resize(jobs[ji].cols.size());
+                ck(cudaMemcpyAsync(results[ji].data(), d_results[ji], results[ji].size() * sizeof(QM31), cudaMemcpyDeviceToHost, st),
+                   "samples d2h");
+            }
+            ck(cudaStreamSynchronize(st), "samples sync");
+            for (size_t ji = 0; ji < jobs.size(); ++ji)
+                for (size_t k = 0; k < jobs[ji].dst.size(); ++k) *jobs[ji].dst[k] = results[ji][k];
+        }
+        {
+            std::vector<QM31> flat;
+            for (int t = 0; t < 4; ++t)
+                for (auto& col : sampled[t])
+                    for (QM31 v : col) flat.push_back(v);
+            channel.mix_felts(flat);
+        }
+        timer.lap();  // stage 3: OODS sampling
+        QM31 rc_q = channel.draw_secure_felt();
+
+        // ---- DEEP quotients (compute_fri_quotients) -----------------------------------------------
+        struct QuotCol {
+            int log;
+            uint32_t* coords[4];
+        };
+        std::vector<QuotCol> quotients;
+        {
+            struct FlatCol {
+                const uint32_t* lde;
+                int log;
+                const std::vector<QPt>* pts;
+                const std::vector<QM31>* vals;
+            };
+            std::vector<FlatCol> flat;
+            for (int t = 0; t < 4; ++t)
+                for (size_t c = 0; c < trees[t].cols.size(); ++c)
+                    flat.push_back({trees[t].cols[c].lde, trees[t].cols[c].log + blowup, &sample_points[t][c], &sampled[t][c]});
+            std::vector<int> sizes;
+            for (auto& f : flat) sizes.push_back(f.log);
+            std::sort(sizes.begin(), sizes.end(), std::greater<int>());
+            sizes.erase(std::unique(sizes.begin(), sizes.end()), sizes.end());
+            for (int lg : sizes) {
+                std::vector<const FlatCol*> grp;
+                for (auto& f : flat)
+                    if (f.log == lg) grp.push_back(&f);
+                // ColumnSampleBatch::new_vec: group by point (BTreeMap order), columns in order
+                typedef HostBatch Batch;
+                std::vector<Batch> batches;
+                for (size_t ci = 0; ci < grp.size(); ++ci)
+                    for (size_t s = 0; s < grp[ci]->pts->size(); ++s) {
+                        const QPt& pt = (*grp[ci]->pts)[s];
+                        Batch* b = nullptr;
+                        for (Batch& bb : batches)
+                            if (qpt_eq(bb.pt, pt)) b = &bb;
+                        if (!b) {
+                            batches.push_back({pt, {}});
+                            b = &batches.back();
+                        }
+                        b->cols.push_back({(int)ci, (*grp[ci]->vals)[s]});
+                    }
+                std::vector<const uint32_t*> colptrs;
+                for (auto* f : grp) colptrs.push_back(f->lde);
+                QuotCol qc;
+                qc.log = lg;
+                uint32_t* buf = arena.alloc<uint32_t>((size_t)4 << lg);
+                for (int k = 0; k < 4; ++k) qc.coords[k] = buf + ((size_t)k << lg);
+                launch_quotients(ctx, arena, lg, colptrs, batches, rc_q, qc.coords);
+                quotients.push_back(qc);
+            }
+        }
+        timer.lap();  // stage 4: DEEP quotients
+
+        // ---- FRI commit (FriProver::commit) ----------------------------------------------------------
+        struct FriLayer {
+            int log;
+            uint32_t* coords[4];
+            MerkleTree tree;
+        };
+        MerkleTree fri_first_tree;
+        {
+            std::vector<ColRef> refs;
+            for (auto& q : quotients)
+                for (int k = 0; k < 4; ++k) refs.push_back({q.coords[k], q.log});
+            merkle_commit(ctx, arena, refs, fri_first_tree);
+            channel.mix_root(fri_first_tree.root);
+        }
+        std::vector<FriLayer> inner;
+        std::vector<QM31> last_layer_poly;
+        {
+            QM31 folding_alpha = channel.draw_secure_felt();
+            int line_log = quotients[0].log - 1;
+            int last_log = (int)(cfg.log_last_layer_degree_bound + cfg.log_blowup_factor);
+            uint32_t* cur = arena.alloc<uint32_t>((size_t)4 << line_log);
+            ck(cudaMemsetAsync(cur, 0, ((size_t)4 << line_log) * sizeof(uint32_t), st), "memset");
+            size_t qi = 0;
+            while (line_log > last_log) {
+                uint32_t* coords[4];
+                for (int k = 0; k < 4; ++k) coords[k] = cur + ((size_t)k << line_log);
+                while (qi < quotients.size() && quotients[qi].log - 1 == line_log) {
+                    ck(fold_circle_into_line(coords, quotients[qi].coords, inv_y_twiddles(tw, quotients[qi].log),
+                                             quotients[qi].log, folding_alpha, st),
+                       "fold circle");
+                    ++qi;
+                }
+                FriLayer L;
+                L.log = line_log;
+                for (int k = 0; k < 4; ++k) L.coords[k] = coords[k];
+                std::vector<ColRef> refs;
+                for (int k = 0; k < 4; ++k) refs.push_back({coords[k], line_log});
+                merkle_commit(ctx, arena, refs, L.tree);
+                channel.mix_root(L.tree.root);
+                folding_alpha = channel.draw_secure_felt();
+                inner.push_back(L);
+                uint32_t* next = arena.alloc<uint32_t>((size_t)4 << (line_log - 1));
+                uint32_t* ncoords[4];
+                for (int k = 0; k < 4; ++k) ncoords[k] = next + ((size_t)k << (line_log - 1));
+                ck(fold_line(ncoords, coords, inv_x_twiddles(tw, line_log), line_log, folding_alpha, st), "fold line");
+                cur = next;
+                --line_log;
+            }
+            if (qi != quotients.size()) fail(LB_ERR_BAD_ARG, "fri: columns left unfolded");
+            // last layer: interpolate on the host (2^(bound + blowup) values)
+            size_t n = (size_t)1 << line_log;
+            std::vector<uint32_t> hv(4 * n);
+            ck(cudaMemcpyAsync(hv.data(), cur, 4 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "last layer d2h");
+            ck(cudaStreamSynchronize(st), "last layer sync");
+            std::vector<QM31> vals(n);
+            for (size_t i = 0; i < n; ++i) {
+                size_t s = bit_reverse((uint32_t)i, line_log);  // natural order
+                vals[i] = q_make(hv[s], hv[n + s], hv[2 * n + s], hv[3 * n + s]);
+            }
+            // LineEvaluation::interpolate on LineDomain(half_odds(line_log))
+            uint32_t d_init = subgroup_gen(line_log + 2), d_step = subgroup_gen(line_log);
+            size_t size = n;
+            while (size > 1) {
+                for (size_t start = 0; start < n; start += size)
+                    for (size_t i = 0; i < size / 2; ++i) {
+                        uint32_t x = host_index_to_point(d_init + d_step * (uint32_t)i).x;
+                        uint32_t xinv = m_inv(x);
+                        QM31 l = vals[start + i], r = vals[start + size / 2 + i];
+                        vals[start + i] = q_add(l, r);
+                        vals[start + size / 2 + i] = q_mul_m(q_sub(l, r), xinv);
+                    }
+                d_init = (d_init * 2) & CIRCLE_ORDER_MASK;
+                d_step = (d_step * 2) & CIRCLE_ORDER_MASK;
+                size /= 2;
+            }
+            uint32_t inv_n = m_inv((uint32_t)(n % P));
+            std::vector<QM31> coeffs(n);
+            for (size_t i = 0; i < n; ++i) coeffs[i] = q_mul_m(vals[bit_reverse((uint32_t)i, line_log)], inv_n);
+            size_t bound = (size_t)1 << cfg.log_last_layer_degree_bound;
+            for (size_t i = bound; i < n; ++i)
+                if (!q_is_zero(coeffs[i])) fail(LB_ERR_CONSTRAINTS, "fri: invalid last-layer degree (ConstraintsNotSatisfied)");
+            last_layer_poly.assign(coeffs.begin(), coeffs.begin() + bound);
+            channel.mix_felts(last_layer_poly);
+        }
+        timer.lap();  // stage 5: FRI commit
+
+        // ---- proof of work --------------------------------------------------------------------------
+        uint64_t nonce = 0;
+        {
+            unsigned long long* d_found = arena.alloc<unsigned long long>(1);
+            uint32_t dg[8];
+            channel.digest_words(dg);
+            uint64_t base = 0;
+            const uint64_t chunk = (uint64_t)1 << 22;
+            for (;;) {
+                ck(cudaMemsetAsync(d_found, 0xFF, 8, st), "grind memset");
+                ck(grind_range(dg, cfg.channel_variant, cfg.pow_bits, base, chunk, d_found, st), "grind");
+                unsigned long long found;
+                ck(cudaMemcpyAsync(&found, d_found, 8, cudaMemcpyDeviceToHost, st), "grind d2h");
+                ck(cudaStreamSynchronize(st), "grind sync");
+                if (found != ~0ull) {
+                    nonce = found;
+                    break;
+                }
+                base += chunk;
+            }
+            channel.mix_u64(nonce);
+        }
+
+        // ---- queries + decommitment plan ---------------------------------------------------------------
+        Gatherer g;
+        int max_lde_log = quotients[0].log;
+        std::vector<uint32_t> queries = generate_queries(channel, max_lde_log, cfg.n_queries);
+        std::map<int, std::vector<uint32_t>> qpos;
+        for (auto& q : quotients) qpos[q.log] = fold_queries(queries, max_lde_log - q.log);
+
+        FriLayerOut first_out;
+        first_out.commitment = fri_first_tree.root;
+        {
+            std::map<int, std::vector<uint32_t>> pos_by_size;
+            for (auto& q : quotients) {
+                std::vector<uint32_t> cq = fold_queries(queries, max_lde_log - q.log);
+                std::vector<uint32_t> positions;
+                fri_positions_and_witness(q.coords, cq, g, positions, first_out.witness);
+                pos_by_size[q.log] = positions;
+            }
+            merkle_decommit_plan(fri_first_tree, pos_by_size, g, first_out.decommit);
+            first_out.decommit.queried_values.clear();
+        }
+        std::vector<FriLayerOut> inner_out(inner.size());
+        {
+            std::vector<uint32_t> lq = fold_queries(queries, 1);
+            for (size_t li = 0; li < inner.size(); ++li) {
+                std::vector<uint32_t> positions;
+                fri_positions_and_witness(inner[li].coords, lq, g, positions, inner_out[li].witness);
+                std::map<int, std::vector<uint32_t>> m;
+                m[inner[li].log] = positions;
+                merkle_decommit_plan(inner[li].tree, m, g, inner_out[li].decommit);
+                inner_out[li].decommit.queried_values.clear();
+                inner_out[li].commitment = inner[li].tree.root;
+                lq = fold_queries(lq, 1);
+            }
+        }
+        std::vector<DecommitIdx> tree_dec(4);
+        for (int t = 0; t < 4; ++t) merkle_decommit_plan(trees[t].merkle, qpos, g, tree_dec[t]);
+
+        // one gather for everything
+        g.values.resize(g.addrs.size());
+        if (!g.addrs.empty()) {
+            const uint32_t** d_addrs = arena.upload(g.addrs);
+            uint32_t* d_vals = arena.alloc<uint32_t>(g.addrs.size());
+            ck(gather_words(d_vals, d_addrs, (int)g.addrs.size(), st), "gather");
+            ck(cudaMemcpyAsync(g.values.data(), d_vals, g.values.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "gather d2h");
+            ck(cudaStreamSynchronize(st), "gather sync");
+        }
+        timer.lap();  // stage 6: grind + queries + decommitment
+
+        // ---- OODS check (prove() returns ConstraintsNotSatisfied otherwise) ------------------------------
+        {
+            QM31 e[4] = {sampled[3][0][0], sampled[3][1][0], sampled[3][2][0], sampled[3][3][0]};
+            QM31 composition_oods = q_from_partial_evals(e);
+            QM31 accv = q_zero();
+            for (const Component& c : comps) {
+                PointEval pe;
+                pe.main = &sampled[1];
+                pe.inter = &sampled[2];
+                pe.mc = c.main_loc;
+                pe.ic = c.inter_loc;
+                pe.random_coeff = random_coeff;
+                pe.denom_inverse = q_inv(coset_vanishing_q(c.log, oods));
+                pe.acc = &accv;
+                pe.cumsum_shift = q_mul_m(c.claimed_sum, m_inv((uint32_t)(((uint64_t)1 << c.log) % P)));
+                eval_component(c.kind, pe, node);
+            }
+            if (!q_eq(composition_oods, accv)) fail(LB_ERR_CONSTRAINTS, "ConstraintsNotSatisfied");
+        }
+
+        // ---- bincode -----------------------------------------------------------------------------------------
+        out.clear();
+        Writer w{out};
+        for (int s = 0; s < cfg.n_slots; ++s) {
+            if (claim[s] < 0)
+                w.u8(0);
+            else {
+                w.u8(1);
+                w.u32((uint32_t)claim[s]);
+            }
+        }
+        {
+            std::vector<const Component*> slot_comp(cfg.n_slots, nullptr);
+            for (const Component& c : comps) slot_comp[c.slot] = &c;
+            for (int s = 0; s < cfg.n_slots; ++s) {
+                if (!slot_comp[s])
+                    w.u8(0);
+                else {
+                    w.u8(1);
+                    w.qm31(slot_comp[s]->claimed_sum);
+                }
+            }
+        }
+        w.u32(cfg.pow_bits);
+        w.u32(cfg.log_blowup_factor);
+        w.u32(cfg.log_last_layer_degree_bound);
+        w.u64(cfg.n_queries);
+        w.u64(4);
+        for (int t = 0; t < 4; ++t) w.hash(trees[t].merkle.root);
+        w.u64(4);
+        for (int t = 0; t < 4; ++t) {
+            w.u64(sampled[t].size());
+            for (auto& col : sampled[t]) {
+                w.u64(col.size());
+                for (QM31 v : col) w.qm31(v);
+            }
+        }
+        w.u64(4);
+        for (int t = 0; t < 4; ++t) write_decommit(w, tree_dec[t], g);
+        w.u64(4);
+        for (int t = 0; t < 4; ++t) {
+            w.u64(tree_dec[t].queried_values.size());
+            for (size_t i : tree_dec[t].queried_values) w.u32(g.values[i]);
+        }
+        w.u64(nonce);
+        write_fri_layer(w, first_out, g);
+        w.u64(inner_out.size());
+        for (auto& l : inner_out) write_fri_layer(w, l, g);
+        w.u64(last_layer_poly.size());
+        for (QM31 v : last_layer_poly) w.qm31(v);
+        {
+            uint32_t lg = 0;
+            while (((size_t)1 << lg) < last_layer_poly.size()) ++lg;
+            w.u32(lg);
+        }
+        timer.lap();  // stage 7: OODS check + serialisation
+        return LB_OK;
+    } catch (const ProveError& e) {
+        cudaStreamSynchronize(ctx->stream);
+        ctx->err = e.msg;
+        return e.code;
+    }
+}
+
+// ======================================================================================
+// trait-level entry points (bound one by one by a Rust `CudaBackend`)
+// ======================================================================================
+namespace {
+inline QM31 q_from_words(const uint32_t* w) { return q_make(w[0], w[1], w[2], w[3]); }
+void ensure_kernels(lb_ctx* ctx) {
+    ck(cudaSetDevice(ctx->device), "set device");
+    if (!ctx->kernels_ready) {
+        ck(kernels_init(ctx->stream), "kernels init");
+        ctx->kernels_ready = true;
+    }
+}
+template <class Fn>
+int guarded(lb_ctx* ctx, Fn&& fn) {
+    try {
+        fn();
+        return LB_OK;
+    } catch (const ProveError& e) {
+        cudaStreamSynchronize(ctx->stream);
+        ctx->err = e.msg;
+        return e.code;
+    }
+}
+}  // namespace
+
+int eval_at_point_impl(lb_ctx* ctx, const uint32_t* const* h_cols, int n_cols, int log, const uint32_t point[8],
+                       uint32_t* h_out) {
+    return guarded(ctx, [&] {
+        ensure_kernels(ctx);
+        Arena arena(ctx->stream);
+        std::vector<const uint32_t*> cols(h_cols, h_cols + n_cols);
+        QPt pt{q_from_words(point), q_from_words(point + 4)};
+        QM31* d_out = arena.alloc<QM31>(n_cols);
+        launch_eval_at_point(ctx, arena, cols, log, pt, d_out);
+        ck(cudaMemcpyAsync(h_out, d_out, (size_t)n_cols * sizeof(QM31), cudaMemcpyDeviceToHost, ctx->stream), "eval d2h");
+        ck(cudaStreamSynchronize(ctx->stream), "eval sync");
+    });
+}
+
+int accumulate_quotients_impl(lb_ctx* ctx, int log, const uint32_t* const* h_cols, int n_cols,
+                              const lb_sample_batch* batches, int n_batches, const uint32_t random_coeff[4],
+                              uint32_t* const d_out[4]) {
+    return guarded(ctx, [&] {
+        ensure_kernels(ctx);
+        Arena arena(ctx->stream);
+        std::vector<const uint32_t*> cols(h_cols, h_cols + n_cols);
+        std::vector<HostBatch> hb(n_batches);
+        for (int b = 0; b < n_batches; ++b) {
+            hb[b].pt = QPt{q_from_words(batches[b].point), q_from_words(batches[b].point + 4)};
+            for (int k = 0; k < batches[b].n_cols; ++k)
+                hb[b].cols.push_back({batches[b].col_idx[k], q_from_words(batches[b].values + 4 * k)});
+        }
+        launch_quotients(ctx, arena, log, cols, hb, q_from_words(random_coeff), d_out);
+        ck(cudaStreamSynchronize(ctx->stream), "quotients sync");  // arena scratch is released on return
+    });
+}
+
+int fold_impl(lb_ctx* ctx, int circle, uint32_t* const d_dst[4], const uint32_t* const d_src[4], int log,
+              const uint32_t alpha[4]) {
+    return guarded(ctx, [&] {
+        ensure_kernels(ctx);
+        if (log < 1) fail(LB_ERR_BAD_ARG, "fold: log_size < 1");
+        int r = lb_twiddles_ensure(ctx, circle ? log : log + 1);
+        if (r) fail(r, ctx->err);
+        if (circle)
+            ck(fold_circle_into_line(d_dst, d_src, inv_y_twiddles(ctx->tw, log), log, q_from_words(alpha), ctx->stream), "fold circle");
+        else
+            ck(fold_line(d_dst, d_src, inv_x_twiddles(ctx->tw, log), log, q_from_words(alpha), ctx->stream), "fold line");
+    });
+}
+
+int grind_impl(lb_ctx* ctx, const uint32_t digest[8], int variant, uint32_t pow_bits, uint64_t* nonce_out) {
+    return guarded(ctx, [&] {
+        ensure_kernels(ctx);
+        if (pow_bits > 64) fail(LB_ERR_BAD_ARG, "grind: pow_bits > 64");
+        Arena arena(ctx->stream);
+        unsigned long long* d_found = arena.alloc<unsigned long long>(1);
+        uint64_t base = 0;
+        const uint64_t chunk = (uint64_t)1 << 24;
+        for (;;) {
+            ck(cudaMemsetAsync(d_found, 0xFF, 8, ctx->stream), "grind memset");
+            ck(grind_range(digest, variant, pow_bits, base, chunk, d_found, ctx->stream), "grind");
+            unsigned long long found;
+            ck(cudaMemcpyAsync(&found, d_found, 8, cudaMemcpyDeviceToHost, ctx->stream), "grind d2h");
+            ck(cudaStreamSynchronize(ctx->stream), "grind sync");
+            if (found != ~0ull) {
+                *nonce_out = found;
+                return;
+            }
+            base += chunk;
+        }
+    });
+}
+
+int logup_impl(lb_ctx* ctx, int kind, const uint32_t* d_main, size_t main_stride, uint32_t* d_inter, size_t inter_stride,
+               int log, const uint32_t z[4], const uint32_t alpha[4], uint32_t claimed_out[4]) {
+    return guarded(ctx, [&] {
+        ensure_kernels(ctx);
+        if (kind < 0 || kind >= COMP_KIND_COUNT || log < 1) fail(LB_ERR_BAD_ARG, "logup: bad args");
+        Arena arena(ctx->stream);
+        size_t n = (size_t)1 << log;
+        uint32_t* scan_tmp = arena.alloc<uint32_t>(4 * n);
+        uint32_t* block_sums = arena.alloc<uint32_t>(4 * (n / 1024 + 1));
+        uint32_t* d_claimed = arena.alloc<uint32_t>(4);
+        Relation2 node{q_from_words(z), q_from_words(alpha)};
+        ck(logup_interaction_trace(kind, d_main, main_stride, d_inter, inter_stride, log, node, scan_tmp, block_sums, d_claimed,
+                                   ctx->stream),
+           "logup");
+        ck(cudaMemcpyAsync(claimed_out, d_claimed, 16, cudaMemcpyDeviceToHost, ctx->stream), "claimed d2h");
+        ck(cudaStreamSynchronize(ctx->stream), "logup sync");
+    });
+}
+
+int constraint_quotients_impl(lb_ctx* ctx, int kind, const uint32_t* d_main, size_t main_stride, const uint32_t* d_inter,
+                              size_t inter_stride, int log_size, const uint32_t z[4], const uint32_t alpha[4],
+                              const uint32_t claimed_sum[4], const uint32_t* pows, int n_pows, uint32_t* const d_acc[4],
+                              int accumulate) {
+    return guarded(ctx, [&] {
+        ensure_kernels(ctx);
+        if (kind < 0 || kind >= COMP_KIND_COUNT) fail(LB_ERR_BAD_ARG, "constraints: unknown component");
+        ComponentShape sh = component_shape(kind);
+        if (n_pows != sh.n_constraints) fail(LB_ERR_BAD_ARG, "constraints: wrong number of random-coefficient powers");
+        ConstraintParams p{};
+        int eval_log = log_size + 1;
+        p.main = d_main;
+        p.main_stride = main_stride;
+        p.inter = d_inter;
+        p.inter_stride = inter_stride;
+        for (int k = 0; k < 4; ++k) p.acc[k] = d_acc[k];
+        p.accumulate = accumulate;
+        p.log_size = log_size;
+        p.eval_log = eval_log;
+        p.node = Relation2{q_from_words(z), q_from_words(alpha)};
+        p.cumsum_shift = q_mul_m(q_from_words(claimed_sum), m_inv((uint32_t)(((uint64_t)1 << log_size) % P)));
+        for (int k = 0; k < n_pows; ++k) p.pows[k] = q_from_words(pows + 4 * k);
+        uint32_t init = subgroup_gen(eval_log + 1), step = subgroup_gen(eval_log - 1);
+        for (uint32_t i = 0; i < 2; ++i) {
+            Pt pt = host_index_to_point(init + step * i);
+            p.denom_inv[i] = m_inv(coset_vanishing_m(log_size, pt));
+        }
+        ck(constraint_quotients(kind, p, ctx->stream), "constraint quotients");
+    });
+}
+
+}  // namespace lb

@@ -96,3 +96,34 @@ def synthetic_mul_table(log_rows: int, seed: int, node_id: int = 3) -> np.ndarra
     rows[:, 11] = q
     rows[:, 12] = r
     return (rows % P).astype(U64)
+
+
+def graph_pie(log_n: int, seed: int = 42, with_mul: bool = True):
+    """Trace tables of the element-wise graph  c = a + b ; e = c * a  over n = 2^log_n elements
+    (BASELINE cfg 3 shape when with_mul=False: Add 2^log_n rows, Inputs 2^(log_n+1) rows), built the
+    way the operators emit rows (crates/graph/src/op/prim.rs:72-84, 967-1013) with consistent LogUp
+    multiplicities, so the proof verifies (claimed sums cancel).  Node ids: a=0, b=1, add=2, mul=3.
+    Inputs: Fixed<12> of uniform(-0.5, 0.5), PCG64(seed)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = 1 << log_n
+    a = np.round(rng.uniform(-0.5, 0.5, n) * SCALE).astype(np.int64)
+    b = np.round(rng.uniform(-0.5, 0.5, n) * SCALE).astype(np.int64)
+    c = a + b
+    idx = np.arange(n, dtype=np.int64)
+    last = (idx == n - 1).astype(np.int64)
+
+    def table(cols):
+        return (np.stack([np.broadcast_to(np.asarray(x, dtype=np.int64), (n,)) for x in cols], axis=1) % P).astype(U64)
+
+    add = table([2, 0, 1, idx, last, 2, 0, 1, idx + 1, a, b, c, -1, -1, 1 if with_mul else 0])
+    a_mult = 2 if with_mul else 1
+    inp = np.concatenate([table([0, idx, last, 0, idx + 1, a, a_mult]), table([1, idx, last, 1, idx + 1, b, 1])])
+    pie = [("add", add)]
+    if with_mul:
+        p = c * a
+        q = p // SCALE
+        r = p - q * SCALE
+        mul = table([3, 2, 0, idx, last, 3, 2, 0, idx + 1, c, a, q, r, -1, -1, 0])
+        pie.append(("mul", mul))
+    pie.append(("inputs", inp))
+    return pie
