@@ -109,6 +109,18 @@ def cpu_roundtrip(sample_cols, threads, reps=1):
     return best
 
 
+def cpu_prove_baseline(log=14):
+    """The CPU restatement of prove() (oracle/, numpy, 1 core) on a bounded sample of the cfg-3 graph."""
+    from oracle import examples, prover as oprover
+    pie = examples.graph_pie(log, seed=42, with_mul=False)
+    t0 = time.perf_counter()
+    oprover.prove(pie)
+    dt = time.perf_counter() - t0
+    return {"value": dt * 1e3, "unit": "ms per proof", "cores": 1, "kind": "port",
+            "sample": f"a+b graph at 2^{log} elements (64x smaller than the GPU workload), numpy restatement (oracle/prover.py); "
+                      "not stwo SimdBackend (Rust toolchain absent)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -229,6 +241,11 @@ def run_gpu(args):
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
 
+    # ---- full prove() on the BASELINE cfg-3 shape (Add 2^20 rows + Inputs 2^21 rows), rank-local
+    prove_info = None
+    if not args.no_prove:
+        prove_info = bench_prove(be, torch, args)
+
     # ---- reduce over ranks (max time)
     t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
     if distributed:
@@ -262,6 +279,8 @@ def run_gpu(args):
                          "algorithmic_bytes_per_launch": alg_bytes_launch, "avg_launch_ms": avg_launch_ms,
                          "interpolate_ms": t_int, "evaluate_ms": t_ev},
         }
+        if prove_info:
+            line["prove"] = prove_info
         if world == 1 and not args.no_cpu:
             threads = min(os.cpu_count() or 1, N_COLS)
             sample_cols = min(N_COLS, max(threads, 8))
@@ -270,10 +289,70 @@ def run_gpu(args):
                                     "cores": threads, "kind": "port",
                                     "sample": f"{sample_cols} of {N_COLS} columns x 2^{LOG_N}, one interpolate+evaluate "
                                               "round trip, C restatement (oracle/c) with OpenMP over columns"}
+            if prove_info:
+                line["cpu_baseline"]["prove"] = cpu_prove_baseline()
         print(json.dumps(line))
     if distributed:
         dist.destroy_process_group()
     be.close()
+
+
+def bench_prove(be, torch, args):
+    """luminair_prover::prover::prove on the cfg-3 graph (a + b over 2^log elements): device-resident
+    tables (value) and host tables in pinned memory (e2e: H2D of the trace + proof bytes back)."""
+    from luminair_b200.pie import synthetic_add_graph_pie
+    from luminair_b200.prover import STAGE_NAMES, last_stage_ms, prove
+    log = args.prove_log
+    pie = synthetic_add_graph_pie(log, seed=42)
+    pinned, host_pie, dev = [], [], {}
+    for name, rows in pie:
+        t = torch.empty(rows.shape, dtype=torch.int32, pin_memory=True)
+        v = t.numpy().view(np.uint32)
+        v[:] = rows
+        pinned.append(t)
+        host_pie.append((name, v))
+        buf = be.upload(v.reshape(-1))
+        dev[name] = (buf.ptr, rows.shape[0], rows.shape[1])
+        pinned.append(buf)
+    reps = max(3, min(args.steps, 10))
+
+    def run(device_tables):
+        for _ in range(2):
+            prove(host_pie, backend=be, device_tables=device_tables)
+        ts, best_stages, nbytes = [], None, 0
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            proof = prove(host_pie, backend=be, device_tables=device_tables)
+            dt = (time.perf_counter() - t0) * 1e3
+            if not ts or dt < min(ts):
+                best_stages = last_stage_ms(be)
+            ts.append(dt)
+            nbytes = len(proof)
+        return ts, best_stages, nbytes
+
+    ts_dev, st_dev, nbytes = run(dev)
+    ts_host, st_host, _ = run(None)
+    # the reference's one published prove() figure: Add 32x32 (docs/snippets/benchmark-component.mdx:173)
+    small = synthetic_add_graph_pie(10, seed=42)
+    for _ in range(3):
+        prove(small, backend=be)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        prove(small, backend=be)
+    small_ms = (time.perf_counter() - t0) * 1e2
+    h2d = sum(int(v.nbytes) for _, v in host_pie)
+    return {
+        "workload": f"prove(): a+b graph, Add 2^{log} rows x 15 cols + Inputs 2^{log + 1} rows x 7 cols, blow-up 2, Blake2s Merkle, FRI "
+                    "(BASELINE configs[2]); proof bytes bit-exact vs the CPU restatement at test sizes, verifier-accepted at this size",
+        "ms_device_resident": {"min": min(ts_dev), "median": statistics.median(ts_dev)},
+        "ms_e2e_host_tables": {"min": min(ts_host), "median": statistics.median(ts_host), "h2d_bytes": h2d, "d2h_bytes": nbytes},
+        "proofs_per_s_e2e": 1e3 / statistics.median(ts_host),
+        "stages_ms_device_resident": dict(zip(STAGE_NAMES, [round(x, 3) for x in st_dev])),
+        "proof_bytes": nbytes, "timer": "host wall clock around lb_prove (the call synchronises the stream before returning)",
+        "add_32x32_prove_ms": small_ms,
+        "published_reference_add_32x32_prove_ms": 13.05,
+        "published_note": "GitHub Actions ubuntu-latest CPU, Criterion; other hardware, context only",
+    }
 
 
 def main():
@@ -283,6 +362,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-prove", action="store_true")
+    ap.add_argument("--prove-log", type=int, default=20)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
