@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libluminair_b200.so")
+LIB_PATH = os.environ.get("LUMINAIR_B200_LIB") or os.path.join(_HERE, "libluminair_b200.so")
 
 LB_OK = 0
 _ERRS = {-1: "LB_ERR_CUDA", -2: "LB_ERR_OOM", -3: "LB_ERR_BAD_ARG", -4: "LB_ERR_NCCL"}

@@ -126,14 +126,42 @@ static inline const uint2* layer_tw(const Twiddles* tw, bool inverse, int n, int
 // as arbitrary u32 representatives and folded with red() right where a sum could overflow.
 // Both butterflies are closed on the full u32 range.
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ void bfly_fwd(uint32_t& v0, uint32_t& v1, uint2 w) {
-    uint32_t a = red(v0);                 // [0, P+1]
-    uint32_t t = red(mul_shoup(v1, w));   // [0, P]
+// Pipe balance (B200: IMAD-class on the FMA pipe, LOP3/SHF/LEA/IADD3 on the ALU pipe, each one
+// warp-instruction per 2 cycles per SM sub-partition): red() as (x & P) + (x >> 31) is two ALU
+// instructions; red_fma() computes the same value as x - (x >> 31) * P with IMAD.HI + IMAD, the
+// multipliers coming from kernel parameters so ptxas cannot strength-reduce them back to shifts.
+#ifndef LB_BFLY_VARIANT
+#define LB_BFLY_VARIANT 8
+#endif
+struct RedK {
+    uint32_t two, neg_p;  // 2, -P (mod 2^32)
+};
+// red_mix: the same value as red() computed as x - (x >> 31) * P: one shift on the ALU pipe, one IMAD on the FMA pipe
+__device__ __forceinline__ uint32_t red_mix(uint32_t x, RedK k) {
+    uint32_t r;
+    asm("{\n\t.reg .u32 h;\n\tshr.u32 h, %1, 31;\n\tmad.lo.u32 %0, h, %2, %1;\n\t}" : "=r"(r) : "r"(x), "r"(k.neg_p));
+    return r;
+}
+template <int SLOT, int PR>
+__device__ __forceinline__ uint32_t red_sel(uint32_t x, RedK k) {
+    // SLOT 0: the "a" operand, SLOT 1: the multiplied / second operand; PR: butterfly index within the layer
+    if (LB_BFLY_VARIANT == 4) return (SLOT == 1 && (PR & 1)) ? red_mix(x, k) : red(x);
+    if (LB_BFLY_VARIANT == 5) return SLOT == 1 ? red_mix(x, k) : red(x);
+    if (LB_BFLY_VARIANT == 6) return (SLOT == 1 && (PR & 3) == 0) ? red_mix(x, k) : red(x);
+    if (LB_BFLY_VARIANT == 7) return red_mix(x, k);
+    if (LB_BFLY_VARIANT == 8) return min(x, x - P);  // one VIADDMNMX.U32: any u32 -> [0, P+1]
+    return red(x);
+}
+template <int PR = 0>
+__device__ __forceinline__ void bfly_fwd(uint32_t& v0, uint32_t& v1, uint2 w, RedK k = RedK{2u, 0u - P}) {
+    uint32_t a = red_sel<0, PR>(v0, k);                 // [0, P+1]
+    uint32_t t = red_sel<1, PR>(mul_shoup(v1, w), k);   // [0, P]
     v0 = a + t;                           // <= 2P+1
     v1 = a + P - t;                       // <= 2P+1
 }
-__device__ __forceinline__ void bfly_inv(uint32_t& v0, uint32_t& v1, uint2 w) {
-    uint32_t a = red(v0), b = red(v1);  // [0, P] for inputs <= 2P
+template <int PR = 0>
+__device__ __forceinline__ void bfly_inv(uint32_t& v0, uint32_t& v1, uint2 w, RedK k = RedK{2u, 0u - P}) {
+    uint32_t a = red_sel<0, PR>(v0, k), b = red_sel<1, PR>(v1, k);  // [0, P] for inputs <= 2P
     v0 = a + b;                         // [0, 2P]
     v1 = mul_shoup(a + P - b, w);       // [0, 2P)
 }
@@ -150,6 +178,7 @@ struct PassParams {
     int ts;                // log2(FFT elements per tile), ts >= m
     int final_mode;        // 0 lazy store, 1 canonical, 2 scale (interpolate) + canonical
     uint2 scale;
+    RedK redk;             // {2, -P}: opaque multipliers for red_fma
     const uint2* tw[12];   // twiddle arrays of layers i_lo .. i_lo+m-1
 };
 
@@ -310,6 +339,28 @@ __device__ __forceinline__ void load_tw(uint2 (&w)[8], const uint2* p) {
     }
 }
 
+template <bool FWD, int PR>
+__device__ __forceinline__ void bfly_at(uint32_t (&v)[16], const uint2 (&w)[8], int b, RedK k) {
+    const int j0 = ((PR >> b) << (b + 1)) | (PR & ((1 << b) - 1));
+    const int j1 = j0 | (1 << b);
+    if (FWD)
+        bfly_fwd<PR>(v[j0], v[j1], w[PR >> b], k);
+    else
+        bfly_inv<PR>(v[j0], v[j1], w[PR >> b], k);
+}
+// the 8 butterflies of one layer on 16 register-resident elements (b is a compile-time constant after unrolling)
+template <bool FWD>
+__device__ __forceinline__ void layer8(uint32_t (&v)[16], const uint2 (&w)[8], int b, RedK k) {
+    bfly_at<FWD, 0>(v, w, b, k);
+    bfly_at<FWD, 1>(v, w, b, k);
+    bfly_at<FWD, 2>(v, w, b, k);
+    bfly_at<FWD, 3>(v, w, b, k);
+    bfly_at<FWD, 4>(v, w, b, k);
+    bfly_at<FWD, 5>(v, w, b, k);
+    bfly_at<FWD, 6>(v, w, b, k);
+    bfly_at<FWD, 7>(v, w, b, k);
+}
+
 // layers of one index field: field bits [BLO, 4); A = bit position of the field in the tile
 // index; twiddle pointer for field bit b: tw[A+b] + (tile_h << (TS-1-A-b)) + (e0_hi << (3-b))
 template <bool FWD, int A, int BLO, int BHI, int TS>
@@ -324,15 +375,7 @@ __device__ __forceinline__ void field_layers_range(uint32_t (&v)[16], const Pass
         if (b == 1) load_tw<4>(w, twp);
         if (b == 2) load_tw<2>(w, twp);
         if (b == 3) load_tw<1>(w, twp);
-#pragma unroll
-        for (int pr = 0; pr < 8; ++pr) {
-            const int j0 = ((pr >> b) << (b + 1)) | (pr & ((1 << b) - 1));
-            const int j1 = j0 | (1 << b);
-            if (FWD)
-                bfly_fwd(v[j0], v[j1], w[pr >> b]);
-            else
-                bfly_inv(v[j0], v[j1], w[pr >> b]);
-        }
+        layer8<FWD>(v, w, b, p.redk);
     }
 }
 
@@ -421,7 +464,16 @@ __device__ __forceinline__ void low_round(uint32_t* sm, const PassParams& p, uin
 }
 
 template <bool FWD, int M>
-__global__ void __launch_bounds__(256, 4) cfft_low_fast(PassParams p, int cols_per_block) {
+#ifndef LB_LOW_MINB
+#define LB_LOW_MINB 6
+#endif
+#ifndef LB_HIGH_MINB
+#define LB_HIGH_MINB 4
+#endif
+#ifndef LB_CPB_MAX
+#define LB_CPB_MAX 1
+#endif
+__global__ void __launch_bounds__(256, LB_LOW_MINB) cfft_low_fast(PassParams p, int cols_per_block) {
     __shared__ __align__(16) uint32_t sm[LOW_SMEM_WORDS];
     constexpr int NR = (M + 3) / 4;
     const uint32_t tile = blockIdx.x;
@@ -512,7 +564,7 @@ template <int M>
 struct HighGeom {
     static constexpr int W = (M <= 8) ? (1 << (12 - M)) : 16;
     static constexpr int THREADS = (1 << (M - 4)) * W;
-    static constexpr int MIN_BLOCKS = (M <= 8) ? 3 : 1;
+    static constexpr int MIN_BLOCKS = (M <= 8) ? LB_HIGH_MINB : 1;
 };
 
 template <bool FWD, int M, int ILO, int ZEXT>
@@ -597,7 +649,7 @@ static Plan make_plan(int n) {
 static int pick_cols_per_block(size_t tiles, int n_cols, int sm_count) {
     int cpb = 1;
     size_t target_blocks = (size_t)sm_count * 16;
-    while (cpb < n_cols && cpb < 8 && tiles * ((n_cols + cpb - 1) / cpb) > target_blocks) cpb *= 2;
+    while (cpb < n_cols && cpb < LB_CPB_MAX && tiles * ((n_cols + cpb - 1) / cpb) > target_blocks) cpb *= 2;
     return cpb;
 }
 
@@ -703,6 +755,7 @@ cudaError_t cfft_interpolate(const Twiddles* tw, uint32_t* data, size_t stride, 
     uint32_t inv_n = m_inv(1u << log_n);
     for (int k = 0; k < pl.n_pass; ++k) {
         PassParams p{};
+        p.redk = RedK{2u, 0u - P};
         p.src = data;
         p.dst = data;
         p.src_stride = p.dst_stride = stride;
@@ -728,6 +781,7 @@ cudaError_t cfft_evaluate(const Twiddles* tw, const uint32_t* coeffs, size_t src
     Plan pl = make_plan(log_out);
     for (int k = pl.n_pass - 1; k >= 0; --k) {
         PassParams p{};
+        p.redk = RedK{2u, 0u - P};
         bool first = (k == pl.n_pass - 1);
         p.src = first ? coeffs : out;
         p.dst = out;

@@ -26,8 +26,23 @@ __device__ __forceinline__ uint32_t canon(uint32_t x) {
 }
 
 // Shoup multiplication: w = (t, floor(t * 2^32 / P)), t < P, a any u32 -> a*t mod P in [0, 2P)
+// The quotient word comes from a 64-bit IMAD.WIDE rather than IMAD.HI: measured on B200
+// (scripts/ubench/pipes.cu) IMAD.WIDE issues every 2.3 clk per SM sub-partition, IMAD.HI every 4.
+#ifndef LB_MULHI_WIDE
+#define LB_MULHI_WIDE 1
+#endif
+__device__ __forceinline__ uint32_t mulhi_u32(uint32_t a, uint32_t b) {
+#if LB_MULHI_WIDE
+    uint32_t lo, hi;
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+    (void)lo;
+    return hi;
+#else
+    return __umulhi(a, b);
+#endif
+}
 __device__ __forceinline__ uint32_t mul_shoup(uint32_t a, uint2 w) {
-    uint32_t q = __umulhi(a, w.y);
+    uint32_t q = mulhi_u32(a, w.y);
     return a * w.x - q * P;
 }
 __host__ __device__ __forceinline__ uint32_t shoup_companion(uint32_t t) {
