@@ -8,9 +8,6 @@ namespace lb {
 
 cudaError_t kernels_init(cudaStream_t stream);  // constant tables (call once per context)
 
-// (x, y) of CanonicCoset(log).circle_domain() at storage index 2h, h < 2^(log-1); index 2h+1 is (x, -y)
-cudaError_t domain_points(uint2* d_pts, int log, cudaStream_t stream);
-
 // ---- PolyOps::eval_at_point ------------------------------------------------------------------
 // d_cols: device table of n_cols coefficient columns (2^log each).  d_mappings: log QM31 fold
 // factors [y, x, pi(x), ...] (host computes them).  d_basis: scratch of 2^min(log,12) QM31.
@@ -36,7 +33,7 @@ struct QuotientParams {
     QuotientBatch b[MAX_QUOTIENT_BATCHES];
 };
 cudaError_t accumulate_quotients(uint32_t* const out[4], const uint32_t* const* d_cols, const QuotientEntry* d_entries,
-                                 const QuotientParams& qp, const uint2* d_pts, int log, cudaStream_t stream);
+                                 const QuotientParams& qp, const Twiddles* tw, int log, cudaStream_t stream);
 
 // ---- FriOps -------------------------------------------------------------------------------------
 // dst (4 coords, n/2) = dst * alpha^2 + fold(src (4 coords, n = 2^log));  itw = inverse y twiddles of the domain

@@ -14,13 +14,22 @@
 
 namespace lb {
 
-// cols: device array of n_cols column base pointers (each 2^log_size u32).
-__global__ void __launch_bounds__(256) merkle_layer_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ prev,
-                                                           const uint32_t* const* __restrict__ cols, int n_cols,
-                                                           uint32_t n_nodes) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_nodes) return;
-    uint32_t h[8];
+#ifndef LB_MERKLE_FMA
+#define LB_MERKLE_FMA 1
+#endif
+
+__device__ __forceinline__ void compress_dev(uint32_t h[8], const uint32_t m[16], uint32_t t0, uint32_t f0, uint32_t one) {
+#if LB_MERKLE_FMA
+    blake2s_compress_fma(h, m, t0, 0, f0, one);
+#else
+    (void)one;
+    blake2s_compress(h, m, t0, 0, f0);
+#endif
+}
+
+// hash of node i of a layer: children (prev != nullptr) then the layer's column values
+__device__ __forceinline__ void hash_node(uint32_t h[8], const uint32_t* __restrict__ prev,
+                                          const uint32_t* const* __restrict__ cols, int n_cols, uint32_t i, uint32_t one) {
     blake2s_init(h);
     uint32_t m[16];
     uint32_t t = 0;
@@ -39,7 +48,7 @@ __global__ void __launch_bounds__(256) merkle_layer_kernel(uint32_t* __restrict_
     while (true) {
         if (have_block) {
             bool last = (c >= n_cols);
-            blake2s_compress(h, m, t, 0, last ? 0xFFFFFFFFu : 0u);
+            compress_dev(h, m, t, last ? 0xFFFFFFFFu : 0u, one);
             if (last) break;
         }
         // build next block from columns c .. c+15
@@ -58,6 +67,16 @@ __global__ void __launch_bounds__(256) merkle_layer_kernel(uint32_t* __restrict_
         t += 4u * take;
         have_block = true;
     }
+}
+
+// cols: device array of n_cols column base pointers (each 2^log_size u32).
+__global__ void __launch_bounds__(256) merkle_layer_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ prev,
+                                                           const uint32_t* const* __restrict__ cols, int n_cols,
+                                                           uint32_t n_nodes, uint32_t one) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    uint32_t h[8];
+    hash_node(h, prev, cols, n_cols, i, one);
     uint4* o = reinterpret_cast<uint4*>(out + (size_t)i * 8);
     o[0] = make_uint4(h[0], h[1], h[2], h[3]);
     o[1] = make_uint4(h[4], h[5], h[6], h[7]);
@@ -66,7 +85,70 @@ __global__ void __launch_bounds__(256) merkle_layer_kernel(uint32_t* __restrict_
 cudaError_t merkle_commit_layer(uint32_t* out, const uint32_t* prev, const uint32_t* const* d_cols, int n_cols,
                                 int log_size, cudaStream_t stream) {
     uint32_t n = 1u << log_size;
-    merkle_layer_kernel<<<(n + 255) / 256, 256, 0, stream>>>(out, prev, d_cols, n_cols, n);
+    merkle_layer_kernel<<<(n + 255) / 256, 256, 0, stream>>>(out, prev, d_cols, n_cols, n, 1u);
+    return cudaGetLastError();
+}
+
+// Same, for layers with at most MERKLE_SMALL_COLS columns: the column pointers travel in the kernel parameters, so
+// no pointer table has to be staged in device memory first (the FRI layer trees: 4 coordinate columns each).
+__global__ void __launch_bounds__(256) merkle_layer_small_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ prev,
+                                                                 const __grid_constant__ MerkleColsArg cols, int n_cols,
+                                                                 uint32_t n_nodes, uint32_t one) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    uint32_t h[8];
+    blake2s_init(h);
+    uint32_t m[16];
+    uint32_t t = 0;
+    if (prev) {
+        const uint4* pp = reinterpret_cast<const uint4*>(prev + (size_t)i * 16);
+        uint4 a = pp[0], b = pp[1], cc = pp[2], d = pp[3];
+        m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w;
+        m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+        m[8] = cc.x; m[9] = cc.y; m[10] = cc.z; m[11] = cc.w;
+        m[12] = d.x; m[13] = d.y; m[14] = d.z; m[15] = d.w;
+        t = 64;
+        compress_dev(h, m, t, n_cols == 0 ? 0xFFFFFFFFu : 0u, one);
+    }
+    if (n_cols > 0 || !prev) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) m[j] = (j < n_cols) ? cols.p[j][i] : 0u;
+        t += 4u * n_cols;
+        compress_dev(h, m, t, 0xFFFFFFFFu, one);
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + (size_t)i * 8);
+    o[0] = make_uint4(h[0], h[1], h[2], h[3]);
+    o[1] = make_uint4(h[4], h[5], h[6], h[7]);
+}
+
+cudaError_t merkle_commit_layer_small(uint32_t* out, const uint32_t* prev, const MerkleColsArg& cols, int n_cols,
+                                      int log_size, cudaStream_t stream) {
+    if (n_cols < 0 || n_cols > MERKLE_SMALL_COLS) return cudaErrorInvalidValue;
+    uint32_t n = 1u << log_size;
+    merkle_layer_small_kernel<<<(n + 255) / 256, 256, 0, stream>>>(out, prev, cols, n_cols, n, 1u);
+    return cudaGetLastError();
+}
+
+// The top of a tree in one launch: given layer `from_log` (<= MERKLE_TOP_MAX_LOG) already hashed, one CTA computes the
+// column-less layers from_log-1 .. 0, each into its own buffer, with a block barrier between levels.  Saves one
+// ~3 us dependent launch per level on every tree (the FRI layers make ~25 trees per proof).
+__global__ void __launch_bounds__(512) merkle_top_kernel(MerkleTopArgs a, uint32_t one) {
+    for (int log = a.from_log - 1; log >= 0; --log) {
+        uint32_t n = 1u << log;
+        if (threadIdx.x < n) {
+            uint32_t h[8];
+            hash_node(h, a.layers[log + 1], nullptr, 0, threadIdx.x, one);
+            uint4* o = reinterpret_cast<uint4*>(a.layers[log] + (size_t)threadIdx.x * 8);
+            o[0] = make_uint4(h[0], h[1], h[2], h[3]);
+            o[1] = make_uint4(h[4], h[5], h[6], h[7]);
+        }
+        __syncthreads();  // the level just written is read by other threads of this CTA next
+    }
+}
+
+cudaError_t merkle_commit_top(const MerkleTopArgs& args, cudaStream_t stream) {
+    if (args.from_log < 1 || args.from_log > MERKLE_TOP_MAX_LOG) return cudaErrorInvalidValue;
+    merkle_top_kernel<<<1, 512, 0, stream>>>(args, 1u);
     return cudaGetLastError();
 }
 

@@ -6,6 +6,19 @@ namespace lb {
 // d_cols: DEVICE array of n_cols device column pointers (each >= 2^log_size u32).
 cudaError_t merkle_commit_layer(uint32_t* out, const uint32_t* prev, const uint32_t* const* d_cols, int n_cols,
                                 int log_size, cudaStream_t stream);
+constexpr int MERKLE_SMALL_COLS = 16;
+struct MerkleColsArg {
+    const uint32_t* p[MERKLE_SMALL_COLS];
+};
+cudaError_t merkle_commit_layer_small(uint32_t* out, const uint32_t* prev, const MerkleColsArg& cols, int n_cols,
+                                      int log_size, cudaStream_t stream);
+// column-less layers from_log-1 .. 0 in one launch; layers[k] = buffer of layer k (2^k digests), layers[from_log] given
+constexpr int MERKLE_TOP_MAX_LOG = 10;
+struct MerkleTopArgs {
+    uint32_t* layers[MERKLE_TOP_MAX_LOG + 1];
+    int from_log;
+};
+cudaError_t merkle_commit_top(const MerkleTopArgs& args, cudaStream_t stream);
 cudaError_t gather_rows(uint32_t* d_out, const uint32_t* const* d_cols, int n_cols, const uint32_t* d_idx, int n_idx,
                         cudaStream_t stream);
 }  // namespace lb

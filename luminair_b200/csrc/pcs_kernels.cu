@@ -37,26 +37,6 @@ __device__ __forceinline__ Pt k_point_of_index(uint32_t idx) {
     return r;
 }
 
-// half_odds(log-1).at(bitrev(h, log-1)): initial = 2^(30-log), step = 2^(32-log)
-__global__ void domain_points_kernel(uint2* pts, int log) {
-    uint32_t bits = log - 1;
-    uint32_t n = 1u << bits;
-    uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= n) return;
-    uint32_t i = bits ? (__brev(h) >> (32 - bits)) : 0;
-    uint32_t init = 1u << (30 - log);
-    uint32_t step = (log >= 1 && log <= 31) ? (uint32_t)(((uint64_t)1 << (32 - log)) & 0x7FFFFFFFu) : 0;
-    uint32_t idx = (init + i * step) & 0x7FFFFFFFu;
-    Pt p = k_point_of_index(idx);
-    pts[h] = make_uint2(p.x, p.y);
-}
-
-cudaError_t domain_points(uint2* d_pts, int log, cudaStream_t stream) {
-    uint32_t n = 1u << (log - 1);
-    domain_points_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_pts, log);
-    return cudaGetLastError();
-}
-
 // ------------------------------------------------------------------------------------
 // eval_at_point:  f(P) = sum_k c_k * prod_{bit b of k} mappings[b]
 // The index is split k = (chunk << m) | e.  basis[e] covers the low m bits and is shared by all
@@ -165,63 +145,101 @@ cudaError_t eval_at_point(const uint32_t* const* d_cols, int n_cols, int log, co
 // ------------------------------------------------------------------------------------
 // DEEP quotients.  Per row:  acc = sum over batches (Horner in rc_pow) of
 //     ( sum_j c_j * f_j(row) - (A * y + B) ) * 1 / ((Pr.x - x) Pi.y - (Pr.y - y) Pi.x)
-// One thread per row; every column value is read once per batch it belongs to (4 B per
-// column per row + 16 B written).  The per-row CM31 inversions of all batches share one
-// field inversion (Montgomery's trick across the batches).
+// Every column value is read once per batch it belongs to (4 B per column per row + 16 B written).
 // ------------------------------------------------------------------------------------
+// Domain points come from the CFFT twiddle tables: storage row 2h is (x_h, y_h) with y_h = Y[log-1][h] and
+// x_h = +-X[log-1][h >> 1] (sign by the low bit of h: adjacent half-coset points differ by the order-2 point),
+// row 2h+1 is the conjugate.  Each thread handles QROWS rows 256 apart so that all QROWS * n_batches
+// denominators share ONE field inversion.
+constexpr int QROWS = 4;
+
+template <int NB>
 __global__ void __launch_bounds__(256) quotients_kernel(uint32_t* __restrict__ o0, uint32_t* __restrict__ o1,
                                                         uint32_t* __restrict__ o2, uint32_t* __restrict__ o3,
                                                         const uint32_t* const* __restrict__ cols,
-                                                        const QuotientEntry* __restrict__ entries, QuotientParams qp,
-                                                        const uint2* __restrict__ pts, uint32_t n) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    uint2 pt = pts[j >> 1];
-    uint32_t x = pt.x, y = (j & 1) ? m_neg(pt.y) : pt.y;
-    CM31 den[MAX_QUOTIENT_BATCHES];
-    CM31 pre[MAX_QUOTIENT_BATCHES];
+                                                        const QuotientEntry* __restrict__ entries,
+                                                        const __grid_constant__ QuotientParams qp,
+                                                        const uint2* __restrict__ tw_x, const uint2* __restrict__ tw_y,
+                                                        uint32_t n) {
+    const uint32_t j0 = blockIdx.x * (256 * QROWS) + threadIdx.x;
+    uint32_t ys[QROWS];
+    CM31 den[QROWS * NB], pre[QROWS * NB];
     CM31 run = {1, 0};
-    for (int b = 0; b < qp.n_batches; ++b) {
-        const QuotientBatch& B = qp.b[b];
-        CM31 dx = {m_sub(B.prx.a, x), B.prx.b};
-        CM31 dy = {m_sub(B.pry.a, y), B.pry.b};
-        CM31 d = c_sub(c_mul(dx, B.piy), c_mul(dy, B.pix));
-        den[b] = d;
-        pre[b] = run;
-        run = c_mul(run, d);
+#pragma unroll
+    for (int r = 0; r < QROWS; ++r) {
+        uint32_t j = j0 + r * 256;
+        if (j >= n) j = n - 1;  // clamp (results of clamped rows are not stored)
+        uint32_t h = j >> 1;
+        uint32_t x = tw_x[h >> 1].x;
+        if (h & 1) x = m_neg(x);
+        uint32_t y = tw_y[h].x;
+        if (j & 1) y = m_neg(y);
+        ys[r] = y;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const QuotientBatch& B = qp.b[b];
+            CM31 dx = {m_sub(B.prx.a, x), B.prx.b};
+            CM31 dy = {m_sub(B.pry.a, y), B.pry.b};
+            CM31 d = c_sub(c_mul(dx, B.piy), c_mul(dy, B.pix));
+            den[r * NB + b] = d;
+            pre[r * NB + b] = run;
+            run = c_mul(run, d);
+        }
     }
     CM31 inv = c_inv(run);
-    QM31 acc = q_zero();
-    // inverses come out last-to-first; the Horner accumulation runs first-to-last, so keep them
-    CM31 dinv[MAX_QUOTIENT_BATCHES];
-    for (int b = qp.n_batches - 1; b >= 0; --b) {
-        dinv[b] = c_mul(inv, pre[b]);
-        inv = c_mul(inv, den[b]);
+#pragma unroll
+    for (int k = QROWS * NB - 1; k >= 0; --k) {
+        CM31 di = c_mul(inv, pre[k]);
+        inv = c_mul(inv, den[k]);
+        den[k] = di;  // now the inverse
     }
-    for (int b = 0; b < qp.n_batches; ++b) {
-        const QuotientBatch& B = qp.b[b];
-        QM31 num = q_zero();
-        for (int k = 0; k < B.count; ++k) {
-            const QuotientEntry& e = entries[B.first + k];
-            uint32_t v = cols[e.col][j];
-            num = q_add(num, q_mul_m(e.c, v));
+#pragma unroll
+    for (int r = 0; r < QROWS; ++r) {
+        uint32_t j = j0 + r * 256;
+        if (j >= n) continue;
+        QM31 acc = q_zero();
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const QuotientBatch& B = qp.b[b];
+            QM31 num = q_zero();
+            for (int k = 0; k < B.count; ++k) {
+                const QuotientEntry& e = entries[B.first + k];
+                uint32_t v = cols[e.col][j];
+                num = q_add(num, q_mul_m(e.c, v));
+            }
+            QM31 lin = q_add(q_mul_m(B.sum_a, ys[r]), B.sum_b);
+            num = q_sub(num, lin);
+            QM31 q = q_mul_c(num, den[r * NB + b]);
+            acc = (b == 0) ? q : q_add(q_mul(acc, B.rc_pow), q);
         }
-        QM31 lin = q_add(q_mul_m(B.sum_a, y), B.sum_b);
-        num = q_sub(num, lin);
-        QM31 q = q_mul_c(num, dinv[b]);
-        acc = (b == 0) ? q : q_add(q_mul(acc, B.rc_pow), q);
+        o0[j] = acc.a.a;
+        o1[j] = acc.a.b;
+        o2[j] = acc.b.a;
+        o3[j] = acc.b.b;
     }
-    o0[j] = acc.a.a;
-    o1[j] = acc.a.b;
-    o2[j] = acc.b.a;
-    o3[j] = acc.b.b;
 }
 
 cudaError_t accumulate_quotients(uint32_t* const out[4], const uint32_t* const* d_cols, const QuotientEntry* d_entries,
-                                 const QuotientParams& qp, const uint2* d_pts, int log, cudaStream_t stream) {
+                                 const QuotientParams& qp, const Twiddles* tw, int log, cudaStream_t stream) {
     if (qp.n_batches < 1 || qp.n_batches > MAX_QUOTIENT_BATCHES) return cudaErrorInvalidValue;
+    if (log < 2 || log > tw->max_log) return cudaErrorInvalidValue;
     uint32_t n = 1u << log;
-    quotients_kernel<<<(n + 255) / 256, 256, 0, stream>>>(out[0], out[1], out[2], out[3], d_cols, d_entries, qp, d_pts, n);
+    const uint2* tw_x = tw->fwd + ((size_t)1 << (log - 2));              // X[log-1]
+    const uint2* tw_y = tw->fwd + tw->y_off + ((size_t)1 << (log - 1));  // Y[log-1]
+    unsigned blocks = (n + 256 * QROWS - 1) / (256 * QROWS);
+#define LB_Q_LAUNCH(NB) \
+    quotients_kernel<NB><<<blocks, 256, 0, stream>>>(out[0], out[1], out[2], out[3], d_cols, d_entries, qp, tw_x, tw_y, n)
+    switch (qp.n_batches) {
+        case 1: LB_Q_LAUNCH(1); break;
+        case 2: LB_Q_LAUNCH(2); break;
+        case 3: LB_Q_LAUNCH(3); break;
+        case 4: LB_Q_LAUNCH(4); break;
+        case 5: LB_Q_LAUNCH(5); break;
+        case 6: LB_Q_LAUNCH(6); break;
+        case 7: LB_Q_LAUNCH(7); break;
+        default: LB_Q_LAUNCH(8); break;
+    }
+#undef LB_Q_LAUNCH
     return cudaGetLastError();
 }
 

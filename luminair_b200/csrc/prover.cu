@@ -262,12 +262,33 @@ void merkle_commit(lb_ctx* ctx, Arena& arena, const std::vector<ColRef>& cols, M
             if (c.log == log) table.push_back(c.ptr);
         count[log] = (int)table.size() - first[log];
     }
-    const uint32_t** d_table = arena.upload(table);
+    bool small = true;
+    for (int log = 0; log <= t.max_log; ++log) small = small && count[log] <= MERKLE_SMALL_COLS;
+    const uint32_t** d_table = small ? nullptr : arena.upload(table);
+    // layers below `fused_from` hold no columns and fit one CTA: they are hashed by a single launch
+    int fused_from = 0;
+    while (fused_from < t.max_log && fused_from < MERKLE_TOP_MAX_LOG && count[fused_from] == 0) ++fused_from;
     const uint32_t* prev = nullptr;
-    for (int log = t.max_log; log >= 0; --log) {
-        t.layers[log] = arena.alloc<uint32_t>((size_t)8 << log);
-        ck(merkle_commit_layer(t.layers[log], prev, d_table + first[log], count[log], log, ctx->stream), "merkle layer");
+    {
+        // one allocation for all layers: layer k (2^k digests of 8 words) at word offset 8 * (2^k - 1)
+        uint32_t* all = arena.alloc<uint32_t>((size_t)16 << t.max_log);
+        for (int log = t.max_log; log >= 0; --log) t.layers[log] = all + 8 * (((size_t)1 << log) - 1);
+    }
+    for (int log = t.max_log; log >= fused_from; --log) {
+        if (small) {
+            MerkleColsArg ca{};
+            for (int k = 0; k < count[log]; ++k) ca.p[k] = table[first[log] + k];
+            ck(merkle_commit_layer_small(t.layers[log], prev, ca, count[log], log, ctx->stream), "merkle layer");
+        } else {
+            ck(merkle_commit_layer(t.layers[log], prev, d_table + first[log], count[log], log, ctx->stream), "merkle layer");
+        }
         prev = t.layers[log];
+    }
+    if (fused_from >= 1) {
+        MerkleTopArgs a{};
+        for (int k = 0; k <= fused_from; ++k) a.layers[k] = t.layers[k];
+        a.from_log = fused_from;
+        ck(merkle_commit_top(a, ctx->stream), "merkle top");
     }
     ck(cudaMemcpyAsync(t.root.b, t.layers[0], 32, cudaMemcpyDeviceToHost, ctx->stream), "root d2h");
     ck(cudaStreamSynchronize(ctx->stream), "root sync");
@@ -522,9 +543,11 @@ void launch_quotients(lb_ctx* ctx, Arena& arena, int lg, const std::vector<const
     }
     const uint32_t** d_cols = arena.upload(colptrs);
     QuotientEntry* d_entries = arena.upload(entries);
-    uint2* d_pts = arena.alloc<uint2>((size_t)1 << (lg - 1));
-    ck(domain_points(d_pts, lg, ctx->stream), "domain points");
-    ck(accumulate_quotients(out, d_cols, d_entries, qp, d_pts, lg, ctx->stream), "accumulate quotients");
+    {
+        int r = lb_twiddles_ensure(ctx, lg);  // domain points are read from the twiddle tables
+        if (r) fail(r, ctx->err);
+    }
+    ck(accumulate_quotients(out, d_cols, d_entries, qp, &ctx->tw, lg, ctx->stream), "accumulate quotients");
 }
 
 // ------------------------------------------------------------------------------------
@@ -978,7 +1001,10 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             QM31 folding_alpha = channel.draw_secure_felt();
             int line_log = quotients[0].log - 1;
             int last_log = (int)(cfg.log_last_layer_degree_bound + cfg.log_blowup_factor);
-            uint32_t* cur = arena.alloc<uint32_t>((size_t)4 << line_log);
+            // all line-layer evaluations in one allocation: layer of log k (4 coordinate columns) at word offset 4 * (2^k - 1)
+            uint32_t* fri_buf = arena.alloc<uint32_t>((size_t)8 << line_log);
+            auto layer_at = [&](int lg) { return fri_buf + 4 * (((size_t)1 << lg) - 1); };
+            uint32_t* cur = layer_at(line_log);
             ck(cudaMemsetAsync(cur, 0, ((size_t)4 << line_log) * sizeof(uint32_t), st), "memset");
             size_t qi = 0;
             while (line_log > last_log) {
@@ -999,7 +1025,7 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                 channel.mix_root(L.tree.root);
                 folding_alpha = channel.draw_secure_felt();
                 inner.push_back(L);
-                uint32_t* next = arena.alloc<uint32_t>((size_t)4 << (line_log - 1));
+                uint32_t* next = layer_at(line_log - 1);
                 uint32_t* ncoords[4];
                 for (int k = 0; k < 4; ++k) ncoords[k] = next + ((size_t)k << (line_log - 1));
                 ck(fold_line(ncoords, coords, inv_x_twiddles(tw, line_log), line_log, folding_alpha, st), "fold line");
