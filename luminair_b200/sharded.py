@@ -1,0 +1,142 @@
+"""Column-sharded commitment across GPUs (BASELINE cfg 5).
+
+Trace columns are independent through interpolate / low-degree extension, so each rank owns a
+contiguous range of columns and transforms them with no communication.  A Merkle leaf, however,
+hashes *every* column of a row in column order (stwo ``MerkleOps::commit_on_layer`` as reached
+from ``tree_builder.commit``, crates/prover/src/prover.rs:59,179,298), so a root that is
+bit-identical to the single-device tree needs one real exchange:
+
+  1. per rank:  interpolate + LDE of its columns                         (no collective)
+  2. all-to-all: column shards -> row shards; rank r receives rows [r*R/W, (r+1)*R/W) of ALL columns
+  3. per rank:  leaf layer + sub-tree over its row range                  (no collective)
+  4. all-gather of the W sub-tree roots (32 B each), then every rank hashes the log2(W) top levels
+
+One process per GPU, ``torch.distributed`` (NCCL over NVLink on GPUs; gloo in the CPU tests) is
+the plumbing; the kernels are the library's own (``ShardOps`` wraps the C ABI).  The host logic
+below is backend-agnostic so that tests can drive it with a CPU stand-in for the kernels.
+"""
+from __future__ import annotations
+
+import time
+from typing import List, Optional, Protocol
+
+import torch
+import torch.distributed as dist
+
+
+class ShardOps(Protocol):
+    """The three device operations the sharded pipeline needs."""
+
+    def lde(self, trace: torch.Tensor, log_size: int, log_blowup: int) -> torch.Tensor:
+        """trace [n_cols, 2^log] (values, bit-reversed circle-domain order) -> evaluations [n_cols, 2^(log+blowup)]."""
+
+    def merkle_layer(self, log_size: int, prev: Optional[torch.Tensor], cols: Optional[torch.Tensor]) -> torch.Tensor:
+        """-> [2^log, 8] digests; prev [2^(log+1), 8] or None; cols [n_cols, 2^log] or None."""
+
+    def sync(self) -> None:
+        ...
+
+
+class CudaShardOps:
+    """ShardOps over libluminair_b200 (device pointers of torch CUDA tensors cross the C ABI)."""
+
+    def __init__(self, backend):
+        self.be = backend
+
+    def lde(self, trace, log_size, log_blowup):
+        import ctypes as C
+        from ._lib import check
+        be = self.be
+        n_cols = trace.shape[0]
+        n = 1 << log_size
+        assert trace.is_cuda and trace.dtype == torch.int32 and trace.is_contiguous() and trace.shape[1] == n
+        torch.cuda.current_stream().synchronize()
+        check(be.ctx, be.lib.lb_interpolate_batch(be.ctx, C.c_void_p(trace.data_ptr()), n, n_cols, log_size), "lb_interpolate_batch")
+        out = torch.empty((n_cols, n << log_blowup), dtype=torch.int32, device=trace.device)
+        check(be.ctx, be.lib.lb_evaluate_batch(be.ctx, C.c_void_p(trace.data_ptr()), n, log_size, C.c_void_p(out.data_ptr()),
+                                                n << log_blowup, log_size + log_blowup, n_cols), "lb_evaluate_batch")
+        return out
+
+    def merkle_layer(self, log_size, prev, cols):
+        n = 1 << log_size
+        dev = prev.device if prev is not None else cols.device
+        out = torch.empty((n, 8), dtype=torch.int32, device=dev)
+        ptrs = [] if cols is None else [cols.data_ptr() + 4 * n * c for c in range(cols.shape[0])]
+        if cols is not None:
+            assert cols.is_contiguous() and cols.shape[1] == n
+        self.be.merkle_commit_layer(log_size, prev.data_ptr() if prev is not None else None, ptrs, out.data_ptr())
+        return out
+
+    def sync(self):
+        self.be.sync()
+
+
+def column_range(n_cols_total: int, rank: int, world: int):
+    """Contiguous column shard of `rank` (cfg 5: 256 columns / 8 ranks = 32 each)."""
+    if n_cols_total % world:
+        raise ValueError("the column count must be a multiple of the world size")
+    per = n_cols_total // world
+    return rank * per, (rank + 1) * per
+
+
+def sharded_commit(ops: ShardOps, trace_local: torch.Tensor, log_size: int, log_blowup: int = 1, group=None,
+                   timings: Optional[dict] = None) -> bytes:
+    """Commit `world * n_cols_local` columns of 2^log_size rows, `n_cols_local` of them on each rank
+    (rank r holds columns [r * n_cols_local, (r+1) * n_cols_local)).  Returns the 32-byte Merkle root,
+    identical on every rank and identical to a single-device commit of all columns."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world & (world - 1):
+        raise ValueError("world size must be a power of two")
+    log_w = world.bit_length() - 1
+    lde_log = log_size + log_blowup
+    if lde_log < log_w:
+        raise ValueError("fewer rows than ranks")
+    n_cols_local = trace_local.shape[0]
+    rows_local = (1 << lde_log) // world
+    t0 = time.perf_counter()
+
+    # 1. transform own columns
+    lde = ops.lde(trace_local, log_size, log_blowup)  # [n_cols_local, 2^lde_log]
+    ops.sync()
+    t1 = time.perf_counter()
+
+    # 2. column shards -> row shards
+    if world > 1:
+        send = lde.view(n_cols_local, world, rows_local).transpose(0, 1).contiguous()  # [world, n_cols_local, rows_local]
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=group)
+        cols = recv.view(world * n_cols_local, rows_local)  # all columns, global order, my rows
+        del send
+    else:
+        cols = lde
+    if cols.is_cuda:
+        torch.cuda.current_stream().synchronize()
+    t2 = time.perf_counter()
+
+    # 3. sub-tree over my rows
+    sub_log = lde_log - log_w
+    layer = ops.merkle_layer(sub_log, None, cols)
+    for lg in range(sub_log - 1, -1, -1):
+        layer = ops.merkle_layer(lg, layer, None)
+    ops.sync()
+    t3 = time.perf_counter()
+
+    # 4. gather the sub-tree roots, hash the top levels everywhere
+    if world > 1:
+        roots = torch.empty((world, 8), dtype=torch.int32, device=layer.device)
+        dist.all_gather_into_tensor(roots, layer.reshape(1, 8).contiguous(), group=group)
+        if roots.is_cuda:
+            torch.cuda.current_stream().synchronize()
+        layer = roots
+        for lg in range(log_w - 1, -1, -1):
+            layer = ops.merkle_layer(lg, layer, None)
+        ops.sync()
+    root = layer.reshape(-1).cpu().numpy().astype("<u4").tobytes()
+    t4 = time.perf_counter()
+    if timings is not None:
+        timings.update({"lde_ms": (t1 - t0) * 1e3, "all_to_all_ms": (t2 - t1) * 1e3, "subtree_ms": (t3 - t2) * 1e3,
+                        "root_allgather_ms": (t4 - t3) * 1e3, "total_ms": (t4 - t0) * 1e3,
+                        "all_to_all_bytes_per_rank": int(n_cols_local * (1 << lde_log) * 4 * (world - 1) // world),
+                        "rank": rank, "world": world})
+    return root

@@ -288,3 +288,16 @@ def test_full_size_proof_verifies(be):
     assert overifier.log_sum_valid(lp.interaction_claim)
     overifier.verify(lp)
     assert len(last_stage_ms(be)) == 8
+
+
+def test_sharded_commit_single_gpu_matches_oracle(be):
+    """CudaShardOps (the per-rank kernels of the column-sharded commit) at world size 1."""
+    import torch
+    from luminair_b200.sharded import CudaShardOps, sharded_commit
+    from oracle import merkle as omerkle
+    log, n_cols = 9, 20
+    vals = _rand_cols(77, n_cols, log)
+    lde = ocfft.evaluate(ocfft.interpolate(vals, CanonicCoset(log).circle_domain()), CanonicCoset(log + 1).circle_domain())
+    want = omerkle.MerkleProver.commit(list(lde)).root()
+    t = torch.from_numpy(vals.astype(np.uint32).view(np.int32).copy()).cuda()
+    assert sharded_commit(CudaShardOps(be), t, log, 1) == want
