@@ -26,6 +26,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 489.3e6  # measured once with ncu --set full (profiles/), not re-measured by this script
 LOG_N = 20
 N_COLS = 64
 SEED = 20260101
@@ -211,16 +212,23 @@ def run_gpu(args):
         raise SystemExit("bench: CFFT round trip did not reproduce its input")
 
     # ---- device-resident timing (inputs already in HBM), CUDA events on the launching stream
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     be.timer_start()
     for _ in range(args.steps):
         step()
     total_ms = be.timer_stop_ms()
     barrier()
+    # keep the GPU under the same load while nvidia-smi samples (a 15 ms timed region is shorter than one sample period):
+    # the clocks reported are those of a >= 1 s run of the very same step
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < 1.2:
+        for _ in range(50):
+            step()
+        be.sync()
     clocks = sampler.stop()
 
     # per-kernel (dominant: cfft_pass_kernel) timing: interpolate and evaluate separately
@@ -279,8 +287,9 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "M31 field-ops/s", "h2d_bytes_per_step": N_COLS * n * 4 * world,
                     "d2h_bytes_per_step": N_COLS * n * 4 * world, "ms_per_step": e2e_s * 1e3},
             "gpu_launches": args.steps * n_launch_per_step,
-            "roofline": {"bound": "hbm", "kernel": "cfft_pass_kernel", "achieved": achieved, "peak": peak,
-                         "peak_source": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": "cfft_low_fast / cfft_high_fast (the 4 CFFT passes of a step)", "achieved": achieved, "peak": peak,
+                         "peak_source": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, mean of the 4 passes, profiles/r1_cfft_v5_ncu_full_summary.csv",
                          "algorithmic_bytes_per_launch": alg_bytes_launch, "avg_launch_ms": avg_launch_ms,
                          "interpolate_ms": t_int, "evaluate_ms": t_ev},
         }
