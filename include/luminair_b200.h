@@ -65,6 +65,13 @@ int lb_interpolate_batch(lb_ctx* ctx, uint32_t* d_cols, size_t stride, int n_col
 int lb_evaluate_batch(lb_ctx* ctx, const uint32_t* d_coeffs, size_t src_stride, int log_in, uint32_t* d_out,
                       size_t dst_stride, int log_out, int n_cols);
 
+/* Host-buffer form of extend_evals + commit's evaluate (values -> coefficients -> evaluations on CanonicCoset(log_out)):
+ * h_values: n_cols x 2^log_in, h_evals: n_cols x 2^log_out, h_coeffs (optional, may be NULL): n_cols x 2^log_in, all HOST.
+ * Columns are processed in chunks (chunk_cols, 0 = automatic) over three streams, so the upload of chunk k+1, the two
+ * transforms of chunk k and the download of chunk k-1 overlap; the host buffers should be page-locked for that. */
+int lb_lde_host(lb_ctx* ctx, const uint32_t* h_values, uint32_t* h_evals, int n_cols, int log_in, int log_out,
+                uint32_t* h_coeffs, int chunk_cols);
+
 /* ---- MerkleOps<Blake2sMerkleHasher> ------------------------------------------------------- */
 /* commit_on_layer: d_out = 2^log_size digests (8 u32 each); d_prev = child layer or NULL;
  * h_cols = HOST array of n_cols DEVICE column pointers (columns of exactly this log size) */

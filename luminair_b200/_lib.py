@@ -75,6 +75,7 @@ SIGNATURES.update({
                                              u32p, u32p]),
     "lb_constraint_quotients": (C.c_int, [ctxp, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, u32p, u32p,
                                           u32p, u32p, C.c_int, C.POINTER(C.c_void_p), C.c_int]),
+    "lb_lde_host": (C.c_int, [ctxp, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "lb_prove": (C.c_int, [ctxp, C.POINTER(TraceTable), C.c_int, C.POINTER(ProveConfig), C.POINTER(C.c_void_p),
                            C.POINTER(C.c_size_t)]),
     "lb_free_host": (None, [C.c_void_p]),

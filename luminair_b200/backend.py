@@ -130,6 +130,21 @@ class CudaBackend:
         check(self.ctx, self.lib.lb_evaluate_batch(self.ctx, C.c_void_p(coeffs.ptr), coeffs.stride, coeffs.log_size,
                                                     C.c_void_p(out.ptr), out.stride, out.log_size, out.n_cols), "lb_evaluate_batch")
 
+    def lde_host(self, values: np.ndarray, log_out: int | None = None, out: np.ndarray | None = None,
+                 coeffs_out: np.ndarray | None = None, chunk_cols: int = 0) -> np.ndarray:
+        """values [n_cols, 2^log] (host) -> evaluations [n_cols, 2^log_out] (host); chunked, copy/compute overlapped."""
+        assert values.dtype == np.uint32 and values.ndim == 2 and values.flags.c_contiguous
+        n_cols, n = values.shape
+        log_in = n.bit_length() - 1
+        log_out = log_in if log_out is None else log_out
+        if out is None:
+            out = np.empty((n_cols, 1 << log_out), dtype=np.uint32)
+        assert out.dtype == np.uint32 and out.shape == (n_cols, 1 << log_out) and out.flags.c_contiguous
+        cptr = C.c_void_p(coeffs_out.ctypes.data) if coeffs_out is not None else C.c_void_p(0)
+        check(self.ctx, self.lib.lb_lde_host(self.ctx, C.c_void_p(values.ctypes.data), C.c_void_p(out.ctypes.data), n_cols,
+                                              log_in, log_out, cptr, chunk_cols), "lb_lde_host")
+        return out
+
     # ---- MerkleOps -------------------------------------------------------------------
     def merkle_commit_layer(self, log_size: int, prev_ptr: int | None, col_ptrs, out_ptr: int):
         n = len(col_ptrs)

@@ -70,6 +70,14 @@ void lb_ctx_destroy(lb_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     lb::twiddles_destroy(&ctx->tw);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    for (int i = 0; i < lb_ctx::PIPE_SLOTS; ++i) {
+        if (ctx->pipe_buf[i]) cudaFree(ctx->pipe_buf[i]);
+        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]);
+        if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+    }
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -275,6 +283,76 @@ int lb_constraint_quotients(lb_ctx* ctx, int component, const uint32_t* d_main, 
         return fail(ctx, LB_ERR_BAD_ARG, "constraint_quotients: bad args");
     return lb::constraint_quotients_impl(ctx, component, d_main, main_stride, d_inter, inter_stride, log_size, z, alpha,
                                          claimed_sum, pows, n_pows, d_acc, accumulate);
+}
+
+int lb_lde_host(lb_ctx* ctx, const uint32_t* h_values, uint32_t* h_evals, int n_cols, int log_in, int log_out,
+                uint32_t* h_coeffs, int chunk_cols) {
+    if (!ctx || !h_values || !h_evals || n_cols < 0 || log_in < 1 || log_out < log_in || log_out > 28)
+        return fail(ctx, LB_ERR_BAD_ARG, "lde_host: bad args");
+    if (n_cols == 0) return LB_OK;
+    cudaSetDevice(ctx->device);
+    int r = lb_twiddles_ensure(ctx, log_out);
+    if (r) return r;
+    const size_t n_in = (size_t)1 << log_in, n_out = (size_t)1 << log_out;
+    if (chunk_cols <= 0) {
+        // ~32 MiB of output per chunk: long enough copies for full PCIe rate, short enough pipeline fill
+        chunk_cols = (int)(((size_t)8 << 20) / n_out);
+        if (chunk_cols < 1) chunk_cols = 1;
+    }
+    if (chunk_cols > n_cols) chunk_cols = n_cols;
+    const bool in_place = (log_in == log_out);
+    // staging: each slot holds one chunk of inputs and (unless in place) one chunk of outputs
+    size_t slot_words = (size_t)chunk_cols * (in_place ? n_in : n_in + n_out);
+    if (!ctx->s_in) {
+        CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking), "lde_host/stream");
+        CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking), "lde_host/stream");
+        for (int i = 0; i < lb_ctx::PIPE_SLOTS; ++i) {
+            CK(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming), "lde_host/event");
+            CK(cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming), "lde_host/event");
+            CK(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming), "lde_host/event");
+        }
+    }
+    if (slot_words > ctx->pipe_buf_words) {
+        CK(cudaDeviceSynchronize(), "lde_host/sync");
+        for (int i = 0; i < lb_ctx::PIPE_SLOTS; ++i) {
+            if (ctx->pipe_buf[i]) cudaFree(ctx->pipe_buf[i]);
+            ctx->pipe_buf[i] = nullptr;
+        }
+        ctx->pipe_buf_words = 0;
+        for (int i = 0; i < lb_ctx::PIPE_SLOTS; ++i) CK(cudaMalloc(&ctx->pipe_buf[i], slot_words * sizeof(uint32_t)), "lde_host/alloc");
+        ctx->pipe_buf_words = slot_words;
+    }
+    // the compute stream may still be running earlier work that owns the twiddle tables etc.: order after it
+    int n_chunks = (n_cols + chunk_cols - 1) / chunk_cols;
+    for (int k = 0; k < n_chunks; ++k) {
+        int slot = k % lb_ctx::PIPE_SLOTS;
+        int c0 = k * chunk_cols, nc = (c0 + chunk_cols <= n_cols) ? chunk_cols : (n_cols - c0);
+        uint32_t* d_in = ctx->pipe_buf[slot];
+        uint32_t* d_out = in_place ? d_in : d_in + (size_t)chunk_cols * n_in;
+        if (k >= lb_ctx::PIPE_SLOTS) CK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_out[slot], 0), "lde_host/wait");  // slot drained
+        CK(cudaMemcpyAsync(d_in, h_values + (size_t)c0 * n_in, (size_t)nc * n_in * 4, cudaMemcpyHostToDevice, ctx->s_in), "lde_host/h2d");
+        CK(cudaEventRecord(ctx->ev_in[slot], ctx->s_in), "lde_host/record");
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[slot], 0), "lde_host/wait");
+        CK(lb::cfft_interpolate(&ctx->tw, d_in, n_in, nc, log_in, ctx->sm_count, ctx->stream), "lde_host/interpolate");
+        if (h_coeffs) {
+            // coefficients leave from the compute stream's view: record, copy on the output stream before the evaluate overwrites (in place)
+            CK(cudaEventRecord(ctx->ev_comp[slot], ctx->stream), "lde_host/record");
+            CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[slot], 0), "lde_host/wait");
+            CK(cudaMemcpyAsync(h_coeffs + (size_t)c0 * n_in, d_in, (size_t)nc * n_in * 4, cudaMemcpyDeviceToHost, ctx->s_out), "lde_host/d2h");
+            if (in_place) {
+                CK(cudaEventRecord(ctx->ev_out[slot], ctx->s_out), "lde_host/record");
+                CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[slot], 0), "lde_host/wait");
+            }
+        }
+        CK(lb::cfft_evaluate(&ctx->tw, d_in, n_in, log_in, d_out, n_out, log_out, nc, ctx->sm_count, ctx->stream), "lde_host/evaluate");
+        CK(cudaEventRecord(ctx->ev_comp[slot], ctx->stream), "lde_host/record");
+        CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[slot], 0), "lde_host/wait");
+        CK(cudaMemcpyAsync(h_evals + (size_t)c0 * n_out, d_out, (size_t)nc * n_out * 4, cudaMemcpyDeviceToHost, ctx->s_out), "lde_host/d2h");
+        CK(cudaEventRecord(ctx->ev_out[slot], ctx->s_out), "lde_host/record");
+    }
+    CK(cudaStreamSynchronize(ctx->s_out), "lde_host/sync");
+    CK(cudaStreamSynchronize(ctx->stream), "lde_host/sync");
+    return LB_OK;
 }
 
 int lb_prove(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_prove_config* cfg, uint8_t** proof_out,

@@ -19,6 +19,12 @@ struct lb_ctx {
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
     bool kernels_ready = false;
+    // host-buffer pipeline (lb_lde_host): copy streams, rotating staging buffers and their events
+    static constexpr int PIPE_SLOTS = 3;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[PIPE_SLOTS] = {}, ev_comp[PIPE_SLOTS] = {}, ev_out[PIPE_SLOTS] = {};
+    uint32_t* pipe_buf[PIPE_SLOTS] = {};
+    size_t pipe_buf_words = 0;
     // diagnostics of the last lb_prove call
     std::vector<lb::Hash32> transcript;  // channel digest after every mix
     std::vector<float> stage_ms;         // wall-clock per stage (stream-synchronised)

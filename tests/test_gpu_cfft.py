@@ -142,3 +142,23 @@ def test_evaluate_in_place(be):
     be.interpolate(cb)
     be.evaluate(cb, cb)
     assert np.array_equal(be.download(cb.buf).reshape(ncols, -1), vals)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("log_in,log_out,n_cols,chunk", [(10, 10, 7, 2), (12, 13, 5, 0), (14, 15, 9, 4)])
+def test_lde_host_pipeline(log_in, log_out, n_cols, chunk):
+    """lb_lde_host (chunked upload / interpolate / evaluate / download over three streams) == oracle, incl. ragged last chunk."""
+    from luminair_b200.backend import CudaBackend
+    from oracle import cfft as ocfft
+    from oracle.circle import CanonicCoset
+    from oracle.fields import P
+    be = CudaBackend(0)
+    rng = np.random.Generator(np.random.PCG64(log_in * 100 + n_cols))
+    vals = rng.integers(0, P, size=(n_cols, 1 << log_in), dtype=np.uint64)
+    coeffs = np.empty((n_cols, 1 << log_in), dtype=np.uint32)
+    got = be.lde_host(vals.astype(np.uint32), log_out, coeffs_out=coeffs, chunk_cols=chunk)
+    want_c = ocfft.interpolate(vals, CanonicCoset(log_in).circle_domain())
+    want = ocfft.evaluate(want_c, CanonicCoset(log_out).circle_domain())
+    assert np.array_equal(coeffs, want_c.astype(np.uint32))
+    assert np.array_equal(got, want.astype(np.uint32))
+    be.close()
