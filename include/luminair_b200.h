@@ -116,6 +116,9 @@ int lb_grind(lb_ctx* ctx, const uint32_t digest[8], int channel_variant, uint32_
 #define LB_COMP_ADD 0    /* components/add    (component.rs:38-116, witness.rs:126-167) */
 #define LB_COMP_MUL 1    /* components/mul    */
 #define LB_COMP_INPUTS 2 /* components/inputs */
+#define LB_COMP_SUM_REDUCE 4   /* components/sum_reduce */
+#define LB_COMP_MAX_REDUCE 5   /* components/max_reduce */
+#define LB_COMP_CONTIGUOUS 6   /* components/contiguous */
 #define LB_COMP_MUL_ARTIFACT 3 /* Mul AIR of the revision that produced ui/demo/public/proof (KAT only) */
 /* InteractionClaimGenerator::write_interaction_trace: LogUp columns from the main trace (values, not
  * coefficients).  d_inter receives 4*k columns of 2^log_size; claimed_out = claimed sum (4 u32, HOST). */
@@ -135,7 +138,7 @@ int lb_constraint_quotients(lb_ctx* ctx, int component, const uint32_t* d_main, 
 /* one `TraceTable` of the LuminairPie (crates/air/src/pie.rs:143-148): row-major rows of the component's
  * main-trace columns, canonical M31 values */
 typedef struct {
-    int slot;             /* field index in LuminairClaim (crates/air/src/lib.rs:30-48): add 0, mul 1, inputs 15 */
+    int slot;             /* field index in LuminairClaim (crates/air/src/lib.rs:30-48): add 0, mul 1, sum_reduce 5, max_reduce 6, inputs 15, contiguous 16 */
     int n_cols;
     uint64_t n_rows;      /* unpadded */
     const uint32_t* rows; /* n_rows x n_cols, HOST (or DEVICE when rows_on_device != 0) */

@@ -100,7 +100,16 @@ struct LogupMixin {
 // COMP_MUL_ARTIFACT: the Mul AIR of the LuminAIR revision that produced the reference's committed proof
 // (ui/demo/public/proof): one more constraint slot after eval_fixed_mul, identically zero.  It exists
 // only so the known-answer test can replay that proof byte-for-byte.
-enum ComponentKind { COMP_ADD = 0, COMP_MUL = 1, COMP_INPUTS = 2, COMP_MUL_ARTIFACT = 3, COMP_KIND_COUNT = 4 };
+enum ComponentKind {
+    COMP_ADD = 0,
+    COMP_MUL = 1,
+    COMP_INPUTS = 2,
+    COMP_MUL_ARTIFACT = 3,
+    COMP_SUM_REDUCE = 4,  // components/sum_reduce/component.rs:37-110
+    COMP_MAX_REDUCE = 5,  // components/max_reduce/component.rs:37-121
+    COMP_CONTIGUOUS = 6,  // components/contiguous/component.rs:37-101
+    COMP_KIND_COUNT = 7
+};
 
 struct ComponentShape {
     int n_main;         // main-trace columns (add/witness.rs:24 etc.)
@@ -112,6 +121,9 @@ __host__ __device__ constexpr ComponentShape component_shape(int kind) {
     return kind == COMP_ADD            ? ComponentShape{15, 3, 9, 4}
            : kind == COMP_MUL          ? ComponentShape{16, 3, 9, 4}
            : kind == COMP_MUL_ARTIFACT ? ComponentShape{16, 3, 10, 4}
+           : kind == COMP_SUM_REDUCE   ? ComponentShape{14, 2, 9, 3}
+           : kind == COMP_MAX_REDUCE   ? ComponentShape{15, 2, 11, 3}
+           : kind == COMP_CONTIGUOUS   ? ComponentShape{11, 2, 6, 3}
                                        : ComponentShape{7, 1, 4, 2};
 }
 
@@ -208,6 +220,115 @@ __host__ __device__ __forceinline__ void eval_inputs(E& ev, const Relation2& nod
 }
 
 #pragma nv_exec_check_disable
+// head shared by SumReduce / MaxReduce / Contiguous: ids, index, next-row copies
+template <class E>
+struct ReduceHead {
+    typename E::F node_id, input_id, idx, is_last_idx, next_node_id, next_input_id, next_idx;
+};
+#pragma nv_exec_check_disable
+template <class E>
+__host__ __device__ __forceinline__ void read_reduce_head(E& ev, ReduceHead<E>& h) {
+    h.node_id = ev.next_trace_mask();
+    h.input_id = ev.next_trace_mask();
+    h.idx = ev.next_trace_mask();
+    h.is_last_idx = ev.next_trace_mask();
+    h.next_node_id = ev.next_trace_mask();
+    h.next_input_id = ev.next_trace_mask();
+    h.next_idx = ev.next_trace_mask();
+}
+#pragma nv_exec_check_disable
+template <class E>
+__host__ __device__ __forceinline__ void reduce_transitions(E& ev, const ReduceHead<E>& h) {
+    typedef typename E::F F;
+    F one = ev.constant(1);
+    F not_last = one - h.is_last_idx;
+    ev.add_constraint(not_last * (h.next_node_id - h.node_id));
+    ev.add_constraint(not_last * (h.next_input_id - h.input_id));
+    ev.add_constraint(not_last * (h.next_idx - h.idx - one));
+}
+
+#pragma nv_exec_check_disable
+template <class E>
+__host__ __device__ __forceinline__ void eval_sum_reduce(E& ev, const Relation2& node) {
+    typedef typename E::F F;
+    ReduceHead<E> h;
+    read_reduce_head(ev, h);
+    F input_val = ev.next_trace_mask();
+    F out_val = ev.next_trace_mask();
+    F acc_val = ev.next_trace_mask();
+    F next_acc_val = ev.next_trace_mask();
+    F is_last_step = ev.next_trace_mask();
+    F input_mult = ev.next_trace_mask();
+    F out_mult = ev.next_trace_mask();
+    F one = ev.constant(1);
+    ev.add_constraint(h.is_last_idx * (h.is_last_idx - one));
+    ev.add_constraint(is_last_step * (is_last_step - one));
+    ev.add_constraint(next_acc_val - (acc_val + input_val));
+    ev.add_constraint((out_val - next_acc_val) * is_last_step);
+    reduce_transitions(ev, h);
+    ev.add_to_relation(node, input_mult, input_val, h.input_id);
+    ev.add_to_relation(node, out_mult, out_val, h.node_id);
+    ev.finalize_logup();
+}
+
+#pragma nv_exec_check_disable
+template <class E>
+__host__ __device__ __forceinline__ void eval_max_reduce(E& ev, const Relation2& node) {
+    typedef typename E::F F;
+    ReduceHead<E> h;
+    read_reduce_head(ev, h);
+    F input_val = ev.next_trace_mask();
+    F out_val = ev.next_trace_mask();
+    F max_val = ev.next_trace_mask();
+    F next_max_val = ev.next_trace_mask();
+    F is_last_step = ev.next_trace_mask();
+    F is_max = ev.next_trace_mask();
+    F input_mult = ev.next_trace_mask();
+    F out_mult = ev.next_trace_mask();
+    F one = ev.constant(1);
+    ev.add_constraint(h.is_last_idx * (h.is_last_idx - one));
+    ev.add_constraint(is_last_step * (is_last_step - one));
+    ev.add_constraint(is_max * (is_max - one));
+    ev.add_constraint(is_max * (next_max_val - input_val));
+    ev.add_constraint((one - is_max) * (next_max_val - max_val));
+    ev.add_constraint((out_val - next_max_val) * is_last_step);
+    reduce_transitions(ev, h);
+    ev.add_to_relation(node, input_mult, input_val, h.input_id);
+    ev.add_to_relation(node, out_mult, out_val, h.node_id);
+    ev.finalize_logup();
+}
+
+#pragma nv_exec_check_disable
+template <class E>
+__host__ __device__ __forceinline__ void eval_contiguous(E& ev, const Relation2& node) {
+    typedef typename E::F F;
+    ReduceHead<E> h;
+    read_reduce_head(ev, h);
+    F input = ev.next_trace_mask();
+    F out = ev.next_trace_mask();
+    F input_mult = ev.next_trace_mask();
+    F out_mult = ev.next_trace_mask();
+    F one = ev.constant(1);
+    ev.add_constraint(h.is_last_idx * (h.is_last_idx - one));
+    reduce_transitions(ev, h);
+    ev.add_to_relation(node, input_mult, input, h.input_id);
+    ev.add_to_relation(node, out_mult, out, h.node_id);
+    ev.finalize_logup();
+}
+
+// compile-time dispatch (device kernels) and run-time dispatch (host evaluators)
+#pragma nv_exec_check_disable
+template <int KIND, class E>
+__host__ __device__ __forceinline__ void eval_kind(E& ev, const Relation2& node) {
+    if (KIND == COMP_ADD) eval_add(ev, node);
+    else if (KIND == COMP_MUL) eval_mul<E, false>(ev, node);
+    else if (KIND == COMP_MUL_ARTIFACT) eval_mul<E, true>(ev, node);
+    else if (KIND == COMP_SUM_REDUCE) eval_sum_reduce(ev, node);
+    else if (KIND == COMP_MAX_REDUCE) eval_max_reduce(ev, node);
+    else if (KIND == COMP_CONTIGUOUS) eval_contiguous(ev, node);
+    else eval_inputs(ev, node);
+}
+
 template <class E>
 __host__ __device__ __forceinline__ void eval_component(int kind, E& ev, const Relation2& node) {
     if (kind == COMP_ADD)
@@ -216,6 +337,12 @@ __host__ __device__ __forceinline__ void eval_component(int kind, E& ev, const R
         eval_mul<E, false>(ev, node);
     else if (kind == COMP_MUL_ARTIFACT)
         eval_mul<E, true>(ev, node);
+    else if (kind == COMP_SUM_REDUCE)
+        eval_sum_reduce(ev, node);
+    else if (kind == COMP_MAX_REDUCE)
+        eval_max_reduce(ev, node);
+    else if (kind == COMP_CONTIGUOUS)
+        eval_contiguous(ev, node);
     else
         eval_inputs(ev, node);
 }
@@ -229,7 +356,10 @@ __host__ __device__ constexpr LookupTerm lookup_term(int kind, int k) {
     return kind == COMP_ADD   ? (k == 0 ? LookupTerm{12, 9, 1} : k == 1 ? LookupTerm{13, 10, 2} : LookupTerm{14, 11, 0})
            : (kind == COMP_MUL || kind == COMP_MUL_ARTIFACT)
                ? (k == 0 ? LookupTerm{13, 9, 1} : k == 1 ? LookupTerm{14, 10, 2} : LookupTerm{15, 11, 0})
-               : LookupTerm{6, 5, 0};
+           : kind == COMP_SUM_REDUCE ? (k == 0 ? LookupTerm{12, 7, 1} : LookupTerm{13, 8, 0})
+           : kind == COMP_MAX_REDUCE ? (k == 0 ? LookupTerm{13, 7, 1} : LookupTerm{14, 8, 0})
+           : kind == COMP_CONTIGUOUS ? (k == 0 ? LookupTerm{9, 7, 1} : LookupTerm{10, 8, 0})
+                                     : LookupTerm{6, 5, 0};
 }
 
 }  // namespace lb

@@ -147,6 +147,9 @@ cudaError_t logup_interaction_trace(int kind, const uint32_t* main, size_t main_
         case COMP_MUL:
         case COMP_MUL_ARTIFACT: logup_fracs_kernel<COMP_MUL><<<blocks, 256, 0, stream>>>(main, main_stride, inter, inter_stride, n, node); break;
         case COMP_INPUTS: logup_fracs_kernel<COMP_INPUTS><<<blocks, 256, 0, stream>>>(main, main_stride, inter, inter_stride, n, node); break;
+        case COMP_SUM_REDUCE: logup_fracs_kernel<COMP_SUM_REDUCE><<<blocks, 256, 0, stream>>>(main, main_stride, inter, inter_stride, n, node); break;
+        case COMP_MAX_REDUCE: logup_fracs_kernel<COMP_MAX_REDUCE><<<blocks, 256, 0, stream>>>(main, main_stride, inter, inter_stride, n, node); break;
+        case COMP_CONTIGUOUS: logup_fracs_kernel<COMP_CONTIGUOUS><<<blocks, 256, 0, stream>>>(main, main_stride, inter, inter_stride, n, node); break;
         default: return cudaErrorInvalidValue;
     }
     uint32_t* last = inter + (size_t)(4 * (nf - 1)) * inter_stride;
@@ -223,14 +226,7 @@ __global__ void __launch_bounds__(256) constraint_quotients_kernel(const __grid_
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     DomainEval ev(p, j, prev_row_index(j, p.log_size, p.eval_log));
-    if (KIND == COMP_ADD)
-        eval_add(ev, p.node);
-    else if (KIND == COMP_MUL)
-        eval_mul<DomainEval, false>(ev, p.node);
-    else if (KIND == COMP_MUL_ARTIFACT)
-        eval_mul<DomainEval, true>(ev, p.node);
-    else
-        eval_inputs(ev, p.node);
+    eval_kind<KIND>(ev, p.node);
     QM31 r = q_mul_m(ev.res, p.denom_inv[j >> p.log_size]);
     if (p.accumulate) r = q_add(r, q_make(p.acc[0][j], p.acc[1][j], p.acc[2][j], p.acc[3][j]));
     p.acc[0][j] = r.a.a;
@@ -248,6 +244,9 @@ cudaError_t constraint_quotients(int kind, const ConstraintParams& p, cudaStream
         case COMP_MUL: constraint_quotients_kernel<COMP_MUL><<<blocks, 256, 0, stream>>>(p); break;
         case COMP_MUL_ARTIFACT: constraint_quotients_kernel<COMP_MUL_ARTIFACT><<<blocks, 256, 0, stream>>>(p); break;
         case COMP_INPUTS: constraint_quotients_kernel<COMP_INPUTS><<<blocks, 256, 0, stream>>>(p); break;
+        case COMP_SUM_REDUCE: constraint_quotients_kernel<COMP_SUM_REDUCE><<<blocks, 256, 0, stream>>>(p); break;
+        case COMP_MAX_REDUCE: constraint_quotients_kernel<COMP_MAX_REDUCE><<<blocks, 256, 0, stream>>>(p); break;
+        case COMP_CONTIGUOUS: constraint_quotients_kernel<COMP_CONTIGUOUS><<<blocks, 256, 0, stream>>>(p); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -363,8 +363,8 @@ __device__ __forceinline__ void layer8(uint32_t (&v)[16], const uint2 (&w)[8], i
 
 // layers of one index field: field bits [BLO, 4); A = bit position of the field in the tile
 // index; twiddle pointer for field bit b: tw[A+b] + (tile_h << (TS-1-A-b)) + (e0_hi << (3-b))
-template <bool FWD, int A, int BLO, int BHI, int TS>
-__device__ __forceinline__ void field_layers_range(uint32_t (&v)[16], const PassParams& p, uint32_t tile_h, int e0_hi) {
+template <bool FWD, int A, int BLO, int BHI, int TS, int NC = 1>
+__device__ __forceinline__ void field_layers_range_nc(uint32_t (&v)[NC][16], const PassParams& p, uint32_t tile_h, int e0_hi) {
 #pragma unroll
     for (int bb = 0; bb < BHI - BLO; ++bb) {
         const int b = FWD ? (BHI - 1 - bb) : (BLO + bb);
@@ -375,8 +375,14 @@ __device__ __forceinline__ void field_layers_range(uint32_t (&v)[16], const Pass
         if (b == 1) load_tw<4>(w, twp);
         if (b == 2) load_tw<2>(w, twp);
         if (b == 3) load_tw<1>(w, twp);
-        layer8<FWD>(v, w, b, p.redk);
+        // the twiddles depend on the position only: one load serves all NC columns held by this thread
+#pragma unroll
+        for (int c = 0; c < NC; ++c) layer8<FWD>(v[c], w, b, p.redk);
     }
+}
+template <bool FWD, int A, int BLO, int BHI, int TS>
+__device__ __forceinline__ void field_layers_range(uint32_t (&v)[16], const PassParams& p, uint32_t tile_h, int e0_hi) {
+    field_layers_range_nc<FWD, A, BLO, BHI, TS, 1>(reinterpret_cast<uint32_t (&)[1][16]>(v), p, tile_h, e0_hi);
 }
 
 __device__ __forceinline__ uint32_t finalize(uint32_t x, int mode, uint2 scale) {
@@ -392,7 +398,7 @@ struct RoundGeom {
 };
 
 // ---- low pass ---------------------------------------------------------------------------
-template <bool FWD, int M, int R>
+template <bool FWD, int M, int R, int NC>
 __device__ __forceinline__ void low_round(uint32_t* sm, const PassParams& p, uint32_t tile, const uint32_t* src,
                                           uint32_t* dst, bool first, bool last) {
     constexpr int A = RoundGeom<M, R>::A;
@@ -401,71 +407,86 @@ __device__ __forceinline__ void low_round(uint32_t* sm, const PassParams& p, uin
     const int e0_hi = g >> A;
     const int e0 = (e0_hi << (A + 4)) | (g & ((1 << A) - 1));
     const size_t gbase = ((size_t)tile << 12) + e0;
-    uint32_t v[16];
-    if (first) {
-        if (A == 0) {
-            const size_t n_src = (size_t)1 << p.log_src;  // zero extension beyond n_src
-            if (gbase + 16 <= n_src) {
-                const uint4* s4 = reinterpret_cast<const uint4*>(src + gbase);
+    uint32_t v[NC][16];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const uint32_t* srcc = src + (size_t)c * p.src_stride;
+        uint32_t* smc = sm + c * LOW_SMEM_WORDS;
+        if (first) {
+            if (A == 0) {
+                const size_t n_src = (size_t)1 << p.log_src;  // zero extension beyond n_src
+                if (gbase + 16 <= n_src) {
+                    const uint4* s4 = reinterpret_cast<const uint4*>(srcc + gbase);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 t = s4[q];
+                        v[c][4 * q] = t.x; v[c][4 * q + 1] = t.y; v[c][4 * q + 2] = t.z; v[c][4 * q + 3] = t.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[c][j] = gbase + j < n_src ? srcc[gbase + j] : 0u;
+                }
+            } else {
+                const size_t n_src = (size_t)1 << p.log_src;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    size_t gi = gbase + ((size_t)j << A);
+                    v[c][j] = gi < n_src ? srcc[gi] : 0u;
+                }
+            }
+        } else {
+            const int sb = low_pad(e0);
+            if (A == 0) {
+                const uint4* s4 = reinterpret_cast<const uint4*>(smc + sb);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     uint4 t = s4[q];
-                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+                    v[c][4 * q] = t.x; v[c][4 * q + 1] = t.y; v[c][4 * q + 2] = t.z; v[c][4 * q + 3] = t.w;
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = gbase + j < n_src ? src[gbase + j] : 0u;
+                for (int j = 0; j < 16; ++j) v[c][j] = smc[sb + low_pad(j << A)];
             }
-        } else {
-            const size_t n_src = (size_t)1 << p.log_src;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                size_t gi = gbase + ((size_t)j << A);
-                v[j] = gi < n_src ? src[gi] : 0u;
-            }
-        }
-    } else {
-        const int sb = low_pad(e0);
-        if (A == 0) {
-            const uint4* s4 = reinterpret_cast<const uint4*>(sm + sb);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint4 t = s4[q];
-                v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = sm[sb + low_pad(j << A)];
         }
     }
-    field_layers_range<FWD, A, BLO, 4, 12>(v, p, tile, e0_hi);
-    if (last) {
-        if (A == 0) {
-            uint4* d4 = reinterpret_cast<uint4*>(dst + gbase);
+    field_layers_range_nc<FWD, A, BLO, 4, 12, NC>(v, p, tile, e0_hi);
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                d4[q] = make_uint4(finalize(v[4 * q], p.final_mode, p.scale), finalize(v[4 * q + 1], p.final_mode, p.scale),
-                                   finalize(v[4 * q + 2], p.final_mode, p.scale), finalize(v[4 * q + 3], p.final_mode, p.scale));
+    for (int c = 0; c < NC; ++c) {
+        uint32_t* dstc = dst + (size_t)c * p.dst_stride;
+        uint32_t* smc = sm + c * LOW_SMEM_WORDS;
+        if (last) {
+            if (A == 0) {
+                uint4* d4 = reinterpret_cast<uint4*>(dstc + gbase);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    d4[q] = make_uint4(finalize(v[c][4 * q], p.final_mode, p.scale), finalize(v[c][4 * q + 1], p.final_mode, p.scale),
+                                       finalize(v[c][4 * q + 2], p.final_mode, p.scale), finalize(v[c][4 * q + 3], p.final_mode, p.scale));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) dstc[gbase + ((size_t)j << A)] = finalize(v[c][j], p.final_mode, p.scale);
+            }
         } else {
+            const int sb = low_pad(e0);
+            if (A == 0) {
+                uint4* d4 = reinterpret_cast<uint4*>(smc + sb);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) dst[gbase + ((size_t)j << A)] = finalize(v[j], p.final_mode, p.scale);
-        }
-    } else {
-        const int sb = low_pad(e0);
-        if (A == 0) {
-            uint4* d4 = reinterpret_cast<uint4*>(sm + sb);
+                for (int q = 0; q < 4; ++q) d4[q] = make_uint4(v[c][4 * q], v[c][4 * q + 1], v[c][4 * q + 2], v[c][4 * q + 3]);
+            } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) d4[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) sm[sb + low_pad(j << A)] = v[j];
+                for (int j = 0; j < 16; ++j) smc[sb + low_pad(j << A)] = v[c][j];
+            }
         }
     }
 }
 
-template <bool FWD, int M>
 #ifndef LB_LOW_MINB
 #define LB_LOW_MINB 6
+#endif
+#ifndef LB_LOW_MINB2
+#define LB_LOW_MINB2 4
+#endif
+#ifndef LB_LOW_NC
+#define LB_LOW_NC 2
 #endif
 #ifndef LB_HIGH_MINB
 #define LB_HIGH_MINB 4
@@ -473,25 +494,28 @@ template <bool FWD, int M>
 #ifndef LB_CPB_MAX
 #define LB_CPB_MAX 1
 #endif
-__global__ void __launch_bounds__(256, LB_LOW_MINB) cfft_low_fast(PassParams p, int cols_per_block) {
-    __shared__ __align__(16) uint32_t sm[LOW_SMEM_WORDS];
+// NC columns per thread: the NC tiles (same position, adjacent columns) go through the rounds together, so every
+// twiddle load and index computation is shared by NC butterflies and each warp has NC x the independent work.
+template <bool FWD, int M, int NC>
+__global__ void __launch_bounds__(256, NC == 1 ? LB_LOW_MINB : LB_LOW_MINB2) cfft_low_fast(PassParams p, int cols_per_block) {
+    __shared__ __align__(16) uint32_t sm[NC * LOW_SMEM_WORDS];
     constexpr int NR = (M + 3) / 4;
     const uint32_t tile = blockIdx.x;
-    const int c0 = blockIdx.y * cols_per_block;
-    const int c1 = min(p.n_cols, c0 + cols_per_block);
-    for (int c = c0; c < c1; ++c) {
+    const int c0 = blockIdx.y * cols_per_block * NC;
+    const int c1 = min(p.n_cols, c0 + cols_per_block * NC);
+    for (int c = c0; c < c1; c += NC) {
         const uint32_t* src = p.src + (size_t)c * p.src_stride;
         uint32_t* dst = p.dst + (size_t)c * p.dst_stride;
         if (FWD) {
-            if constexpr (NR == 3) { low_round<FWD, M, 2>(sm, p, tile, src, dst, true, false); __syncthreads(); }
-            low_round<FWD, M, 1>(sm, p, tile, src, dst, NR == 2, false);
+            if constexpr (NR == 3) { low_round<FWD, M, 2, NC>(sm, p, tile, src, dst, true, false); __syncthreads(); }
+            low_round<FWD, M, 1, NC>(sm, p, tile, src, dst, NR == 2, false);
             __syncthreads();
-            low_round<FWD, M, 0>(sm, p, tile, src, dst, false, true);
+            low_round<FWD, M, 0, NC>(sm, p, tile, src, dst, false, true);
         } else {
-            low_round<FWD, M, 0>(sm, p, tile, src, dst, true, false);
+            low_round<FWD, M, 0, NC>(sm, p, tile, src, dst, true, false);
             __syncthreads();
-            low_round<FWD, M, 1>(sm, p, tile, src, dst, false, NR == 2);
-            if constexpr (NR == 3) { __syncthreads(); low_round<FWD, M, 2>(sm, p, tile, src, dst, false, true); }
+            low_round<FWD, M, 1, NC>(sm, p, tile, src, dst, false, NR == 2);
+            if constexpr (NR == 3) { __syncthreads(); low_round<FWD, M, 2, NC>(sm, p, tile, src, dst, false, true); }
         }
         __syncthreads();
     }
@@ -665,14 +689,37 @@ static cudaError_t launch_generic(const PassParams& p, int sm_count, cudaStream_
     return cudaGetLastError();
 }
 
+template <bool FWD, int M, int NC>
+static cudaError_t launch_low_nc(const PassParams& p, int sm_count, cudaStream_t stream) {
+    size_t tiles = (size_t)1 << (p.log_n - 12);
+    int groups = p.n_cols / NC;  // the caller passes a multiple of NC
+    int cpb = pick_cols_per_block(tiles, groups, sm_count);
+    dim3 grid((unsigned)tiles, (unsigned)((groups + cpb - 1) / cpb));
+    if (grid.y > 65535) return cudaErrorInvalidValue;
+    cfft_low_fast<FWD, M, NC><<<grid, 256, 0, stream>>>(p, cpb);
+    return cudaGetLastError();
+}
+
 template <bool FWD, int M>
 static cudaError_t launch_low_m(const PassParams& p, int sm_count, cudaStream_t stream) {
-    size_t tiles = (size_t)1 << (p.log_n - 12);
-    int cpb = pick_cols_per_block(tiles, p.n_cols, sm_count);
-    dim3 grid((unsigned)tiles, (unsigned)((p.n_cols + cpb - 1) / cpb));
-    if (grid.y > 65535) return cudaErrorInvalidValue;
-    cfft_low_fast<FWD, M><<<grid, 256, 0, stream>>>(p, cpb);
-    return cudaGetLastError();
+    constexpr int NC = LB_LOW_NC;
+    int main_cols = (p.n_cols / NC) * NC;
+    if (NC > 1 && main_cols > 0) {
+        PassParams q = p;
+        q.n_cols = main_cols;
+        cudaError_t e = launch_low_nc<FWD, M, NC>(q, sm_count, stream);
+        if (e != cudaSuccess) return e;
+    }
+    int rest = (NC > 1) ? p.n_cols - main_cols : p.n_cols;
+    if (rest > 0) {
+        PassParams q = p;
+        int skip = (NC > 1) ? main_cols : 0;
+        q.src = p.src + (size_t)skip * p.src_stride;
+        q.dst = p.dst + (size_t)skip * p.dst_stride;
+        q.n_cols = rest;
+        return launch_low_nc<FWD, M, 1>(q, sm_count, stream);
+    }
+    return cudaSuccess;
 }
 
 template <bool FWD>

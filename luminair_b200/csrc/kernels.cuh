@@ -16,7 +16,7 @@ cudaError_t eval_at_point(const uint32_t* const* d_cols, int n_cols, int log, co
                           QM31* d_partials, QM31* d_out, cudaStream_t stream);
 
 // ---- QuotientOps::accumulate_quotients ---------------------------------------------------------
-constexpr int MAX_QUOTIENT_BATCHES = 8;
+constexpr int MAX_QUOTIENT_BATCHES = 4;  // distinct sample points per column size (LuminAIR: the OODS point and its predecessor)
 struct QuotientBatch {
     CM31 prx, pry, pix, piy;  // sample point: real / imaginary CM31 halves of x and y
     QM31 sum_a, sum_b;        // sum_j alpha^j a_j, sum_j alpha^j b_j  (line coefficients, folded on host)

@@ -233,11 +233,7 @@ cudaError_t accumulate_quotients(uint32_t* const out[4], const uint32_t* const* 
         case 1: LB_Q_LAUNCH(1); break;
         case 2: LB_Q_LAUNCH(2); break;
         case 3: LB_Q_LAUNCH(3); break;
-        case 4: LB_Q_LAUNCH(4); break;
-        case 5: LB_Q_LAUNCH(5); break;
-        case 6: LB_Q_LAUNCH(6); break;
-        case 7: LB_Q_LAUNCH(7); break;
-        default: LB_Q_LAUNCH(8); break;
+        default: LB_Q_LAUNCH(4); break;
     }
 #undef LB_Q_LAUNCH
     return cudaGetLastError();

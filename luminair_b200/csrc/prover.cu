@@ -574,7 +574,10 @@ int kind_of_slot(int slot, int n_slots, int air_era) {
     // LuminairClaim field order, crates/air/src/lib.rs:30-48 (17 slots): add, mul, ..., inputs (15), contiguous
     if (slot == 0) return COMP_ADD;
     if (slot == 1) return air_era == 1 ? COMP_MUL_ARTIFACT : COMP_MUL;
+    if (n_slots == 17 && slot == 5) return COMP_SUM_REDUCE;
+    if (n_slots == 17 && slot == 6) return COMP_MAX_REDUCE;
     if (n_slots == 17 && slot == 15) return COMP_INPUTS;
+    if (n_slots == 17 && slot == 16) return COMP_CONTIGUOUS;
     return -1;
 }
 

@@ -18,7 +18,7 @@ from ._lib import LuminairB200Error, ProveConfig, TraceTable, check
 from .backend import CudaBackend
 
 # field index of each component in LuminairClaim (crates/air/src/lib.rs:30-48)
-CLAIM_SLOT = {"add": 0, "mul": 1, "inputs": 15}
+CLAIM_SLOT = {"add": 0, "mul": 1, "sum_reduce": 5, "max_reduce": 6, "inputs": 15, "contiguous": 16}
 N_CLAIM_SLOTS = 17
 
 

@@ -434,6 +434,117 @@ class InputsEval:
         return r
 
 
+class _ReduceLike:
+    """Shared head of SumReduce / MaxReduce / Contiguous: node_id, input_id, idx, is_last_idx, next_*."""
+
+    def __init__(self, log_size, node_elements: RelationElements):
+        self.log_size = log_size
+        self.node_elements = node_elements
+
+    def max_constraint_log_degree_bound(self):
+        return self.log_size + 1
+
+    @classmethod
+    def padding_row(cls):
+        r = [0] * cls.n_main
+        r[3] = 1
+        return r
+
+    @staticmethod
+    def _transitions(ev, is_last_idx, node_id, input_id, idx, next_node_id, next_input_id, next_idx):
+        not_last = 1 - is_last_idx
+        ev.add_constraint(not_last * (next_node_id - node_id))
+        ev.add_constraint(not_last * (next_input_id - input_id))
+        ev.add_constraint(not_last * (next_idx - idx - 1))
+
+
+class SumReduceEval(_ReduceLike):
+    """crates/air/src/components/sum_reduce/component.rs:37-110 (no numerair call: fully in-tree)."""
+    name = "sum_reduce"
+    n_main = 14
+    n_interaction = 2
+
+    def evaluate(self, ev):
+        node_id, input_id, idx, is_last_idx, next_node_id, next_input_id, next_idx = (ev.next_trace_mask() for _ in range(7))
+        input_val = ev.next_trace_mask()
+        out_val = ev.next_trace_mask()
+        acc_val = ev.next_trace_mask()
+        next_acc_val = ev.next_trace_mask()
+        is_last_step = ev.next_trace_mask()
+        input_mult = ev.next_trace_mask()
+        out_mult = ev.next_trace_mask()
+        ev.add_constraint(is_last_idx * (is_last_idx - 1))
+        ev.add_constraint(is_last_step * (is_last_step - 1))
+        ev.add_constraint(next_acc_val - (acc_val + input_val))
+        ev.add_constraint((out_val - next_acc_val) * is_last_step)
+        self._transitions(ev, is_last_idx, node_id, input_id, idx, next_node_id, next_input_id, next_idx)
+        ev.add_to_relation(self.node_elements, input_mult, [input_val, input_id])
+        ev.add_to_relation(self.node_elements, out_mult, [out_val, node_id])
+        ev.finalize_logup()
+        return ev
+
+    @staticmethod
+    def lookup_terms(cols):
+        return [(cols[12], [cols[7], cols[1]]), (cols[13], [cols[8], cols[0]])]
+
+
+class MaxReduceEval(_ReduceLike):
+    """crates/air/src/components/max_reduce/component.rs:37-121."""
+    name = "max_reduce"
+    n_main = 15
+    n_interaction = 2
+
+    def evaluate(self, ev):
+        node_id, input_id, idx, is_last_idx, next_node_id, next_input_id, next_idx = (ev.next_trace_mask() for _ in range(7))
+        input_val = ev.next_trace_mask()
+        out_val = ev.next_trace_mask()
+        max_val = ev.next_trace_mask()
+        next_max_val = ev.next_trace_mask()
+        is_last_step = ev.next_trace_mask()
+        is_max = ev.next_trace_mask()
+        input_mult = ev.next_trace_mask()
+        out_mult = ev.next_trace_mask()
+        ev.add_constraint(is_last_idx * (is_last_idx - 1))
+        ev.add_constraint(is_last_step * (is_last_step - 1))
+        ev.add_constraint(is_max * (is_max - 1))
+        ev.add_constraint(is_max * (next_max_val - input_val))
+        ev.add_constraint((1 - is_max) * (next_max_val - max_val))
+        ev.add_constraint((out_val - next_max_val) * is_last_step)
+        self._transitions(ev, is_last_idx, node_id, input_id, idx, next_node_id, next_input_id, next_idx)
+        ev.add_to_relation(self.node_elements, input_mult, [input_val, input_id])
+        ev.add_to_relation(self.node_elements, out_mult, [out_val, node_id])
+        ev.finalize_logup()
+        return ev
+
+    @staticmethod
+    def lookup_terms(cols):
+        return [(cols[13], [cols[7], cols[1]]), (cols[14], [cols[8], cols[0]])]
+
+
+class ContiguousEval(_ReduceLike):
+    """crates/air/src/components/contiguous/component.rs:37-101."""
+    name = "contiguous"
+    n_main = 11
+    n_interaction = 2
+
+    def evaluate(self, ev):
+        node_id, input_id, idx, is_last_idx, next_node_id, next_input_id, next_idx = (ev.next_trace_mask() for _ in range(7))
+        inp = ev.next_trace_mask()
+        out = ev.next_trace_mask()
+        input_mult = ev.next_trace_mask()
+        out_mult = ev.next_trace_mask()
+        ev.add_constraint(is_last_idx * (is_last_idx - 1))
+        self._transitions(ev, is_last_idx, node_id, input_id, idx, next_node_id, next_input_id, next_idx)
+        ev.add_to_relation(self.node_elements, input_mult, [inp, input_id])
+        ev.add_to_relation(self.node_elements, out_mult, [out, node_id])
+        ev.finalize_logup()
+        return ev
+
+    @staticmethod
+    def lookup_terms(cols):
+        return [(cols[9], [cols[7], cols[1]]), (cols[10], [cols[8], cols[0]])]
+
+
 # ---------------------------------------------------------------------------
 # FrameworkComponent
 # ---------------------------------------------------------------------------

@@ -127,3 +127,42 @@ def graph_pie(log_n: int, seed: int = 42, with_mul: bool = True):
         pie.append(("mul", mul))
     pie.append(("inputs", inp))
     return pie
+
+
+def reduce_pie(log_n: int, log_group: int = 2, seed: int = 1):
+    """Graph with the reduction / copy operators:  x (input, node 0, n = 2^log_n elements) feeds
+    SumReduce (node 1), MaxReduce (node 2) over groups of 2^log_group elements, and Contiguous (node 3).
+    Rows as emitted by LuminairSumReduce / LuminairMaxReduce / LuminairContiguous::process_trace
+    (crates/graph/src/op/prim.rs:1517-1565 and siblings): one row per (output element, step); all three
+    outputs are final (multiplicity 0), x is consumed three times."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = 1 << log_n
+    k = 1 << log_group
+    m = n // k
+    x = np.round(rng.uniform(-0.5, 0.5, n) * SCALE).astype(np.int64)
+    xs = x.reshape(m, k)
+    out_idx = np.repeat(np.arange(m, dtype=np.int64), k)
+    step = np.tile(np.arange(k, dtype=np.int64), m)
+    last_idx = (out_idx == m - 1).astype(np.int64)
+    last_step = (step == k - 1).astype(np.int64)
+
+    def table(cols):
+        return (np.stack([np.broadcast_to(np.asarray(c, dtype=np.int64), (n,)) for c in cols], axis=1) % P).astype(U64)
+
+    # sum reduce
+    nxt = np.cumsum(xs, axis=1)
+    acc = nxt - xs
+    out = np.repeat(nxt[:, -1], k)
+    sum_t = table([1, 0, out_idx, last_idx, 1, 0, out_idx + 1, x, out, acc.reshape(-1), nxt.reshape(-1), last_step, -1, 0])
+    # max reduce: running max starts at the first element (is_max = 1 on step 0)
+    run = np.maximum.accumulate(xs, axis=1)
+    prev = np.concatenate([np.zeros((m, 1), dtype=np.int64), run[:, :-1]], axis=1)
+    is_max = np.concatenate([np.ones((m, 1), dtype=np.int64), (xs[:, 1:] > run[:, :-1]).astype(np.int64)], axis=1)
+    mout = np.repeat(run[:, -1], k)
+    max_t = table([2, 0, out_idx, last_idx, 2, 0, out_idx + 1, x, mout, prev.reshape(-1), run.reshape(-1), last_step,
+                   is_max.reshape(-1), -1, 0])
+    idx = np.arange(n, dtype=np.int64)
+    last = (idx == n - 1).astype(np.int64)
+    inp = table([0, idx, last, 0, idx + 1, x, 3])
+    cont = table([3, 0, idx, last, 3, 0, idx + 1, x, x, -1, 0])
+    return [("sum_reduce", sum_t), ("max_reduce", max_t), ("inputs", inp), ("contiguous", cont)]

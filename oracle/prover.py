@@ -173,7 +173,7 @@ def stark_prove(components, channel, scheme: CommitmentSchemeProver) -> StarkPro
 # ---------------------------------------------------------------------------
 # LuminAIR prove()  (crates/prover/src/prover.rs:28-319)
 # ---------------------------------------------------------------------------
-SLOT_OF = {"add": 0, "mul": 1, "inputs": 15}
+SLOT_OF = {"add": 0, "mul": 1, "sum_reduce": 5, "max_reduce": 6, "inputs": 15, "contiguous": 16}
 N_LANES = 16
 
 

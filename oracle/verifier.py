@@ -13,7 +13,10 @@ from .air import (
     ORIGINAL_TRACE_IDX,
     PREPROCESSED_TRACE_IDX,
     AddEval,
+    ContiguousEval,
     FrameworkComponent,
+    MaxReduceEval,
+    SumReduceEval,
     InputsEval,
     MulEval,
     PointEvaluationAccumulator,
@@ -142,7 +145,7 @@ def stark_verify(components, channel, scheme: CommitmentSchemeVerifier, proof: S
 # ---------------------------------------------------------------------------
 # component slot order: crates/air/src/lib.rs:30-48.  The UI artifact predates
 # the 17-slot schema and has 8 slots with add, mul first.
-SLOT_EVALS = {0: AddEval, 1: MulEval, 15: InputsEval}
+SLOT_EVALS = {0: AddEval, 1: MulEval, 5: SumReduceEval, 6: MaxReduceEval, 15: InputsEval, 16: ContiguousEval}
 
 
 def luminair_components(claim, interaction_claim, node_elements, slot_evals=SLOT_EVALS, preprocessed_ids=()):

@@ -119,11 +119,13 @@ def test_grind(be, variant):
         assert got == want
 
 
-KINDS = {"add": (0, air.AddEval), "mul": (1, air.MulEval), "inputs": (2, air.InputsEval)}
+KINDS = {"add": (0, air.AddEval), "mul": (1, air.MulEval), "inputs": (2, air.InputsEval),
+         "sum_reduce": (4, air.SumReduceEval), "max_reduce": (5, air.MaxReduceEval), "contiguous": (6, air.ContiguousEval)}
 
 
 def _component_tables(log):
     pie = dict(examples.graph_pie(log, seed=7))
+    pie.update({k: v for k, v in examples.reduce_pie(log, 2, seed=8) if k != "inputs"})
     out = {}
     for name, rows in pie.items():
         cls = KINDS[name][1]
@@ -132,7 +134,7 @@ def _component_tables(log):
     return out
 
 
-@pytest.mark.parametrize("name", ["add", "mul", "inputs"])
+@pytest.mark.parametrize("name", ["add", "mul", "inputs", "sum_reduce", "max_reduce", "contiguous"])
 @pytest.mark.parametrize("log", [4, 11])
 def test_logup_and_constraint_quotients(be, name, log):
     from luminair_b200.backend import ColumnBatch
@@ -233,6 +235,42 @@ def test_graph_proof_bytes(be, log, with_mul):
     want = to_bincode(lp)
     got = prove(pie, backend=be)
     _assert_same_proof(be, got, want, digests)
+    overifier.verify(from_bincode(got))
+
+
+@pytest.mark.parametrize("log", [4, 8, 12])
+def test_reduce_graph_proof_bytes(be, log):
+    """SumReduce + MaxReduce + Inputs + Contiguous (AIRs fully defined in the reference tree)."""
+    from luminair_b200.prover import prove
+    pie = examples.reduce_pie(log, 2, seed=log)
+    lp, digests = _oracle_transcript(lambda: oprover.prove(pie))
+    got = prove(pie, backend=be)
+    _assert_same_proof(be, got, to_bincode(lp), digests)
+    overifier.verify(from_bincode(got))
+
+
+def test_all_six_components_mixed_sizes(be):
+    """Every supported component in one proof, tables of different heights (mixed-height Merkle trees, several FRI
+    circle columns)."""
+    from luminair_b200.prover import prove
+    g = dict(examples.graph_pie(9, seed=21))
+    r = dict(examples.reduce_pie(6, 3, seed=22))
+    # disjoint node ids between the two sub-graphs
+    shift = 10
+    for name in ("sum_reduce", "max_reduce", "contiguous"):
+        t = r[name].copy()
+        for c in (0, 1, 4, 5):
+            t[:, c] += shift
+        r[name] = t
+    ri = r["inputs"].copy()
+    for c in (0, 3):
+        ri[:, c] += shift
+    pie = [("add", g["add"]), ("mul", g["mul"]), ("sum_reduce", r["sum_reduce"]), ("max_reduce", r["max_reduce"]),
+           ("inputs", np.concatenate([g["inputs"], ri])), ("contiguous", r["contiguous"])]
+    # the concatenated Inputs table: clear the is_last flag of the first part's last row? no - the flag is per node
+    lp, digests = _oracle_transcript(lambda: oprover.prove(pie))
+    got = prove(pie, backend=be)
+    _assert_same_proof(be, got, to_bincode(lp), digests)
     overifier.verify(from_bincode(got))
 
 
