@@ -156,7 +156,7 @@ def run_reference(args):
                                    "CPU restatement (oracle/c), not stwo SimdBackend (Rust toolchain absent)"},
         "e2e": {"value": value, "unit": "M31 field-ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------
@@ -314,7 +314,7 @@ def run_gpu(args):
                                               "round trip, C restatement (oracle/c) with OpenMP over columns"}
             if prove_info:
                 line["cpu_baseline"]["prove"] = cpu_prove_baseline()
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if distributed:
         dist.destroy_process_group()
     be.close()
@@ -344,7 +344,38 @@ def bench_sharded_commit(be, torch, dist, args, rank, world, local_rank):
             best = [float(x) for x in t]
             a2a = tm["all_to_all_bytes_per_rank"]
         del trace
-    return {"workload": f"column-sharded commit: {ncols} columns x 2^{log} rows per GPU ({ncols * world} columns total), blow-up 2, "
+    # fused variant: the all-to-all is done by the last CFFT pass storing into NVLink peer memory (no NCCL data-path call)
+    fused = None
+    try:
+        from luminair_b200.sharded import FusedShardedCommitter
+        fc = FusedShardedCommitter(be, ncols, log, 1)
+        fc.setup()
+        fbest = None
+        froot = None
+        for it in range(4):
+            tr = be.alloc(ncols << log)
+            be.lib.lb_copy(be.ctx, C.c_void_p(tr.ptr), C.c_void_p(base.data_ptr()), ncols << log)
+            be.sync()
+            torch.cuda.synchronize()
+            dist.barrier()
+            tm = {}
+            froot = fc.commit(tr.ptr, timings=tm)
+            t = torch.tensor([tm["total_ms"], tm["lde_scatter_ms"], tm["subtree_ms"], tm["root_allgather_ms"]],
+                             dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if it > 0 and (fbest is None or float(t[0]) < fbest[0]):
+                fbest = [float(x) for x in t]
+            tr.free()
+        dist.barrier()
+        fc.close()
+        fused = {"ms_total_max_over_ranks": fbest[0], "ms_lde_with_peer_scatter": fbest[1], "ms_subtree": fbest[2],
+                 "ms_root_allgather_and_top": fbest[3], "nvlink_store_bytes_per_rank": tm["nvlink_store_bytes_per_rank"],
+                 "root_equals_nccl_variant": froot == root,
+                 "how": "last CFFT pass stores each 4096-row tile into the owner rank's buffer (CUDA IPC peer memory); no pack copy, no NCCL all-to-all"}
+    except Exception as e:  # report, do not hide
+        fused = {"error": repr(e)}
+    return {"fused_all_to_all": fused,
+            "workload": f"column-sharded commit: {ncols} columns x 2^{log} rows per GPU ({ncols * world} columns total), blow-up 2, "
                         "interpolate + LDE -> NCCL all-to-all (columns -> rows) -> Blake2s sub-trees -> all-gather of roots "
                         "(BASELINE configs[4] shape; root bit-identical to a single-device tree, tests/test_sharded_gloo.py)",
             "ms_total_max_over_ranks": best[0], "ms_lde": best[1], "ms_all_to_all": best[2], "ms_subtree": best[3],

@@ -65,6 +65,18 @@ int lb_interpolate_batch(lb_ctx* ctx, uint32_t* d_cols, size_t stride, int n_col
 int lb_evaluate_batch(lb_ctx* ctx, const uint32_t* d_coeffs, size_t src_stride, int log_in, uint32_t* d_out,
                       size_t dst_stride, int log_out, int n_cols);
 
+/* evaluate_polynomials fused with the column->row all-to-all of a column-sharded commit: the final pass stores
+ * rows [s*R/W, (s+1)*R/W) (R = 2^log_out, W = n_peers) of column c into h_peers[s] + (peer_col0 + c) * (R/W).
+ * h_peers: HOST array of W DEVICE pointers (this GPU's own buffer or lb_ipc_open'ed NVLink peer buffers).
+ * d_scratch (n_cols x 2^log_out at dst_stride) holds the intermediate passes.  Needs log_out >= 16 and R/W >= 4096. */
+int lb_evaluate_batch_scatter(lb_ctx* ctx, const uint32_t* d_coeffs, size_t src_stride, int log_in, uint32_t* d_scratch,
+                              size_t dst_stride, int log_out, int n_cols, uint32_t* const* h_peers, int n_peers,
+                              size_t peer_col0);
+/* CUDA IPC plumbing for the above: export an lb_alloc'ed buffer, open a peer's handle, close it */
+int lb_ipc_export(lb_ctx* ctx, const uint32_t* d_ptr, uint8_t handle_out[64]);
+int lb_ipc_open(lb_ctx* ctx, const uint8_t handle[64], uint32_t** d_ptr_out);
+int lb_ipc_close(lb_ctx* ctx, uint32_t* d_ptr);
+
 /* Host-buffer form of extend_evals + commit's evaluate (values -> coefficients -> evaluations on CanonicCoset(log_out)):
  * h_values: n_cols x 2^log_in, h_evals: n_cols x 2^log_out, h_coeffs (optional, may be NULL): n_cols x 2^log_in, all HOST.
  * Columns are processed in chunks (chunk_cols, 0 = automatic) over three streams, so the upload of chunk k+1, the two

@@ -75,6 +75,11 @@ SIGNATURES.update({
                                              u32p, u32p]),
     "lb_constraint_quotients": (C.c_int, [ctxp, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, u32p, u32p,
                                           u32p, u32p, C.c_int, C.POINTER(C.c_void_p), C.c_int]),
+    "lb_evaluate_batch_scatter": (C.c_int, [ctxp, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                                            C.POINTER(C.c_void_p), C.c_int, C.c_size_t]),
+    "lb_ipc_export": (C.c_int, [ctxp, C.c_void_p, C.c_char_p]),
+    "lb_ipc_open": (C.c_int, [ctxp, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "lb_ipc_close": (C.c_int, [ctxp, C.c_void_p]),
     "lb_lde_host": (C.c_int, [ctxp, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "lb_prove": (C.c_int, [ctxp, C.POINTER(TraceTable), C.c_int, C.POINTER(ProveConfig), C.POINTER(C.c_void_p),
                            C.POINTER(C.c_size_t)]),

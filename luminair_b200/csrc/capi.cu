@@ -285,6 +285,48 @@ int lb_constraint_quotients(lb_ctx* ctx, int component, const uint32_t* d_main, 
                                          claimed_sum, pows, n_pows, d_acc, accumulate);
 }
 
+int lb_evaluate_batch_scatter(lb_ctx* ctx, const uint32_t* d_coeffs, size_t src_stride, int log_in, uint32_t* d_scratch,
+                              size_t dst_stride, int log_out, int n_cols, uint32_t* const* h_peers, int n_peers,
+                              size_t peer_col0) {
+    if (!ctx || n_cols < 0 || log_out < 1 || log_in < 0 || log_in > log_out || n_peers < 1 || n_peers > 8 || !h_peers)
+        return fail(ctx, LB_ERR_BAD_ARG, "evaluate_scatter: bad args");
+    int r = lb_twiddles_ensure(ctx, log_out);
+    if (r) return r;
+    CK(lb::cfft_evaluate_scatter(&ctx->tw, d_coeffs, src_stride, log_in, d_scratch, dst_stride, log_out, n_cols, h_peers, n_peers,
+                                 peer_col0, ctx->sm_count, ctx->stream),
+       "evaluate_scatter");
+    return LB_OK;
+}
+
+int lb_ipc_export(lb_ctx* ctx, const uint32_t* d_ptr, uint8_t handle_out[64]) {
+    if (!ctx || !d_ptr || !handle_out) return fail(ctx, LB_ERR_BAD_ARG, "ipc_export: bad args");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaSetDevice(ctx->device);
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, (void*)d_ptr), "ipc export");
+    std::memcpy(handle_out, &h, 64);
+    return LB_OK;
+}
+
+int lb_ipc_open(lb_ctx* ctx, const uint8_t handle[64], uint32_t** d_ptr_out) {
+    if (!ctx || !handle || !d_ptr_out) return fail(ctx, LB_ERR_BAD_ARG, "ipc_open: bad args");
+    cudaSetDevice(ctx->device);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "ipc open");
+    *d_ptr_out = (uint32_t*)p;
+    return LB_OK;
+}
+
+int lb_ipc_close(lb_ctx* ctx, uint32_t* d_ptr) {
+    if (!ctx) return LB_ERR_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream), "ipc close/sync");
+    CK(cudaIpcCloseMemHandle(d_ptr), "ipc close");
+    return LB_OK;
+}
+
 int lb_lde_host(lb_ctx* ctx, const uint32_t* h_values, uint32_t* h_evals, int n_cols, int log_in, int log_out,
                 uint32_t* h_coeffs, int chunk_cols) {
     if (!ctx || !h_values || !h_evals || n_cols < 0 || log_in < 1 || log_out < log_in || log_out > 28)

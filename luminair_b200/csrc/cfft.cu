@@ -179,6 +179,12 @@ struct PassParams {
     int final_mode;        // 0 lazy store, 1 canonical, 2 scale (interpolate) + canonical
     uint2 scale;
     RedK redk;             // {2, -P}: opaque multipliers for red_fma
+    // row-sharded scatter of the final (low) pass of an evaluate: tile rows [s*R/W, (s+1)*R/W) of column c go to
+    // peer[s] + (peer_col0 + c) * (R/W) + local row  (peer[] are device pointers, local or NVLink peer-mapped)
+    uint32_t* peer[8];
+    int n_peers;           // 0: plain store to dst
+    int peer_tile_shift;   // log2(tiles per rank) = log_n - log2(W) - 12
+    size_t peer_col0;      // global index of this launch's column 0
     const uint2* tw[12];   // twiddle arrays of layers i_lo .. i_lo+m-1
 };
 
@@ -400,7 +406,7 @@ struct RoundGeom {
 // ---- low pass ---------------------------------------------------------------------------
 template <bool FWD, int M, int R, int NC>
 __device__ __forceinline__ void low_round(uint32_t* sm, const PassParams& p, uint32_t tile, const uint32_t* src,
-                                          uint32_t* dst, bool first, bool last) {
+                                          uint32_t* dst, bool first, bool last, int col = 0) {
     constexpr int A = RoundGeom<M, R>::A;
     constexpr int BLO = RoundGeom<M, R>::BLO;
     const int g = threadIdx.x;
@@ -457,6 +463,14 @@ __device__ __forceinline__ void low_round(uint32_t* sm, const PassParams& p, uin
         if (last) {
             if (A == 0) {
                 uint4* d4 = reinterpret_cast<uint4*>(dstc + gbase);
+                if (FWD && p.n_peers > 0) {
+                    // fused all-to-all: this tile belongs to the row shard of rank `tile >> peer_tile_shift`; store it straight
+                    // into that rank's receive buffer (NVLink peer memory), already in [column][local row] layout
+                    const uint32_t owner = tile >> p.peer_tile_shift;
+                    const size_t rows_local = (size_t)4096 << p.peer_tile_shift;
+                    const size_t local_row = ((size_t)(tile & ((1u << p.peer_tile_shift) - 1)) << 12) + e0;
+                    d4 = reinterpret_cast<uint4*>(p.peer[owner] + (p.peer_col0 + col + c) * rows_local + local_row);
+                }
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     d4[q] = make_uint4(finalize(v[c][4 * q], p.final_mode, p.scale), finalize(v[c][4 * q + 1], p.final_mode, p.scale),
@@ -507,15 +521,15 @@ __global__ void __launch_bounds__(256, NC == 1 ? LB_LOW_MINB : LB_LOW_MINB2) cff
         const uint32_t* src = p.src + (size_t)c * p.src_stride;
         uint32_t* dst = p.dst + (size_t)c * p.dst_stride;
         if (FWD) {
-            if constexpr (NR == 3) { low_round<FWD, M, 2, NC>(sm, p, tile, src, dst, true, false); __syncthreads(); }
-            low_round<FWD, M, 1, NC>(sm, p, tile, src, dst, NR == 2, false);
+            if constexpr (NR == 3) { low_round<FWD, M, 2, NC>(sm, p, tile, src, dst, true, false, c); __syncthreads(); }
+            low_round<FWD, M, 1, NC>(sm, p, tile, src, dst, NR == 2, false, c);
             __syncthreads();
-            low_round<FWD, M, 0, NC>(sm, p, tile, src, dst, false, true);
+            low_round<FWD, M, 0, NC>(sm, p, tile, src, dst, false, true, c);
         } else {
-            low_round<FWD, M, 0, NC>(sm, p, tile, src, dst, true, false);
+            low_round<FWD, M, 0, NC>(sm, p, tile, src, dst, true, false, c);
             __syncthreads();
-            low_round<FWD, M, 1, NC>(sm, p, tile, src, dst, false, NR == 2);
-            if constexpr (NR == 3) { __syncthreads(); low_round<FWD, M, 2, NC>(sm, p, tile, src, dst, false, true); }
+            low_round<FWD, M, 1, NC>(sm, p, tile, src, dst, false, NR == 2, c);
+            if constexpr (NR == 3) { __syncthreads(); low_round<FWD, M, 2, NC>(sm, p, tile, src, dst, false, true, c); }
         }
         __syncthreads();
     }
@@ -716,6 +730,7 @@ static cudaError_t launch_low_m(const PassParams& p, int sm_count, cudaStream_t 
         int skip = (NC > 1) ? main_cols : 0;
         q.src = p.src + (size_t)skip * p.src_stride;
         q.dst = p.dst + (size_t)skip * p.dst_stride;
+        q.peer_col0 = p.peer_col0 + skip;
         q.n_cols = rest;
         return launch_low_nc<FWD, M, 1>(q, sm_count, stream);
     }
@@ -823,8 +838,20 @@ cudaError_t cfft_interpolate(const Twiddles* tw, uint32_t* data, size_t stride, 
 
 cudaError_t cfft_evaluate(const Twiddles* tw, const uint32_t* coeffs, size_t src_stride, int log_in, uint32_t* out,
                           size_t dst_stride, int log_out, int n_cols, int sm_count, cudaStream_t stream) {
+    return cfft_evaluate_scatter(tw, coeffs, src_stride, log_in, out, dst_stride, log_out, n_cols, nullptr, 0, 0, sm_count, stream);
+}
+
+cudaError_t cfft_evaluate_scatter(const Twiddles* tw, const uint32_t* coeffs, size_t src_stride, int log_in, uint32_t* out,
+                                  size_t dst_stride, int log_out, int n_cols, uint32_t* const* peers, int n_peers,
+                                  size_t peer_col0, int sm_count, cudaStream_t stream) {
     if (log_out < 1 || log_out > tw->max_log || log_in > log_out || log_in < 0) return cudaErrorInvalidValue;
     if (n_cols == 0) return cudaSuccess;
+    int log_w = 0;
+    if (n_peers > 0) {
+        if (n_peers > 8 || (n_peers & (n_peers - 1)) || !peers) return cudaErrorInvalidValue;
+        while ((1 << log_w) < n_peers) ++log_w;
+        if (log_out - log_w < 12 || log_out < 16) return cudaErrorInvalidValue;  // whole 4096-row tiles per rank, multi-pass plan
+    }
     Plan pl = make_plan(log_out);
     for (int k = pl.n_pass - 1; k >= 0; --k) {
         PassParams p{};
@@ -841,6 +868,12 @@ cudaError_t cfft_evaluate(const Twiddles* tw, const uint32_t* coeffs, size_t src
         p.m = pl.m[k];
         p.ts = (k == 0) ? std::min(log_out, LOW_TS_MAX) : p.m;
         p.final_mode = (k == 0) ? 1 : 0;
+        if (k == 0 && n_peers > 0) {
+            p.n_peers = n_peers;
+            for (int r = 0; r < n_peers; ++r) p.peer[r] = peers[r];
+            p.peer_tile_shift = log_out - log_w - 12;
+            p.peer_col0 = peer_col0;
+        }
         for (int b = 0; b < p.m; ++b) p.tw[b] = layer_tw(tw, false, log_out, p.i_lo + b);
         cudaError_t e = launch_pass<true>(p, pl, k, sm_count, stream);
         if (e != cudaSuccess) return e;

@@ -23,4 +23,11 @@ cudaError_t cfft_interpolate(const Twiddles* tw, uint32_t* data, size_t stride, 
 cudaError_t cfft_evaluate(const Twiddles* tw, const uint32_t* coeffs, size_t src_stride, int log_in, uint32_t* out,
                           size_t dst_stride, int log_out, int n_cols, int sm_count, cudaStream_t stream);
 
+// same, but the final pass stores row shard s (rows [s*R/W, (s+1)*R/W), R = 2^log_out, W = n_peers) of column c into
+// peers[s] + (peer_col0 + c) * (R/W): the column->row all-to-all of a sharded commit fused into the transform.
+// `out` is still needed as the scratch of the earlier passes.  Requires log_out >= 16 and R/W >= 4096.
+cudaError_t cfft_evaluate_scatter(const Twiddles* tw, const uint32_t* coeffs, size_t src_stride, int log_in, uint32_t* out,
+                                  size_t dst_stride, int log_out, int n_cols, uint32_t* const* peers, int n_peers,
+                                  size_t peer_col0, int sm_count, cudaStream_t stream);
+
 }  // namespace lb

@@ -140,3 +140,104 @@ def sharded_commit(ops: ShardOps, trace_local: torch.Tensor, log_size: int, log_
                         "all_to_all_bytes_per_rank": int(n_cols_local * (1 << lde_log) * 4 * (world - 1) // world),
                         "rank": rank, "world": world})
     return root
+
+
+class FusedShardedCommitter:
+    """The same commitment with the all-to-all FUSED into the transform: the last pass of each rank's LDE stores every
+    4096-row tile straight into the receive buffer of the rank that owns those rows (CUDA IPC peer memory over
+    NVLink / NVSwitch), already in [column][local row] layout.  No pack copy, no NCCL data-path call; the transfer
+    overlaps the butterflies tile by tile.  torch.distributed only carries the 64-byte IPC handles (once), a barrier
+    and the 32-byte sub-tree roots.
+
+    setup() allocates and exchanges the buffers once; commit() can then be called repeatedly."""
+
+    def __init__(self, backend, n_cols_local: int, log_size: int, log_blowup: int = 1, group=None):
+        self.be, self.group = backend, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.world & (self.world - 1) or self.world > 8:
+            raise ValueError("world size must be a power of two <= 8")
+        self.log_w = self.world.bit_length() - 1
+        self.log_size, self.lde_log = log_size, log_size + log_blowup
+        if self.lde_log < 16 or self.lde_log - self.log_w < 12:
+            raise ValueError("fused path needs 2^16 LDE rows and 4096 rows per rank")
+        self.n_cols_local = n_cols_local
+        self.rows_local = (1 << self.lde_log) >> self.log_w
+        self.recv = None
+        self.peers: List[int] = []
+        self._opened: List[int] = []
+
+    def setup(self):
+        import ctypes as C
+        from ._lib import check
+        be = self.be
+        total_cols = self.n_cols_local * self.world
+        self.recv = be.alloc(total_cols * self.rows_local)          # all columns x my rows
+        self.scratch = be.alloc(self.n_cols_local << self.lde_log)  # intermediate passes of my columns
+        handle = C.create_string_buffer(64)
+        check(be.ctx, be.lib.lb_ipc_export(be.ctx, C.c_void_p(self.recv.ptr), handle), "lb_ipc_export")
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, handle.raw, group=self.group)
+        else:
+            handles = [handle.raw]
+        self.peers = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.peers.append(self.recv.ptr)
+                continue
+            p = C.c_void_p()
+            check(be.ctx, be.lib.lb_ipc_open(be.ctx, h, C.byref(p)), "lb_ipc_open")
+            self.peers.append(p.value)
+            self._opened.append(p.value)
+        # tree layers over my rows + the top levels
+        sub_log = self.lde_log - self.log_w
+        self.layers = [be.alloc(8 << lg) for lg in range(sub_log + 1)]
+        self.top = [be.alloc(8 << lg) for lg in range(self.log_w + 1)]
+
+    def close(self):
+        import ctypes as C
+        for p in self._opened:
+            self.be.lib.lb_ipc_close(self.be.ctx, C.c_void_p(p))
+        self._opened = []
+
+    def commit(self, trace_ptr: int, timings: Optional[dict] = None) -> bytes:
+        """trace_ptr: device pointer of my n_cols_local x 2^log_size trace values (overwritten by the coefficients)."""
+        import ctypes as C
+        import numpy as np
+        from ._lib import check
+        be, W = self.be, self.world
+        n = 1 << self.log_size
+        t0 = time.perf_counter()
+        check(be.ctx, be.lib.lb_interpolate_batch(be.ctx, C.c_void_p(trace_ptr), n, self.n_cols_local, self.log_size), "lb_interpolate_batch")
+        peers = (C.c_void_p * W)(*self.peers)
+        check(be.ctx, be.lib.lb_evaluate_batch_scatter(be.ctx, C.c_void_p(trace_ptr), n, self.log_size, C.c_void_p(self.scratch.ptr),
+                                                        1 << self.lde_log, self.lde_log, self.n_cols_local, peers, W,
+                                                        self.rank * self.n_cols_local), "lb_evaluate_batch_scatter")
+        be.sync()
+        if W > 1:
+            dist.barrier(group=self.group)  # every rank's remote stores have landed
+        t1 = time.perf_counter()
+        sub_log = self.lde_log - self.log_w
+        cols = [self.recv.ptr + 4 * self.rows_local * c for c in range(self.n_cols_local * W)]
+        be.merkle_commit_layer(sub_log, None, cols, self.layers[sub_log].ptr)
+        for lg in range(sub_log - 1, -1, -1):
+            be.merkle_commit_layer(lg, self.layers[lg + 1].ptr, [], self.layers[lg].ptr)
+        my_root = be.download(self.layers[0])
+        t2 = time.perf_counter()
+        if W > 1:
+            mine = torch.from_numpy(my_root.view(np.int32).copy()).cuda().reshape(1, 8)
+            roots = torch.empty((W, 8), dtype=torch.int32, device=mine.device)
+            dist.all_gather_into_tensor(roots, mine, group=self.group)
+            be.upload(roots.cpu().numpy().view(np.uint32).reshape(-1), self.top[self.log_w])
+            for lg in range(self.log_w - 1, -1, -1):
+                be.merkle_commit_layer(lg, self.top[lg + 1].ptr, [], self.top[lg].ptr)
+            root = be.download(self.top[0]).astype("<u4").tobytes()
+        else:
+            root = my_root.astype("<u4").tobytes()
+        t3 = time.perf_counter()
+        if timings is not None:
+            timings.update({"lde_scatter_ms": (t1 - t0) * 1e3, "subtree_ms": (t2 - t1) * 1e3, "root_allgather_ms": (t3 - t2) * 1e3,
+                            "total_ms": (t3 - t0) * 1e3,
+                            "nvlink_store_bytes_per_rank": int(self.n_cols_local * (1 << self.lde_log) * 4 * (W - 1) // W)})
+        return root

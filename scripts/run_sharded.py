@@ -26,6 +26,20 @@ for lg in range(log, -1, -1):
     layer = ops.merkle_layer(lg, layer, None)
 be.sync()
 want = layer.reshape(-1).cpu().numpy().astype("<u4").tobytes()
+# the fused variant: all-to-all done by the last CFFT pass through peer memory
+from luminair_b200.sharded import FusedShardedCommitter
+fc = FusedShardedCommitter(be, hi - lo, log, 1)
+fc.setup()
+ftm = {}
+for it in range(3):
+    tr = be.upload(full[lo:hi].reshape(-1))
+    be.sync(); dist.barrier()
+    froot = fc.commit(tr.ptr, timings=ftm)
+print(f"rank {rank}/{world}: FUSED root {froot.hex()[:16]} equal={froot == want} total {ftm['total_ms']:.2f} ms "
+      f"(lde+scatter {ftm['lde_scatter_ms']:.2f}, subtree {ftm['subtree_ms']:.2f}, roots {ftm['root_allgather_ms']:.2f})", flush=True)
+assert froot == want
+dist.barrier()
+fc.close()
 print(f"rank {rank}/{world}: sharded root {root.hex()[:16]} single-device root {want.hex()[:16]} equal={root == want} "
       f"total {tm['total_ms']:.2f} ms (lde {tm['lde_ms']:.2f}, a2a {tm['all_to_all_ms']:.2f}, subtree {tm['subtree_ms']:.2f})", flush=True)
 assert root == want

@@ -339,3 +339,19 @@ def test_sharded_commit_single_gpu_matches_oracle(be):
     want = omerkle.MerkleProver.commit(list(lde)).root()
     t = torch.from_numpy(vals.astype(np.uint32).view(np.int32).copy()).cuda()
     assert sharded_commit(CudaShardOps(be), t, log, 1) == want
+
+
+def test_fused_scatter_commit_single_gpu(be):
+    """The peer-scatter form of the LDE (the all-to-all fused into the last CFFT pass) with the GPU as its own only
+    peer: same root as the plain commit.  The multi-GPU run is scripts/run_sharded.py."""
+    from luminair_b200.sharded import FusedShardedCommitter
+    from oracle import merkle as omerkle
+    log, n_cols = 15, 5
+    vals = _rand_cols(91, n_cols, log)
+    lde = ocfft.evaluate(ocfft.interpolate(vals, CanonicCoset(log).circle_domain()), CanonicCoset(log + 1).circle_domain())
+    want = omerkle.MerkleProver.commit(list(lde)).root()
+    fc = FusedShardedCommitter(be, n_cols, log, 1)
+    fc.setup()
+    tr = be.upload(vals.astype(np.uint32).reshape(-1))
+    assert fc.commit(tr.ptr) == want
+    fc.close()
