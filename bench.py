@@ -368,6 +368,7 @@ def bench_sharded_commit(be, torch, dist, args, rank, world, local_rank):
             tr.free()
         dist.barrier()
         fc.close()
+        dist.barrier()  # nobody frees an exported buffer while a peer still has it mapped
         fused = {"ms_total_max_over_ranks": fbest[0], "ms_lde_with_peer_scatter": fbest[1], "ms_subtree": fbest[2],
                  "ms_root_allgather_and_top": fbest[3], "nvlink_store_bytes_per_rank": tm["nvlink_store_bytes_per_rank"],
                  "root_equals_nccl_variant": froot == root,

@@ -40,6 +40,7 @@ print(f"rank {rank}/{world}: FUSED root {froot.hex()[:16]} equal={froot == want}
 assert froot == want
 dist.barrier()
 fc.close()
+dist.barrier()
 print(f"rank {rank}/{world}: sharded root {root.hex()[:16]} single-device root {want.hex()[:16]} equal={root == want} "
       f"total {tm['total_ms']:.2f} ms (lde {tm['lde_ms']:.2f}, a2a {tm['all_to_all_ms']:.2f}, subtree {tm['subtree_ms']:.2f})", flush=True)
 assert root == want
