@@ -327,7 +327,7 @@ __device__ __forceinline__ int high_word(int e, int w) {
     return e * W + w + (W == 16 ? ((e >> 4) << 4) : 0);
 }
 template <int M, int W>
-constexpr int high_smem_words() {
+__host__ __device__ constexpr int high_smem_words() {
     return (1 << M) * W + (W == 16 ? (1 << M) : 0);
 }
 
@@ -539,12 +539,13 @@ __global__ void __launch_bounds__(256, NC == 1 ? LB_LOW_MINB : LB_LOW_MINB2) cff
 // ILO: compile-time i_lo (0 = runtime) so the 16 strided global offsets become immediates.
 // ZEXT (forward first pass only): 0 = source is full size; 1 = source is the lower half
 // (blow-up 2: the upper half is zero, the top layer degenerates to a copy); 2 = generic bound check.
-template <bool FWD, int M, int W, int R, int ILO, int ZEXT>
+template <bool FWD, int M, int W, int R, int ILO, int ZEXT, int NC>
 __device__ __forceinline__ void high_round(uint32_t* sm, const PassParams& p, uint32_t tile_h, size_t g_base,
                                            const uint32_t* src, uint32_t* dst, bool first, bool last) {
     constexpr int A = RoundGeom<M, R>::A;
     constexpr int BLO = RoundGeom<M, R>::BLO;
     constexpr bool TOP = (A + 4 == M);
+    constexpr int SMW = high_smem_words<M, W>();
     const int ilo = ILO ? ILO : p.i_lo;
     const int w = threadIdx.x % W;
     const int g = threadIdx.x / W;
@@ -552,49 +553,55 @@ __device__ __forceinline__ void high_round(uint32_t* sm, const PassParams& p, ui
     const int e0 = (e0_hi << (A + 4)) | (g & ((1 << A) - 1));
     const size_t gb = g_base + ((size_t)e0 << ilo) + w;
     const int sb = high_word<W>(e0, w);
-    uint32_t v[16];
+    uint32_t v[NC][16];
     bool half_zero = false;
-    if (first) {
-        const uint32_t* sp = src + gb;
-        if (ZEXT == 2) {
-            const size_t n_src = (size_t)1 << p.log_src;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                size_t off = (size_t)(j << A) << ilo;
-                v[j] = gb + off < n_src ? sp[off] : 0u;
+    for (int c = 0; c < NC; ++c) {
+        if (first) {
+            const uint32_t* sp = src + (size_t)c * p.src_stride + gb;
+            if (ZEXT == 2) {
+                const size_t n_src = (size_t)1 << p.log_src;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    size_t off = (size_t)(j << A) << ilo;
+                    v[c][j] = gb + off < n_src ? sp[off] : 0u;
+                }
+            } else if (ZEXT == 1 && TOP) {
+                // tile covers the top layers (tile_h == 0): elements with the top index bit set are zero
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[c][j] = sp[(size_t)(j << A) << ilo];
+#pragma unroll
+                for (int j = 8; j < 16; ++j) v[c][j] = v[c][j - 8];
+                half_zero = true;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[c][j] = sp[(size_t)(j << A) << ilo];
             }
-        } else if (ZEXT == 1 && TOP) {
-            // tile covers the top layers (tile_h == 0): elements with the top index bit set are zero
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = sp[(size_t)(j << A) << ilo];
-#pragma unroll
-            for (int j = 8; j < 16; ++j) v[j] = v[j - 8];
-            half_zero = true;
         } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = sp[(size_t)(j << A) << ilo];
+            for (int j = 0; j < 16; ++j) v[c][j] = sm[c * SMW + sb + high_word<W>(j << A, 0)];
         }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = sm[sb + high_word<W>(j << A, 0)];
     }
     if (ZEXT == 1 && TOP && FWD && BLO < 4) {
         // top layer on (v, 0) pairs is the identity copy done above; run the remaining layers
         if (half_zero) {
-            field_layers_range<FWD, A, BLO, 3, M>(v, p, tile_h, e0_hi);
+            field_layers_range_nc<FWD, A, BLO, 3, M, NC>(v, p, tile_h, e0_hi);
         } else {
-            field_layers_range<FWD, A, BLO, 4, M>(v, p, tile_h, e0_hi);
+            field_layers_range_nc<FWD, A, BLO, 4, M, NC>(v, p, tile_h, e0_hi);
         }
     } else {
-        field_layers_range<FWD, A, BLO, 4, M>(v, p, tile_h, e0_hi);
+        field_layers_range_nc<FWD, A, BLO, 4, M, NC>(v, p, tile_h, e0_hi);
     }
-    if (last) {
-        uint32_t* dp = dst + gb;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) dp[(size_t)(j << A) << ilo] = finalize(v[j], p.final_mode, p.scale);
-    } else {
+    for (int c = 0; c < NC; ++c) {
+        if (last) {
+            uint32_t* dp = dst + (size_t)c * p.dst_stride + gb;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) sm[sb + high_word<W>(j << A, 0)] = v[j];
+            for (int j = 0; j < 16; ++j) dp[(size_t)(j << A) << ilo] = finalize(v[c][j], p.final_mode, p.scale);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sm[c * SMW + sb + high_word<W>(j << A, 0)] = v[c][j];
+        }
     }
 }
 
@@ -605,8 +612,15 @@ struct HighGeom {
     static constexpr int MIN_BLOCKS = (M <= 8) ? LB_HIGH_MINB : 1;
 };
 
-template <bool FWD, int M, int ILO, int ZEXT>
-__global__ void __launch_bounds__(HighGeom<M>::THREADS, HighGeom<M>::MIN_BLOCKS) cfft_high_fast(PassParams p, int cols_per_block) {
+#ifndef LB_HIGH_NC
+#define LB_HIGH_NC 1  // measured: two columns per thread pay off in the low pass (twiddle reuse), not here
+#endif
+#ifndef LB_HIGH_MINB2
+#define LB_HIGH_MINB2 2
+#endif
+template <bool FWD, int M, int ILO, int ZEXT, int NC>
+__global__ void __launch_bounds__(HighGeom<M>::THREADS, NC == 1 ? HighGeom<M>::MIN_BLOCKS : ((M <= 8) ? LB_HIGH_MINB2 : 1))
+    cfft_high_fast(PassParams p, int cols_per_block) {
     constexpr int W = HighGeom<M>::W;
     constexpr int NR = (M + 3) / 4;
     extern __shared__ __align__(16) uint32_t smh[];
@@ -614,24 +628,24 @@ __global__ void __launch_bounds__(HighGeom<M>::THREADS, HighGeom<M>::MIN_BLOCKS)
     const uint32_t l_tiles = (1u << ilo) / W;
     const uint32_t tile_h = blockIdx.x / l_tiles, lt = blockIdx.x % l_tiles;
     const size_t g_base = ((size_t)tile_h << (ilo + M)) + (size_t)lt * W;
-    const int c0 = blockIdx.y * cols_per_block;
-    const int c1 = min(p.n_cols, c0 + cols_per_block);
-    for (int c = c0; c < c1; ++c) {
+    const int c0 = blockIdx.y * cols_per_block * NC;
+    const int c1 = min(p.n_cols, c0 + cols_per_block * NC);
+    for (int c = c0; c < c1; c += NC) {
         const uint32_t* src = p.src + (size_t)c * p.src_stride;
         uint32_t* dst = p.dst + (size_t)c * p.dst_stride;
         if constexpr (NR == 1) {
-            high_round<FWD, M, W, 0, ILO, ZEXT>(smh, p, tile_h, g_base, src, dst, true, true);
+            high_round<FWD, M, W, 0, ILO, ZEXT, NC>(smh, p, tile_h, g_base, src, dst, true, true);
         } else if constexpr (FWD) {
-            if constexpr (NR == 3) { high_round<FWD, M, W, 2, ILO, ZEXT>(smh, p, tile_h, g_base, src, dst, true, false); __syncthreads(); }
-            high_round<FWD, M, W, 1, ILO, ZEXT>(smh, p, tile_h, g_base, src, dst, NR == 2, false);
+            if constexpr (NR == 3) { high_round<FWD, M, W, 2, ILO, ZEXT, NC>(smh, p, tile_h, g_base, src, dst, true, false); __syncthreads(); }
+            high_round<FWD, M, W, 1, ILO, ZEXT, NC>(smh, p, tile_h, g_base, src, dst, NR == 2, false);
             __syncthreads();
-            high_round<FWD, M, W, 0, ILO, ZEXT>(smh, p, tile_h, g_base, src, dst, false, true);
+            high_round<FWD, M, W, 0, ILO, ZEXT, NC>(smh, p, tile_h, g_base, src, dst, false, true);
             __syncthreads();
         } else {
-            high_round<FWD, M, W, 0, ILO, 0>(smh, p, tile_h, g_base, src, dst, true, false);
+            high_round<FWD, M, W, 0, ILO, 0, NC>(smh, p, tile_h, g_base, src, dst, true, false);
             __syncthreads();
-            high_round<FWD, M, W, 1, ILO, 0>(smh, p, tile_h, g_base, src, dst, false, NR == 2);
-            if constexpr (NR == 3) { __syncthreads(); high_round<FWD, M, W, 2, ILO, 0>(smh, p, tile_h, g_base, src, dst, false, true); }
+            high_round<FWD, M, W, 1, ILO, 0, NC>(smh, p, tile_h, g_base, src, dst, false, NR == 2);
+            if constexpr (NR == 3) { __syncthreads(); high_round<FWD, M, W, 2, ILO, 0, NC>(smh, p, tile_h, g_base, src, dst, false, true); }
             __syncthreads();
         }
     }
@@ -749,22 +763,46 @@ static cudaError_t launch_low(const PassParams& p, int sm_count, cudaStream_t st
     return cudaErrorInvalidValue;
 }
 
-template <bool FWD, int M, int ILO, int ZEXT>
-static cudaError_t launch_high_k(const PassParams& p, int sm_count, cudaStream_t stream) {
+template <bool FWD, int M, int ILO, int ZEXT, int NC>
+static cudaError_t launch_high_nc(const PassParams& p, int sm_count, cudaStream_t stream) {
     constexpr int W = HighGeom<M>::W;
     if (((size_t)1 << p.i_lo) < (size_t)W) return cudaErrorInvalidValue;
     size_t tiles = ((size_t)1 << (p.log_n - p.i_lo - M)) * (((size_t)1 << p.i_lo) / W);
-    size_t smem = (size_t)high_smem_words<M, W>() * sizeof(uint32_t);
-    int cpb = pick_cols_per_block(tiles, p.n_cols, sm_count);
-    dim3 grid((unsigned)tiles, (unsigned)((p.n_cols + cpb - 1) / cpb));
+    size_t smem = (size_t)NC * high_smem_words<M, W>() * sizeof(uint32_t);
+    int groups = p.n_cols / NC;
+    int cpb = pick_cols_per_block(tiles, groups, sm_count);
+    dim3 grid((unsigned)tiles, (unsigned)((groups + cpb - 1) / cpb));
     if (grid.y > 65535) return cudaErrorInvalidValue;
-    auto k = cfft_high_fast<FWD, M, ILO, ZEXT>;
+    auto k = cfft_high_fast<FWD, M, ILO, ZEXT, NC>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     k<<<grid, HighGeom<M>::THREADS, smem, stream>>>(p, cpb);
     return cudaGetLastError();
+}
+
+template <bool FWD, int M, int ILO, int ZEXT>
+static cudaError_t launch_high_k(const PassParams& p, int sm_count, cudaStream_t stream) {
+    // two columns per thread where the doubled tile still leaves room for several CTAs per SM
+    constexpr int NC = (M <= 8) ? LB_HIGH_NC : 1;
+    int main_cols = (p.n_cols / NC) * NC;
+    if (NC > 1 && main_cols > 0) {
+        PassParams q = p;
+        q.n_cols = main_cols;
+        cudaError_t e = launch_high_nc<FWD, M, ILO, ZEXT, NC>(q, sm_count, stream);
+        if (e != cudaSuccess) return e;
+    }
+    int rest = (NC > 1) ? p.n_cols - main_cols : p.n_cols;
+    if (rest > 0) {
+        PassParams q = p;
+        int skip = (NC > 1) ? main_cols : 0;
+        q.src = p.src + (size_t)skip * p.src_stride;
+        q.dst = p.dst + (size_t)skip * p.dst_stride;
+        q.n_cols = rest;
+        return launch_high_nc<FWD, M, ILO, ZEXT, 1>(q, sm_count, stream);
+    }
+    return cudaSuccess;
 }
 
 template <bool FWD, int M>
