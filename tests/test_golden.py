@@ -1,0 +1,44 @@
+"""Committed fixtures (tests/golden, made by scripts/make_golden.py): integrity, the oracle against them (CPU),
+the CUDA prover against them (GPU) without running the oracle."""
+import hashlib
+import json
+import os
+
+import pytest
+
+from oracle import examples
+
+CASES = {
+    "simple_current.proof.bin": lambda: examples.simple_pie("current"),
+    "graph_log6_mul.proof.bin": lambda: examples.graph_pie(6, seed=6, with_mul=True),
+    "reduce_log5.proof.bin": lambda: examples.reduce_pie(5, 2, seed=5),
+}
+
+
+def _meta(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "golden.json")))
+
+
+def test_fixture_integrity(golden_dir):
+    meta = _meta(golden_dir)
+    assert set(CASES) | {"demo_proof.bin"} == set(meta)
+    for name, m in meta.items():
+        data = open(os.path.join(golden_dir, name), "rb").read()
+        assert len(data) == m["bytes"] and hashlib.sha256(data).hexdigest() == m["sha256"], name
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_reproduces_fixture(golden_dir, name):
+    from oracle import prover, verifier
+    from oracle.proof import from_bincode, to_bincode
+    want = open(os.path.join(golden_dir, name), "rb").read()
+    assert to_bincode(prover.prove(CASES[name]())) == want
+    verifier.verify(from_bincode(want))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cuda_prover_reproduces_fixture(golden_dir, name):
+    from luminair_b200.prover import prove
+    want = open(os.path.join(golden_dir, name), "rb").read()
+    assert prove(CASES[name]()) == want
