@@ -45,3 +45,328 @@ def synthetic_add_graph_pie(log_n: int, seed: int = 42):
     a = to_fixed(rng.uniform(-0.5, 0.5, n))
     b = to_fixed(rng.uniform(-0.5, 0.5, n))
     return add_graph_pie(a, b)
+
+
+# ---------------------------------------------------------------------------------------------
+# Trace tables of arbitrary operator graphs (all 17 components)
+# ---------------------------------------------------------------------------------------------
+def _round_fixed(x) -> np.ndarray:
+    return np.round(np.asarray(x, dtype=np.float64) * FP_SCALE).astype(np.int64)
+
+
+def _from_fixed(v) -> np.ndarray:
+    return np.asarray(v, dtype=np.float64) / FP_SCALE
+
+
+LUT_FUNCS = {"sin": np.sin, "exp2": np.exp2, "log2": np.log2}
+RANGE_CHECK_BITS = 8  # RangeCheckLookup<1> over the 8-bit limbs of less_than (less_than/component.rs:105-133)
+
+
+class LookupLayout:
+    """crates/air/src/preprocessed.rs:41-116: sorted, disjoint value ranges [(lo, hi)] (inclusive raw Fixed<12>
+    values); entry i of the table is the i-th value of the concatenated ranges."""
+
+    def __init__(self, ranges):
+        self.ranges = sorted((int(lo), int(hi)) for lo, hi in ranges)
+        count = sum(hi - lo + 1 for lo, hi in self.ranges)
+        # calculate_log_size, crates/air/src/utils.rs:22-27
+        self.log_size = max(((count + 15) >> 4) - 1, 0).bit_length() + 4
+        self.values = np.concatenate([np.arange(lo, hi + 1, dtype=np.int64) for lo, hi in self.ranges])
+
+    @staticmethod
+    def covering(values, pad: int = 0):
+        """One range covering the given raw values (the reference derives ranges from a calibration run,
+        crates/graph/src/graph.rs gen_circuit_settings)."""
+        v = np.asarray(values, dtype=np.int64)
+        return LookupLayout([(int(v.min()) - pad, int(v.max()) + pad)])
+
+    def find_index(self, target: np.ndarray) -> np.ndarray:
+        idx = np.searchsorted(self.values, target)
+        if np.any(idx >= self.values.size) or np.any(self.values[np.minimum(idx, self.values.size - 1)] != target):
+            raise ValueError("Value should fit in range.")
+        return idx
+
+
+def lut_columns(name: str, layout: LookupLayout):
+    """Preprocessed LUT columns as the reference generates them on the host (preprocessed.rs:351-383 sin,
+    :436-462 exp2, log2 likewise): column 0 = the input values, column 1 = f(value) through f64 and
+    Fixed::from_f64, zero beyond the enumerated values.  -> [(id, values[2^log_size])]"""
+    n = 1 << layout.log_size
+    c0 = np.zeros(n, dtype=np.int64)
+    c1 = np.zeros(n, dtype=np.int64)
+    c0[: layout.values.size] = layout.values
+    with np.errstate(divide="ignore", invalid="ignore"):
+        c1[: layout.values.size] = _round_fixed(np.nan_to_num(LUT_FUNCS[name](_from_fixed(layout.values)), neginf=0.0))
+    return [(f"{name}_lut_0", (c0 % P).astype(np.uint32)), (f"{name}_lut_1", (c1 % P).astype(np.uint32))]
+
+
+def range_check_column(n_bits: int = RANGE_CHECK_BITS):
+    """preprocessed.rs:233-248,289-307: the enumeration 0 .. 2^n_bits - 1 (one segment)."""
+    log_size = max(n_bits, 4)
+    col = np.zeros(1 << log_size, dtype=np.uint32)
+    col[: 1 << n_bits] = np.arange(1 << n_bits, dtype=np.uint32)
+    return [(f"range_check_{n_bits}_column_0", col)]
+
+
+class GraphTrace:
+    """Builds the ``LuminairPie`` trace tables of an operator graph over Fixed<12> tensors the way
+    ``LuminairGraph::gen_trace`` does (crates/graph/src/graph.rs:161-604 with the row emitters of
+    crates/graph/src/op/prim.rs): every operator node appends one row per output element (per step for the
+    reductions) to its component's table; producers yield each element with multiplicity = number of rows that
+    read it, consumers take it with -1; LUT operators count their lookups in the table's multiplicity column.
+
+    Operands are (node, gather index) pairs so broadcasts / expands are explicit: ``idx[i]`` is the element of
+    the input tensor that output row ``i`` reads (default: the identity).
+    """
+
+    def __init__(self):
+        self.values = []     # node -> raw int64 tensor (flattened)
+        self.uses = []       # node -> per-element consumer count
+        self.ops = []        # (kind, node, dict)
+        self.lut_inputs = {"sin": [], "exp2": [], "log2": []}
+        self.limbs = []
+
+    # -- nodes ------------------------------------------------------------------------------
+    def _node(self, vals):
+        self.values.append(np.asarray(vals, dtype=np.int64).reshape(-1))
+        self.uses.append(np.zeros(self.values[-1].size, dtype=np.int64))
+        return len(self.values) - 1
+
+    def _read(self, operand, n=None):
+        node, idx = operand if isinstance(operand, tuple) else (operand, None)
+        if idx is None:
+            idx = np.arange(self.values[node].size if n is None else n, dtype=np.int64)
+        idx = np.asarray(idx, dtype=np.int64)
+        np.add.at(self.uses[node], idx, 1)
+        return node, self.values[node][idx]
+
+    def input(self, raw):
+        """CopyToStwo of a graph input / initializer (op/prim.rs:72-84) -> Inputs table."""
+        node = self._node(raw)
+        self.ops.append(("inputs", node, {}))
+        return node
+
+    def _binary(self, kind, a, b, fn):
+        ia, va = self._read(a)
+        ib, vb = self._read(b)
+        out, extra = fn(va, vb)
+        node = self._node(out)
+        self.ops.append((kind, node, dict(lhs_id=ia, rhs_id=ib, lhs=va, rhs=vb, **extra)))
+        return node
+
+    def add(self, a, b):
+        return self._binary("add", a, b, lambda x, y: (x + y, {}))
+
+    def mul(self, a, b):
+        def f(x, y):
+            p = x * y
+            q = p // FP_SCALE
+            return q, {"rem": p - q * FP_SCALE}
+        return self._binary("mul", a, b, f)
+
+    def rem(self, a, b):
+        def f(x, y):
+            q = x // y
+            r = x - q * y
+            return r, {"quotient": q}
+        return self._binary("rem", a, b, f)
+
+    def less_than(self, a, b):
+        def f(x, y):
+            lt = x < y
+            diff = np.where(lt, y - x, y - x + P)  # op/prim.rs:1209-1213 (two_pow_k = 2^31 - 1)
+            d32 = diff.astype(np.uint32)
+            limbs = [((d32 >> (8 * k)) & 0xFF).astype(np.int64) for k in range(4)]
+            self.limbs.extend(limbs)
+            return np.where(lt, FP_SCALE, 0).astype(np.int64), {"borrow": (~lt).astype(np.int64), "diff": diff % P, "limbs": limbs}
+        return self._binary("less_than", a, b, f)
+
+    def _unary(self, kind, a, fn):
+        ia, va = self._read(a)
+        out, extra = fn(va)
+        node = self._node(out)
+        self.ops.append((kind, node, dict(input_id=ia, input=va, **extra)))
+        return node
+
+    def recip(self, a):
+        def f(x):
+            q = (FP_SCALE * FP_SCALE) // x
+            return q, {"rem": FP_SCALE * FP_SCALE - q * x}
+        return self._unary("recip", a, f)
+
+    def sqrt(self, a):
+        def f(x):
+            t = x * FP_SCALE
+            s = np.floor(np.sqrt(t.astype(np.float64))).astype(np.int64)
+            s = np.where(s * s > t, s - 1, s)
+            s = np.where((s + 1) * (s + 1) <= t, s + 1, s)
+            return s, {"rem": t - s * s}
+        return self._unary("sqrt", a, f)
+
+    def _lut(self, name, a):
+        def f(x):
+            self.lut_inputs[name].append(x)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                return _round_fixed(LUT_FUNCS[name](_from_fixed(x))), {}
+        return self._unary(name, a, f)
+
+    def sin(self, a):
+        return self._lut("sin", a)
+
+    def exp2(self, a):
+        return self._lut("exp2", a)
+
+    def log2(self, a):
+        return self._lut("log2", a)
+
+    def contiguous(self, a):
+        return self._unary("contiguous", a, lambda x: (x.copy(), {}))
+
+    def _reduce(self, kind, a, group):
+        """a: operand whose gathered tensor is [n_out, group] row-major (op/prim.rs:1517-1565)."""
+        ia, va = self._read(a)
+        xs = va.reshape(-1, group)
+        if kind == "sum_reduce":
+            nxt = np.cumsum(xs, axis=1)
+            extra = {"acc": nxt - xs, "next": nxt}
+        else:
+            run = np.maximum.accumulate(xs, axis=1)
+            prev = np.concatenate([np.zeros((xs.shape[0], 1), dtype=np.int64), run[:, :-1]], axis=1)
+            is_max = np.concatenate([np.ones((xs.shape[0], 1), dtype=np.int64), (xs[:, 1:] > run[:, :-1]).astype(np.int64)], axis=1)
+            extra = {"acc": prev, "next": run, "is_max": is_max}
+        node = self._node(extra["next"][:, -1])
+        self.ops.append((kind, node, dict(input_id=ia, input=xs, **extra)))
+        return node
+
+    def sum_reduce(self, a, group):
+        return self._reduce("sum_reduce", a, group)
+
+    def max_reduce(self, a, group):
+        return self._reduce("max_reduce", a, group)
+
+    # -- tables ------------------------------------------------------------------------------
+    def finish(self, lut_pad: int = 0):
+        """-> (pie, preprocessed): trace tables in claim-slot order (graph.rs:502-593) and the LUT columns in
+        ``lookups_to_preprocessed_column`` order (preprocessed.rs:181-206).  Nodes nobody reads are the graph's
+        final outputs (multiplicity 0)."""
+        rows = {}
+
+        def emit(kind, cols, n):
+            rows.setdefault(kind, []).append(_table(n, cols))
+
+        for kind, node, d in self.ops:
+            out = self.values[node]
+            mult = self.uses[node]
+            n = out.size
+            idx = np.arange(n, dtype=np.int64)
+            last = (idx == n - 1).astype(np.int64)
+            if kind == "inputs":
+                emit(kind, [node, idx, last, node, idx + 1, out, mult], n)
+            elif kind in ("add", "mul", "rem", "less_than"):
+                head = [node, d["lhs_id"], d["rhs_id"], idx, last, node, d["lhs_id"], d["rhs_id"], idx + 1]
+                if kind == "add":
+                    emit(kind, head + [d["lhs"], d["rhs"], out, -1, -1, mult], n)
+                elif kind == "mul":
+                    emit(kind, head + [d["lhs"], d["rhs"], out, d["rem"], -1, -1, mult], n)
+                elif kind == "rem":
+                    emit(kind, head + [d["lhs"], d["rhs"], out, d["quotient"], -1, -1, mult], n)
+                else:
+                    emit(kind, head + [d["lhs"], d["rhs"], out, d["diff"], d["borrow"]] + d["limbs"] + [-1, -1, mult, 1], n)
+            elif kind in ("recip", "sqrt"):
+                emit(kind, [node, d["input_id"], idx, last, node, d["input_id"], idx + 1, d["input"], out, d["rem"], FP_SCALE, -1, mult], n)
+            elif kind in ("sin", "exp2", "log2"):
+                emit(kind, [node, d["input_id"], idx, last, node, d["input_id"], idx + 1, d["input"], out, -1, mult, 1], n)
+            elif kind == "contiguous":
+                emit(kind, [node, d["input_id"], idx, last, node, d["input_id"], idx + 1, d["input"], out, -1, mult], n)
+            else:  # reductions: one row per (output element, step)
+                m, k = d["input"].shape
+                out_idx = np.repeat(np.arange(m, dtype=np.int64), k)
+                step = np.tile(np.arange(k, dtype=np.int64), m)
+                last_idx = (out_idx == m - 1).astype(np.int64)
+                last_step = (step == k - 1).astype(np.int64)
+                # the finished value is yielded once per output element, on its last step
+                cols = [node, d["input_id"], out_idx, last_idx, node, d["input_id"], out_idx + 1, d["input"].reshape(-1),
+                        np.repeat(out, k), d["acc"].reshape(-1), d["next"].reshape(-1), last_step]
+                if kind == "max_reduce":
+                    cols.append(d["is_max"].reshape(-1))
+                cols += [-1, np.repeat(mult, k) * last_step]
+                emit(kind, cols, m * k)
+
+        preprocessed = []
+        lut_tables = {}
+        for name in ("sin", "exp2", "log2"):
+            if not self.lut_inputs[name]:
+                continue
+            x = np.concatenate(self.lut_inputs[name])
+            layout = LookupLayout.covering(x, lut_pad)
+            preprocessed += lut_columns(name, layout)
+            mult = np.zeros(1 << layout.log_size, dtype=np.int64)
+            np.add.at(mult, layout.find_index(x), 1)
+            lut_tables[name + "_lookup"] = mult.reshape(-1, 1)
+        if self.limbs:
+            preprocessed += range_check_column()
+            mult = np.zeros(1 << max(RANGE_CHECK_BITS, 4), dtype=np.int64)
+            np.add.at(mult, np.concatenate(self.limbs), 1)
+            lut_tables["range_check_lookup"] = mult.reshape(-1, 1)
+
+        order = ["add", "mul", "recip", "sin", "sin_lookup", "sum_reduce", "max_reduce", "sqrt", "rem", "exp2", "exp2_lookup",
+                 "log2", "log2_lookup", "less_than", "range_check_lookup", "inputs", "contiguous"]
+        pie = []
+        for kind in order:
+            if kind in rows:
+                pie.append((kind, np.concatenate(rows[kind])))
+            elif kind in lut_tables:
+                pie.append((kind, (lut_tables[kind] % P).astype(np.uint32)))
+        return pie, preprocessed
+
+
+def all_components_graph(n: int = 24, seed: int = 3):
+    """A graph that touches all 17 components (tests)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    g = GraphTrace()
+    x = g.input(to_fixed(rng.uniform(0.25, 2.0, n)))
+    y = g.input(to_fixed(rng.uniform(-1.0, 1.0, n)))
+    s = g.add(x, y)
+    p = g.mul(s, x)
+    r = g.recip(x)
+    q = g.sqrt(x)
+    e = g.exp2(y)
+    l = g.log2(x)
+    t = g.sin(p)
+    m = g.rem(x, q)
+    c = g.less_than(y, r)
+    k = 4
+    sr = g.sum_reduce(e, k)
+    mr = g.max_reduce(l, k)
+    g.contiguous(t)
+    g.add(m, c)
+    g.mul(sr, mr)
+    return g.finish()
+
+
+def mlp_graph(widths=(2, 64, 64, 1), x=(15.0, 0.5), seed: int = 7, scale: float = 0.3):
+    """BASELINE cfg 4 shape (examples/black-schole-nn/src/main.rs: Linear 2-64-64-1 with tanh between, input
+    [15.0, 0.5]); synthetic weights uniform(-scale, scale), PCG64(seed) (the reference's weights are git-ignored).
+    Each Linear is Mul over the expanded [out, in] operands + SumReduce + bias Add; tanh(z) lowers the way luminal
+    does it: 2 * sigmoid(2z) - 1 with sigmoid(v) = 1 / (1 + exp2(-v * log2 e))  ->  Mul, Exp2, Add, Recip."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    g = GraphTrace()
+    act = g.input(to_fixed(np.asarray(x, dtype=np.float64)))
+    n_layers = len(widths) - 1
+    for li in range(n_layers):
+        d_in, d_out = widths[li], widths[li + 1]
+        w = g.input(to_fixed(rng.uniform(-scale, scale, d_out * d_in)))
+        b = g.input(to_fixed(rng.uniform(-scale, scale, d_out)))
+        prod = g.mul(w, (act, np.tile(np.arange(d_in, dtype=np.int64), d_out)))
+        z = g.add(g.sum_reduce(prod, d_in), b) if d_in > 1 else g.add(prod, b)
+        if li == n_layers - 1:
+            act = z
+            break
+        c_m2log2e = g.input(np.full(d_out, int(round(-2.0 * np.log2(np.e) * FP_SCALE))))
+        one = g.input(np.full(d_out, FP_SCALE))
+        two = g.input(np.full(d_out, 2 * FP_SCALE))
+        neg_one = g.input(np.full(d_out, -FP_SCALE))
+        e = g.exp2(g.mul(z, c_m2log2e))
+        sig = g.recip(g.add(e, one))
+        act = g.add(g.mul(sig, two), neg_one)
+    return g.finish()

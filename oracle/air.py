@@ -275,6 +275,22 @@ def eval_fixed_mul(ev, lhs, rhs, scale, out, rem):
     ev.add_constraint(lhs * rhs - (out * scale + rem))
 
 
+# The three helpers below are NOT covered by the reference's committed proof (it holds Add and Mul
+# only): "parity unpinned".  They follow the identities the operators emit rows for
+# (crates/graph/src/op/prim.rs:375 recip, :604 sqrt, :1359 div_rem) written in the same
+# "dividend - (quotient * divisor + remainder)" form as the pinned eval_fixed_mul.
+def eval_fixed_recip(ev, inp, scale, out, rem):
+    ev.add_constraint(scale * scale - (inp * out + rem))
+
+
+def eval_fixed_sqrt(ev, inp, out, rem, scale):
+    ev.add_constraint(inp * scale - (out * out + rem))
+
+
+def eval_fixed_rem(ev, lhs, rhs, quotient, rem):
+    ev.add_constraint(lhs - (quotient * rhs + rem))
+
+
 # ---------------------------------------------------------------------------
 # LuminAIR evaluators
 # ---------------------------------------------------------------------------
@@ -283,7 +299,7 @@ class AddEval:
     n_main = 15  # add/witness.rs:24
     n_interaction = 3  # add/table.rs TraceColumn::count
 
-    def __init__(self, log_size, node_elements: RelationElements):
+    def __init__(self, log_size, node_elements: RelationElements, lookups=None, lut_logs=None):
         self.log_size = log_size
         self.node_elements = node_elements
 
@@ -343,7 +359,7 @@ class MulEval:
     # to 1 to replay that proof; the current schema (mul/component.rs:40-128) uses 0.
     n_legacy_extra_constraints = 0
 
-    def __init__(self, log_size, node_elements: RelationElements):
+    def __init__(self, log_size, node_elements: RelationElements, lookups=None, lut_logs=None):
         self.log_size = log_size
         self.node_elements = node_elements
 
@@ -400,7 +416,7 @@ class InputsEval:
     n_main = 7
     n_interaction = 1
 
-    def __init__(self, log_size, node_elements: RelationElements):
+    def __init__(self, log_size, node_elements: RelationElements, lookups=None, lut_logs=None):
         self.log_size = log_size
         self.node_elements = node_elements
 
@@ -437,7 +453,7 @@ class InputsEval:
 class _ReduceLike:
     """Shared head of SumReduce / MaxReduce / Contiguous: node_id, input_id, idx, is_last_idx, next_*."""
 
-    def __init__(self, log_size, node_elements: RelationElements):
+    def __init__(self, log_size, node_elements: RelationElements, lookups=None, lut_logs=None):
         self.log_size = log_size
         self.node_elements = node_elements
 
@@ -545,6 +561,280 @@ class ContiguousEval(_ReduceLike):
         return [(cols[9], [cols[7], cols[1]]), (cols[10], [cols[8], cols[0]])]
 
 
+class _UnaryFixed(_ReduceLike):
+    """Recip / Sqrt: head, input, out, rem, scale, input_mult, out_mult (13 columns, 2 relation uses).
+    recip/component.rs:39-107, sqrt/component.rs:38-107."""
+    n_main = 13
+    n_interaction = 2
+
+    def _arith(self, ev, input_val, out_val, rem_val, scale):
+        raise NotImplementedError
+
+    def evaluate(self, ev):
+        node_id, input_id, idx, is_last_idx, next_node_id, next_input_id, next_idx = (ev.next_trace_mask() for _ in range(7))
+        input_val = ev.next_trace_mask()
+        out_val = ev.next_trace_mask()
+        rem_val = ev.next_trace_mask()
+        scale = ev.next_trace_mask()
+        input_mult = ev.next_trace_mask()
+        out_mult = ev.next_trace_mask()
+        ev.add_constraint(is_last_idx * (is_last_idx - 1))
+        self._arith(ev, input_val, out_val, rem_val, scale)
+        self._transitions(ev, is_last_idx, node_id, input_id, idx, next_node_id, next_input_id, next_idx)
+        ev.add_to_relation(self.node_elements, input_mult, [input_val, input_id])
+        ev.add_to_relation(self.node_elements, out_mult, [out_val, node_id])
+        ev.finalize_logup()
+        return ev
+
+    @staticmethod
+    def lookup_terms(cols):
+        return [(cols[11], [cols[7], cols[1]]), (cols[12], [cols[8], cols[0]])]
+
+
+class RecipEval(_UnaryFixed):
+    name = "recip"
+
+    def _arith(self, ev, input_val, out_val, rem_val, scale):
+        eval_fixed_recip(ev, input_val, scale, out_val, rem_val)
+
+
+class SqrtEval(_UnaryFixed):
+    name = "sqrt"
+
+    def _arith(self, ev, input_val, out_val, rem_val, scale):
+        eval_fixed_sqrt(ev, input_val, out_val, rem_val, scale)
+
+
+class RemEval:
+    """crates/air/src/components/rem/component.rs:38-124."""
+    name = "rem"
+    n_main = 16
+    n_interaction = 3
+
+    def __init__(self, log_size, node_elements: RelationElements, lookups=None, lut_logs=None):
+        self.log_size = log_size
+        self.node_elements = node_elements
+
+    def max_constraint_log_degree_bound(self):
+        return self.log_size + 1
+
+    def evaluate(self, ev):
+        node_id, lhs_id, rhs_id, idx, is_last_idx, next_node_id, next_lhs_id, next_rhs_id, next_idx = (
+            ev.next_trace_mask() for _ in range(9))
+        lhs_val = ev.next_trace_mask()
+        rhs_val = ev.next_trace_mask()
+        rem_val = ev.next_trace_mask()
+        quotient = ev.next_trace_mask()
+        lhs_mult = ev.next_trace_mask()
+        rhs_mult = ev.next_trace_mask()
+        out_mult = ev.next_trace_mask()
+        ev.add_constraint(is_last_idx * (is_last_idx - 1))
+        eval_fixed_rem(ev, lhs_val, rhs_val, quotient, rem_val)
+        not_last = 1 - is_last_idx
+        ev.add_constraint(not_last * (next_node_id - node_id))
+        ev.add_constraint(not_last * (next_lhs_id - lhs_id))
+        ev.add_constraint(not_last * (next_rhs_id - rhs_id))
+        ev.add_constraint(not_last * (next_idx - idx - 1))
+        ev.add_to_relation(self.node_elements, lhs_mult, [lhs_val, lhs_id])
+        ev.add_to_relation(self.node_elements, rhs_mult, [rhs_val, rhs_id])
+        ev.add_to_relation(self.node_elements, out_mult, [rem_val, node_id])
+        ev.finalize_logup()
+        return ev
+
+    @staticmethod
+    def lookup_terms(cols):
+        return [(cols[13], [cols[9], cols[1]]), (cols[14], [cols[10], cols[2]]), (cols[15], [cols[11], cols[0]])]
+
+    @staticmethod
+    def padding_row():
+        r = [0] * 16
+        r[4] = 1
+        return r
+
+
+class _LutConsumer(_ReduceLike):
+    """Sin / Exp2 / Log2: head, input, out, input_mult, out_mult, lookup_mult (12 columns); the third relation
+    use is the (input, output) pair against the function's lookup table.
+    sin/component.rs:51-123, exp2/component.rs:46-118, log2/component.rs:46-117."""
+    n_main = 12
+    n_interaction = 3
+    lut = None  # key of LookupElements
+
+    def __init__(self, log_size, node_elements: RelationElements, lookups=None, lut_logs=None):
+        super().__init__(log_size, node_elements)
+        self.lookup_elements = lookups[self.lut]
+        self.lut_log_size = lut_logs[self.lut]
+
+    def max_constraint_log_degree_bound(self):
+        return max(self.log_size, self.lut_log_size) + 1
+
+    def evaluate(self, ev):
+        node_id, input_id, idx, is_last_idx, next_node_id, next_input_id, next_idx = (ev.next_trace_mask() for _ in range(7))
+        input_val = ev.next_trace_mask()
+        out_val = ev.next_trace_mask()
+        input_mult = ev.next_trace_mask()
+        out_mult = ev.next_trace_mask()
+        lookup_mult = ev.next_trace_mask()
+        ev.add_constraint(is_last_idx * (is_last_idx - 1))
+        self._transitions(ev, is_last_idx, node_id, input_id, idx, next_node_id, next_input_id, next_idx)
+        ev.add_to_relation(self.node_elements, input_mult, [input_val, input_id])
+        ev.add_to_relation(self.node_elements, out_mult, [out_val, node_id])
+        ev.add_to_relation(self.lookup_elements, lookup_mult, [input_val, out_val])
+        ev.finalize_logup()
+        return ev
+
+    @classmethod
+    def lookup_terms(cls, cols):
+        return [(cols[9], [cols[7], cols[1]]), (cols[10], [cols[8], cols[0]]), (cols[11], [cols[7], cols[8]], cls.lut)]
+
+
+class SinEval(_LutConsumer):
+    name = "sin"
+    lut = "sin"
+
+
+class Exp2Eval(_LutConsumer):
+    name = "exp2"
+    lut = "exp2"
+
+
+class Log2Eval(_LutConsumer):
+    name = "log2"
+    lut = "log2"
+
+
+class _LutTable:
+    """SinLookup / Exp2Lookup / Log2Lookup / RangeCheckLookup: one multiplicity column; the table's rows are the
+    preprocessed columns and every row yields -multiplicity.
+    lookups/exp2/component.rs:41-59 (and siblings), lookups/range_check/component.rs:44-60."""
+    n_main = 1
+    n_interaction = 1
+    lut = None
+    n_lut_cols = 2
+
+    def __init__(self, log_size, node_elements: RelationElements, lookups=None, lut_logs=None):
+        self.log_size = log_size
+        self.lookup_elements = lookups[self.lut]
+
+    def max_constraint_log_degree_bound(self):
+        return self.log_size + 1
+
+    @classmethod
+    def preprocessed_ids(cls):
+        return [f"{cls.lut}_lut_{k}" for k in range(cls.n_lut_cols)]
+
+    def evaluate(self, ev):
+        lut_cols = [ev.get_preprocessed_column(i) for i in self.preprocessed_ids()]
+        multiplicity = ev.next_trace_mask()
+        ev.add_to_relation(self.lookup_elements, -multiplicity, lut_cols)
+        ev.finalize_logup()
+        return ev
+
+    @classmethod
+    def lookup_terms(cls, cols, pre):
+        return [(m_neg(cols[0]), [pre[i] for i in cls.preprocessed_ids()], cls.lut)]
+
+    @staticmethod
+    def padding_row():
+        return [0]
+
+
+class SinLookupEval(_LutTable):
+    name = "sin_lookup"
+    lut = "sin"
+
+
+class Exp2LookupEval(_LutTable):
+    name = "exp2_lookup"
+    lut = "exp2"
+
+
+class Log2LookupEval(_LutTable):
+    name = "log2_lookup"
+    lut = "log2"
+
+
+class RangeCheckLookupEval(_LutTable):
+    name = "range_check_lookup"
+    lut = "range_check"
+    n_lut_cols = 1
+    n_bit = 8  # the reference instantiates RangeCheckLookup<1> over 8-bit limbs (less_than/component.rs:105)
+
+    @classmethod
+    def preprocessed_ids(cls):
+        return [f"range_check_{cls.n_bit}_column_0"]  # preprocessed.rs:289-296
+
+
+TWO_POW_31_MINUS_1 = P  # crates/air/src/lib.rs:26
+
+
+class LessThanEval:
+    """crates/air/src/components/less_than/component.rs:49-184 (22 columns, 7 relation uses)."""
+    name = "less_than"
+    n_main = 22
+    n_interaction = 7
+
+    def __init__(self, log_size, node_elements: RelationElements, lookups=None, lut_logs=None):
+        self.log_size = log_size
+        self.node_elements = node_elements
+        self.range_check_elements = lookups["range_check"]
+        self.range_check_log_size = lut_logs["range_check"]
+
+    def max_constraint_log_degree_bound(self):
+        return max(self.log_size, self.range_check_log_size) + 1
+
+    def evaluate(self, ev):
+        two_pow_k = TWO_POW_31_MINUS_1 % P  # the reference passes 2^31 - 1 == 0 (mod p) as "2^k"
+        scale_factor = 1 << DEFAULT_FP_SCALE
+        node_id, lhs_id, rhs_id, idx, is_last_idx, next_node_id, next_lhs_id, next_rhs_id, next_idx = (
+            ev.next_trace_mask() for _ in range(9))
+        lhs_val = ev.next_trace_mask()
+        rhs_val = ev.next_trace_mask()
+        out_val = ev.next_trace_mask()
+        diff_val = ev.next_trace_mask()
+        borrow = ev.next_trace_mask()
+        limb0, limb1, limb2, limb3 = (ev.next_trace_mask() for _ in range(4))
+        lhs_mult = ev.next_trace_mask()
+        rhs_mult = ev.next_trace_mask()
+        out_mult = ev.next_trace_mask()
+        diff_mult = ev.next_trace_mask()
+        ev.add_constraint(is_last_idx * (is_last_idx - 1))
+        ev.add_constraint(borrow * (borrow - 1))
+        ev.add_constraint(out_val - ((1 - borrow) * scale_factor))
+        ev.add_constraint(lhs_val + diff_val - rhs_val - (borrow * two_pow_k))
+        recomposed = limb3 * (1 << 24) + limb2 * (1 << 16) + limb1 * (1 << 8) + limb0
+        ev.add_constraint(diff_val - recomposed)
+        not_last = 1 - is_last_idx
+        ev.add_constraint(not_last * (next_node_id - node_id))
+        ev.add_constraint(not_last * (next_lhs_id - lhs_id))
+        ev.add_constraint(not_last * (next_rhs_id - rhs_id))
+        ev.add_constraint(not_last * (next_idx - idx - 1))
+        ev.add_to_relation(self.node_elements, lhs_mult, [lhs_val, lhs_id])
+        ev.add_to_relation(self.node_elements, rhs_mult, [rhs_val, rhs_id])
+        ev.add_to_relation(self.node_elements, out_mult, [out_val, node_id])
+        for limb in (limb0, limb1, limb2, limb3):
+            ev.add_to_relation(self.range_check_elements, diff_mult, [limb])
+        ev.finalize_logup()
+        return ev
+
+    @staticmethod
+    def lookup_terms(cols):
+        return [(cols[18], [cols[9], cols[1]]), (cols[19], [cols[10], cols[2]]), (cols[20], [cols[11], cols[0]]),
+                (cols[21], [cols[14]], "range_check"), (cols[21], [cols[15]], "range_check"),
+                (cols[21], [cols[16]], "range_check"), (cols[21], [cols[17]], "range_check")]
+
+    @staticmethod
+    def padding_row():
+        """less_than/table.rs padding(): 0 < 1 -> out = 1.0, diff = 1, limb0 = 1."""
+        r = [0] * 22
+        r[4] = 1
+        r[10] = 1
+        r[11] = 1 << DEFAULT_FP_SCALE
+        r[12] = 1
+        r[14] = 1
+        return r
+
+
 # ---------------------------------------------------------------------------
 # FrameworkComponent
 # ---------------------------------------------------------------------------
@@ -608,17 +898,31 @@ class FrameworkComponent:
         denom_inv = coset_vanishing(CanonicCoset(self.log_size).coset, point).inv()
         self.eval.evaluate(PointEvaluator(sub, pre, accumulator, denom_inv, self.log_size, self.claimed_sum))
 
-    def evaluate_constraint_quotients_on_domain(self, lde_trace, random_coeff_powers):
-        """lde_trace[tree] = list of LDE columns (global indexing) on CanonicCoset(log+1).
+    def evaluate_constraint_quotients_on_domain(self, lde_trace, random_coeff_powers, polys=None):
+        """lde_trace[tree] = list of committed LDE columns (global indexing); polys[tree] = their coefficients.
         random_coeff_powers: this component's slice, reversed (first constraint first).
-        Returns the QM31 accumulation (arrays of 2^(log+1))."""
+        Returns the QM31 accumulation (arrays of 2^eval_log).  When a column this component reads is not
+        committed on the evaluation domain CanonicCoset(max_constraint_log_degree_bound) - a LUT consumer whose
+        table is larger than its own trace - every column is re-evaluated there from its polynomial
+        (constraint-framework component.rs ``need_to_extend``)."""
+        from . import cfft
         eval_log = self.max_constraint_log_degree_bound()
-        sub = {}
+        sub, sub_polys = {}, {}
         for t in (ORIGINAL_TRACE_IDX, INTERACTION_TRACE_IDX):
             s, e = self.locations[t]
-            sub[t] = lde_trace[t][s:e]
+            sub[t] = list(lde_trace[t][s:e])
+            sub_polys[t] = None if polys is None else list(polys[t][s:e])
         pre = {cid: lde_trace[PREPROCESSED_TRACE_IDX][i] for cid, i in zip(self.preprocessed_ids, self.preprocessed_indices)}
         eval_domain = CanonicCoset(eval_log).circle_domain()
+        n_eval = 1 << eval_log
+        need_to_extend = any(len(c) != n_eval for t in sub for c in sub[t]) or any(len(c) != n_eval for c in pre.values())
+        if need_to_extend:
+            if polys is None:
+                raise ValueError("component needs its trace extended to the evaluation domain: pass polys")
+            for t in sub:
+                sub[t] = [cfft.evaluate(np.asarray(c, dtype=U64), eval_domain) for c in sub_polys[t]]
+            pre = {cid: cfft.evaluate(np.asarray(polys[PREPROCESSED_TRACE_IDX][i], dtype=U64), eval_domain)
+                   for cid, i in zip(self.preprocessed_ids, self.preprocessed_indices)}
         trace_coset = CanonicCoset(self.log_size).coset
         log_expand = eval_log - self.log_size
         dinv = [pow(int(coset_vanishing(trace_coset, eval_domain.at(i))), P - 2, P) for i in range(1 << log_expand)]
@@ -644,15 +948,23 @@ def coset_order_storage_perm(log_size: int) -> np.ndarray:
     return inv_br[dom]
 
 
-def gen_interaction_trace(ev_cls, main_cols, log_size, relation: RelationElements):
+def gen_interaction_trace(ev_cls, main_cols, log_size, relation: RelationElements, lookups=None, preprocessed=None):
     """-> (list of 4*k uint64 columns, claimed_sum QM31).  Mirrors
-    ``write_interaction_trace`` (e.g. add/witness.rs:126-167)."""
+    ``write_interaction_trace`` (e.g. add/witness.rs:126-167).  ``lookups``: LookupElements by name for the
+    components that also use a LUT relation (exp2/witness.rs:119-160, less_than/witness.rs:144-226);
+    ``preprocessed``: {id: column values} for the LUT table components (lookups/exp2/witness.rs:117-144)."""
     cols = [np.asarray(c, dtype=U64) for c in main_cols]
     n = 1 << log_size
     trace = []
     prev = None
-    for mult, values in ev_cls.lookup_terms(cols):
-        denom = relation.combine(values)
+    if getattr(ev_cls, "n_lut_cols", None) is not None:
+        terms = ev_cls.lookup_terms(cols, {k: np.asarray(v, dtype=U64) for k, v in preprocessed.items()})
+    else:
+        terms = ev_cls.lookup_terms(cols)
+    for term in terms:
+        mult, values = term[0], term[1]
+        rel = relation if len(term) == 2 else lookups[term[2]]
+        denom = rel.combine(values)
         val = denom.inv() * mult
         if prev is not None:
             val = val + prev

@@ -25,7 +25,7 @@ from .fields import P, U64, QM31, m_add
 from .fri import FriProver
 from .proof import LuminairProof, MerkleDecommitment, PcsConfig, StarkProof
 from .quotients import compute_fri_quotients
-from .verifier import SLOT_EVALS, draw_interaction_elements, get_random_point, luminair_components
+from .verifier import SLOT_EVALS, draw_interaction_elements, get_random_point, luminair_components, sort_preprocessed
 
 
 class ProvingError(Exception):
@@ -108,7 +108,7 @@ class CommitmentSchemeProver:
         return StarkProof(self.config, self.roots(), sampled_values, decommitments, queried, nonce, fri_proof)
 
 
-def compute_composition_polynomial(components, random_coeff: QM31, lde_trace):
+def compute_composition_polynomial(components, random_coeff: QM31, lde_trace, polys=None):
     """ComponentProvers::compute_composition_polynomial + DomainEvaluationAccumulator::finalize.
     lde_trace[tree] = list of LDE columns.  -> 4 coefficient arrays of log = max bound."""
     total = sum(c.n_constraints for c in components)
@@ -122,7 +122,7 @@ def compute_composition_polynomial(components, random_coeff: QM31, lde_trace):
         mine = powers[len(powers) - n:]
         powers = powers[: len(powers) - n]
         mine = mine[::-1]
-        acc = c.evaluate_constraint_quotients_on_domain(lde_trace, mine)
+        acc = c.evaluate_constraint_quotients_on_domain(lde_trace, mine, polys)
         log = c.max_constraint_log_degree_bound()
         sub[log] = acc if log not in sub else sub[log] + acc
     assert not powers
@@ -143,7 +143,8 @@ def stark_prove(components, channel, scheme: CommitmentSchemeProver) -> StarkPro
     """stwo::prover::prove."""
     random_coeff = channel.draw_secure_felt()
     lde = {t: scheme.trees[t].evals for t in (PREPROCESSED_TRACE_IDX, ORIGINAL_TRACE_IDX, INTERACTION_TRACE_IDX)}
-    comp = compute_composition_polynomial(components, random_coeff, lde)
+    polys = {t: scheme.trees[t].polys for t in (PREPROCESSED_TRACE_IDX, ORIGINAL_TRACE_IDX, INTERACTION_TRACE_IDX)}
+    comp = compute_composition_polynomial(components, random_coeff, lde, polys)
     tb = scheme.tree_builder()
     tb.extend_polys(comp)
     tb.commit(channel)
@@ -173,7 +174,9 @@ def stark_prove(components, channel, scheme: CommitmentSchemeProver) -> StarkPro
 # ---------------------------------------------------------------------------
 # LuminAIR prove()  (crates/prover/src/prover.rs:28-319)
 # ---------------------------------------------------------------------------
-SLOT_OF = {"add": 0, "mul": 1, "sum_reduce": 5, "max_reduce": 6, "inputs": 15, "contiguous": 16}
+SLOT_OF = {"add": 0, "mul": 1, "recip": 2, "sin": 3, "sin_lookup": 4, "sum_reduce": 5, "max_reduce": 6, "sqrt": 7, "rem": 8,
+           "exp2": 9, "exp2_lookup": 10, "log2": 11, "log2_lookup": 12, "less_than": 13, "range_check_lookup": 14,
+           "inputs": 15, "contiguous": 16}  # LuminairClaim field order, crates/air/src/lib.rs:30-48
 N_LANES = 16
 
 
@@ -190,14 +193,20 @@ def pad_table(rows: np.ndarray, padding_row) -> np.ndarray:
 
 
 def prove(pie, n_slots: int = 17, slot_evals=SLOT_EVALS, slot_of=SLOT_OF, channel_variant="legacy",
-          config: PcsConfig | None = None, draw_lookup_elements=True, return_debug=False):
+          config: PcsConfig | None = None, draw_lookup_elements=True, return_debug=False, preprocessed=()):
     """pie: list of (name, rows[n, n_cols] M31 values) in ``pie.trace_tables`` order.
-    No preprocessed (LUT) columns are supported by the oracle yet (tree 0 is empty)."""
+    preprocessed: [(id, values[2^k])] LUT columns in ``lookups_to_preprocessed_column`` order
+    (preprocessed.rs:181-206: sin 0/1, exp2 0/1, log2 0/1, range_check 0); they are generated by the caller
+    (host libm, preprocessed.rs:351-383) - the prover only commits to them."""
     config = config or PcsConfig()
     channel = Blake2sChannel(channel_variant)
     scheme = CommitmentSchemeProver(config)
-    # phase 0: preprocessed
+    # phase 0: preprocessed (prover.rs:52-59)
+    preprocessed = sort_preprocessed([(cid, np.asarray(v, dtype=U64)) for cid, v in preprocessed])
+    pre_vals = dict(preprocessed)
+    pre_meta = [(cid, len(v).bit_length() - 1) for cid, v in preprocessed]
     tb = scheme.tree_builder()
+    tb.extend_evals([v for _, v in preprocessed])
     tb.commit(channel)
     # phase 1: main trace
     tb = scheme.tree_builder()
@@ -218,8 +227,9 @@ def prove(pie, n_slots: int = 17, slot_evals=SLOT_EVALS, slot_of=SLOT_OF, channe
             channel.mix_u64(c)
     tb.commit(channel)
     # phase 2: interaction trace
+    lookups = None
     if draw_lookup_elements:
-        node, _ = draw_interaction_elements(channel)
+        node, lookups = draw_interaction_elements(channel)
     else:
         node = RelationElements.draw(channel, 2)
     tb = scheme.tree_builder()
@@ -227,16 +237,16 @@ def prove(pie, n_slots: int = 17, slot_evals=SLOT_EVALS, slot_of=SLOT_OF, channe
     for slot in range(n_slots):
         if claim[slot] is None:
             continue
-        cols, cs = gen_interaction_trace(slot_evals[slot], mains[slot], claim[slot], node)
+        cols, cs = gen_interaction_trace(slot_evals[slot], mains[slot], claim[slot], node, lookups, pre_vals)
         tb.extend_evals(cols)
         iclaim[slot] = cs
     for c in iclaim:
         if c is not None:
             channel.mix_felts([c])
     tb.commit(channel)
-    comps = luminair_components(claim, iclaim, node, slot_evals)
+    comps = luminair_components(claim, iclaim, node, slot_evals, pre_meta, lookups)
     proof = stark_prove(comps, channel, scheme)
     lp = LuminairProof(claim, iclaim, proof)
     if return_debug:
-        return lp, {"scheme": scheme, "channel": channel, "components": comps, "node": node}
+        return lp, {"scheme": scheme, "channel": channel, "components": comps, "node": node, "lookups": lookups}
     return lp

@@ -14,8 +14,19 @@ from .air import (
     PREPROCESSED_TRACE_IDX,
     AddEval,
     ContiguousEval,
+    Exp2Eval,
+    Exp2LookupEval,
     FrameworkComponent,
+    LessThanEval,
+    Log2Eval,
+    Log2LookupEval,
     MaxReduceEval,
+    RangeCheckLookupEval,
+    RecipEval,
+    RemEval,
+    SinEval,
+    SinLookupEval,
+    SqrtEval,
     SumReduceEval,
     InputsEval,
     MulEval,
@@ -145,17 +156,42 @@ def stark_verify(components, channel, scheme: CommitmentSchemeVerifier, proof: S
 # ---------------------------------------------------------------------------
 # component slot order: crates/air/src/lib.rs:30-48.  The UI artifact predates
 # the 17-slot schema and has 8 slots with add, mul first.
-SLOT_EVALS = {0: AddEval, 1: MulEval, 5: SumReduceEval, 6: MaxReduceEval, 15: InputsEval, 16: ContiguousEval}
+SLOT_EVALS = {0: AddEval, 1: MulEval, 2: RecipEval, 3: SinEval, 4: SinLookupEval, 5: SumReduceEval, 6: MaxReduceEval,
+              7: SqrtEval, 8: RemEval, 9: Exp2Eval, 10: Exp2LookupEval, 11: Log2Eval, 12: Log2LookupEval,
+              13: LessThanEval, 14: RangeCheckLookupEval, 15: InputsEval, 16: ContiguousEval}
 
 
-def luminair_components(claim, interaction_claim, node_elements, slot_evals=SLOT_EVALS, preprocessed_ids=()):
-    alloc = TraceLocationAllocator(preprocessed_ids)
+def lut_log_sizes(preprocessed):
+    """{lut name: log_size} from the preprocessed column list [(id, log_size)]
+    (``lookups.<lut>.layout.log_size``, crates/air/src/components/mod.rs:299,366,399,432)."""
+    out = {}
+    for cid, log in preprocessed:
+        for name in ("sin", "exp2", "log2", "range_check"):
+            if cid.startswith(name + "_"):
+                out[name] = log
+    return out
+
+
+def sort_preprocessed(columns):
+    """PreProcessedTrace::new (preprocessed.rs:152-155): stable sort by log_size, descending.
+    columns: [(id, log_size or values, ...)] with the log size derivable from item[1]."""
+    def log_of(item):
+        v = item[1]
+        return v if isinstance(v, int) else (len(v).bit_length() - 1)
+    return sorted(columns, key=lambda it: -log_of(it))
+
+
+def luminair_components(claim, interaction_claim, node_elements, slot_evals=SLOT_EVALS, preprocessed=(), lookups=None):
+    """LuminairComponents::new (crates/air/src/components/mod.rs:261-527).  preprocessed: [(id, log_size)] in
+    committed (sorted) order."""
+    alloc = TraceLocationAllocator([cid for cid, _ in preprocessed])
+    lut_logs = lut_log_sizes(preprocessed)
     comps = []
     for slot, log_size in enumerate(claim):
         if log_size is None:
             continue
         cls = slot_evals[slot]
-        comps.append(FrameworkComponent(alloc, cls(log_size, node_elements), interaction_claim[slot]))
+        comps.append(FrameworkComponent(alloc, cls(log_size, node_elements, lookups, lut_logs), interaction_claim[slot]))
     return comps
 
 
@@ -182,14 +218,16 @@ def draw_interaction_elements(channel):
 
 
 def verify(proof: LuminairProof, channel_variant="legacy", slot_evals=SLOT_EVALS, draw_lookup_elements=True,
-           preprocessed_log_sizes=(), config=None, _skip_oods=False):
-    """crates/verifiers/rust/src/verifier.rs:21-143.  Returns the channel (for transcript tests)."""
+           preprocessed=(), config=None, _skip_oods=False):
+    """crates/verifiers/rust/src/verifier.rs:21-143.  Returns the channel (for transcript tests).
+    preprocessed: [(id, log_size)] of the LUT columns named by the circuit settings (any order)."""
     sp = proof.proof
     config = config or sp.config
     channel = Blake2sChannel(channel_variant)
     scheme = CommitmentSchemeVerifier(config)
     # preprocessed
-    scheme.commit(sp.commitments[PREPROCESSED_TRACE_IDX], list(preprocessed_log_sizes), channel)
+    preprocessed = sort_preprocessed(list(preprocessed))
+    scheme.commit(sp.commitments[PREPROCESSED_TRACE_IDX], [log for _, log in preprocessed], channel)
     # main: claim.mix_into then commit
     main_sizes, int_sizes = [], []
     for slot, log_size in enumerate(proof.claim):
@@ -200,8 +238,9 @@ def verify(proof: LuminairProof, channel_variant="legacy", slot_evals=SLOT_EVALS
         main_sizes += [log_size] * cls.n_main
         int_sizes += [log_size] * (4 * cls.n_interaction)
     scheme.commit(sp.commitments[ORIGINAL_TRACE_IDX], main_sizes, channel)
+    lookups = None
     if draw_lookup_elements:
-        node, _ = draw_interaction_elements(channel)
+        node, lookups = draw_interaction_elements(channel)
     else:
         node = RelationElements.draw(channel, 2)
     if not log_sum_valid(proof.interaction_claim):
@@ -210,6 +249,6 @@ def verify(proof: LuminairProof, channel_variant="legacy", slot_evals=SLOT_EVALS
         if c is not None:
             channel.mix_felts([c])
     scheme.commit(sp.commitments[INTERACTION_TRACE_IDX], int_sizes, channel)
-    comps = luminair_components(proof.claim, proof.interaction_claim, node, slot_evals)
+    comps = luminair_components(proof.claim, proof.interaction_claim, node, slot_evals, preprocessed, lookups)
     stark_verify(comps, channel, scheme, sp, _skip_oods)
     return channel

@@ -355,3 +355,15 @@ def test_fused_scatter_commit_single_gpu(be):
     tr = be.upload(vals.astype(np.uint32).reshape(-1))
     assert fc.commit(tr.ptr) == want
     fc.close()
+
+
+@pytest.mark.parametrize("pow_bits,last_bound,n_queries", [(0, 0, 1), (9, 3, 11), (12, 2, 40)])
+def test_non_default_pcs_config(be, pow_bits, last_bound, n_queries):
+    """PcsConfig other than the default: more queries (duplicates collapse), a longer FRI last layer, harder grind."""
+    from luminair_b200.prover import PcsConfig, prove
+    from oracle.proof import PcsConfig as OPcs
+    pie = examples.graph_pie(7, seed=31)
+    lp, digests = _oracle_transcript(lambda: oprover.prove(pie, config=OPcs(pow_bits, 1, last_bound, n_queries)))
+    got = prove(pie, backend=be, config=PcsConfig(pow_bits, 1, last_bound, n_queries))
+    _assert_same_proof(be, got, to_bincode(lp), digests)
+    overifier.verify(from_bincode(got))
