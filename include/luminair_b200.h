@@ -132,11 +132,37 @@ int lb_grind(lb_ctx* ctx, const uint32_t digest[8], int channel_variant, uint32_
 #define LB_COMP_MAX_REDUCE 5   /* components/max_reduce */
 #define LB_COMP_CONTIGUOUS 6   /* components/contiguous */
 #define LB_COMP_MUL_ARTIFACT 3 /* Mul AIR of the revision that produced ui/demo/public/proof (KAT only) */
+#define LB_COMP_RECIP 7        /* components/recip   (component.rs:39-107) */
+#define LB_COMP_SQRT 8         /* components/sqrt    */
+#define LB_COMP_REM 9          /* components/rem     */
+#define LB_COMP_SIN 10         /* components/sin     (component.rs:51-123; third relation use = the sin LUT) */
+#define LB_COMP_EXP2 11        /* components/exp2    */
+#define LB_COMP_LOG2 12        /* components/log2    */
+#define LB_COMP_SIN_LOOKUP 13  /* components/lookups/sin  (component.rs:41-59: -multiplicity per table row) */
+#define LB_COMP_EXP2_LOOKUP 14 /* components/lookups/exp2 */
+#define LB_COMP_LOG2_LOOKUP 15 /* components/lookups/log2 */
+#define LB_COMP_LESS_THAN 16   /* components/less_than (component.rs:49-184: 4 limbs range-checked) */
+#define LB_COMP_RANGE_CHECK_LOOKUP 17 /* components/lookups/range_check */
+/* LuminairInteractionElements (components/mod.rs:220-236, lookups/mod.rs:31-51), in draw order */
+#define LB_REL_NODE 0
+#define LB_REL_SIN 1
+#define LB_REL_EXP2 2
+#define LB_REL_LOG2 3
+#define LB_REL_RANGE_CHECK 4
+#define LB_REL_COUNT 5
+typedef struct {
+    uint32_t z[4], alpha[4]; /* relation!(X, N): combine(v) = sum_i alpha^i v_i - z */
+} lb_relation;
 /* InteractionClaimGenerator::write_interaction_trace: LogUp columns from the main trace (values, not
  * coefficients).  d_inter receives 4*k columns of 2^log_size; claimed_out = claimed sum (4 u32, HOST). */
 int lb_logup_interaction_trace(lb_ctx* ctx, int component, const uint32_t* d_main, size_t main_stride, uint32_t* d_inter,
                                size_t inter_stride, int log_size, const uint32_t z[4], const uint32_t alpha[4],
                                uint32_t claimed_out[4]);
+/* the same for every component: rels = all LB_REL_COUNT relations; d_lut = the preprocessed LUT column values
+ * (2^log_size each) a lookup-table component tabulates (lookups/exp2/witness.rs:117-144), NULL otherwise */
+int lb_logup_interaction_trace_lut(lb_ctx* ctx, int component, const uint32_t* d_main, size_t main_stride,
+                                   const uint32_t* const d_lut[2], uint32_t* d_inter, size_t inter_stride, int log_size,
+                                   const lb_relation rels[LB_REL_COUNT], uint32_t claimed_out[4]);
 /* ComponentProver::evaluate_constraint_quotients_on_domain for FrameworkComponent<XEval>
  * (crates/air/src/components/mod.rs:530-601): d_main / d_inter are the LDE columns on CanonicCoset(log_size+1);
  * pows = this component's random-coefficient powers, first constraint first (4 u32 each);
@@ -146,11 +172,21 @@ int lb_constraint_quotients(lb_ctx* ctx, int component, const uint32_t* d_main, 
                             const uint32_t claimed_sum[4], const uint32_t* pows, int n_pows, uint32_t* const d_acc[4],
                             int accumulate);
 
+/* the same for every component, on the evaluation domain CanonicCoset(eval_log_size) =
+ * max_constraint_log_degree_bound (LUT consumers: max(log_size, lut_log_size) + 1, exp2/component.rs:41-43): every
+ * column (d_main, d_inter, d_lut) holds 2^eval_log_size values; d_lut = the LUT columns a lookup-table component reads */
+int lb_constraint_quotients_lut(lb_ctx* ctx, int component, const uint32_t* d_main, size_t main_stride, const uint32_t* d_inter,
+                                size_t inter_stride, const uint32_t* const d_lut[2], int log_size, int eval_log_size,
+                                const lb_relation rels[LB_REL_COUNT], const uint32_t claimed_sum[4], const uint32_t* pows,
+                                int n_pows, uint32_t* const d_acc[4], int accumulate);
+
 /* ---- luminair_prover::prover::prove (crates/prover/src/prover.rs:28-319) ---------------------------- */
 /* one `TraceTable` of the LuminairPie (crates/air/src/pie.rs:143-148): row-major rows of the component's
  * main-trace columns, canonical M31 values */
 typedef struct {
-    int slot;             /* field index in LuminairClaim (crates/air/src/lib.rs:30-48): add 0, mul 1, sum_reduce 5, max_reduce 6, inputs 15, contiguous 16 */
+    int slot;             /* field index in LuminairClaim (crates/air/src/lib.rs:30-48): add 0, mul 1, recip 2, sin 3, sin_lookup 4,
+                             sum_reduce 5, max_reduce 6, sqrt 7, rem 8, exp2 9, exp2_lookup 10, log2 11, log2_lookup 12,
+                             less_than 13, range_check_lookup 14, inputs 15, contiguous 16 */
     int n_cols;
     uint64_t n_rows;      /* unpadded */
     const uint32_t* rows; /* n_rows x n_cols, HOST (or DEVICE when rows_on_device != 0) */
@@ -165,11 +201,25 @@ typedef struct {
                             (8 claim slots, Mul AIR with one extra, identically-zero constraint) - known-answer test only */
     int draw_lookup_elements; /* 1: LuminairInteractionElements::draw also draws the 4 LUT relations (components/mod.rs:227-235) */
 } lb_prove_config;
+/* one preprocessed (LUT) column of `lookups_to_preprocessed_column(&settings.lookups)`
+ * (crates/air/src/preprocessed.rs:181-206), in that order: sin 0/1, exp2 0/1, log2 0/1, range_check 0.  The values
+ * (2^log_size canonical M31, storage order) are generated by the caller exactly as the reference does on the host
+ * (preprocessed.rs:233-248, 351-383); lb_prove_with_lookups sorts the columns as PreProcessedTrace::new does. */
+typedef struct {
+    int lut;                /* LB_REL_SIN .. LB_REL_RANGE_CHECK */
+    int col_index;          /* 0: input values, 1: function values */
+    int log_size;
+    const uint32_t* values; /* HOST (or DEVICE when on_device != 0) */
+    int on_device;
+} lb_preprocessed_column;
 /* Tables in pie order.  On success *proof_out is a malloc'd bincode `LuminairProof` (free with lb_free_host).
  * cfg == NULL: the reference's defaults.  Errors: LB_ERR_BAD_ARG ("TraceError::EmptyTrace", unsupported
  * component), LB_ERR_CONSTRAINTS (ProvingError::ConstraintsNotSatisfied). */
 int lb_prove(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_prove_config* cfg, uint8_t** proof_out,
              size_t* proof_len);
+/* prove() for graphs with lookup tables: the preprocessed trace (prover.rs:52-59) holds `lut_columns` */
+int lb_prove_with_lookups(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_preprocessed_column* lut_columns,
+                          int n_lut_columns, const lb_prove_config* cfg, uint8_t** proof_out, size_t* proof_len);
 void lb_free_host(void* p);
 /* diagnostics of the last lb_prove: channel digest after every mix (32 B each) and per-stage wall-clock ms */
 int lb_prove_transcript(lb_ctx* ctx, uint8_t* out, size_t cap_hashes, size_t* n_hashes);

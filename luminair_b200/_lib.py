@@ -58,6 +58,17 @@ class ProveConfig(C.Structure):
                 ("draw_lookup_elements", C.c_int)]
 
 
+class PreprocessedColumn(C.Structure):
+    """lb_preprocessed_column"""
+    _fields_ = [("lut", C.c_int), ("col_index", C.c_int), ("log_size", C.c_int), ("values", C.c_void_p),
+                ("on_device", C.c_int)]
+
+
+class Relation(C.Structure):
+    """lb_relation"""
+    _fields_ = [("z", C.c_uint32 * 4), ("alpha", C.c_uint32 * 4)]
+
+
 class SampleBatch(C.Structure):
     """lb_sample_batch"""
     _fields_ = [("point", C.c_uint32 * 8), ("n_cols", C.c_int), ("col_idx", C.POINTER(C.c_int)),
@@ -75,6 +86,13 @@ SIGNATURES.update({
                                              u32p, u32p]),
     "lb_constraint_quotients": (C.c_int, [ctxp, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, u32p, u32p,
                                           u32p, u32p, C.c_int, C.POINTER(C.c_void_p), C.c_int]),
+    "lb_logup_interaction_trace_lut": (C.c_int, [ctxp, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p,
+                                                 C.c_size_t, C.c_int, C.POINTER(Relation), u32p]),
+    "lb_constraint_quotients_lut": (C.c_int, [ctxp, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                              C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(Relation), u32p, u32p, C.c_int,
+                                              C.POINTER(C.c_void_p), C.c_int]),
+    "lb_prove_with_lookups": (C.c_int, [ctxp, C.POINTER(TraceTable), C.c_int, C.POINTER(PreprocessedColumn), C.c_int,
+                                        C.POINTER(ProveConfig), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "lb_evaluate_batch_scatter": (C.c_int, [ctxp, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                             C.POINTER(C.c_void_p), C.c_int, C.c_size_t]),
     "lb_ipc_export": (C.c_int, [ctxp, C.c_void_p, C.c_char_p]),

@@ -223,6 +223,39 @@ class CudaBackend:
               "lb_logup_interaction_trace")
         return np.array(list(claimed), dtype=np.uint32)
 
+    @staticmethod
+    def _relations(rels):
+        """rels: 5 (z, alpha) pairs of 4 u32 in LB_REL_* order -> lb_relation[5]"""
+        from ._lib import Relation
+        arr = (Relation * 5)()
+        for k, (z, alpha) in enumerate(rels):
+            arr[k].z = (C.c_uint32 * 4)(*[int(v) for v in z])
+            arr[k].alpha = (C.c_uint32 * 4)(*[int(v) for v in alpha])
+        return arr
+
+    def logup_interaction_trace_lut(self, component: int, main: ColumnBatch, inter: ColumnBatch, rels, lut_ptrs=()) -> np.ndarray:
+        """Any component: rels = all 5 relations; lut_ptrs = device pointers of the LUT columns a table component reads."""
+        claimed = (C.c_uint32 * 4)()
+        lut = (C.c_void_p * 2)(*(list(lut_ptrs) + [None] * (2 - len(lut_ptrs))))
+        check(self.ctx, self.lib.lb_logup_interaction_trace_lut(self.ctx, component, C.c_void_p(main.ptr), main.stride, lut,
+                                                                 C.c_void_p(inter.ptr), inter.stride, main.log_size,
+                                                                 self._relations(rels), claimed),
+              "lb_logup_interaction_trace_lut")
+        return np.array(list(claimed), dtype=np.uint32)
+
+    def constraint_quotients_lut(self, component: int, main_ev: ColumnBatch, inter_ev: ColumnBatch, log_size: int, eval_log: int,
+                                 rels, claimed_sum, pows, acc_ptrs, lut_ptrs=(), accumulate: bool = False):
+        cs = (C.c_uint32 * 4)(*[int(v) for v in claimed_sum])
+        flat = [int(x) for p in pows for x in p]
+        pw = (C.c_uint32 * len(flat))(*flat)
+        acc = (C.c_void_p * 4)(*acc_ptrs)
+        lut = (C.c_void_p * 2)(*(list(lut_ptrs) + [None] * (2 - len(lut_ptrs))))
+        check(self.ctx, self.lib.lb_constraint_quotients_lut(self.ctx, component, C.c_void_p(main_ev.ptr), main_ev.stride,
+                                                              C.c_void_p(inter_ev.ptr), inter_ev.stride, lut, log_size, eval_log,
+                                                              self._relations(rels), cs, pw, len(pows), acc,
+                                                              1 if accumulate else 0),
+              "lb_constraint_quotients_lut")
+
     def constraint_quotients(self, component: int, main_lde: ColumnBatch, inter_lde: ColumnBatch, log_size: int, z, alpha,
                              claimed_sum, pows, acc_ptrs, accumulate: bool = False):
         zz = (C.c_uint32 * 4)(*[int(v) for v in z])

@@ -19,9 +19,9 @@ namespace lb {
 // denom = alpha * id + val - z.  The n_fracs inversions of a row share one QM31 inversion.
 // ------------------------------------------------------------------------------------
 template <int KIND>
-__global__ void __launch_bounds__(256) logup_fracs_kernel(const uint32_t* __restrict__ main, size_t main_stride,
+__global__ void __launch_bounds__(256) logup_fracs_kernel(const uint32_t* __restrict__ main, size_t main_stride, const PreCols pre_cols,
                                                           uint32_t* __restrict__ inter, size_t inter_stride, uint32_t n,
-                                                          Relation2 node) {
+                                                          const __grid_constant__ Relations rels) {
     constexpr int NF = component_shape(KIND).n_fracs;
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
@@ -31,12 +31,19 @@ __global__ void __launch_bounds__(256) logup_fracs_kernel(const uint32_t* __rest
 #pragma unroll
     for (int k = 0; k < NF; ++k) {
         const LookupTerm t = lookup_term(KIND, k);
-        uint32_t val = main[(size_t)t.val * main_stride + j];
-        uint32_t id = main[(size_t)t.id * main_stride + j];
-        mult[k] = main[(size_t)t.mult * main_stride + j];
-        QM31 d = q_mul_m(node.alpha, id);
-        d.a.a = m_add(d.a.a, val);
-        d = q_sub(d, node.z);
+        const Relation2& rel = rels.r[t.rel];
+        uint32_t v0 = t.pre ? pre_cols.p[t.v0][j] : main[(size_t)t.v0 * main_stride + j];
+        uint32_t m = main[(size_t)t.mult * main_stride + j];
+        mult[k] = t.neg ? m_neg(m) : m;
+        QM31 d;
+        if (t.v1 >= 0) {
+            uint32_t v1 = t.pre ? pre_cols.p[t.v1][j] : main[(size_t)t.v1 * main_stride + j];
+            d = q_mul_m(rel.alpha, v1);
+            d.a.a = m_add(d.a.a, v0);
+        } else {
+            d = q_from_m(v0);
+        }
+        d = q_sub(d, rel.z);
         den[k] = d;
         pre[k] = run;
         run = q_mul(run, d);
@@ -136,22 +143,35 @@ __global__ void __launch_bounds__(256) logup_scan_apply_kernel(uint32_t* __restr
     col[(size_t)coord * coord_stride + coset_to_storage(k, log)] = v;
 }
 
-cudaError_t logup_interaction_trace(int kind, const uint32_t* main, size_t main_stride, uint32_t* inter,
-                                    size_t inter_stride, int log, const Relation2& node, uint32_t* d_scan_tmp,
+namespace {
+struct LogupLaunch {
+    const uint32_t* main;
+    size_t main_stride;
+    PreCols pre;
+    uint32_t* inter;
+    size_t inter_stride;
+    uint32_t n;
+    const Relations& rels;
+    cudaStream_t stream;
+    template <int KIND>
+    void operator()() {
+        // the artifact-era Mul shares the LogUp terms of Mul
+        constexpr int K = KIND == COMP_MUL_ARTIFACT ? COMP_MUL : KIND;
+        logup_fracs_kernel<K><<<(n + 255) / 256, 256, 0, stream>>>(main, main_stride, pre, inter, inter_stride, n, rels);
+    }
+};
+}  // namespace
+
+cudaError_t logup_interaction_trace(int kind, const uint32_t* main, size_t main_stride, PreCols pre, uint32_t* inter,
+                                    size_t inter_stride, int log, const Relations& rels, uint32_t* d_scan_tmp,
                                     uint32_t* d_block_sums, uint32_t* d_claimed, cudaStream_t stream) {
     uint32_t n = 1u << log;
     unsigned blocks = (n + 255) / 256;
+    if (kind < 0 || kind >= COMP_KIND_COUNT) return cudaErrorInvalidValue;
     int nf = component_shape(kind).n_fracs;
-    switch (kind) {
-        case COMP_ADD: logup_fracs_kernel<COMP_ADD><<<blocks, 256, 0, stream>>>(main, main_stride, inter, inter_stride, n, node); break;
-        case COMP_MUL:
-        case COMP_MUL_ARTIFACT: logup_fracs_kernel<COMP_MUL><<<blocks, 256, 0, stream>>>(main, main_stride, inter, inter_stride, n, node); break;
-        case COMP_INPUTS: logup_fracs_kernel<COMP_INPUTS><<<blocks, 256, 0, stream>>>(main, main_stride, inter, inter_stride, n, node); break;
-        case COMP_SUM_REDUCE: logup_fracs_kernel<COMP_SUM_REDUCE><<<blocks, 256, 0, stream>>>(main, main_stride, inter, inter_stride, n, node); break;
-        case COMP_MAX_REDUCE: logup_fracs_kernel<COMP_MAX_REDUCE><<<blocks, 256, 0, stream>>>(main, main_stride, inter, inter_stride, n, node); break;
-        case COMP_CONTIGUOUS: logup_fracs_kernel<COMP_CONTIGUOUS><<<blocks, 256, 0, stream>>>(main, main_stride, inter, inter_stride, n, node); break;
-        default: return cudaErrorInvalidValue;
-    }
+    if (component_shape(kind).n_pre > 0 && !pre.p[0]) return cudaErrorInvalidValue;
+    LogupLaunch launch{main, main_stride, pre, inter, inter_stride, n, rels, stream};
+    if (!dispatch_kind(kind, launch)) return cudaErrorInvalidValue;
     uint32_t* last = inter + (size_t)(4 * (nf - 1)) * inter_stride;
     uint32_t n_blocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
     logup_scan_local_kernel<<<dim3(n_blocks, 4), 256, 0, stream>>>(last, inter_stride, d_scan_tmp, d_block_sums, log);
@@ -178,6 +198,7 @@ struct DomainEval : LogupMixin<DomainEval, FM, FQ> {
         : p(p_), row(row_), row_prev(row_prev_), res(q_zero()), cumsum_shift(p_.cumsum_shift) {}
 
     __device__ __forceinline__ FM constant(uint32_t c) const { return {c}; }
+    __device__ __forceinline__ FM get_preprocessed_column(int k) const { return {p.pre.p[k][row]}; }
     __device__ __forceinline__ FM next_trace_mask() {
         FM v = {p.main[(size_t)mc * p.main_stride + row]};
         ++mc;
@@ -226,7 +247,7 @@ __global__ void __launch_bounds__(256) constraint_quotients_kernel(const __grid_
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     DomainEval ev(p, j, prev_row_index(j, p.log_size, p.eval_log));
-    eval_kind<KIND>(ev, p.node);
+    eval_kind<KIND>(ev, p.rels);
     QM31 r = q_mul_m(ev.res, p.denom_inv[j >> p.log_size]);
     if (p.accumulate) r = q_add(r, q_make(p.acc[0][j], p.acc[1][j], p.acc[2][j], p.acc[3][j]));
     p.acc[0][j] = r.a.a;
@@ -235,20 +256,24 @@ __global__ void __launch_bounds__(256) constraint_quotients_kernel(const __grid_
     p.acc[3][j] = r.b.b;
 }
 
-cudaError_t constraint_quotients(int kind, const ConstraintParams& p, cudaStream_t stream) {
-    if (p.eval_log - p.log_size < 1 || p.eval_log - p.log_size > 2) return cudaErrorInvalidValue;
-    uint32_t n = 1u << p.eval_log;
-    unsigned blocks = (n + 255) / 256;
-    switch (kind) {
-        case COMP_ADD: constraint_quotients_kernel<COMP_ADD><<<blocks, 256, 0, stream>>>(p); break;
-        case COMP_MUL: constraint_quotients_kernel<COMP_MUL><<<blocks, 256, 0, stream>>>(p); break;
-        case COMP_MUL_ARTIFACT: constraint_quotients_kernel<COMP_MUL_ARTIFACT><<<blocks, 256, 0, stream>>>(p); break;
-        case COMP_INPUTS: constraint_quotients_kernel<COMP_INPUTS><<<blocks, 256, 0, stream>>>(p); break;
-        case COMP_SUM_REDUCE: constraint_quotients_kernel<COMP_SUM_REDUCE><<<blocks, 256, 0, stream>>>(p); break;
-        case COMP_MAX_REDUCE: constraint_quotients_kernel<COMP_MAX_REDUCE><<<blocks, 256, 0, stream>>>(p); break;
-        case COMP_CONTIGUOUS: constraint_quotients_kernel<COMP_CONTIGUOUS><<<blocks, 256, 0, stream>>>(p); break;
-        default: return cudaErrorInvalidValue;
+namespace {
+struct ConstraintLaunch {
+    const ConstraintParams& p;
+    cudaStream_t stream;
+    template <int KIND>
+    void operator()() {
+        uint32_t n = 1u << p.eval_log;
+        constraint_quotients_kernel<KIND><<<(n + 255) / 256, 256, 0, stream>>>(p);
     }
+};
+}  // namespace
+
+cudaError_t constraint_quotients(int kind, const ConstraintParams& p, cudaStream_t stream) {
+    if (p.eval_log - p.log_size < 1 || p.eval_log > 30 || !p.denom_inv) return cudaErrorInvalidValue;
+    if (kind < 0 || kind >= COMP_KIND_COUNT) return cudaErrorInvalidValue;
+    if (component_shape(kind).n_pre > 0 && !p.pre.p[0]) return cudaErrorInvalidValue;
+    ConstraintLaunch launch{p, stream};
+    if (!dispatch_kind(kind, launch)) return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 

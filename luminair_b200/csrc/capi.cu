@@ -272,7 +272,19 @@ int lb_logup_interaction_trace(lb_ctx* ctx, int component, const uint32_t* d_mai
                                uint32_t claimed_out[4]) {
     if (!ctx || !d_main || !d_inter || !z || !alpha || !claimed_out || log_size < 1 || log_size > 30)
         return fail(ctx, LB_ERR_BAD_ARG, "logup: bad args");
-    return lb::logup_impl(ctx, component, d_main, main_stride, d_inter, inter_stride, log_size, z, alpha, claimed_out);
+    lb_relation node;
+    std::memcpy(node.z, z, 16);
+    std::memcpy(node.alpha, alpha, 16);
+    return lb::logup_impl(ctx, component, d_main, main_stride, nullptr, d_inter, inter_stride, log_size, &node, 1, claimed_out);
+}
+
+int lb_logup_interaction_trace_lut(lb_ctx* ctx, int component, const uint32_t* d_main, size_t main_stride,
+                                   const uint32_t* const d_lut[2], uint32_t* d_inter, size_t inter_stride, int log_size,
+                                   const lb_relation rels[LB_REL_COUNT], uint32_t claimed_out[4]) {
+    if (!ctx || !d_main || !d_inter || !rels || !claimed_out || log_size < 1 || log_size > 30)
+        return fail(ctx, LB_ERR_BAD_ARG, "logup: bad args");
+    return lb::logup_impl(ctx, component, d_main, main_stride, d_lut, d_inter, inter_stride, log_size, rels, LB_REL_COUNT,
+                          claimed_out);
 }
 
 int lb_constraint_quotients(lb_ctx* ctx, int component, const uint32_t* d_main, size_t main_stride, const uint32_t* d_inter,
@@ -281,8 +293,21 @@ int lb_constraint_quotients(lb_ctx* ctx, int component, const uint32_t* d_main, 
                             int accumulate) {
     if (!ctx || !d_main || !d_inter || !z || !alpha || !claimed_sum || !pows || !d_acc || log_size < 1 || log_size > 29)
         return fail(ctx, LB_ERR_BAD_ARG, "constraint_quotients: bad args");
-    return lb::constraint_quotients_impl(ctx, component, d_main, main_stride, d_inter, inter_stride, log_size, z, alpha,
-                                         claimed_sum, pows, n_pows, d_acc, accumulate);
+    lb_relation node;
+    std::memcpy(node.z, z, 16);
+    std::memcpy(node.alpha, alpha, 16);
+    return lb::constraint_quotients_impl(ctx, component, d_main, main_stride, d_inter, inter_stride, nullptr, log_size,
+                                         log_size + 1, &node, 1, claimed_sum, pows, n_pows, d_acc, accumulate);
+}
+
+int lb_constraint_quotients_lut(lb_ctx* ctx, int component, const uint32_t* d_main, size_t main_stride, const uint32_t* d_inter,
+                                size_t inter_stride, const uint32_t* const d_lut[2], int log_size, int eval_log_size,
+                                const lb_relation rels[LB_REL_COUNT], const uint32_t claimed_sum[4], const uint32_t* pows,
+                                int n_pows, uint32_t* const d_acc[4], int accumulate) {
+    if (!ctx || !d_main || !d_inter || !rels || !claimed_sum || !pows || !d_acc || log_size < 1 || log_size > 29)
+        return fail(ctx, LB_ERR_BAD_ARG, "constraint_quotients: bad args");
+    return lb::constraint_quotients_impl(ctx, component, d_main, main_stride, d_inter, inter_stride, d_lut, log_size,
+                                         eval_log_size, rels, LB_REL_COUNT, claimed_sum, pows, n_pows, d_acc, accumulate);
 }
 
 int lb_evaluate_batch_scatter(lb_ctx* ctx, const uint32_t* d_coeffs, size_t src_stride, int log_in, uint32_t* d_scratch,
@@ -397,13 +422,13 @@ int lb_lde_host(lb_ctx* ctx, const uint32_t* h_values, uint32_t* h_evals, int n_
     return LB_OK;
 }
 
-int lb_prove(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_prove_config* cfg, uint8_t** proof_out,
-             size_t* proof_len) {
+int lb_prove_with_lookups(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_preprocessed_column* lut_columns,
+                          int n_lut_columns, const lb_prove_config* cfg, uint8_t** proof_out, size_t* proof_len) {
     if (!ctx || !proof_out || !proof_len) return fail(ctx, LB_ERR_BAD_ARG, "prove: bad args");
     *proof_out = nullptr;
     *proof_len = 0;
     std::vector<uint8_t> bytes;
-    int r = lb::prove_impl(ctx, tables, n_tables, cfg, bytes);
+    int r = lb::prove_impl(ctx, tables, n_tables, lut_columns, n_lut_columns, cfg, bytes);
     if (r) return r;
     uint8_t* p = (uint8_t*)std::malloc(bytes.size() ? bytes.size() : 1);
     if (!p) return fail(ctx, LB_ERR_OOM, "prove: host malloc");
@@ -411,6 +436,11 @@ int lb_prove(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_p
     *proof_out = p;
     *proof_len = bytes.size();
     return LB_OK;
+}
+
+int lb_prove(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_prove_config* cfg, uint8_t** proof_out,
+             size_t* proof_len) {
+    return lb_prove_with_lookups(ctx, tables, n_tables, nullptr, 0, cfg, proof_out, proof_len);
 }
 
 void lb_free_host(void* p) { std::free(p); }

@@ -42,8 +42,8 @@ inline int ctx_fail(lb_ctx* ctx, int code, const char* what, cudaError_t e = cud
     return code;
 }
 // the prover proper (prover.cu)
-int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_prove_config* cfg,
-               std::vector<uint8_t>& out);
+int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_preprocessed_column* pre, int n_pre,
+               const lb_prove_config* cfg, std::vector<uint8_t>& out);
 int eval_at_point_impl(lb_ctx* ctx, const uint32_t* const* h_cols, int n_cols, int log, const uint32_t point[8],
                        uint32_t* h_out);
 int accumulate_quotients_impl(lb_ctx* ctx, int log, const uint32_t* const* h_cols, int n_cols,
@@ -52,10 +52,10 @@ int accumulate_quotients_impl(lb_ctx* ctx, int log, const uint32_t* const* h_col
 int fold_impl(lb_ctx* ctx, int circle, uint32_t* const d_dst[4], const uint32_t* const d_src[4], int log,
               const uint32_t alpha[4]);
 int grind_impl(lb_ctx* ctx, const uint32_t digest[8], int variant, uint32_t pow_bits, uint64_t* nonce_out);
-int logup_impl(lb_ctx* ctx, int kind, const uint32_t* d_main, size_t main_stride, uint32_t* d_inter, size_t inter_stride,
-               int log, const uint32_t z[4], const uint32_t alpha[4], uint32_t claimed_out[4]);
+int logup_impl(lb_ctx* ctx, int kind, const uint32_t* d_main, size_t main_stride, const uint32_t* const d_lut[2],
+               uint32_t* d_inter, size_t inter_stride, int log, const lb_relation* rels, int n_rels, uint32_t claimed_out[4]);
 int constraint_quotients_impl(lb_ctx* ctx, int kind, const uint32_t* d_main, size_t main_stride, const uint32_t* d_inter,
-                              size_t inter_stride, int log_size, const uint32_t z[4], const uint32_t alpha[4],
-                              const uint32_t claimed_sum[4], const uint32_t* pows, int n_pows, uint32_t* const d_acc[4],
-                              int accumulate);
+                              size_t inter_stride, const uint32_t* const d_lut[2], int log_size, int eval_log,
+                              const lb_relation* rels, int n_rels, const uint32_t claimed_sum[4], const uint32_t* pows,
+                              int n_pows, uint32_t* const d_acc[4], int accumulate);
 }  // namespace lb

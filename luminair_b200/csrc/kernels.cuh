@@ -51,30 +51,35 @@ cudaError_t grind_range(const uint32_t digest[8], int variant, uint32_t pow_bits
 // ---- small column utilities -----------------------------------------------------------------------
 cudaError_t add_inplace(uint32_t* dst, const uint32_t* src, size_t n, cudaStream_t stream);  // dst += src (M31)
 cudaError_t gather_words(uint32_t* d_out, const uint32_t* const* d_addrs, int n, cudaStream_t stream);
-// rows (row-major n_rows x n_cols) -> n_cols columns of 2^log at `stride`, padded with the row
-// (0,..,1 at pad_one_col,..,0) (write_trace, e.g. add/witness.rs:43-46)
+// rows (row-major n_rows x n_cols) -> n_cols columns of 2^log at `stride`, padded with the component's
+// `padding()` row (write_trace, e.g. add/witness.rs:43-46; air.cuh padding_value)
 cudaError_t transpose_pad(uint32_t* d_cols, size_t stride, const uint32_t* d_rows, uint64_t n_rows, int n_cols, int log,
-                          int pad_one_col, cudaStream_t stream);
+                          int kind, cudaStream_t stream);
 
 // ---- AIR: LogUp interaction trace + constraint quotients -----------------------------------------
-// main: component's n_main trace columns (2^log at main_stride) ; inter: 4*n_fracs columns out.
+// main: component's n_main trace columns (2^log at main_stride) ; pre: the preprocessed LUT columns (values on
+// CanonicCoset(log)) a lookup-table component tabulates, else unused ; inter: 4*n_fracs columns out.
 // d_scan_tmp: 4 * 2^log u32 ; d_block_sums: 4 * (2^log / 1024 + 1) u32 ; d_claimed: 4 u32 out.
-cudaError_t logup_interaction_trace(int kind, const uint32_t* main, size_t main_stride, uint32_t* inter,
-                                    size_t inter_stride, int log, const Relation2& node, uint32_t* d_scan_tmp,
+struct PreCols {
+    const uint32_t* p[2];
+};
+cudaError_t logup_interaction_trace(int kind, const uint32_t* main, size_t main_stride, PreCols pre, uint32_t* inter,
+                                    size_t inter_stride, int log, const Relations& rels, uint32_t* d_scan_tmp,
                                     uint32_t* d_block_sums, uint32_t* d_claimed, cudaStream_t stream);
 
 struct ConstraintParams {
     const uint32_t* main;
-    size_t main_stride;  // LDE columns on CanonicCoset(eval_log)
+    size_t main_stride;  // columns evaluated on CanonicCoset(eval_log)
     const uint32_t* inter;
     size_t inter_stride;
+    PreCols pre;         // preprocessed columns on CanonicCoset(eval_log) (lookup-table components)
     uint32_t* acc[4];
     int accumulate;  // 0: store, 1: add to acc
     int log_size, eval_log;
-    Relation2 node;
+    Relations rels;
     QM31 cumsum_shift;
-    QM31 pows[16];          // this component's random-coefficient powers, first constraint first
-    uint32_t denom_inv[4];  // 1 / Z_H at eval_domain.at(bitrev(i)), i < 2^(eval_log - log_size)
+    QM31 pows[MAX_CONSTRAINTS];  // this component's random-coefficient powers, first constraint first
+    const uint32_t* denom_inv;   // DEVICE: 1 / Z_H at eval_domain.at(bitrev(i)), i < 2^(eval_log - log_size)
 };
 cudaError_t constraint_quotients(int kind, const ConstraintParams& p, cudaStream_t stream);
 

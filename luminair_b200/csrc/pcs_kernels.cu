@@ -380,8 +380,11 @@ cudaError_t gather_words(uint32_t* d_out, const uint32_t* const* d_addrs, int n,
 
 // 32 x 32 tile transpose through shared memory: coalesced reads of the row-major table and
 // coalesced writes of the columns.
+struct PadRow {
+    uint32_t v[MAX_MAIN_COLS];
+};
 __global__ void transpose_pad_kernel(uint32_t* __restrict__ cols, size_t stride, const uint32_t* __restrict__ rows,
-                                     uint64_t n_rows, int n_cols, uint64_t n_padded, int pad_one_col) {
+                                     uint64_t n_rows, int n_cols, uint64_t n_padded, const PadRow pad) {
     __shared__ uint32_t tile[32][33];
     uint64_t r0 = (uint64_t)blockIdx.x * 32;
     int c0 = blockIdx.y * 32;
@@ -394,7 +397,7 @@ __global__ void transpose_pad_kernel(uint32_t* __restrict__ cols, size_t stride,
             if (r < n_rows)
                 v = rows[r * n_cols + c];
             else
-                v = (c == pad_one_col) ? 1u : 0u;
+                v = pad.v[c];
         }
         tile[ty][threadIdx.x] = v;
     }
@@ -407,11 +410,14 @@ __global__ void transpose_pad_kernel(uint32_t* __restrict__ cols, size_t stride,
 }
 
 cudaError_t transpose_pad(uint32_t* d_cols, size_t stride, const uint32_t* d_rows, uint64_t n_rows, int n_cols, int log,
-                          int pad_one_col, cudaStream_t stream) {
+                          int kind, cudaStream_t stream) {
+    if (n_cols > MAX_MAIN_COLS) return cudaErrorInvalidValue;
+    PadRow pad{};
+    for (int c = 0; c < n_cols; ++c) pad.v[c] = padding_value(kind, c);
     uint64_t n = (uint64_t)1 << log;
     dim3 grid((unsigned)((n + 31) / 32), (unsigned)((n_cols + 31) / 32));
     dim3 block(32, 8);
-    transpose_pad_kernel<<<grid, block, 0, stream>>>(d_cols, stride, d_rows, n_rows, n_cols, n, pad_one_col);
+    transpose_pad_kernel<<<grid, block, 0, stream>>>(d_cols, stride, d_rows, n_rows, n_cols, n, pad);
     return cudaGetLastError();
 }
 

@@ -429,9 +429,13 @@ void fri_positions_and_witness(uint32_t* const coords[4], const std::vector<uint
 struct InfoEval : LogupMixin<InfoEval, FQ, FQ> {
     typedef FQ F;
     typedef FQ EF;
-    int n_main = 0, n_inter = 0, n_constraints = 0;
+    int n_main = 0, n_inter = 0, n_constraints = 0, n_pre = 0;
     QM31 cumsum_shift = q_zero();
     FQ constant(uint32_t c) const { return {q_from_m(c)}; }
+    FQ get_preprocessed_column(int k) {
+        n_pre = std::max(n_pre, k + 1);
+        return {q_zero()};
+    }
     FQ next_trace_mask() {
         ++n_main;
         return {q_zero()};
@@ -454,12 +458,15 @@ struct PointEval : LogupMixin<PointEval, FQ, FQ> {
     typedef FQ EF;
     const std::vector<std::vector<QM31>>* main;   // sampled_values[1] (global column index)
     const std::vector<std::vector<QM31>>* inter;  // sampled_values[2]
+    const std::vector<std::vector<QM31>>* pre;    // sampled_values[0]
+    int pre_idx[2];                               // this component's preprocessed columns (global index)
     size_t mc, ic;
     QM31 denom_inverse, random_coeff;
     QM31* acc;
     QM31 cumsum_shift;
 
     FQ constant(uint32_t c) const { return {q_from_m(c)}; }
+    FQ get_preprocessed_column(int k) const { return {(*pre)[pre_idx[k]][0]}; }
     FQ next_trace_mask() { return {(*main)[mc++][0]}; }
     FQ ext_at(size_t k) const {
         QM31 e[4] = {(*inter)[ic][k], (*inter)[ic + 1][k], (*inter)[ic + 2][k], (*inter)[ic + 3][k]};
@@ -568,17 +575,26 @@ struct Component {
     size_t main_loc, inter_loc;  // first column in tree 1 / tree 2
     uint32_t* main_evals;        // trace values (n_main x 2^log), kept for the LogUp pass
     QM31 claimed_sum;
+    int pre_idx[2] = {-1, -1};   // preprocessed columns read by a lookup-table component (index into tree 0)
+    int eval_log = 0;            // max_constraint_log_degree_bound
+};
+
+// one preprocessed column as committed in tree 0
+struct PreCol {
+    int lut, col_index, log;
+    uint32_t* evals;  // values on CanonicCoset(log) as the caller generated them (kept for the LogUp pass)
 };
 
 int kind_of_slot(int slot, int n_slots, int air_era) {
-    // LuminairClaim field order, crates/air/src/lib.rs:30-48 (17 slots): add, mul, ..., inputs (15), contiguous
+    // LuminairClaim field order, crates/air/src/lib.rs:30-48 (17 slots)
     if (slot == 0) return COMP_ADD;
     if (slot == 1) return air_era == 1 ? COMP_MUL_ARTIFACT : COMP_MUL;
-    if (n_slots == 17 && slot == 5) return COMP_SUM_REDUCE;
-    if (n_slots == 17 && slot == 6) return COMP_MAX_REDUCE;
-    if (n_slots == 17 && slot == 15) return COMP_INPUTS;
-    if (n_slots == 17 && slot == 16) return COMP_CONTIGUOUS;
-    return -1;
+    if (n_slots != 17) return -1;
+    static const int kinds[17] = {COMP_ADD,        COMP_MUL,         COMP_RECIP,     COMP_SIN,         COMP_SIN_LOOKUP,
+                                  COMP_SUM_REDUCE, COMP_MAX_REDUCE,  COMP_SQRT,      COMP_REM,         COMP_EXP2,
+                                  COMP_EXP2_LOOKUP, COMP_LOG2,       COMP_LOG2_LOOKUP, COMP_LESS_THAN, COMP_RANGE_CHECK_LOOKUP,
+                                  COMP_INPUTS,     COMP_CONTIGUOUS};
+    return (slot >= 0 && slot < 17) ? kinds[slot] : -1;
 }
 
 const uint2* inv_y_twiddles(const Twiddles& tw, int domain_log) { return tw.inv + tw.y_off + ((size_t)1 << (domain_log - 1)); }
@@ -599,8 +615,8 @@ struct StageTimer {
 }  // namespace
 
 // ======================================================================================
-int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_prove_config* cfg_in,
-               std::vector<uint8_t>& out) {
+int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_preprocessed_column* pre_in, int n_pre,
+               const lb_prove_config* cfg_in, std::vector<uint8_t>& out) {
     try {
         lb_prove_config cfg;
         if (cfg_in)
@@ -642,6 +658,13 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             if (lg > 24) fail(LB_ERR_BAD_ARG, "prove: table too large");
             max_log = std::max(max_log, lg);
         }
+        if (n_pre < 0 || n_pre > 16 || (n_pre > 0 && !pre_in)) fail(LB_ERR_BAD_ARG, "prove: bad preprocessed column list");
+        for (int k = 0; k < n_pre; ++k) {
+            if (pre_in[k].log_size < 4 || pre_in[k].log_size > 24) fail(LB_ERR_BAD_ARG, "prove: bad LUT column size");
+            if (pre_in[k].lut < REL_SIN || pre_in[k].lut > REL_RANGE_CHECK || pre_in[k].col_index < 0 || pre_in[k].col_index > 1)
+                fail(LB_ERR_BAD_ARG, "prove: unknown LUT column");
+            max_log = std::max(max_log, pre_in[k].log_size);
+        }
         {
             int r = lb_twiddles_ensure(ctx, max_log + 1 + blowup);
             if (r) return r;
@@ -675,7 +698,32 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             channel.mix_root(tree.merkle.root);
         };
 
-        // ---- phase 0: preprocessed trace (no LUT columns for Add/Mul/Inputs graphs) ----------
+        // ---- phase 0: preprocessed trace (prover.rs:52-59) -----------------------------------------
+        // lookups_to_preprocessed_column order from the caller, PreProcessedTrace::new sorts it (stable) by
+        // log_size, descending (preprocessed.rs:152-155).  The LUT values themselves are the caller's
+        // (host libm, preprocessed.rs:351-383); the path only interpolates and commits them.
+        std::vector<PreCol> pre_cols;
+        std::vector<int> lut_log(REL_COUNT, -1);
+        {
+            std::vector<int> order(n_pre);
+            for (int k = 0; k < n_pre; ++k) order[k] = k;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pre_in[a].log_size > pre_in[b].log_size; });
+            for (int k : order) {
+                const lb_preprocessed_column& pc = pre_in[k];
+                size_t n = (size_t)1 << pc.log_size;
+                uint32_t* evals = arena.alloc<uint32_t>(n);
+                ck(cudaMemcpyAsync(evals, pc.values, n * sizeof(uint32_t), pc.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st),
+                   "LUT upload");
+                uint32_t* coeffs = arena.alloc<uint32_t>(n);
+                ck(cudaMemcpyAsync(coeffs, evals, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st), "copy");
+                ck(cfft_interpolate(&tw, coeffs, n, 1, pc.log_size, ctx->sm_count, st), "interpolate LUT");
+                trees[0].cols.push_back({coeffs, nullptr, pc.log_size});
+                pre_cols.push_back({pc.lut, pc.col_index, pc.log_size, evals});
+                if (lut_log[pc.lut] >= 0 && lut_log[pc.lut] != pc.log_size) fail(LB_ERR_BAD_ARG, "prove: LUT columns of one table differ in size");
+                lut_log[pc.lut] = pc.log_size;
+            }
+            if (n_pre) ck(cudaStreamSynchronize(st), "LUT upload sync");  // host columns may be pageable
+        }
         commit_tree(trees[0]);
 
         // ---- phase 1: main trace (prover.rs:66-179) ------------------------------------------
@@ -707,7 +755,7 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                 d_rows = staged;
             }
             uint32_t* evals = arena.alloc<uint32_t>(n * sh.n_main);
-            ck(transpose_pad(evals, n, d_rows, tb.n_rows, sh.n_main, lg, sh.padding_one_col, st), "transpose");
+            ck(transpose_pad(evals, n, d_rows, tb.n_rows, sh.n_main, lg, kind, st), "transpose");
             uint32_t* coeffs = arena.alloc<uint32_t>(n * sh.n_main);
             ck(cudaMemcpyAsync(coeffs, evals, n * sh.n_main * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st), "copy");
             ck(cfft_interpolate(&tw, coeffs, n, sh.n_main, lg, ctx->sm_count, st), "interpolate");
@@ -720,6 +768,17 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             c.slot = tb.slot;
             c.log = lg;
             c.main_evals = evals;
+            if (sh.lut) {
+                if (lut_log[sh.lut] < 0) fail(LB_ERR_BAD_ARG, "prove: component needs a lookup table that was not supplied");
+                for (int q = 0; q < sh.n_pre; ++q) {
+                    for (size_t i = 0; i < pre_cols.size(); ++i)
+                        if (pre_cols[i].lut == sh.lut && pre_cols[i].col_index == q) c.pre_idx[q] = (int)i;
+                    if (c.pre_idx[q] < 0) fail(LB_ERR_BAD_ARG, "prove: missing LUT column");
+                    if (pre_cols[c.pre_idx[q]].log != lg) fail(LB_ERR_BAD_ARG, "prove: lookup-table component and LUT column differ in size");
+                }
+            }
+            // max_constraint_log_degree_bound (add/component.rs:33-35; LUT consumers exp2/component.rs:41-43)
+            c.eval_log = (consumes_lut(kind) ? std::max(lg, lut_log[sh.lut]) : lg) + 1;
             c.main_loc = trees[1].cols.size();  // location by pie order; components use slot order (see below)
             for (int k = 0; k < sh.n_main; ++k) trees[1].cols.push_back({coeffs + (size_t)k * n, nullptr, lg});
             claim[tb.slot] = lg;
@@ -732,10 +791,17 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
 
         // ---- phase 2: interaction trace (prover.rs:181-298) -----------------------------------
         // LuminairInteractionElements::draw (components/mod.rs:227-235): node, then sin, exp2, log2, range_check
-        std::vector<QM31> node_el = channel.draw_secure_felts(2);
-        if (cfg.draw_lookup_elements)
-            for (int k = 0; k < 4; ++k) (void)channel.draw_secure_felts(2);
-        Relation2 node{node_el[0], node_el[1]};
+        Relations rels{};
+        {
+            std::vector<QM31> el = channel.draw_secure_felts(2);
+            rels.r[REL_NODE] = Relation2{el[0], el[1]};
+            if (cfg.draw_lookup_elements)
+                for (int k = REL_SIN; k <= REL_RANGE_CHECK; ++k) {
+                    el = channel.draw_secure_felts(2);  // relation!(X, 1) still draws (z, alpha)
+                    rels.r[k] = Relation2{el[0], el[1]};
+                }
+        }
+        if (!cfg.draw_lookup_elements && n_pre) fail(LB_ERR_BAD_ARG, "prove: LUT columns need draw_lookup_elements");
 
         std::vector<Component> comps;  // slot order = LuminairComponents order
         {
@@ -751,7 +817,9 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                 uint32_t* scan_tmp = arena.alloc<uint32_t>(4 * n);
                 uint32_t* block_sums = arena.alloc<uint32_t>(4 * (n / 1024 + 1));
                 uint32_t* d_claimed = arena.alloc<uint32_t>(4);
-                ck(logup_interaction_trace(c.kind, c.main_evals, n, inter, n, c.log, node, scan_tmp, block_sums, d_claimed, st),
+                PreCols pc{};
+                for (int q = 0; q < sh.n_pre; ++q) pc.p[q] = pre_cols[c.pre_idx[q]].evals;
+                ck(logup_interaction_trace(c.kind, c.main_evals, n, pc, inter, n, c.log, rels, scan_tmp, block_sums, d_claimed, st),
                    "logup");
                 uint32_t cl[4];
                 ck(cudaMemcpyAsync(cl, d_claimed, 16, cudaMemcpyDeviceToHost, st), "claimed d2h");
@@ -779,9 +847,10 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
         int total_constraints = 0;
         for (const Component& c : comps) {
             InfoEval info;
-            eval_component(c.kind, info, node);
+            eval_component(c.kind, info, rels);
             ComponentShape sh = component_shape(c.kind);
-            if (info.n_main != sh.n_main || info.n_inter != 4 * sh.n_fracs || info.n_constraints != sh.n_constraints)
+            if (info.n_main != sh.n_main || info.n_inter != 4 * sh.n_fracs || info.n_constraints != sh.n_constraints ||
+                info.n_pre != sh.n_pre || sh.n_constraints > MAX_CONSTRAINTS || sh.n_main > MAX_MAIN_COLS)
                 fail(LB_ERR_BAD_ARG, "internal: component shape table out of date");
             n_constraints.push_back(info.n_constraints);
             total_constraints += info.n_constraints;
@@ -801,20 +870,34 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             for (size_t ci = 0; ci < comps.size(); ++ci) {
                 const Component& c = comps[ci];
                 int nc = n_constraints[ci];
-                int eval_log = c.log + 1;  // max_constraint_log_degree_bound (add/component.rs:33-35)
-                if (eval_log != c.log + blowup) fail(LB_ERR_BAD_ARG, "prove: blow-up != 1 needs a separate evaluation domain");
+                int eval_log = c.eval_log;
+                ComponentShape sh = component_shape(c.kind);
                 ConstraintParams p{};
-                p.main = trees[1].cols[c.main_loc].lde;
-                p.main_stride = (size_t)1 << eval_log;
-                p.inter = trees[2].cols[c.inter_loc].lde;
-                p.inter_stride = (size_t)1 << eval_log;
+                size_t ne = (size_t)1 << eval_log;
+                // constraint-framework `need_to_extend`: columns not committed on the evaluation domain are
+                // re-evaluated there from their polynomials
+                std::vector<uint32_t*> scratch;
+                auto on_eval_domain = [&](CommitTree& tree, size_t first, int n_cols) -> const uint32_t* {
+                    if (tree.cols[first].log + blowup == eval_log) return tree.cols[first].lde;
+                    uint32_t* ext = arena.alloc<uint32_t>(ne * n_cols);
+                    scratch.push_back(ext);
+                    int lg = tree.cols[first].log;
+                    ck(cfft_evaluate(&tw, tree.cols[first].coeffs, (size_t)1 << lg, lg, ext, ne, eval_log, n_cols, ctx->sm_count, st),
+                       "extend to evaluation domain");
+                    return ext;
+                };
+                p.main = on_eval_domain(trees[1], c.main_loc, sh.n_main);
+                p.main_stride = ne;
+                p.inter = on_eval_domain(trees[2], c.inter_loc, 4 * sh.n_fracs);
+                p.inter_stride = ne;
+                for (int q = 0; q < sh.n_pre; ++q) p.pre.p[q] = on_eval_domain(trees[0], (size_t)c.pre_idx[q], 1);
                 bool fresh = acc.find(eval_log) == acc.end();
                 if (fresh) acc[eval_log] = arena.alloc<uint32_t>((size_t)4 << eval_log);
                 for (int k = 0; k < 4; ++k) p.acc[k] = acc[eval_log] + ((size_t)k << eval_log);
                 p.accumulate = fresh ? 0 : 1;
                 p.log_size = c.log;
                 p.eval_log = eval_log;
-                p.node = node;
+                p.rels = rels;
                 p.cumsum_shift = q_mul_m(c.claimed_sum, m_inv((uint32_t)(((uint64_t)1 << c.log) % P)));
                 // this component owns the last `nc` of the remaining powers, highest first
                 for (int k = 0; k < nc; ++k) p.pows[k] = powers[remaining - 1 - k];
@@ -822,11 +905,17 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                 // 1 / Z_H on the 2^(eval_log - log) cosets of the evaluation domain
                 int log_expand = eval_log - c.log;
                 uint32_t init = subgroup_gen(eval_log + 1), step = subgroup_gen(eval_log - 1);
+                std::vector<uint32_t> dinv((size_t)1 << log_expand);
                 for (uint32_t i = 0; i < (1u << log_expand); ++i) {
                     Pt pt = host_index_to_point(init + step * bit_reverse(i, log_expand));
-                    p.denom_inv[i] = m_inv(coset_vanishing_m(c.log, pt));
+                    dinv[i] = m_inv(coset_vanishing_m(c.log, pt));
                 }
+                p.denom_inv = arena.upload(dinv);
                 ck(constraint_quotients(c.kind, p, st), "constraint quotients");
+                if (!scratch.empty()) {
+                    ck(cudaStreamSynchronize(st), "extension sync");
+                    for (uint32_t* e : scratch) arena.release(e);
+                }
             }
         }
         // finalize: lift smaller accumulators into larger ones, interpolate -> composition coefficients
@@ -861,10 +950,12 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
         }
         // sample_points[tree][col] = list of points
         std::vector<std::vector<std::vector<QPt>>> sample_points(4);
+        sample_points[0].resize(trees[0].cols.size());  // only the columns a component reads are sampled
         sample_points[1].resize(trees[1].cols.size());
         sample_points[2].resize(trees[2].cols.size());
         for (const Component& c : comps) {
             ComponentShape sh = component_shape(c.kind);
+            for (int q = 0; q < sh.n_pre; ++q) sample_points[0][c.pre_idx[q]] = {oods};
             for (int k = 0; k < sh.n_main; ++k) sample_points[1][c.main_loc + k] = {oods};
             int n_ic = 4 * sh.n_fracs;
             QPt prev = qpt_add(oods, qpt_lift(host_index_to_point((0u - subgroup_gen(c.log)) & CIRCLE_ORDER_MASK)));
@@ -1153,13 +1244,16 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                 PointEval pe;
                 pe.main = &sampled[1];
                 pe.inter = &sampled[2];
+                pe.pre = &sampled[0];
+                pe.pre_idx[0] = c.pre_idx[0];
+                pe.pre_idx[1] = c.pre_idx[1];
                 pe.mc = c.main_loc;
                 pe.ic = c.inter_loc;
                 pe.random_coeff = random_coeff;
                 pe.denom_inverse = q_inv(coset_vanishing_q(c.log, oods));
                 pe.acc = &accv;
                 pe.cumsum_shift = q_mul_m(c.claimed_sum, m_inv((uint32_t)(((uint64_t)1 << c.log) % P)));
-                eval_component(c.kind, pe, node);
+                eval_component(c.kind, pe, rels);
             }
             if (!q_eq(composition_oods, accv)) fail(LB_ERR_CONSTRAINTS, "ConstraintsNotSatisfied");
         }
@@ -1322,18 +1416,33 @@ int grind_impl(lb_ctx* ctx, const uint32_t digest[8], int variant, uint32_t pow_
     });
 }
 
-int logup_impl(lb_ctx* ctx, int kind, const uint32_t* d_main, size_t main_stride, uint32_t* d_inter, size_t inter_stride,
-               int log, const uint32_t z[4], const uint32_t alpha[4], uint32_t claimed_out[4]) {
+namespace {
+Relations relations_from(const lb_relation* rels, int n) {
+    Relations r{};
+    for (int k = 0; k < n && k < REL_COUNT; ++k) r.r[k] = Relation2{q_from_words(rels[k].z), q_from_words(rels[k].alpha)};
+    return r;
+}
+}  // namespace
+
+int logup_impl(lb_ctx* ctx, int kind, const uint32_t* d_main, size_t main_stride, const uint32_t* const d_lut[2],
+               uint32_t* d_inter, size_t inter_stride, int log, const lb_relation* rels, int n_rels, uint32_t claimed_out[4]) {
     return guarded(ctx, [&] {
         ensure_kernels(ctx);
         if (kind < 0 || kind >= COMP_KIND_COUNT || log < 1) fail(LB_ERR_BAD_ARG, "logup: bad args");
+        ComponentShape sh = component_shape(kind);
+        if (sh.lut && n_rels < REL_COUNT) fail(LB_ERR_BAD_ARG, "logup: component needs the LUT relations");
+        PreCols pc{};
+        for (int q = 0; q < sh.n_pre; ++q) {
+            if (!d_lut || !d_lut[q]) fail(LB_ERR_BAD_ARG, "logup: component needs its LUT columns");
+            pc.p[q] = d_lut[q];
+        }
         Arena arena(ctx->stream);
         size_t n = (size_t)1 << log;
         uint32_t* scan_tmp = arena.alloc<uint32_t>(4 * n);
         uint32_t* block_sums = arena.alloc<uint32_t>(4 * (n / 1024 + 1));
         uint32_t* d_claimed = arena.alloc<uint32_t>(4);
-        Relation2 node{q_from_words(z), q_from_words(alpha)};
-        ck(logup_interaction_trace(kind, d_main, main_stride, d_inter, inter_stride, log, node, scan_tmp, block_sums, d_claimed,
+        Relations r = relations_from(rels, n_rels);
+        ck(logup_interaction_trace(kind, d_main, main_stride, pc, d_inter, inter_stride, log, r, scan_tmp, block_sums, d_claimed,
                                    ctx->stream),
            "logup");
         ck(cudaMemcpyAsync(claimed_out, d_claimed, 16, cudaMemcpyDeviceToHost, ctx->stream), "claimed d2h");
@@ -1342,33 +1451,43 @@ int logup_impl(lb_ctx* ctx, int kind, const uint32_t* d_main, size_t main_stride
 }
 
 int constraint_quotients_impl(lb_ctx* ctx, int kind, const uint32_t* d_main, size_t main_stride, const uint32_t* d_inter,
-                              size_t inter_stride, int log_size, const uint32_t z[4], const uint32_t alpha[4],
-                              const uint32_t claimed_sum[4], const uint32_t* pows, int n_pows, uint32_t* const d_acc[4],
-                              int accumulate) {
+                              size_t inter_stride, const uint32_t* const d_lut[2], int log_size, int eval_log,
+                              const lb_relation* rels, int n_rels, const uint32_t claimed_sum[4], const uint32_t* pows,
+                              int n_pows, uint32_t* const d_acc[4], int accumulate) {
     return guarded(ctx, [&] {
         ensure_kernels(ctx);
         if (kind < 0 || kind >= COMP_KIND_COUNT) fail(LB_ERR_BAD_ARG, "constraints: unknown component");
         ComponentShape sh = component_shape(kind);
         if (n_pows != sh.n_constraints) fail(LB_ERR_BAD_ARG, "constraints: wrong number of random-coefficient powers");
+        if (eval_log <= log_size || eval_log > 30) fail(LB_ERR_BAD_ARG, "constraints: bad evaluation domain");
+        if (sh.lut && n_rels < REL_COUNT) fail(LB_ERR_BAD_ARG, "constraints: component needs the LUT relations");
         ConstraintParams p{};
-        int eval_log = log_size + 1;
         p.main = d_main;
         p.main_stride = main_stride;
         p.inter = d_inter;
         p.inter_stride = inter_stride;
+        for (int q = 0; q < sh.n_pre; ++q) {
+            if (!d_lut || !d_lut[q]) fail(LB_ERR_BAD_ARG, "constraints: component needs its LUT columns");
+            p.pre.p[q] = d_lut[q];
+        }
         for (int k = 0; k < 4; ++k) p.acc[k] = d_acc[k];
         p.accumulate = accumulate;
         p.log_size = log_size;
         p.eval_log = eval_log;
-        p.node = Relation2{q_from_words(z), q_from_words(alpha)};
+        p.rels = relations_from(rels, n_rels);
         p.cumsum_shift = q_mul_m(q_from_words(claimed_sum), m_inv((uint32_t)(((uint64_t)1 << log_size) % P)));
         for (int k = 0; k < n_pows; ++k) p.pows[k] = q_from_words(pows + 4 * k);
+        int log_expand = eval_log - log_size;
         uint32_t init = subgroup_gen(eval_log + 1), step = subgroup_gen(eval_log - 1);
-        for (uint32_t i = 0; i < 2; ++i) {
-            Pt pt = host_index_to_point(init + step * i);
-            p.denom_inv[i] = m_inv(coset_vanishing_m(log_size, pt));
+        std::vector<uint32_t> dinv((size_t)1 << log_expand);
+        for (uint32_t i = 0; i < (1u << log_expand); ++i) {
+            Pt pt = host_index_to_point(init + step * bit_reverse(i, log_expand));
+            dinv[i] = m_inv(coset_vanishing_m(log_size, pt));
         }
+        Arena arena(ctx->stream);
+        p.denom_inv = arena.upload(dinv);
         ck(constraint_quotients(kind, p, ctx->stream), "constraint quotients");
+        ck(cudaStreamSynchronize(ctx->stream), "constraints sync");  // arena scratch is released on return
     });
 }
 

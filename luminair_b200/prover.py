@@ -14,12 +14,23 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from ._lib import LuminairB200Error, ProveConfig, TraceTable, check
+from ._lib import LuminairB200Error, PreprocessedColumn, ProveConfig, TraceTable, check
 from .backend import CudaBackend
 
 # field index of each component in LuminairClaim (crates/air/src/lib.rs:30-48)
-CLAIM_SLOT = {"add": 0, "mul": 1, "sum_reduce": 5, "max_reduce": 6, "inputs": 15, "contiguous": 16}
+CLAIM_SLOT = {"add": 0, "mul": 1, "recip": 2, "sin": 3, "sin_lookup": 4, "sum_reduce": 5, "max_reduce": 6, "sqrt": 7,
+              "rem": 8, "exp2": 9, "exp2_lookup": 10, "log2": 11, "log2_lookup": 12, "less_than": 13,
+              "range_check_lookup": 14, "inputs": 15, "contiguous": 16}
 N_CLAIM_SLOTS = 17
+# LUT of a preprocessed column id (crates/air/src/preprocessed.rs:289-296, 336-340 and siblings) -> LB_REL_*
+LUT_OF_PREFIX = {"sin_lut_": 1, "exp2_lut_": 2, "log2_lut_": 3, "range_check_": 4}
+
+
+def _lut_column(cid: str):
+    for prefix, lut in LUT_OF_PREFIX.items():
+        if cid.startswith(prefix):
+            return lut, int(cid.rsplit("_", 1)[1])
+    raise LuminairB200Error(f"unknown preprocessed column id '{cid}'")
 
 
 class ProvingError(LuminairB200Error):
@@ -40,9 +51,11 @@ class PcsConfig:
 
 
 def prove(pie, backend: CudaBackend | None = None, config: PcsConfig | None = None, channel_variant: str = "legacy",
-          claim_slots=CLAIM_SLOT, n_slots: int = N_CLAIM_SLOTS, device_tables=None, air_era: str = "current") -> bytes:
+          claim_slots=CLAIM_SLOT, n_slots: int = N_CLAIM_SLOTS, device_tables=None, air_era: str = "current",
+          preprocessed=()) -> bytes:
     """pie: [(name, rows[n_rows, n_cols])].  device_tables: optional {name: (device_ptr, n_rows, n_cols)} to prove
-    from tables already resident in HBM (bench.py's device-resident leg)."""
+    from tables already resident in HBM (bench.py's device-resident leg).  preprocessed: [(id, values[2^k])] LUT
+    columns of the circuit settings in ``lookups_to_preprocessed_column`` order (preprocessed.rs:181-206)."""
     own = backend is None
     be = backend or CudaBackend(0)
     try:
@@ -71,9 +84,20 @@ def prove(pie, backend: CudaBackend | None = None, config: PcsConfig | None = No
             tables[i].rows_on_device = 0
         cfg = ProveConfig(config.pow_bits, config.log_blowup_factor, config.log_last_layer_degree_bound, config.n_queries,
                           {"legacy": 0, "v2": 1}[channel_variant], n_slots, {"current": 0, "artifact": 1}[air_era], 1)
+        n_pre = len(preprocessed)
+        pre = (PreprocessedColumn * max(n_pre, 1))()
+        for i, (cid, values) in enumerate(preprocessed):
+            arr = np.ascontiguousarray(np.asarray(values), dtype=np.uint32).reshape(-1)
+            if arr.size < 16 or arr.size & (arr.size - 1):
+                raise LuminairB200Error("LUT column length must be a power of two >= 16")
+            keep.append(arr)
+            pre[i].lut, pre[i].col_index = _lut_column(cid)
+            pre[i].log_size = arr.size.bit_length() - 1
+            pre[i].values = arr.ctypes.data
+            pre[i].on_device = 0
         out = C.c_void_p()
         out_len = C.c_size_t()
-        rc = be.lib.lb_prove(be.ctx, tables, n, C.byref(cfg), C.byref(out), C.byref(out_len))
+        rc = be.lib.lb_prove_with_lookups(be.ctx, tables, n, pre, n_pre, C.byref(cfg), C.byref(out), C.byref(out_len))
         if rc == -5:
             raise ProvingError(be.lib.lb_last_error(be.ctx).decode())
         check(be.ctx, rc, "lb_prove")
