@@ -111,15 +111,22 @@ def cpu_roundtrip(sample_cols, threads, reps=1):
 
 
 def cpu_prove_baseline(log=14):
-    """The CPU restatement of prove() (oracle/, numpy, 1 core) on a bounded sample of the cfg-3 graph."""
+    """The CPU restatement of prove() (oracle/, numpy, 1 core) on a bounded sample of the cfg-3 graph, and on the
+    whole cfg-4 MLP graph."""
+    from luminair_b200.pie import mlp_graph
     from oracle import examples, prover as oprover
     pie = examples.graph_pie(log, seed=42, with_mul=False)
     t0 = time.perf_counter()
     oprover.prove(pie)
     dt = time.perf_counter() - t0
+    mlp_pie, mlp_pre = mlp_graph()
+    t0 = time.perf_counter()
+    oprover.prove(mlp_pie, preprocessed=mlp_pre)
+    dt_mlp = time.perf_counter() - t0
     return {"value": dt * 1e3, "unit": "ms per proof", "cores": 1, "kind": "port",
             "sample": f"a+b graph at 2^{log} elements (64x smaller than the GPU workload), numpy restatement (oracle/prover.py); "
-                      "not stwo SimdBackend (Rust toolchain absent)"}
+                      "not stwo SimdBackend (Rust toolchain absent)",
+            "mlp_ms_per_proof": dt_mlp * 1e3, "mlp_sample": "the same 2-64-64-1 MLP graph as prove.mlp (whole workload)"}
 
 
 def run_reference(args):
@@ -428,7 +435,23 @@ def bench_prove(be, torch, args):
         prove(small, backend=be)
     small_ms = (time.perf_counter() - t0) * 1e2
     h2d = sum(int(v.nbytes) for _, v in host_pie)
+    # BASELINE configs[3] shape: the 2-64-64-1 tanh MLP of examples/black-schole-nn (synthetic weights), 7 components
+    # including the Exp2 lookup table (2^17 rows) and the extended evaluation domain of its consumer
+    from luminair_b200.pie import mlp_graph
+    mlp_pie, mlp_pre = mlp_graph()
+    for _ in range(2):
+        prove(mlp_pie, backend=be, preprocessed=mlp_pre)
+    t_mlp = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        mlp_proof = prove(mlp_pie, backend=be, preprocessed=mlp_pre)
+        t_mlp.append((time.perf_counter() - t0) * 1e3)
+    mlp_info = {"workload": "prove(): Linear 2-64-64-1 with tanh (Mul/SumReduce/Add/Exp2+LUT/Recip/Inputs tables: "
+                            + ", ".join(f"{k} {v.shape[0]}" for k, v in mlp_pie) + " rows), host tables (BASELINE configs[3] shape, "
+                            "synthetic weights)",
+                "ms_e2e_host_tables": {"min": min(t_mlp), "median": statistics.median(t_mlp)}, "proof_bytes": len(mlp_proof)}
     return {
+        "mlp": mlp_info,
         "workload": f"prove(): a+b graph, Add 2^{log} rows x 15 cols + Inputs 2^{log + 1} rows x 7 cols, blow-up 2, Blake2s Merkle, FRI "
                     "(BASELINE configs[2]); proof bytes bit-exact vs the CPU restatement at test sizes, verifier-accepted at this size",
         "ms_device_resident": {"min": min(ts_dev), "median": statistics.median(ts_dev)},

@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <type_traits>
 #include <vector>
 
 namespace lb {
@@ -396,6 +397,16 @@ __device__ __forceinline__ uint32_t finalize(uint32_t x, int mode, uint2 scale) 
     if (mode == 2) return canon2(mul_shoup(x, scale));
     return x;
 }
+// the same with the mode known at compile time: the callers branch once per round (warp-uniform) instead of once per element
+template <int MODE>
+__device__ __forceinline__ uint32_t finalize_m(uint32_t x, uint2 scale) {
+    if (MODE == 1) return canon(x);
+    if (MODE == 2) return canon2(mul_shoup(x, scale));
+    return x;
+}
+#ifndef LB_UNSWITCH_FINAL
+#define LB_UNSWITCH_FINAL 1
+#endif
 
 template <int M, int R>
 struct RoundGeom {
@@ -471,10 +482,24 @@ __device__ __forceinline__ void low_round(uint32_t* sm, const PassParams& p, uin
                     const size_t local_row = ((size_t)(tile & ((1u << p.peer_tile_shift) - 1)) << 12) + e0;
                     d4 = reinterpret_cast<uint4*>(p.peer[owner] + (p.peer_col0 + col + c) * rows_local + local_row);
                 }
+#if LB_UNSWITCH_FINAL
+                // forward: the low pass is the last one (canonical store); inverse: last only for single-pass sizes (scale)
+                auto st4 = [&](auto mode_tag) {
+                    constexpr int MODE = decltype(mode_tag)::value;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        d4[q] = make_uint4(finalize_m<MODE>(v[c][4 * q], p.scale), finalize_m<MODE>(v[c][4 * q + 1], p.scale),
+                                           finalize_m<MODE>(v[c][4 * q + 2], p.scale), finalize_m<MODE>(v[c][4 * q + 3], p.scale));
+                };
+                if (p.final_mode == 0) st4(std::integral_constant<int, 0>{});
+                else if (p.final_mode == 1) st4(std::integral_constant<int, 1>{});
+                else st4(std::integral_constant<int, 2>{});
+#else
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     d4[q] = make_uint4(finalize(v[c][4 * q], p.final_mode, p.scale), finalize(v[c][4 * q + 1], p.final_mode, p.scale),
                                        finalize(v[c][4 * q + 2], p.final_mode, p.scale), finalize(v[c][4 * q + 3], p.final_mode, p.scale));
+#endif
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) dstc[gbase + ((size_t)j << A)] = finalize(v[c][j], p.final_mode, p.scale);
@@ -596,8 +621,19 @@ __device__ __forceinline__ void high_round(uint32_t* sm, const PassParams& p, ui
     for (int c = 0; c < NC; ++c) {
         if (last) {
             uint32_t* dp = dst + (size_t)c * p.dst_stride + gb;
+#if LB_UNSWITCH_FINAL
+            auto st = [&](auto mode_tag) {
+                constexpr int MODE = decltype(mode_tag)::value;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) dp[(size_t)(j << A) << ilo] = finalize_m<MODE>(v[c][j], p.scale);
+            };
+            // forward high passes are never the last pass (lazy store); inverse: the top pass scales by 1/n
+            if (FWD || p.final_mode == 0) st(std::integral_constant<int, 0>{});
+            else st(std::integral_constant<int, 2>{});
+#else
 #pragma unroll
             for (int j = 0; j < 16; ++j) dp[(size_t)(j << A) << ilo] = finalize(v[c][j], p.final_mode, p.scale);
+#endif
         } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) sm[c * SMW + sb + high_word<W>(j << A, 0)] = v[c][j];
