@@ -10,6 +10,7 @@ import hashlib, json, os, shutil, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from luminair_b200 import pie as piemod
 from oracle import examples, prover
 from oracle.proof import to_bincode
 
@@ -23,9 +24,16 @@ cases = {
     "simple_current.proof.bin": ("examples.simple_pie('current')", lambda: examples.simple_pie("current")),
     "graph_log6_mul.proof.bin": ("examples.graph_pie(6, seed=6, with_mul=True)", lambda: examples.graph_pie(6, seed=6, with_mul=True)),
     "reduce_log5.proof.bin": ("examples.reduce_pie(5, 2, seed=5)", lambda: examples.reduce_pie(5, 2, seed=5)),
+    # graphs with lookup tables: (pie, preprocessed LUT columns)
+    "all_components_n24.proof.bin": ("luminair_b200.pie.all_components_graph(n=24, seed=3)  [17 components, LUTs of 2^8..2^15 rows]",
+                                     lambda: piemod.all_components_graph(n=24, seed=3)),
+    "mlp_2_8_8_1.proof.bin": ("luminair_b200.pie.mlp_graph(widths=(2, 8, 8, 1))  [BASELINE cfg 4 shape at reduced width]",
+                              lambda: piemod.mlp_graph(widths=(2, 8, 8, 1))),
 }
 for name, (desc, mk) in cases.items():
-    data = to_bincode(prover.prove(mk()))
+    made = mk()
+    pie, pre = made if isinstance(made, tuple) else (made, ())
+    data = to_bincode(prover.prove(pie, preprocessed=pre))
     open(os.path.join(G, name), "wb").write(data)
     meta[name] = {"source": "oracle/prover.py (CPU restatement), default PcsConfig, legacy channel", "pie": desc}
 for name in meta:

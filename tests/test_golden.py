@@ -6,12 +6,16 @@ import os
 
 import pytest
 
+from luminair_b200 import pie as piemod
 from oracle import examples
 
+# name -> (pie, preprocessed LUT columns)
 CASES = {
-    "simple_current.proof.bin": lambda: examples.simple_pie("current"),
-    "graph_log6_mul.proof.bin": lambda: examples.graph_pie(6, seed=6, with_mul=True),
-    "reduce_log5.proof.bin": lambda: examples.reduce_pie(5, 2, seed=5),
+    "simple_current.proof.bin": lambda: (examples.simple_pie("current"), ()),
+    "graph_log6_mul.proof.bin": lambda: (examples.graph_pie(6, seed=6, with_mul=True), ()),
+    "reduce_log5.proof.bin": lambda: (examples.reduce_pie(5, 2, seed=5), ()),
+    "all_components_n24.proof.bin": lambda: piemod.all_components_graph(n=24, seed=3),
+    "mlp_2_8_8_1.proof.bin": lambda: piemod.mlp_graph(widths=(2, 8, 8, 1)),
 }
 
 
@@ -32,8 +36,9 @@ def test_oracle_reproduces_fixture(golden_dir, name):
     from oracle import prover, verifier
     from oracle.proof import from_bincode, to_bincode
     want = open(os.path.join(golden_dir, name), "rb").read()
-    assert to_bincode(prover.prove(CASES[name]())) == want
-    verifier.verify(from_bincode(want))
+    pie, pre = CASES[name]()
+    assert to_bincode(prover.prove(pie, preprocessed=pre)) == want
+    verifier.verify(from_bincode(want), preprocessed=[(cid, len(v).bit_length() - 1) for cid, v in pre])
 
 
 @pytest.mark.gpu
@@ -41,4 +46,5 @@ def test_oracle_reproduces_fixture(golden_dir, name):
 def test_cuda_prover_reproduces_fixture(golden_dir, name):
     from luminair_b200.prover import prove
     want = open(os.path.join(golden_dir, name), "rb").read()
-    assert prove(CASES[name]()) == want
+    pie, pre = CASES[name]()
+    assert prove(pie, preprocessed=pre) == want
