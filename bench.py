@@ -382,7 +382,33 @@ def bench_sharded_commit(be, torch, dist, args, rank, world, local_rank):
                  "how": "last CFFT pass stores each 4096-row tile into the owner rank's buffer (CUDA IPC peer memory); no pack copy, no NCCL all-to-all"}
     except Exception as e:  # report, do not hide
         fused = {"error": repr(e)}
-    return {"fused_all_to_all": fused,
+    # OODS sampling + DEEP quotient accumulation over the column shards (SURVEY 8e collectives (2), (3))
+    quot = None
+    try:
+        from luminair_b200.sharded import sharded_quotient_accumulation
+        coeffs = base.clone()
+        lde = ops.lde(coeffs, log, 1)
+        qbest = None
+        for it in range(3):
+            torch.cuda.synchronize()
+            dist.barrier()
+            tm = {}
+            sharded_quotient_accumulation(ops, coeffs, lde, log, 1, [11, 22, 33, 44, 55, 66, 77, 88], [5, 6, 7, 8], timings=tm)
+            t = torch.tensor([tm["total_ms"], tm["sample_ms"], tm["sample_allgather_ms"], tm["quotients_ms"],
+                              tm["quotient_allreduce_ms"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if it > 0 and (qbest is None or float(t[0]) < qbest[0]):
+                qbest = [float(x) for x in t]
+        quot = {"ms_total_max_over_ranks": qbest[0], "ms_eval_at_point": qbest[1], "ms_sample_allgather": qbest[2],
+                "ms_partial_quotients": qbest[3], "ms_quotient_allreduce": qbest[4],
+                "nccl_allgather_bytes_per_rank": tm["allgather_bytes_per_rank"],
+                "nccl_allreduce_bytes_per_rank": tm["allreduce_bytes_per_rank"],
+                "how": "each rank samples and accumulates its own columns with the global random-coefficient powers "
+                       "(lb_accumulate_quotients_shard); partial quotients are summed with one int64 all-reduce"}
+        del coeffs, lde
+    except Exception as e:  # report, do not hide
+        quot = {"error": repr(e)}
+    return {"fused_all_to_all": fused, "quotient_accumulation": quot,
             "workload": f"column-sharded commit: {ncols} columns x 2^{log} rows per GPU ({ncols * world} columns total), blow-up 2, "
                         "interpolate + LDE -> NCCL all-to-all (columns -> rows) -> Blake2s sub-trees -> all-gather of roots "
                         "(BASELINE configs[4] shape; root bit-identical to a single-device tree, tests/test_sharded_gloo.py)",

@@ -112,6 +112,17 @@ int lb_accumulate_quotients(lb_ctx* ctx, int log_size, const uint32_t* const* h_
                             const lb_sample_batch* batches, int n_batches, const uint32_t random_coeff[4],
                             uint32_t* const d_out[4]);
 
+/* Column-sharded form (BASELINE cfg 5): this device holds columns [col_offset, col_offset + batch.n_cols) of a
+ * ColumnSampleBatch that has n_cols_global columns across all devices.  d_out receives this device's PARTIAL sum (the
+ * line-coefficient terms of its own columns only, weighted with the global powers of random_coeff); the coordinate-wise
+ * M31 sum of all devices' outputs equals lb_accumulate_quotients over all columns. */
+typedef struct {
+    int col_offset, n_cols_global;
+} lb_batch_shard;
+int lb_accumulate_quotients_shard(lb_ctx* ctx, int log_size, const uint32_t* const* h_cols, int n_cols,
+                                  const lb_sample_batch* batches, const lb_batch_shard* shards, int n_batches,
+                                  const uint32_t random_coeff[4], uint32_t* const d_out[4]);
+
 /* ---- FriOps ------------------------------------------------------------------------------------- */
 /* dst (4 coords of 2^(log_size-1)) = dst * alpha^2 + fold(src (4 coords of 2^log_size on CanonicCoset(log_size))) */
 int lb_fold_circle_into_line(lb_ctx* ctx, uint32_t* const d_dst[4], const uint32_t* const d_src[4], int log_size,

@@ -69,6 +69,11 @@ class Relation(C.Structure):
     _fields_ = [("z", C.c_uint32 * 4), ("alpha", C.c_uint32 * 4)]
 
 
+class BatchShard(C.Structure):
+    """lb_batch_shard"""
+    _fields_ = [("col_offset", C.c_int), ("n_cols_global", C.c_int)]
+
+
 class SampleBatch(C.Structure):
     """lb_sample_batch"""
     _fields_ = [("point", C.c_uint32 * 8), ("n_cols", C.c_int), ("col_idx", C.POINTER(C.c_int)),
@@ -79,6 +84,8 @@ SIGNATURES.update({
     "lb_eval_at_point": (C.c_int, [ctxp, C.POINTER(C.c_void_p), C.c_int, C.c_int, u32p, u32p]),
     "lb_accumulate_quotients": (C.c_int, [ctxp, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(SampleBatch), C.c_int,
                                           u32p, C.POINTER(C.c_void_p)]),
+    "lb_accumulate_quotients_shard": (C.c_int, [ctxp, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(SampleBatch),
+                                                C.POINTER(BatchShard), C.c_int, u32p, C.POINTER(C.c_void_p)]),
     "lb_fold_circle_into_line": (C.c_int, [ctxp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, u32p]),
     "lb_fold_line": (C.c_int, [ctxp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, u32p]),
     "lb_grind": (C.c_int, [ctxp, u32p, C.c_int, C.c_uint32, C.POINTER(C.c_uint64)]),

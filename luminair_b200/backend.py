@@ -173,9 +173,10 @@ class CudaBackend:
         return out
 
     # ---- QuotientOps ---------------------------------------------------------------------
-    def accumulate_quotients(self, log_size: int, col_ptrs, batches, random_coeff, out_ptrs):
-        """batches: list of (point[8], [(col_idx, value[4])...]); out_ptrs: 4 device coordinate columns."""
-        from ._lib import SampleBatch
+    def accumulate_quotients(self, log_size: int, col_ptrs, batches, random_coeff, out_ptrs, shards=None):
+        """batches: list of (point[8], [(col_idx, value[4])...]); out_ptrs: 4 device coordinate columns.
+        shards: optional [(col_offset, n_cols_global)] per batch -> this device's partial sum (lb_accumulate_quotients_shard)."""
+        from ._lib import BatchShard, SampleBatch
         n = len(col_ptrs)
         arr = (C.c_void_p * n)(*col_ptrs)
         keep = []
@@ -190,6 +191,13 @@ class CudaBackend:
             sb[i].values = vals
         rc = (C.c_uint32 * 4)(*[int(v) for v in random_coeff])
         outs = (C.c_void_p * 4)(*out_ptrs)
+        if shards is not None:
+            sh = (BatchShard * len(batches))()
+            for i, (off, tot) in enumerate(shards):
+                sh[i].col_offset, sh[i].n_cols_global = int(off), int(tot)
+            check(self.ctx, self.lib.lb_accumulate_quotients_shard(self.ctx, log_size, arr, n, sb, sh, len(batches), rc, outs),
+                  "lb_accumulate_quotients_shard")
+            return
         check(self.ctx, self.lib.lb_accumulate_quotients(self.ctx, log_size, arr, n, sb, len(batches), rc, outs),
               "lb_accumulate_quotients")
 

@@ -245,9 +245,18 @@ int lb_eval_at_point(lb_ctx* ctx, const uint32_t* const* h_cols, int n_cols, int
 int lb_accumulate_quotients(lb_ctx* ctx, int log_size, const uint32_t* const* h_cols, int n_cols,
                             const lb_sample_batch* batches, int n_batches, const uint32_t random_coeff[4],
                             uint32_t* const d_out[4]) {
-    if (!ctx || log_size < 1 || log_size > 30 || n_cols < 1 || !h_cols || !batches || n_batches < 1 || !random_coeff || !d_out)
+    if (!ctx || !h_cols || !batches || !random_coeff || !d_out || n_cols < 1 || n_batches < 1 || log_size < 1 || log_size > 30)
         return fail(ctx, LB_ERR_BAD_ARG, "accumulate_quotients: bad args");
-    return lb::accumulate_quotients_impl(ctx, log_size, h_cols, n_cols, batches, n_batches, random_coeff, d_out);
+    return lb::accumulate_quotients_impl(ctx, log_size, h_cols, n_cols, batches, nullptr, n_batches, random_coeff, d_out);
+}
+
+int lb_accumulate_quotients_shard(lb_ctx* ctx, int log_size, const uint32_t* const* h_cols, int n_cols,
+                                  const lb_sample_batch* batches, const lb_batch_shard* shards, int n_batches,
+                                  const uint32_t random_coeff[4], uint32_t* const d_out[4]) {
+    if (!ctx || !h_cols || !batches || !shards || !random_coeff || !d_out || n_cols < 1 || n_batches < 1 || log_size < 1 ||
+        log_size > 30)
+        return fail(ctx, LB_ERR_BAD_ARG, "accumulate_quotients_shard: bad args");
+    return lb::accumulate_quotients_impl(ctx, log_size, h_cols, n_cols, batches, shards, n_batches, random_coeff, d_out);
 }
 
 int lb_fold_circle_into_line(lb_ctx* ctx, uint32_t* const d_dst[4], const uint32_t* const d_src[4], int log_size,

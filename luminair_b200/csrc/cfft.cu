@@ -404,6 +404,9 @@ __device__ __forceinline__ uint32_t finalize_m(uint32_t x, uint2 scale) {
     if (MODE == 2) return canon2(mul_shoup(x, scale));
     return x;
 }
+#ifndef LB_PEER_STAGE
+#define LB_PEER_STAGE 1  // fused all-to-all: send tiles to the owner rank through a shared-memory stage (coalesced NVLink stores)
+#endif
 #ifndef LB_UNSWITCH_FINAL
 #define LB_UNSWITCH_FINAL 1
 #endif
@@ -472,7 +475,13 @@ __device__ __forceinline__ void low_round(uint32_t* sm, const PassParams& p, uin
         uint32_t* dstc = dst + (size_t)c * p.dst_stride;
         uint32_t* smc = sm + c * LOW_SMEM_WORDS;
         if (last) {
-            if (A == 0) {
+            if (A == 0 && FWD && LB_PEER_STAGE && p.n_peers > 0) {
+                // fused all-to-all, staged: park the finished tile in shared memory; the copy loop below sends it to the owner
+                // rank with warp-contiguous 512-byte stores (a thread's own 64-byte run would reach NVLink as 16-byte writes)
+                uint4* s4 = reinterpret_cast<uint4*>(smc + low_pad(e0));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) s4[q] = make_uint4(v[c][4 * q], v[c][4 * q + 1], v[c][4 * q + 2], v[c][4 * q + 3]);
+            } else if (A == 0) {
                 uint4* d4 = reinterpret_cast<uint4*>(dstc + gbase);
                 if (FWD && p.n_peers > 0) {
                     // fused all-to-all: this tile belongs to the row shard of rank `tile >> peer_tile_shift`; store it straight
@@ -513,6 +522,24 @@ __device__ __forceinline__ void low_round(uint32_t* sm, const PassParams& p, uin
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) smc[sb + low_pad(j << A)] = v[c][j];
+            }
+        }
+    }
+    if (last && A == 0 && FWD && LB_PEER_STAGE && p.n_peers > 0) {
+        __syncthreads();
+        const uint32_t owner = tile >> p.peer_tile_shift;
+        const size_t rows_local = (size_t)4096 << p.peer_tile_shift;
+        const size_t row0 = (size_t)(tile & ((1u << p.peer_tile_shift) - 1)) << 12;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const uint32_t* smc = sm + c * LOW_SMEM_WORDS;
+            uint4* d4 = reinterpret_cast<uint4*>(p.peer[owner] + (p.peer_col0 + col + c) * rows_local + row0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int chunk = threadIdx.x + 256 * k;  // 16-byte chunk of the 4096-element tile
+                uint4 t = *reinterpret_cast<const uint4*>(smc + low_pad(4 * chunk));
+                d4[chunk] = make_uint4(finalize(t.x, p.final_mode, p.scale), finalize(t.y, p.final_mode, p.scale),
+                                       finalize(t.z, p.final_mode, p.scale), finalize(t.w, p.final_mode, p.scale));
             }
         }
     }

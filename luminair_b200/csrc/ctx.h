@@ -47,8 +47,8 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
 int eval_at_point_impl(lb_ctx* ctx, const uint32_t* const* h_cols, int n_cols, int log, const uint32_t point[8],
                        uint32_t* h_out);
 int accumulate_quotients_impl(lb_ctx* ctx, int log, const uint32_t* const* h_cols, int n_cols,
-                              const lb_sample_batch* batches, int n_batches, const uint32_t random_coeff[4],
-                              uint32_t* const d_out[4]);
+                              const lb_sample_batch* batches, const lb_batch_shard* shards, int n_batches,
+                              const uint32_t random_coeff[4], uint32_t* const d_out[4]);
 int fold_impl(lb_ctx* ctx, int circle, uint32_t* const d_dst[4], const uint32_t* const d_src[4], int log,
               const uint32_t alpha[4]);
 int grind_impl(lb_ctx* ctx, const uint32_t digest[8], int variant, uint32_t pow_bits, uint64_t* nonce_out);

@@ -492,6 +492,10 @@ struct PointEval : LogupMixin<PointEval, FQ, FQ> {
 struct HostBatch {  // ColumnSampleBatch: one sample point and the (column, value) pairs sampled there
     QPt pt;
     std::vector<std::pair<int, QM31>> cols;
+    // column-sharded accumulation: this rank holds columns [col_offset, col_offset + cols.size()) of a
+    // batch of n_cols_global columns; the partial sums of all ranks add up to the full quotient
+    int col_offset = 0;
+    int n_cols_global = -1;  // -1: cols.size()
 };
 
 // PolyOps::eval_at_point for a set of equally sized coefficient columns
@@ -532,7 +536,7 @@ void launch_quotients(lb_ctx* ctx, Arena& arena, int lg, const std::vector<const
         o.count = (int)b.cols.size();
         o.sum_a = q_zero();
         o.sum_b = q_zero();
-        QM31 alpha = q_one();
+        QM31 alpha = q_pow(rc_q, (uint64_t)b.col_offset);
         QM31 cc = q_sub(q_conj(b.pt.y), b.pt.y);
         for (auto& cv : b.cols) {
             if (cv.first < 0 || cv.first >= (int)colptrs.size()) fail(LB_ERR_BAD_ARG, "quotients: column index out of range");
@@ -546,7 +550,7 @@ void launch_quotients(lb_ctx* ctx, Arena& arena, int lg, const std::vector<const
             e.col = cv.first;
             entries.push_back(e);
         }
-        o.rc_pow = q_pow(rc_q, b.cols.size());
+        o.rc_pow = q_pow(rc_q, b.n_cols_global >= 0 ? (uint64_t)b.n_cols_global : (uint64_t)b.cols.size());
     }
     const uint32_t** d_cols = arena.upload(colptrs);
     QuotientEntry* d_entries = arena.upload(entries);
@@ -1362,8 +1366,8 @@ int eval_at_point_impl(lb_ctx* ctx, const uint32_t* const* h_cols, int n_cols, i
 }
 
 int accumulate_quotients_impl(lb_ctx* ctx, int log, const uint32_t* const* h_cols, int n_cols,
-                              const lb_sample_batch* batches, int n_batches, const uint32_t random_coeff[4],
-                              uint32_t* const d_out[4]) {
+                              const lb_sample_batch* batches, const lb_batch_shard* shards, int n_batches,
+                              const uint32_t random_coeff[4], uint32_t* const d_out[4]) {
     return guarded(ctx, [&] {
         ensure_kernels(ctx);
         Arena arena(ctx->stream);
@@ -1373,6 +1377,12 @@ int accumulate_quotients_impl(lb_ctx* ctx, int log, const uint32_t* const* h_col
             hb[b].pt = QPt{q_from_words(batches[b].point), q_from_words(batches[b].point + 4)};
             for (int k = 0; k < batches[b].n_cols; ++k)
                 hb[b].cols.push_back({batches[b].col_idx[k], q_from_words(batches[b].values + 4 * k)});
+            if (shards) {
+                if (shards[b].col_offset < 0 || shards[b].n_cols_global < shards[b].col_offset + batches[b].n_cols)
+                    fail(LB_ERR_BAD_ARG, "quotients: bad shard description");
+                hb[b].col_offset = shards[b].col_offset;
+                hb[b].n_cols_global = shards[b].n_cols_global;
+            }
         }
         launch_quotients(ctx, arena, log, cols, hb, q_from_words(random_coeff), d_out);
         ck(cudaStreamSynchronize(ctx->stream), "quotients sync");  // arena scratch is released on return

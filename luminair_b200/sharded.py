@@ -33,6 +33,13 @@ class ShardOps(Protocol):
     def merkle_layer(self, log_size: int, prev: Optional[torch.Tensor], cols: Optional[torch.Tensor]) -> torch.Tensor:
         """-> [2^log, 8] digests; prev [2^(log+1), 8] or None; cols [n_cols, 2^log] or None."""
 
+    def eval_at_point(self, coeffs: torch.Tensor, log_size: int, point) -> torch.Tensor:
+        """coeffs [n_cols, 2^log] -> sampled values [n_cols, 4] (QM31 coordinates); point = 8 u32 (x then y)."""
+
+    def quotients_partial(self, lde: torch.Tensor, lde_log: int, point, values: torch.Tensor, random_coeff, col_offset: int,
+                          n_cols_global: int) -> torch.Tensor:
+        """Partial DEEP quotient [4, 2^lde_log] of this rank's columns (global column indices col_offset ..)."""
+
     def sync(self) -> None:
         ...
 
@@ -65,6 +72,25 @@ class CudaShardOps:
         if cols is not None:
             assert cols.is_contiguous() and cols.shape[1] == n
         self.be.merkle_commit_layer(log_size, prev.data_ptr() if prev is not None else None, ptrs, out.data_ptr())
+        return out
+
+    def eval_at_point(self, coeffs, log_size, point):
+        import numpy as np
+        n = 1 << log_size
+        ptrs = [coeffs.data_ptr() + 4 * n * c for c in range(coeffs.shape[0])]
+        out = self.be.eval_at_point(ptrs, log_size, list(point))
+        return torch.from_numpy(out.view(np.int32).copy())
+
+    def quotients_partial(self, lde, lde_log, point, values, random_coeff, col_offset, n_cols_global):
+        import numpy as np
+        n = 1 << lde_log
+        n_cols = lde.shape[0]
+        ptrs = [lde.data_ptr() + 4 * n * c for c in range(n_cols)]
+        vals = values.numpy().view(np.uint32)
+        out = torch.empty((4, n), dtype=torch.int32, device=lde.device)
+        batch = (list(point), [(c, [int(x) for x in vals[c]]) for c in range(n_cols)])
+        self.be.accumulate_quotients(lde_log, ptrs, [batch], random_coeff, [out.data_ptr() + 4 * n * k for k in range(4)],
+                                     shards=[(col_offset, n_cols_global)])
         return out
 
     def sync(self):
@@ -140,6 +166,58 @@ def sharded_commit(ops: ShardOps, trace_local: torch.Tensor, log_size: int, log_
                         "all_to_all_bytes_per_rank": int(n_cols_local * (1 << lde_log) * 4 * (world - 1) // world),
                         "rank": rank, "world": world})
     return root
+
+
+M31_P = (1 << 31) - 1
+
+
+def sharded_quotient_accumulation(ops: ShardOps, coeffs_local: torch.Tensor, lde_local: torch.Tensor, log_size: int,
+                                  log_blowup: int, point, random_coeff, group=None, timings: Optional[dict] = None):
+    """OODS sampling + DEEP quotient accumulation of a column-sharded commitment (SURVEY 8e collectives (2), (3)):
+
+      1. per rank:   eval_at_point of its own polynomials                                     (no collective)
+      2. all-gather: the sampled values, 16 B per column (they are mixed into the channel in global column order)
+      3. per rank:   partial quotient of its own columns, weighted with the GLOBAL powers of the random coefficient
+      4. all-reduce: coordinate-wise sum of the partial quotients (int64 sum, then mod p)
+
+    `point` = 8 u32 (QM31 x, y), `random_coeff` = 4 u32.  Returns (sampled [n_cols_total, 4], quotient [4, 2^lde_log]),
+    both identical on every rank and identical to the single-device ``eval_at_point`` / ``accumulate_quotients``
+    over all columns (every column sampled at `point` only, as in a synthetic trace without LogUp columns)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n_local = coeffs_local.shape[0]
+    lde_log = log_size + log_blowup
+    t0 = time.perf_counter()
+    sampled_local = ops.eval_at_point(coeffs_local, log_size, point)  # [n_local, 4] on the host
+    ops.sync()
+    t1 = time.perf_counter()
+    if world > 1:
+        dev = lde_local.device
+        mine = sampled_local.to(dev)
+        gathered = torch.empty((world * n_local, 4), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(gathered, mine, group=group)
+        sampled = gathered.cpu()
+    else:
+        sampled = sampled_local
+    t2 = time.perf_counter()
+    partial = ops.quotients_partial(lde_local, lde_log, point, sampled_local, random_coeff, rank * n_local, world * n_local)
+    ops.sync()
+    t3 = time.perf_counter()
+    if world > 1:
+        acc = partial.to(torch.int64)
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+        quotient = (acc % M31_P).to(torch.int32)
+        if quotient.is_cuda:
+            torch.cuda.current_stream().synchronize()
+    else:
+        quotient = partial
+    t4 = time.perf_counter()
+    if timings is not None:
+        timings.update({"sample_ms": (t1 - t0) * 1e3, "sample_allgather_ms": (t2 - t1) * 1e3, "quotients_ms": (t3 - t2) * 1e3,
+                        "quotient_allreduce_ms": (t4 - t3) * 1e3, "total_ms": (t4 - t0) * 1e3,
+                        "allgather_bytes_per_rank": int(16 * n_local * (world - 1)),
+                        "allreduce_bytes_per_rank": int(8 * 4 * (1 << lde_log)) if world > 1 else 0})
+    return sampled, quotient
 
 
 class FusedShardedCommitter:

@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
 from luminair_b200.backend import CudaBackend
-from luminair_b200.sharded import CudaShardOps, column_range, sharded_commit
+from luminair_b200.sharded import CudaShardOps, column_range, sharded_commit, sharded_quotient_accumulation
 
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
@@ -44,4 +44,21 @@ dist.barrier()
 print(f"rank {rank}/{world}: sharded root {root.hex()[:16]} single-device root {want.hex()[:16]} equal={root == want} "
       f"total {tm['total_ms']:.2f} ms (lde {tm['lde_ms']:.2f}, a2a {tm['all_to_all_ms']:.2f}, subtree {tm['subtree_ms']:.2f})", flush=True)
 assert root == want
+# OODS sampling + DEEP quotient accumulation over the column shards vs one device holding every column
+POINT, RC = [11, 22, 33, 44, 55, 66, 77, 88], [5, 6, 7, 8]
+n = 1 << log
+coeffs_local = torch.from_numpy(full[lo:hi].view(np.int32).copy()).cuda()
+lde_local = ops.lde(coeffs_local, log, 1)  # coeffs_local now holds the coefficients
+qtm = {}
+sampled, quot = sharded_quotient_accumulation(ops, coeffs_local, lde_local, log, 1, POINT, RC, timings=qtm)
+coeffs_all = torch.from_numpy(full.view(np.int32).copy()).cuda()
+lde_all = ops.lde(coeffs_all, log, 1)
+want_s = ops.eval_at_point(coeffs_all, log, POINT)
+want_q = ops.quotients_partial(lde_all, log + 1, POINT, want_s, RC, 0, n_cols)
+be.sync()
+ok_s = bool(torch.equal(sampled, want_s)); ok_q = bool(torch.equal(quot.cpu(), want_q.cpu()))
+print(f"rank {rank}/{world}: sharded sampled values equal={ok_s} quotient equal={ok_q} total {qtm['total_ms']:.2f} ms "
+      f"(sample {qtm['sample_ms']:.2f}, allgather {qtm['sample_allgather_ms']:.2f}, quotients {qtm['quotients_ms']:.2f}, "
+      f"allreduce {qtm['quotient_allreduce_ms']:.2f})", flush=True)
+assert ok_s and ok_q
 dist.destroy_process_group()
