@@ -166,6 +166,25 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def pin_to_gpu_numa_node(index):
+    """Bind this rank to the CPUs NVML reports as local to its GPU, so the pinned host buffers of the e2e leg are
+    first-touched on that NUMA node (8 ranks otherwise share one node's memory controllers).  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus local to GPU {index}"
+    except Exception as e:  # containers may forbid it
+        return f"not applied ({type(e).__name__})"
+    return "not applied"
+
+
 # ---------------------------------------------------------------------------------------
 def run_gpu(args):
     import torch
@@ -176,6 +195,7 @@ def run_gpu(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     distributed = world > 1
     torch.cuda.set_device(local_rank)
+    numa = pin_to_gpu_numa_node(local_rank)  # before any pinned allocation: first touch lands on the GPU's NUMA node
     if distributed:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -299,7 +319,7 @@ def run_gpu(args):
                        "sharding": "columns, no collective"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "M31 field-ops/s", "h2d_bytes_per_step": N_COLS * n * 4 * world,
-                    "d2h_bytes_per_step": N_COLS * n * 4 * world, "ms_per_step": e2e_s * 1e3},
+                    "d2h_bytes_per_step": N_COLS * n * 4 * world, "ms_per_step": e2e_s * 1e3, "host_numa_binding": numa},
             "gpu_launches": args.steps * n_launch_per_step,
             "roofline": {"bound": "hbm", "kernel": "cfft_low_fast / cfft_high_fast (the 4 CFFT passes of a step)", "achieved": achieved, "peak": peak,
                          "peak_source": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
