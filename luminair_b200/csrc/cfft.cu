@@ -564,7 +564,7 @@ __device__ __forceinline__ void low_round(uint32_t* sm, const PassParams& p, uin
 // twiddle load and index computation is shared by NC butterflies and each warp has NC x the independent work.
 template <bool FWD, int M, int NC>
 __global__ void __launch_bounds__(256, NC == 1 ? LB_LOW_MINB : LB_LOW_MINB2) cfft_low_fast(PassParams p, int cols_per_block) {
-    __shared__ __align__(16) uint32_t sm[NC * LOW_SMEM_WORDS];
+    extern __shared__ __align__(16) uint32_t sm[];  // NC * LOW_SMEM_WORDS
     constexpr int NR = (M + 3) / 4;
     const uint32_t tile = blockIdx.x;
     const int c0 = blockIdx.y * cols_per_block * NC;
@@ -787,7 +787,13 @@ static cudaError_t launch_low_nc(const PassParams& p, int sm_count, cudaStream_t
     int cpb = pick_cols_per_block(tiles, groups, sm_count);
     dim3 grid((unsigned)tiles, (unsigned)((groups + cpb - 1) / cpb));
     if (grid.y > 65535) return cudaErrorInvalidValue;
-    cfft_low_fast<FWD, M, NC><<<grid, 256, 0, stream>>>(p, cpb);
+    constexpr size_t smem = (size_t)NC * LOW_SMEM_WORDS * sizeof(uint32_t);
+    auto k = cfft_low_fast<FWD, M, NC>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k<<<grid, 256, smem, stream>>>(p, cpb);
     return cudaGetLastError();
 }
 
