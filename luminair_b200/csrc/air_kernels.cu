@@ -113,18 +113,34 @@ __global__ void __launch_bounds__(256) logup_scan_local_kernel(const uint32_t* _
     if (threadIdx.x == 255) block_sums[(size_t)coord * gridDim.x + blockIdx.x] = m_add(s, woff);
 }
 
-// phase 2: exclusive scan of the CTA totals (<= 2^21 / 1024 entries per coordinate); total -> claimed
-__global__ void logup_scan_sums_kernel(uint32_t* block_sums, uint32_t n_blocks, uint32_t* claimed) {
-    int coord = threadIdx.x;
-    if (coord >= 4) return;
+// phase 2: exclusive scan of the CTA totals (<= 2^24 / 1024 entries per coordinate); total -> claimed.
+// One CTA per coordinate: every thread scans a contiguous chunk, the 256 chunk totals are scanned in shared memory.
+__global__ void __launch_bounds__(256) logup_scan_sums_kernel(uint32_t* block_sums, uint32_t n_blocks, uint32_t* claimed) {
+    __shared__ uint32_t s_tot[256];
+    const int coord = blockIdx.x;
     uint32_t* s = block_sums + (size_t)coord * n_blocks;
+    const uint32_t per = (n_blocks + 255) / 256;
+    const uint32_t b0 = min(threadIdx.x * per, n_blocks), b1 = min(b0 + per, n_blocks);
     uint32_t run = 0;
-    for (uint32_t b = 0; b < n_blocks; ++b) {
+    for (uint32_t b = b0; b < b1; ++b) run = m_add(run, s[b]);
+    s_tot[threadIdx.x] = run;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int t = 0; t < 256; ++t) {
+            uint32_t v = s_tot[t];
+            s_tot[t] = acc;
+            acc = m_add(acc, v);
+        }
+        claimed[coord] = acc;
+    }
+    __syncthreads();
+    run = s_tot[threadIdx.x];
+    for (uint32_t b = b0; b < b1; ++b) {
         uint32_t t = s[b];
         s[b] = run;
         run = m_add(run, t);
     }
-    claimed[coord] = run;
 }
 
 // phase 3: out[storage(k)] = local[k] + offset[block] - (k + 1) * claimed / n
@@ -175,7 +191,7 @@ cudaError_t logup_interaction_trace(int kind, const uint32_t* main, size_t main_
     uint32_t* last = inter + (size_t)(4 * (nf - 1)) * inter_stride;
     uint32_t n_blocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
     logup_scan_local_kernel<<<dim3(n_blocks, 4), 256, 0, stream>>>(last, inter_stride, d_scan_tmp, d_block_sums, log);
-    logup_scan_sums_kernel<<<1, 32, 0, stream>>>(d_block_sums, n_blocks, d_claimed);
+    logup_scan_sums_kernel<<<4, 256, 0, stream>>>(d_block_sums, n_blocks, d_claimed);
     uint32_t inv_n = m_inv(n % P);
     logup_scan_apply_kernel<<<dim3(blocks, 4), 256, 0, stream>>>(last, inter_stride, d_scan_tmp, d_block_sums, d_claimed, log,
                                                                  inv_n);

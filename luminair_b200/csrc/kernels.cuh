@@ -43,6 +43,21 @@ cudaError_t fold_circle_into_line(uint32_t* const dst[4], const uint32_t* const 
 cudaError_t fold_line(uint32_t* const dst[4], const uint32_t* const src[4], const uint2* itw, int log, QM31 alpha,
                       cudaStream_t stream);
 
+// the same with the folding coefficient in device memory
+cudaError_t fold_circle_into_line_dev(uint32_t* const dst[4], const uint32_t* const src[4], const uint2* itw, int log,
+                                      const QM31* d_alpha, cudaStream_t stream);
+cudaError_t fold_line_dev(uint32_t* const dst[4], const uint32_t* const src[4], const uint2* itw, int log, const QM31* d_alpha,
+                          cudaStream_t stream);
+// device-side Blake2sChannel state for the FRI commit loop: digest <- mix_root(*d_root); *d_alpha_out = draw_secure_felt();
+// the new digest is also written to d_digest_log (8 words)
+struct DevChannel {
+    uint32_t digest[8];
+    uint32_t n_sent;
+    uint32_t pad[7];
+};
+cudaError_t channel_mix_root_draw(DevChannel* d_ch, const uint32_t* d_root, int variant, QM31* d_alpha_out, uint32_t* d_digest_log,
+                                  cudaStream_t stream);
+
 // ---- GrindOps ------------------------------------------------------------------------------------
 // tests nonces [base, base + count); *d_found = min nonce that works (or UINT64_MAX)
 cudaError_t grind_range(const uint32_t digest[8], int variant, uint32_t pow_bits, uint64_t base, uint64_t count,

@@ -154,7 +154,7 @@ cudaError_t eval_at_point(const uint32_t* const* d_cols, int n_cols, int log, co
 constexpr int QROWS = 4;
 
 template <int NB>
-__global__ void __launch_bounds__(256) quotients_kernel(uint32_t* __restrict__ o0, uint32_t* __restrict__ o1,
+__global__ void __launch_bounds__(256, 2) quotients_kernel(uint32_t* __restrict__ o0, uint32_t* __restrict__ o1,
                                                         uint32_t* __restrict__ o2, uint32_t* __restrict__ o3,
                                                         const uint32_t* const* __restrict__ cols,
                                                         const QuotientEntry* __restrict__ entries,
@@ -193,29 +193,78 @@ __global__ void __launch_bounds__(256) quotients_kernel(uint32_t* __restrict__ o
         inv = c_mul(inv, den[k]);
         den[k] = di;  // now the inverse
     }
+    // Numerators sum_j c_j * f_j(row): the four coordinates of every row are kept as lazy 64-bit sums (one IMAD.WIDE per
+    // coordinate and column; products are < 2^62, so a fold every third column keeps them below 2^64) and reduced once per
+    // batch.  The QROWS rows of a thread go through the column loop together: one entry / pointer load serves all of them
+    // and the rows give the loads and multiply-adds independent chains.
+    uint32_t jr[QROWS];
+#pragma unroll
+    for (int r = 0; r < QROWS; ++r) {
+        uint32_t j = j0 + r * 256;
+        jr[r] = j < n ? j : n - 1;  // clamp (results of clamped rows are not stored)
+    }
+    QM31 acc[QROWS];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const QuotientBatch& B = qp.b[b];
+        uint64_t s[QROWS][4];
+#pragma unroll
+        for (int r = 0; r < QROWS; ++r) s[r][0] = s[r][1] = s[r][2] = s[r][3] = 0;
+        // columns go three at a time: 3 x QROWS independent loads in flight per thread (the kernel is latency-bound
+        // otherwise: ~100 registers per thread leave 16 warps per SM), then one fold of the twelve products
+        int k = 0;
+        for (; k + 3 <= B.count; k += 3) {
+            const QuotientEntry e0 = entries[B.first + k], e1 = entries[B.first + k + 1], e2 = entries[B.first + k + 2];
+            const uint32_t* __restrict__ c0 = cols[e0.col];
+            const uint32_t* __restrict__ c1 = cols[e1.col];
+            const uint32_t* __restrict__ c2 = cols[e2.col];
+            uint32_t v0[QROWS], v1[QROWS], v2[QROWS];
+#pragma unroll
+            for (int r = 0; r < QROWS; ++r) {
+                v0[r] = c0[jr[r]];
+                v1[r] = c1[jr[r]];
+                v2[r] = c2[jr[r]];
+            }
+#pragma unroll
+            for (int r = 0; r < QROWS; ++r) {
+                const uint64_t a = v0[r], b2 = v1[r], c = v2[r];
+                s[r][0] += a * e0.c.a.a + b2 * e1.c.a.a + c * e2.c.a.a;
+                s[r][1] += a * e0.c.a.b + b2 * e1.c.a.b + c * e2.c.a.b;
+                s[r][2] += a * e0.c.b.a + b2 * e1.c.b.a + c * e2.c.b.a;
+                s[r][3] += a * e0.c.b.b + b2 * e1.c.b.b + c * e2.c.b.b;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) s[r][q] = (s[r][q] & P) + (s[r][q] >> 31);
+            }
+        }
+        for (; k < B.count; ++k) {  // at most two more columns: folded sums (< 2^34) + 2 products (< 2^63) fit
+            const QuotientEntry e = entries[B.first + k];
+            const uint32_t* __restrict__ col = cols[e.col];
+#pragma unroll
+            for (int r = 0; r < QROWS; ++r) {
+                const uint64_t v = col[jr[r]];
+                s[r][0] += v * e.c.a.a;
+                s[r][1] += v * e.c.a.b;
+                s[r][2] += v * e.c.b.a;
+                s[r][3] += v * e.c.b.b;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < QROWS; ++r) {
+            QM31 num = q_make(fold64(s[r][0]), fold64(s[r][1]), fold64(s[r][2]), fold64(s[r][3]));
+            QM31 lin = q_add(q_mul_m(B.sum_a, ys[r]), B.sum_b);
+            num = q_sub(num, lin);
+            QM31 q = q_mul_c(num, den[r * NB + b]);
+            acc[r] = (b == 0) ? q : q_add(q_mul(acc[r], B.rc_pow), q);
+        }
+    }
 #pragma unroll
     for (int r = 0; r < QROWS; ++r) {
         uint32_t j = j0 + r * 256;
         if (j >= n) continue;
-        QM31 acc = q_zero();
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            const QuotientBatch& B = qp.b[b];
-            QM31 num = q_zero();
-            for (int k = 0; k < B.count; ++k) {
-                const QuotientEntry& e = entries[B.first + k];
-                uint32_t v = cols[e.col][j];
-                num = q_add(num, q_mul_m(e.c, v));
-            }
-            QM31 lin = q_add(q_mul_m(B.sum_a, ys[r]), B.sum_b);
-            num = q_sub(num, lin);
-            QM31 q = q_mul_c(num, den[r * NB + b]);
-            acc = (b == 0) ? q : q_add(q_mul(acc, B.rc_pow), q);
-        }
-        o0[j] = acc.a.a;
-        o1[j] = acc.a.b;
-        o2[j] = acc.b.a;
-        o3[j] = acc.b.b;
+        o0[j] = acc[r].a.a;
+        o1[j] = acc[r].a.b;
+        o2[j] = acc[r].b.a;
+        o3[j] = acc[r].b.b;
     }
 }
 
@@ -299,6 +348,120 @@ cudaError_t fold_line(uint32_t* const dst[4], const uint32_t* const src[4], cons
     }
     uint32_t n_out = 1u << (log - 1);
     fold_kernel<false><<<(n_out + 255) / 256, 256, 0, stream>>>(d, s, itw, n_out, alpha, q_zero());
+    return cudaGetLastError();
+}
+
+// the same folds with the folding coefficient read from device memory (drawn there by the device-side channel)
+template <bool CIRCLE>
+__global__ void __launch_bounds__(256) fold_kernel_dev_alpha(Coords4 dst, CCoords4 src, const uint2* __restrict__ itw,
+                                                             uint32_t n_out, const QM31* __restrict__ alpha_ptr) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    const QM31 alpha = *alpha_ptr;
+    uint32_t a[4], b[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint2 v = *reinterpret_cast<const uint2*>(src.p[c] + 2 * (size_t)i);
+        a[c] = v.x;
+        b[c] = v.y;
+    }
+    uint32_t tinv = itw[i].x;
+    QM31 f_p = q_make(a[0], a[1], a[2], a[3]), f_n = q_make(b[0], b[1], b[2], b[3]);
+    QM31 f0 = q_add(f_p, f_n);
+    QM31 f1 = q_mul_m(q_sub(f_p, f_n), tinv);
+    QM31 r = q_add(q_mul(alpha, f1), f0);
+    if (CIRCLE) {
+        QM31 d = q_make(dst.p[0][i], dst.p[1][i], dst.p[2][i], dst.p[3][i]);
+        r = q_add(q_mul(d, q_mul(alpha, alpha)), r);
+    }
+    dst.p[0][i] = r.a.a;
+    dst.p[1][i] = r.a.b;
+    dst.p[2][i] = r.b.a;
+    dst.p[3][i] = r.b.b;
+}
+
+cudaError_t fold_circle_into_line_dev(uint32_t* const dst[4], const uint32_t* const src[4], const uint2* itw, int log,
+                                      const QM31* d_alpha, cudaStream_t stream) {
+    Coords4 d;
+    CCoords4 s;
+    for (int c = 0; c < 4; ++c) {
+        d.p[c] = dst[c];
+        s.p[c] = src[c];
+    }
+    uint32_t n_out = 1u << (log - 1);
+    fold_kernel_dev_alpha<true><<<(n_out + 255) / 256, 256, 0, stream>>>(d, s, itw, n_out, d_alpha);
+    return cudaGetLastError();
+}
+
+cudaError_t fold_line_dev(uint32_t* const dst[4], const uint32_t* const src[4], const uint2* itw, int log, const QM31* d_alpha,
+                          cudaStream_t stream) {
+    Coords4 d;
+    CCoords4 s;
+    for (int c = 0; c < 4; ++c) {
+        d.p[c] = dst[c];
+        s.p[c] = src[c];
+    }
+    uint32_t n_out = 1u << (log - 1);
+    fold_kernel_dev_alpha<false><<<(n_out + 255) / 256, 256, 0, stream>>>(d, s, itw, n_out, d_alpha);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
+// Device-side Fiat-Shamir step of the FRI commit loop (FriProver::commit: per inner layer
+// `mix_root(layer root); alpha = draw_secure_felt()`), so that fold -> Merkle -> mix -> draw -> fold runs
+// on the stream without a host round trip per layer.  Same Blake2sChannel as prover.cu's host class
+// (core/channel/blake2s.rs; variant 0 "legacy" / 1 "v2").  One thread.
+// ------------------------------------------------------------------------------------
+__global__ void channel_mix_root_draw_kernel(DevChannel* ch, const uint32_t* __restrict__ root, int variant, QM31* alpha_out,
+                                             uint32_t* digest_log) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t h[8], m[16];
+    // mix_root: digest <- Blake2s(digest || root), one 64-byte final block
+    blake2s_init(h);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        m[i] = ch->digest[i];
+        m[8 + i] = root[i];
+    }
+    blake2s_compress(h, m, 64, 0, 0xFFFFFFFFu);
+    uint32_t dg[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        dg[i] = h[i];
+        ch->digest[i] = h[i];
+        digest_log[i] = h[i];
+    }
+    // draw_secure_felt: draw_base_felts retries until all eight words are < 2p
+    uint32_t n_sent = 0;
+    for (;;) {
+        blake2s_init(h);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = dg[i];
+        m[8] = n_sent;
+#pragma unroll
+        for (int i = 9; i < 16; ++i) m[i] = 0;
+        ++n_sent;
+        if (variant == 0) {
+            blake2s_compress(h, m, 64, 0, 0xFFFFFFFFu);
+        } else {
+            blake2s_compress(h, m, 64, 0, 0);  // 65-byte message: a full block, then the 0x00 domain byte
+#pragma unroll
+            for (int i = 0; i < 16; ++i) m[i] = 0;
+            blake2s_compress(h, m, 65, 0, 0xFFFFFFFFu);
+        }
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ok = ok && (h[i] < 2 * P);
+        if (ok) break;
+    }
+    ch->n_sent = n_sent;
+    *alpha_out = q_make(h[0] >= P ? h[0] - P : h[0], h[1] >= P ? h[1] - P : h[1], h[2] >= P ? h[2] - P : h[2],
+                        h[3] >= P ? h[3] - P : h[3]);
+}
+
+cudaError_t channel_mix_root_draw(DevChannel* d_ch, const uint32_t* d_root, int variant, QM31* d_alpha_out, uint32_t* d_digest_log,
+                                  cudaStream_t stream) {
+    channel_mix_root_draw_kernel<<<1, 32, 0, stream>>>(d_ch, d_root, variant, d_alpha_out, d_digest_log);
     return cudaGetLastError();
 }
 

@@ -191,6 +191,16 @@ class Channel {
         return out;
     }
 
+    // hand-over to / from the device-side channel of the FRI commit loop
+    uint32_t n_sent() const { return n_sent_; }
+    void adopt(const Hash32& d, uint32_t n_sent) {
+        digest_ = d;
+        n_sent_ = n_sent;
+    }
+    void log_digest(const Hash32& d) {
+        if (log_) log_->push_back(d);
+    }
+
    private:
     void update(const Hash32& d) {
         digest_ = d;
@@ -241,7 +251,7 @@ struct DecommitIdx {
     std::vector<size_t> queried_values;  // word index
 };
 
-void merkle_commit(lb_ctx* ctx, Arena& arena, const std::vector<ColRef>& cols, MerkleTree& t) {
+void merkle_commit(lb_ctx* ctx, Arena& arena, const std::vector<ColRef>& cols, MerkleTree& t, bool fetch_root = true) {
     if (cols.empty()) {
         t.empty = true;
         t.max_log = 0;
@@ -290,6 +300,7 @@ void merkle_commit(lb_ctx* ctx, Arena& arena, const std::vector<ColRef>& cols, M
         a.from_log = fused_from;
         ck(merkle_commit_top(a, ctx->stream), "merkle top");
     }
+    if (!fetch_root) return;  // the caller reads t.layers[0] on the device and fetches the root later
     ck(cudaMemcpyAsync(t.root.b, t.layers[0], 32, cudaMemcpyDeviceToHost, ctx->stream), "root d2h");
     ck(cudaStreamSynchronize(ctx->stream), "root sync");
 }
@@ -1104,13 +1115,27 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             auto layer_at = [&](int lg) { return fri_buf + 4 * (((size_t)1 << lg) - 1); };
             uint32_t* cur = layer_at(line_log);
             ck(cudaMemsetAsync(cur, 0, ((size_t)4 << line_log) * sizeof(uint32_t), st), "memset");
+            // The per-layer Fiat-Shamir step (mix_root, draw the next folding coefficient) runs on the device
+            // (channel_mix_root_draw), so fold -> Merkle -> mix -> draw -> fold is enqueued for every layer without a host
+            // round trip; roots, digests and the final channel state come back in one copy after the loop.
+            int n_layers = std::max(0, line_log - last_log);
+            DevChannel h_ch{};
+            channel.digest_words(h_ch.digest);
+            h_ch.n_sent = channel.n_sent();
+            DevChannel* d_ch = arena.alloc<DevChannel>(1);
+            QM31* d_alphas = arena.alloc<QM31>(n_layers + 1);
+            uint32_t* d_digests = arena.alloc<uint32_t>(8 * (size_t)std::max(n_layers, 1));
+            ck(cudaMemcpyAsync(d_ch, &h_ch, sizeof(h_ch), cudaMemcpyHostToDevice, st), "channel h2d");
+            ck(cudaMemcpyAsync(d_alphas, &folding_alpha, sizeof(QM31), cudaMemcpyHostToDevice, st), "alpha h2d");
+            ck(cudaStreamSynchronize(st), "channel h2d sync");  // h_ch / folding_alpha are stack objects
             size_t qi = 0;
+            int li = 0;
             while (line_log > last_log) {
                 uint32_t* coords[4];
                 for (int k = 0; k < 4; ++k) coords[k] = cur + ((size_t)k << line_log);
                 while (qi < quotients.size() && quotients[qi].log - 1 == line_log) {
-                    ck(fold_circle_into_line(coords, quotients[qi].coords, inv_y_twiddles(tw, quotients[qi].log),
-                                             quotients[qi].log, folding_alpha, st),
+                    ck(fold_circle_into_line_dev(coords, quotients[qi].coords, inv_y_twiddles(tw, quotients[qi].log),
+                                                 quotients[qi].log, d_alphas + li, st),
                        "fold circle");
                     ++qi;
                 }
@@ -1119,16 +1144,33 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                 for (int k = 0; k < 4; ++k) L.coords[k] = coords[k];
                 std::vector<ColRef> refs;
                 for (int k = 0; k < 4; ++k) refs.push_back({coords[k], line_log});
-                merkle_commit(ctx, arena, refs, L.tree);
-                channel.mix_root(L.tree.root);
-                folding_alpha = channel.draw_secure_felt();
+                merkle_commit(ctx, arena, refs, L.tree, /*fetch_root=*/false);
+                ck(channel_mix_root_draw(d_ch, L.tree.layers[0], cfg.channel_variant, d_alphas + li + 1, d_digests + 8 * (size_t)li, st),
+                   "channel mix/draw");
                 inner.push_back(L);
                 uint32_t* next = layer_at(line_log - 1);
                 uint32_t* ncoords[4];
                 for (int k = 0; k < 4; ++k) ncoords[k] = next + ((size_t)k << (line_log - 1));
-                ck(fold_line(ncoords, coords, inv_x_twiddles(tw, line_log), line_log, folding_alpha, st), "fold line");
+                ck(fold_line_dev(ncoords, coords, inv_x_twiddles(tw, line_log), line_log, d_alphas + li + 1, st), "fold line");
                 cur = next;
                 --line_log;
+                ++li;
+            }
+            if (n_layers > 0) {
+                std::vector<uint32_t> h_digests(8 * (size_t)n_layers);
+                for (int k = 0; k < n_layers; ++k)
+                    ck(cudaMemcpyAsync(inner[k].tree.root.b, inner[k].tree.layers[0], 32, cudaMemcpyDeviceToHost, st), "root d2h");
+                ck(cudaMemcpyAsync(h_digests.data(), d_digests, h_digests.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "digests d2h");
+                ck(cudaMemcpyAsync(&h_ch, d_ch, sizeof(h_ch), cudaMemcpyDeviceToHost, st), "channel d2h");
+                ck(cudaStreamSynchronize(st), "fri loop sync");
+                for (int k = 0; k < n_layers; ++k) {
+                    Hash32 d;
+                    std::memcpy(d.b, h_digests.data() + 8 * (size_t)k, 32);
+                    channel.log_digest(d);
+                }
+                Hash32 d;
+                std::memcpy(d.b, h_ch.digest, 32);
+                channel.adopt(d, h_ch.n_sent);
             }
             if (qi != quotients.size()) fail(LB_ERR_BAD_ARG, "fri: columns left unfolded");
             // last layer: interpolate on the host (2^(bound + blowup) values)
