@@ -27,9 +27,12 @@ __device__ __forceinline__ void compress_dev(uint32_t h[8], const uint32_t m[16]
 #endif
 }
 
-// hash of node i of a layer: children (prev != nullptr) then the layer's column values
-__device__ __forceinline__ void hash_node(uint32_t h[8], const uint32_t* __restrict__ prev,
-                                          const uint32_t* const* __restrict__ cols, int n_cols, uint32_t i, uint32_t one) {
+// hash of node i of a layer: children (prev != nullptr) then the layer's column values.
+// SAME_KERNEL: the children were written earlier by this kernel (another thread of the CTA, before a block barrier):
+// they are read with ld.global.cg so the loads can never be served by the non-coherent read-only path.
+template <bool SAME_KERNEL = false>
+__device__ __forceinline__ void hash_node(uint32_t h[8], const uint32_t* prev, const uint32_t* const* __restrict__ cols,
+                                          int n_cols, uint32_t i, uint32_t one) {
     blake2s_init(h);
     uint32_t m[16];
     uint32_t t = 0;
@@ -37,7 +40,12 @@ __device__ __forceinline__ void hash_node(uint32_t h[8], const uint32_t* __restr
     bool have_block = false;
     if (prev) {
         const uint4* pp = reinterpret_cast<const uint4*>(prev + (size_t)i * 16);
-        uint4 a = pp[0], b = pp[1], cc = pp[2], d = pp[3];
+        uint4 a, b, cc, d;
+        if (SAME_KERNEL) {
+            a = __ldcg(pp); b = __ldcg(pp + 1); cc = __ldcg(pp + 2); d = __ldcg(pp + 3);
+        } else {
+            a = pp[0]; b = pp[1]; cc = pp[2]; d = pp[3];
+        }
         m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w;
         m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
         m[8] = cc.x; m[9] = cc.y; m[10] = cc.z; m[11] = cc.w;
@@ -91,41 +99,63 @@ cudaError_t merkle_commit_layer(uint32_t* out, const uint32_t* prev, const uint3
 
 // Same, for layers with at most MERKLE_SMALL_COLS columns: the column pointers travel in the kernel parameters, so
 // no pointer table has to be staged in device memory first (the FRI layer trees: 4 coordinate columns each).
-__global__ void __launch_bounds__(256) merkle_layer_small_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ prev,
-                                                                 const __grid_constant__ MerkleColsArg cols, int n_cols,
-                                                                 uint32_t n_nodes, uint32_t one) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_nodes) return;
-    uint32_t h[8];
-    blake2s_init(h);
-    uint32_t m[16];
+// NH nodes per thread (256 apart, so every access stays coalesced): Blake2s is one dependent chain of 4-wide G steps,
+// and a second independent compression per thread lets the scheduler keep both integer pipes busy - measured with
+// scripts/ubench/b2s.cu, register-only: 23.4 -> 26.8 G compressions/s.
+template <int NH>
+__global__ void __launch_bounds__(256, NH == 1 ? 4 : 2) merkle_layer_small_kernel(uint32_t* __restrict__ out,
+                                                                                  const uint32_t* __restrict__ prev,
+                                                                                  const __grid_constant__ MerkleColsArg cols,
+                                                                                  int n_cols, uint32_t n_nodes, uint32_t one) {
+    const uint32_t i0 = blockIdx.x * (256 * NH) + threadIdx.x;
+    if (i0 >= n_nodes) return;  // NH > 1 is only launched for n_nodes that are multiples of 256 * NH
+    uint32_t h[NH][8], m[NH][16];
     uint32_t t = 0;
+#pragma unroll
+    for (int q = 0; q < NH; ++q) blake2s_init(h[q]);
     if (prev) {
-        const uint4* pp = reinterpret_cast<const uint4*>(prev + (size_t)i * 16);
-        uint4 a = pp[0], b = pp[1], cc = pp[2], d = pp[3];
-        m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w;
-        m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
-        m[8] = cc.x; m[9] = cc.y; m[10] = cc.z; m[11] = cc.w;
-        m[12] = d.x; m[13] = d.y; m[14] = d.z; m[15] = d.w;
+#pragma unroll
+        for (int q = 0; q < NH; ++q) {
+            const uint4* pp = reinterpret_cast<const uint4*>(prev + (size_t)(i0 + 256 * q) * 16);
+            uint4 a = pp[0], b = pp[1], cc = pp[2], d = pp[3];
+            m[q][0] = a.x; m[q][1] = a.y; m[q][2] = a.z; m[q][3] = a.w;
+            m[q][4] = b.x; m[q][5] = b.y; m[q][6] = b.z; m[q][7] = b.w;
+            m[q][8] = cc.x; m[q][9] = cc.y; m[q][10] = cc.z; m[q][11] = cc.w;
+            m[q][12] = d.x; m[q][13] = d.y; m[q][14] = d.z; m[q][15] = d.w;
+        }
         t = 64;
-        compress_dev(h, m, t, n_cols == 0 ? 0xFFFFFFFFu : 0u, one);
+#pragma unroll
+        for (int q = 0; q < NH; ++q) compress_dev(h[q], m[q], t, n_cols == 0 ? 0xFFFFFFFFu : 0u, one);
     }
     if (n_cols > 0 || !prev) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) m[j] = (j < n_cols) ? cols.p[j][i] : 0u;
+        for (int q = 0; q < NH; ++q)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) m[q][j] = (j < n_cols) ? cols.p[j][i0 + 256 * q] : 0u;
         t += 4u * n_cols;
-        compress_dev(h, m, t, 0xFFFFFFFFu, one);
+#pragma unroll
+        for (int q = 0; q < NH; ++q) compress_dev(h[q], m[q], t, 0xFFFFFFFFu, one);
     }
-    uint4* o = reinterpret_cast<uint4*>(out + (size_t)i * 8);
-    o[0] = make_uint4(h[0], h[1], h[2], h[3]);
-    o[1] = make_uint4(h[4], h[5], h[6], h[7]);
+#pragma unroll
+    for (int q = 0; q < NH; ++q) {
+        uint4* o = reinterpret_cast<uint4*>(out + (size_t)(i0 + 256 * q) * 8);
+        o[0] = make_uint4(h[q][0], h[q][1], h[q][2], h[q][3]);
+        o[1] = make_uint4(h[q][4], h[q][5], h[q][6], h[q][7]);
+    }
 }
 
+#ifndef LB_MERKLE_NH
+#define LB_MERKLE_NH 2
+#endif
 cudaError_t merkle_commit_layer_small(uint32_t* out, const uint32_t* prev, const MerkleColsArg& cols, int n_cols,
                                       int log_size, cudaStream_t stream) {
     if (n_cols < 0 || n_cols > MERKLE_SMALL_COLS) return cudaErrorInvalidValue;
     uint32_t n = 1u << log_size;
-    merkle_layer_small_kernel<<<(n + 255) / 256, 256, 0, stream>>>(out, prev, cols, n_cols, n, 1u);
+    // two nodes per thread once the layer still fills the machine that way (148 SMs x 2 CTAs x 512 nodes)
+    if (LB_MERKLE_NH == 2 && log_size >= 18)
+        merkle_layer_small_kernel<2><<<n / 512, 256, 0, stream>>>(out, prev, cols, n_cols, n, 1u);
+    else
+        merkle_layer_small_kernel<1><<<(n + 255) / 256, 256, 0, stream>>>(out, prev, cols, n_cols, n, 1u);
     return cudaGetLastError();
 }
 
@@ -137,7 +167,7 @@ __global__ void __launch_bounds__(512) merkle_top_kernel(MerkleTopArgs a, uint32
         uint32_t n = 1u << log;
         if (threadIdx.x < n) {
             uint32_t h[8];
-            hash_node(h, a.layers[log + 1], nullptr, 0, threadIdx.x, one);
+            hash_node<true>(h, a.layers[log + 1], nullptr, 0, threadIdx.x, one);
             uint4* o = reinterpret_cast<uint4*>(a.layers[log] + (size_t)threadIdx.x * 8);
             o[0] = make_uint4(h[0], h[1], h[2], h[3]);
             o[1] = make_uint4(h[4], h[5], h[6], h[7]);
