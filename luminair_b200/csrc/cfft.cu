@@ -714,6 +714,105 @@ __global__ void __launch_bounds__(HighGeom<M>::THREADS, NC == 1 ? HighGeom<M>::M
     }
 }
 
+// ---- high pass, vectorised along the offset dimension ---------------------------------------------------
+// Each thread owns FOUR adjacent offsets (one 128-bit access) of its 16 strided rows: 64 register-resident elements, i.e.
+// four independent radix-16 groups that share every twiddle (twiddles depend on the row only).  Versus the scalar high pass
+// this quarters the load/store, address and twiddle instructions per butterfly and doubles the independent work per thread;
+// a tile is 2^M rows x 64 offsets (M = 8: 64 KiB of shared memory, 256 threads, 2 CTAs per SM).
+#ifndef LB_HIGH_VEC
+#define LB_HIGH_VEC 1
+#endif
+template <bool FWD, int M, int R, int ILO, int ZEXT>
+__device__ __forceinline__ void high_round_vec(uint32_t* sm, const PassParams& p, uint32_t tile_h, size_t g_base,
+                                               const uint32_t* src, uint32_t* dst, bool first, bool last) {
+    constexpr int A = RoundGeom<M, R>::A;
+    constexpr int BLO = RoundGeom<M, R>::BLO;
+    constexpr bool TOP = (A + 4 == M);
+    constexpr int WT = 16, W = 64;
+    const int wt = threadIdx.x % WT;
+    const int g = threadIdx.x / WT;
+    const int e0_hi = g >> A;
+    const int e0 = (e0_hi << (A + 4)) | (g & ((1 << A) - 1));
+    const size_t gb = g_base + ((size_t)e0 << ILO) + 4 * wt;
+    const int sb = e0 * W + 4 * wt;
+    uint32_t v[4][16];
+    constexpr bool HALF = (ZEXT == 1 && TOP && FWD);  // the upper half of the rows is the zero extension
+    if (first) {
+        const uint32_t* sp = src + gb;
+#pragma unroll
+        for (int j = 0; j < (HALF ? 8 : 16); ++j) {
+            const uint4 t = *reinterpret_cast<const uint4*>(sp + ((size_t)(j << A) << ILO));
+            v[0][j] = t.x; v[1][j] = t.y; v[2][j] = t.z; v[3][j] = t.w;
+        }
+        if (HALF) {
+#pragma unroll
+            for (int j = 8; j < 16; ++j) {
+                v[0][j] = v[0][j - 8]; v[1][j] = v[1][j - 8]; v[2][j] = v[2][j - 8]; v[3][j] = v[3][j - 8];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint4 t = *reinterpret_cast<const uint4*>(sm + sb + (j << A) * W);
+            v[0][j] = t.x; v[1][j] = t.y; v[2][j] = t.z; v[3][j] = t.w;
+        }
+    }
+    if (HALF && first && BLO < 4)
+        field_layers_range_nc<FWD, A, BLO, 3, M, 4>(v, p, tile_h, e0_hi);  // the top layer on (v, 0) pairs is the copy above
+    else
+        field_layers_range_nc<FWD, A, BLO, 4, M, 4>(v, p, tile_h, e0_hi);
+    if (last) {
+        uint32_t* dp = dst + gb;
+        auto st = [&](auto mode_tag) {
+            constexpr int MODE = decltype(mode_tag)::value;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                *reinterpret_cast<uint4*>(dp + ((size_t)(j << A) << ILO)) =
+                    make_uint4(finalize_m<MODE>(v[0][j], p.scale), finalize_m<MODE>(v[1][j], p.scale),
+                               finalize_m<MODE>(v[2][j], p.scale), finalize_m<MODE>(v[3][j], p.scale));
+        };
+        if (FWD || p.final_mode == 0) st(std::integral_constant<int, 0>{});
+        else st(std::integral_constant<int, 2>{});
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            *reinterpret_cast<uint4*>(sm + sb + (j << A) * W) = make_uint4(v[0][j], v[1][j], v[2][j], v[3][j]);
+    }
+}
+
+template <bool FWD, int M, int ILO, int ZEXT>
+__global__ void __launch_bounds__((1 << (M - 4)) * 16, 2) cfft_high_vec(PassParams p) {
+    static_assert(M == 8, "two rounds of four layers");
+    extern __shared__ __align__(16) uint32_t smv[];
+    constexpr uint32_t l_tiles = (1u << ILO) / 64;
+    const uint32_t tile_h = blockIdx.x / l_tiles, lt = blockIdx.x % l_tiles;
+    const size_t g_base = ((size_t)tile_h << (ILO + M)) + (size_t)lt * 64;
+    const uint32_t* src = p.src + (size_t)blockIdx.y * p.src_stride;
+    uint32_t* dst = p.dst + (size_t)blockIdx.y * p.dst_stride;
+    if constexpr (FWD) {
+        high_round_vec<FWD, M, 1, ILO, ZEXT>(smv, p, tile_h, g_base, src, dst, true, false);
+        __syncthreads();
+        high_round_vec<FWD, M, 0, ILO, ZEXT>(smv, p, tile_h, g_base, src, dst, false, true);
+    } else {
+        high_round_vec<FWD, M, 0, ILO, 0>(smv, p, tile_h, g_base, src, dst, true, false);
+        __syncthreads();
+        high_round_vec<FWD, M, 1, ILO, 0>(smv, p, tile_h, g_base, src, dst, false, true);
+    }
+}
+
+template <bool FWD, int M, int ILO, int ZEXT>
+static cudaError_t launch_high_vec(const PassParams& p, cudaStream_t stream) {
+    size_t tiles = ((size_t)1 << (p.log_n - ILO - M)) * (((size_t)1 << ILO) / 64);
+    constexpr size_t smem = ((size_t)1 << M) * 64 * sizeof(uint32_t);
+    if (p.n_cols > 65535) return cudaErrorInvalidValue;
+    auto k = cfft_high_vec<FWD, M, ILO, ZEXT>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)tiles, (unsigned)p.n_cols);
+    k<<<grid, (1 << (M - 4)) * 16, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------
 // Host-side pass planning
 // ------------------------------------------------------------------------------------
@@ -881,6 +980,13 @@ static cudaError_t launch_high_m(const PassParams& p, int sm_count, cudaStream_t
     if (FWD && p.log_src < p.log_n) {
         bool top = (p.i_lo + M == p.log_n);
         zext = (top && p.log_src == p.log_n - 1 && M >= 4) ? 1 : 2;
+    }
+    if constexpr (M == 8 && LB_HIGH_VEC) {
+        // the vectorised kernel needs whole 64-offset tiles below the pass (i_lo = 12) and no ragged zero extension
+        if (p.i_lo == 12 && zext != 2) {
+            if (FWD && zext == 1) return launch_high_vec<FWD, M, 12, 1>(p, stream);
+            return launch_high_vec<FWD, M, 12, 0>(p, stream);
+        }
     }
     if constexpr (FWD) {
         if (p.i_lo == 12) {
