@@ -715,99 +715,142 @@ __global__ void __launch_bounds__(HighGeom<M>::THREADS, NC == 1 ? HighGeom<M>::M
 }
 
 // ---- high pass, vectorised along the offset dimension ---------------------------------------------------
-// Each thread owns FOUR adjacent offsets (one 128-bit access) of its 16 strided rows: 64 register-resident elements, i.e.
-// four independent radix-16 groups that share every twiddle (twiddles depend on the row only).  Versus the scalar high pass
-// this quarters the load/store, address and twiddle instructions per butterfly and doubles the independent work per thread;
-// a tile is 2^M rows x 64 offsets (M = 8: 64 KiB of shared memory, 256 threads, 2 CTAs per SM).
+// Each thread owns VW adjacent offsets (one 64- or 128-bit access) of its 16 strided rows, i.e. VW independent radix-16
+// groups that share every twiddle (twiddles depend on the row only).  Versus the scalar high pass this divides the
+// load/store, address and twiddle instructions per butterfly by VW; a tile is 2^M rows x 16 VW offsets.  VW = 4 executes 21 %
+// fewer instructions than VW = 1 but needs 128 registers; VW = 2 keeps twice the resident warps and is the faster one.
+// (The same idea applied to the low pass - 64 elements per thread, all accesses 128-bit - was measured slower, 0.757 ms
+// per round trip, for the same reason, and is not kept.)
 #ifndef LB_HIGH_VEC
 #define LB_HIGH_VEC 1
 #endif
-template <bool FWD, int M, int R, int ILO, int ZEXT>
+#ifndef LB_HIGH_VW
+#define LB_HIGH_VW 2  // measured: 2 -> 0.592 ms round trip, 4 -> 0.605 ms (128 registers, half the resident warps)
+#endif
+template <int VW>
+struct VecIO;
+template <>
+struct VecIO<4> {
+    __device__ static __forceinline__ void load(const uint32_t* p, uint32_t (&o)[4]) {
+        const uint4 t = *reinterpret_cast<const uint4*>(p);
+        o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+    }
+    __device__ static __forceinline__ void store(uint32_t* p, const uint32_t (&o)[4]) {
+        *reinterpret_cast<uint4*>(p) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+};
+template <>
+struct VecIO<2> {
+    __device__ static __forceinline__ void load(const uint32_t* p, uint32_t (&o)[2]) {
+        const uint2 t = *reinterpret_cast<const uint2*>(p);
+        o[0] = t.x; o[1] = t.y;
+    }
+    __device__ static __forceinline__ void store(uint32_t* p, const uint32_t (&o)[2]) {
+        *reinterpret_cast<uint2*>(p) = make_uint2(o[0], o[1]);
+    }
+};
+
+template <bool FWD, int M, int R, int ILO, int ZEXT, int VW>
 __device__ __forceinline__ void high_round_vec(uint32_t* sm, const PassParams& p, uint32_t tile_h, size_t g_base,
                                                const uint32_t* src, uint32_t* dst, bool first, bool last) {
     constexpr int A = RoundGeom<M, R>::A;
     constexpr int BLO = RoundGeom<M, R>::BLO;
     constexpr bool TOP = (A + 4 == M);
-    constexpr int WT = 16, W = 64;
+    constexpr int WT = 16, W = WT * VW;
     const int wt = threadIdx.x % WT;
     const int g = threadIdx.x / WT;
     const int e0_hi = g >> A;
     const int e0 = (e0_hi << (A + 4)) | (g & ((1 << A) - 1));
-    const size_t gb = g_base + ((size_t)e0 << ILO) + 4 * wt;
-    const int sb = e0 * W + 4 * wt;
-    uint32_t v[4][16];
+    const size_t gb = g_base + ((size_t)e0 << ILO) + VW * wt;
+    const int sb = e0 * W + VW * wt;
+    uint32_t v[VW][16];
     constexpr bool HALF = (ZEXT == 1 && TOP && FWD);  // the upper half of the rows is the zero extension
     if (first) {
         const uint32_t* sp = src + gb;
 #pragma unroll
         for (int j = 0; j < (HALF ? 8 : 16); ++j) {
-            const uint4 t = *reinterpret_cast<const uint4*>(sp + ((size_t)(j << A) << ILO));
-            v[0][j] = t.x; v[1][j] = t.y; v[2][j] = t.z; v[3][j] = t.w;
+            uint32_t t[VW];
+            VecIO<VW>::load(sp + ((size_t)(j << A) << ILO), t);
+#pragma unroll
+            for (int k = 0; k < VW; ++k) v[k][j] = t[k];
         }
         if (HALF) {
 #pragma unroll
-            for (int j = 8; j < 16; ++j) {
-                v[0][j] = v[0][j - 8]; v[1][j] = v[1][j - 8]; v[2][j] = v[2][j - 8]; v[3][j] = v[3][j - 8];
-            }
+            for (int j = 8; j < 16; ++j)
+#pragma unroll
+                for (int k = 0; k < VW; ++k) v[k][j] = v[k][j - 8];
         }
     } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const uint4 t = *reinterpret_cast<const uint4*>(sm + sb + (j << A) * W);
-            v[0][j] = t.x; v[1][j] = t.y; v[2][j] = t.z; v[3][j] = t.w;
+            uint32_t t[VW];
+            VecIO<VW>::load(sm + sb + (j << A) * W, t);
+#pragma unroll
+            for (int k = 0; k < VW; ++k) v[k][j] = t[k];
         }
     }
     if (HALF && first && BLO < 4)
-        field_layers_range_nc<FWD, A, BLO, 3, M, 4>(v, p, tile_h, e0_hi);  // the top layer on (v, 0) pairs is the copy above
+        field_layers_range_nc<FWD, A, BLO, 3, M, VW>(v, p, tile_h, e0_hi);  // the top layer on (v, 0) pairs is the copy above
     else
-        field_layers_range_nc<FWD, A, BLO, 4, M, 4>(v, p, tile_h, e0_hi);
+        field_layers_range_nc<FWD, A, BLO, 4, M, VW>(v, p, tile_h, e0_hi);
     if (last) {
         uint32_t* dp = dst + gb;
         auto st = [&](auto mode_tag) {
             constexpr int MODE = decltype(mode_tag)::value;
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                *reinterpret_cast<uint4*>(dp + ((size_t)(j << A) << ILO)) =
-                    make_uint4(finalize_m<MODE>(v[0][j], p.scale), finalize_m<MODE>(v[1][j], p.scale),
-                               finalize_m<MODE>(v[2][j], p.scale), finalize_m<MODE>(v[3][j], p.scale));
+            for (int j = 0; j < 16; ++j) {
+                uint32_t t[VW];
+#pragma unroll
+                for (int k = 0; k < VW; ++k) t[k] = finalize_m<MODE>(v[k][j], p.scale);
+                VecIO<VW>::store(dp + ((size_t)(j << A) << ILO), t);
+            }
         };
         if (FWD || p.final_mode == 0) st(std::integral_constant<int, 0>{});
         else st(std::integral_constant<int, 2>{});
     } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            *reinterpret_cast<uint4*>(sm + sb + (j << A) * W) = make_uint4(v[0][j], v[1][j], v[2][j], v[3][j]);
+        for (int j = 0; j < 16; ++j) {
+            uint32_t t[VW];
+#pragma unroll
+            for (int k = 0; k < VW; ++k) t[k] = v[k][j];
+            VecIO<VW>::store(sm + sb + (j << A) * W, t);
+        }
     }
 }
 
-template <bool FWD, int M, int ILO, int ZEXT>
-__global__ void __launch_bounds__((1 << (M - 4)) * 16, 2) cfft_high_vec(PassParams p) {
+template <bool FWD, int M, int ILO, int ZEXT, int VW>
+__global__ void __launch_bounds__((1 << (M - 4)) * 16, VW == 4 ? 2 : 4) cfft_high_vec(PassParams p) {
     static_assert(M == 8, "two rounds of four layers");
     extern __shared__ __align__(16) uint32_t smv[];
-    constexpr uint32_t l_tiles = (1u << ILO) / 64;
+    constexpr uint32_t W = 16 * VW;
+    constexpr uint32_t l_tiles = (1u << ILO) / W;
     const uint32_t tile_h = blockIdx.x / l_tiles, lt = blockIdx.x % l_tiles;
-    const size_t g_base = ((size_t)tile_h << (ILO + M)) + (size_t)lt * 64;
+    const size_t g_base = ((size_t)tile_h << (ILO + M)) + (size_t)lt * W;
     const uint32_t* src = p.src + (size_t)blockIdx.y * p.src_stride;
     uint32_t* dst = p.dst + (size_t)blockIdx.y * p.dst_stride;
     if constexpr (FWD) {
-        high_round_vec<FWD, M, 1, ILO, ZEXT>(smv, p, tile_h, g_base, src, dst, true, false);
+        high_round_vec<FWD, M, 1, ILO, ZEXT, VW>(smv, p, tile_h, g_base, src, dst, true, false);
         __syncthreads();
-        high_round_vec<FWD, M, 0, ILO, ZEXT>(smv, p, tile_h, g_base, src, dst, false, true);
+        high_round_vec<FWD, M, 0, ILO, ZEXT, VW>(smv, p, tile_h, g_base, src, dst, false, true);
     } else {
-        high_round_vec<FWD, M, 0, ILO, 0>(smv, p, tile_h, g_base, src, dst, true, false);
+        high_round_vec<FWD, M, 0, ILO, 0, VW>(smv, p, tile_h, g_base, src, dst, true, false);
         __syncthreads();
-        high_round_vec<FWD, M, 1, ILO, 0>(smv, p, tile_h, g_base, src, dst, false, true);
+        high_round_vec<FWD, M, 1, ILO, 0, VW>(smv, p, tile_h, g_base, src, dst, false, true);
     }
 }
 
 template <bool FWD, int M, int ILO, int ZEXT>
 static cudaError_t launch_high_vec(const PassParams& p, cudaStream_t stream) {
-    size_t tiles = ((size_t)1 << (p.log_n - ILO - M)) * (((size_t)1 << ILO) / 64);
-    constexpr size_t smem = ((size_t)1 << M) * 64 * sizeof(uint32_t);
+    constexpr int VW = LB_HIGH_VW;
+    constexpr size_t W = 16 * VW;
+    size_t tiles = ((size_t)1 << (p.log_n - ILO - M)) * (((size_t)1 << ILO) / W);
+    constexpr size_t smem = ((size_t)1 << M) * W * sizeof(uint32_t);
     if (p.n_cols > 65535) return cudaErrorInvalidValue;
-    auto k = cfft_high_vec<FWD, M, ILO, ZEXT>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    auto k = cfft_high_vec<FWD, M, ILO, ZEXT, VW>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
     dim3 grid((unsigned)tiles, (unsigned)p.n_cols);
     k<<<grid, (1 << (M - 4)) * 16, smem, stream>>>(p);
     return cudaGetLastError();
