@@ -45,6 +45,10 @@ int lb_sync(lb_ctx* ctx);
 /* Column<M31>::zeros / uninitialized / to_cpu  (stwo ColumnOps) */
 int lb_alloc(lb_ctx* ctx, size_t n_u32, uint32_t** d_out);
 int lb_free(lb_ctx* ctx, uint32_t* d_ptr);
+/* stream-ordered variants (cudaMallocAsync / cudaFreeAsync on the context's stream; memory stays in the device pool): no
+ * device-wide synchronisation.  For short-lived buffers; not valid for lb_ipc_export. */
+int lb_alloc_pooled(lb_ctx* ctx, size_t n_u32, uint32_t** d_out);
+int lb_free_pooled(lb_ctx* ctx, uint32_t* d_ptr);
 int lb_memset_zero(lb_ctx* ctx, uint32_t* d_ptr, size_t n_u32);
 int lb_upload(lb_ctx* ctx, uint32_t* d_dst, const uint32_t* h_src, size_t n_u32);
 int lb_download(lb_ctx* ctx, uint32_t* h_dst, const uint32_t* d_src, size_t n_u32);
@@ -235,6 +239,20 @@ void lb_free_host(void* p);
 /* diagnostics of the last lb_prove: channel digest after every mix (32 B each) and per-stage wall-clock ms */
 int lb_prove_transcript(lb_ctx* ctx, uint8_t* out, size_t cap_hashes, size_t* n_hashes);
 int lb_prove_stage_ms(lb_ctx* ctx, float* out, int cap, int* n);
+
+/* ---- trace emitters: LuminairOperator::process_trace on the device ------------------------------
+ * CopyToStwo (crates/graph/src/op/prim.rs:72-84), LuminairAdd (:919-1013), LuminairMul: element-wise nodes over device
+ * tensors of raw Fixed<12> values (int32: LuminAIR's values are M31 elements, |v| < 2^31).  Each call computes the node's
+ * output tensor (d_out, may be NULL for inputs) and appends its n rows, in the column order of the component's
+ * *TraceTableRow (components/{inputs,add,mul}/table.rs), to a row-major device table at row `row0` - the format lb_prove takes
+ * with rows_on_device = 1.  Consumers take their operands with multiplicity -1 (as the reference does); `out_mult` is what the
+ * node yields: its number of consumers, 0 for a final output.  Fixed-point product: q = floor(x*y / 2^12), rem = x*y - q*2^12. */
+int lb_trace_inputs(lb_ctx* ctx, uint32_t node_id, const int32_t* d_vals, uint64_t n, uint32_t out_mult, uint32_t* d_rows,
+                    uint64_t row0);
+int lb_trace_add(lb_ctx* ctx, uint32_t node_id, uint32_t lhs_id, uint32_t rhs_id, const int32_t* d_lhs, const int32_t* d_rhs,
+                 uint64_t n, uint32_t out_mult, int32_t* d_out, uint32_t* d_rows, uint64_t row0);
+int lb_trace_mul(lb_ctx* ctx, uint32_t node_id, uint32_t lhs_id, uint32_t rhs_id, const int32_t* d_lhs, const int32_t* d_rhs,
+                 uint64_t n, uint32_t out_mult, int32_t* d_out, uint32_t* d_rows, uint64_t row0);
 
 #ifdef __cplusplus
 }

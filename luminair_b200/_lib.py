@@ -29,6 +29,8 @@ SIGNATURES = {
     "lb_sync": (C.c_int, [ctxp]),
     "lb_alloc": (C.c_int, [ctxp, C.c_size_t, C.POINTER(C.c_void_p)]),
     "lb_free": (C.c_int, [ctxp, C.c_void_p]),
+    "lb_alloc_pooled": (C.c_int, [ctxp, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "lb_free_pooled": (C.c_int, [ctxp, C.c_void_p]),
     "lb_memset_zero": (C.c_int, [ctxp, C.c_void_p, C.c_size_t]),
     "lb_upload": (C.c_int, [ctxp, C.c_void_p, C.c_void_p, C.c_size_t]),
     "lb_download": (C.c_int, [ctxp, C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -109,6 +111,11 @@ SIGNATURES.update({
     "lb_prove": (C.c_int, [ctxp, C.POINTER(TraceTable), C.c_int, C.POINTER(ProveConfig), C.POINTER(C.c_void_p),
                            C.POINTER(C.c_size_t)]),
     "lb_free_host": (None, [C.c_void_p]),
+    "lb_trace_inputs": (C.c_int, [ctxp, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64]),
+    "lb_trace_add": (C.c_int, [ctxp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
+                               C.c_void_p, C.c_void_p, C.c_uint64]),
+    "lb_trace_mul": (C.c_int, [ctxp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
+                               C.c_void_p, C.c_void_p, C.c_uint64]),
     "lb_prove_transcript": (C.c_int, [ctxp, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "lb_prove_stage_ms": (C.c_int, [ctxp, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]),
 })

@@ -17,16 +17,19 @@ from ._lib import LuminairB200Error, check, load_library
 class DeviceBuffer:
     """Owned device allocation of ``n`` u32 (stwo ``Column<M31>`` storage)."""
 
-    def __init__(self, backend: "CudaBackend", n: int):
+    def __init__(self, backend: "CudaBackend", n: int, pooled: bool = False):
         self.backend = backend
         self.n = int(n)
+        self.pooled = pooled  # stream-ordered allocation from the device pool (lb_alloc_pooled)
         p = C.c_void_p()
-        check(backend.ctx, backend.lib.lb_alloc(backend.ctx, self.n, C.byref(p)), "lb_alloc")
+        fn = backend.lib.lb_alloc_pooled if pooled else backend.lib.lb_alloc
+        check(backend.ctx, fn(backend.ctx, self.n, C.byref(p)), "lb_alloc")
         self.ptr = p.value or 0
 
     def free(self):
         if self.ptr and self.backend.ctx:
-            self.backend.lib.lb_free(self.backend.ctx, C.c_void_p(self.ptr))
+            fn = self.backend.lib.lb_free_pooled if self.pooled else self.backend.lib.lb_free
+            fn(self.backend.ctx, C.c_void_p(self.ptr))
             self.ptr = 0
 
     def __del__(self):
@@ -78,8 +81,8 @@ class CudaBackend:
             self.ctx = None
 
     # ---- memory -------------------------------------------------------------------
-    def alloc(self, n: int) -> DeviceBuffer:
-        return DeviceBuffer(self, n)
+    def alloc(self, n: int, pooled: bool = False) -> DeviceBuffer:
+        return DeviceBuffer(self, n, pooled)
 
     def upload(self, arr: np.ndarray, buf: DeviceBuffer | None = None, offset: int = 0) -> DeviceBuffer:
         arr = np.ascontiguousarray(arr, dtype=np.uint32)

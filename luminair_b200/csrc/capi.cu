@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "ctx.h"
+#include "kernels.cuh"
 #include "merkle.cuh"
 
 namespace {
@@ -106,6 +107,24 @@ int lb_free(lb_ctx* ctx, uint32_t* d_ptr) {
     cudaSetDevice(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream), "free/sync");
     CK(cudaFree(d_ptr), "free");
+    return LB_OK;
+}
+
+// stream-ordered variants (cudaMallocAsync on the context's stream, memory kept in the device pool): no device-wide
+// synchronisation, for short-lived buffers such as the tensors and tables of a device-side gen_trace.  Not for lb_ipc_export.
+int lb_alloc_pooled(lb_ctx* ctx, size_t n_u32, uint32_t** d_out) {
+    if (!ctx || !d_out) return LB_ERR_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    void* p = nullptr;
+    CK(cudaMallocAsync(&p, (n_u32 ? n_u32 : 1) * sizeof(uint32_t), ctx->stream), "alloc_pooled");
+    *d_out = (uint32_t*)p;
+    return LB_OK;
+}
+
+int lb_free_pooled(lb_ctx* ctx, uint32_t* d_ptr) {
+    if (!ctx) return LB_ERR_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    CK(cudaFreeAsync(d_ptr, ctx->stream), "free_pooled");
     return LB_OK;
 }
 
@@ -453,6 +472,34 @@ int lb_prove(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_p
 }
 
 void lb_free_host(void* p) { std::free(p); }
+
+int lb_trace_inputs(lb_ctx* ctx, uint32_t node_id, const int32_t* d_vals, uint64_t n, uint32_t out_mult, uint32_t* d_rows,
+                    uint64_t row0) {
+    if (!ctx || !d_vals || !d_rows || node_id >= lb::P || out_mult >= lb::P) return fail(ctx, LB_ERR_BAD_ARG, "trace_inputs: bad args");
+    cudaSetDevice(ctx->device);
+    CK(lb::trace_inputs(d_rows + row0 * 7, d_vals, n, node_id, out_mult, ctx->stream), "trace_inputs");
+    return LB_OK;
+}
+
+static int trace_binary_api(lb_ctx* ctx, bool mul, uint32_t node_id, uint32_t lhs_id, uint32_t rhs_id, const int32_t* d_lhs,
+                            const int32_t* d_rhs, uint64_t n, uint32_t out_mult, int32_t* d_out, uint32_t* d_rows, uint64_t row0) {
+    if (!ctx || !d_lhs || !d_rhs || !d_out || !d_rows || node_id >= lb::P || lhs_id >= lb::P || rhs_id >= lb::P || out_mult >= lb::P)
+        return fail(ctx, LB_ERR_BAD_ARG, "trace_add/mul: bad args");
+    cudaSetDevice(ctx->device);
+    CK(lb::trace_binary(mul, d_rows + row0 * (mul ? 16 : 15), d_lhs, d_rhs, d_out, n, node_id, lhs_id, rhs_id, out_mult, ctx->stream),
+       "trace_binary");
+    return LB_OK;
+}
+
+int lb_trace_add(lb_ctx* ctx, uint32_t node_id, uint32_t lhs_id, uint32_t rhs_id, const int32_t* d_lhs, const int32_t* d_rhs,
+                 uint64_t n, uint32_t out_mult, int32_t* d_out, uint32_t* d_rows, uint64_t row0) {
+    return trace_binary_api(ctx, false, node_id, lhs_id, rhs_id, d_lhs, d_rhs, n, out_mult, d_out, d_rows, row0);
+}
+
+int lb_trace_mul(lb_ctx* ctx, uint32_t node_id, uint32_t lhs_id, uint32_t rhs_id, const int32_t* d_lhs, const int32_t* d_rhs,
+                 uint64_t n, uint32_t out_mult, int32_t* d_out, uint32_t* d_rows, uint64_t row0) {
+    return trace_binary_api(ctx, true, node_id, lhs_id, rhs_id, d_lhs, d_rhs, n, out_mult, d_out, d_rows, row0);
+}
 
 int lb_prove_transcript(lb_ctx* ctx, uint8_t* out, size_t cap_hashes, size_t* n_hashes) {
     if (!ctx || !n_hashes) return LB_ERR_BAD_ARG;

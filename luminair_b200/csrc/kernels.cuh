@@ -98,4 +98,9 @@ struct ConstraintParams {
 };
 cudaError_t constraint_quotients(int kind, const ConstraintParams& p, cudaStream_t stream);
 
+// ---- trace emitters (process_trace on the device): row-major rows of Inputs / Add / Mul ---------------------------
+cudaError_t trace_inputs(uint32_t* rows, const int32_t* vals, uint64_t n, uint32_t node_id, uint32_t mult, cudaStream_t stream);
+cudaError_t trace_binary(bool mul, uint32_t* rows, const int32_t* lhs, const int32_t* rhs, int32_t* out, uint64_t n,
+                         uint32_t node_id, uint32_t lhs_id, uint32_t rhs_id, uint32_t out_mult, cudaStream_t stream);
+
 }  // namespace lb

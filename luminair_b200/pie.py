@@ -38,13 +38,18 @@ def add_graph_pie(a_fixed: np.ndarray, b_fixed: np.ndarray):
     return [("add", add), ("inputs", inp)]
 
 
-def synthetic_add_graph_pie(log_n: int, seed: int = 42):
-    """BASELINE cfg 3: 2^log_n-element a + b with f32 uniform(-0.5, 0.5) inputs, PCG64(seed)."""
+def synthetic_add_graph_inputs(log_n: int, seed: int = 42):
+    """The two input tensors of BASELINE cfg 3 as raw Fixed<12> values: f32 uniform(-0.5, 0.5), PCG64(seed)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     n = 1 << log_n
     a = to_fixed(rng.uniform(-0.5, 0.5, n))
     b = to_fixed(rng.uniform(-0.5, 0.5, n))
-    return add_graph_pie(a, b)
+    return a, b
+
+
+def synthetic_add_graph_pie(log_n: int, seed: int = 42):
+    """BASELINE cfg 3: 2^log_n-element a + b with f32 uniform(-0.5, 0.5) inputs, PCG64(seed)."""
+    return add_graph_pie(*synthetic_add_graph_inputs(log_n, seed))
 
 
 # ---------------------------------------------------------------------------------------------
