@@ -375,3 +375,22 @@ def mlp_graph(widths=(2, 64, 64, 1), x=(15.0, 0.5), seed: int = 7, scale: float 
         sig = g.recip(g.add(e, one))
         act = g.add(g.mul(sig, two), neg_one)
     return g.finish()
+
+
+def wide_graph(log_n: int, seed: int = 64):
+    """The headline trace shape of BASELINE.json ("2^20 x 64"): four 2^log_n-row operator tables over the same two input
+    tensors - Add (15 columns), Mul (16), Rem (16), SumReduce with groups of one (14) = 61 main-trace columns of 2^log_n rows,
+    beside the Inputs table (7 columns, 2^(log_n+1) rows).  Inputs are positive Fixed<12> values (Rem needs a non-zero
+    divisor), uniform(0.25, 2), PCG64(seed)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = 1 << log_n
+    g = GraphTrace()
+    a = g.input(to_fixed(rng.uniform(0.25, 2.0, n)))
+    b = g.input(to_fixed(rng.uniform(0.25, 2.0, n)))
+    g.add(a, b)
+    g.mul(a, b)
+    g.rem(a, b)
+    g.sum_reduce(a, 1)
+    pie, pre = g.finish()
+    assert not pre
+    return pie

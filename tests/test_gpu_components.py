@@ -149,3 +149,14 @@ def test_missing_lut_is_an_error(be):
     pie, pre = piemod.all_components_graph(n=16, seed=5)
     with pytest.raises(LuminairB200Error):
         prove(pie, backend=be, preprocessed=[c for c in pre if not c[0].startswith("exp2")])
+
+
+def test_wide_graph_proof_bytes_and_acceptance(be):
+    """The headline trace shape (Add + Mul + Rem + SumReduce tables over two inputs): bytes vs the oracle at 2^6 rows,
+    oracle-verifier acceptance at 2^16 rows."""
+    from luminair_b200.prover import prove
+    small = piemod.wide_graph(6)
+    _prove_both(be, small, ())
+    big = piemod.wide_graph(16)
+    assert sum(v.shape[1] for k, v in big if k != "inputs") == 61
+    overifier.verify(from_bincode(prove(big, backend=be)))
