@@ -367,3 +367,16 @@ def test_non_default_pcs_config(be, pow_bits, last_bound, n_queries):
     got = prove(pie, backend=be, config=PcsConfig(pow_bits, 1, last_bound, n_queries))
     _assert_same_proof(be, got, to_bincode(lp), digests)
     overifier.verify(from_bincode(got))
+
+
+def test_cpp_caller_reproduces_fixture(golden_dir):
+    """examples/prove_simple.cpp: a compiled caller that only sees include/luminair_b200.h builds the examples/simple
+    tables itself, calls lb_prove and gets the committed fixture's bytes."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(golden_dir.rstrip("/")))
+    exe = os.path.join(root, "examples", "prove_simple")
+    if not os.path.exists(exe):
+        pytest.skip("examples/prove_simple not built (python -c 'import __graft_entry__ as g; g.build()')")
+    out = subprocess.run([exe, os.path.join(golden_dir, "simple_current.proof.bin")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "identical" in out.stdout
