@@ -52,10 +52,16 @@ class PcsConfig:
 
 def prove(pie, backend: CudaBackend | None = None, config: PcsConfig | None = None, channel_variant: str = "legacy",
           claim_slots=CLAIM_SLOT, n_slots: int = N_CLAIM_SLOTS, device_tables=None, air_era: str = "current",
-          preprocessed=()) -> bytes:
+          preprocessed=(), settings=None) -> bytes:
     """pie: [(name, rows[n_rows, n_cols])].  device_tables: optional {name: (device_ptr, n_rows, n_cols)} to prove
     from tables already resident in HBM (bench.py's device-resident leg).  preprocessed: [(id, values[2^k])] LUT
-    columns of the circuit settings in ``lookups_to_preprocessed_column`` order (preprocessed.rs:181-206)."""
+    columns of the circuit settings in ``lookups_to_preprocessed_column`` order (preprocessed.rs:181-206); or pass
+    ``settings`` (``luminair_b200.settings.CircuitSettings``), as the reference's ``prove(pie, settings)`` does
+    (prover.rs:28-31), and the columns are derived from its lookup layouts."""
+    if settings is not None:
+        if preprocessed:
+            raise LuminairB200Error("pass either `settings` or `preprocessed`, not both")
+        preprocessed = settings.preprocessed_columns()
     own = backend is None
     be = backend or CudaBackend(0)
     try:
