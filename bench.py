@@ -26,7 +26,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 489.3e6  # measured once with ncu --set full (profiles/), not re-measured by this script
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 486.0e6  # measured once with ncu --set full (profiles/), not re-measured by this script
 LOG_N = 20
 N_COLS = 64
 SEED = 20260101
@@ -321,9 +321,9 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "M31 field-ops/s", "h2d_bytes_per_step": N_COLS * n * 4 * world,
                     "d2h_bytes_per_step": N_COLS * n * 4 * world, "ms_per_step": e2e_s * 1e3, "host_numa_binding": numa},
             "gpu_launches": args.steps * n_launch_per_step,
-            "roofline": {"bound": "hbm", "kernel": "cfft_low_fast / cfft_high_fast (the 4 CFFT passes of a step)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "cfft_low_fast / cfft_high_vec (the 4 CFFT passes of a step)", "achieved": achieved, "peak": peak,
                          "peak_source": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, mean of the 4 passes, profiles/r1_cfft_v5_ncu_full_summary.csv",
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, mean of the 4 passes, profiles/r1_cfft_v8_ncu_full_summary.csv",
                          "algorithmic_bytes_per_launch": alg_bytes_launch, "avg_launch_ms": avg_launch_ms,
                          "interpolate_ms": t_int, "evaluate_ms": t_ev},
         }
