@@ -541,35 +541,31 @@ cudaError_t gather_words(uint32_t* d_out, const uint32_t* const* d_addrs, int n,
     return cudaGetLastError();
 }
 
-// 32 x 32 tile transpose through shared memory: coalesced reads of the row-major table and
-// coalesced writes of the columns.
+// Row-major table -> padded columns.  A CTA takes 256 consecutive rows: the row-major block is one contiguous run of
+// 256 * n_cols words (read fully coalesced into shared memory, row stride padded to an odd word count so the column reads
+// below are bank-conflict free), then every column is written as 256 contiguous words.
 struct PadRow {
     uint32_t v[MAX_MAIN_COLS];
 };
-__global__ void transpose_pad_kernel(uint32_t* __restrict__ cols, size_t stride, const uint32_t* __restrict__ rows,
-                                     uint64_t n_rows, int n_cols, uint64_t n_padded, const PadRow pad) {
-    __shared__ uint32_t tile[32][33];
-    uint64_t r0 = (uint64_t)blockIdx.x * 32;
-    int c0 = blockIdx.y * 32;
-    // read: thread (ty, tx) reads row r0+ty.., col c0+tx
-    for (int ty = threadIdx.y; ty < 32; ty += blockDim.y) {
-        uint64_t r = r0 + ty;
-        int c = c0 + threadIdx.x;
-        uint32_t v = 0;
-        if (c < n_cols) {
-            if (r < n_rows)
-                v = rows[r * n_cols + c];
-            else
-                v = pad.v[c];
-        }
-        tile[ty][threadIdx.x] = v;
+constexpr int TP_ROWS = 256;
+__global__ void __launch_bounds__(TP_ROWS) transpose_pad_kernel(uint32_t* __restrict__ cols, size_t stride,
+                                                                const uint32_t* __restrict__ rows, uint64_t n_rows, int n_cols,
+                                                                uint64_t n_padded, const PadRow pad) {
+    extern __shared__ uint32_t tp_sm[];
+    const int ncp = n_cols | 1;
+    const uint64_t r0 = (uint64_t)blockIdx.x * TP_ROWS;
+    const uint64_t have = r0 < n_rows ? min((uint64_t)TP_ROWS, n_rows - r0) : 0;  // real rows in this block
+    const uint32_t words = (uint32_t)have * n_cols;
+    const uint32_t* src = rows + r0 * n_cols;
+    for (uint32_t w = threadIdx.x; w < words; w += TP_ROWS) {
+        uint32_t r = w / n_cols, c = w - r * n_cols;
+        tp_sm[r * ncp + c] = src[w];
     }
     __syncthreads();
-    for (int ty = threadIdx.y; ty < 32; ty += blockDim.y) {
-        int c = c0 + ty;
-        uint64_t r = r0 + threadIdx.x;
-        if (c < n_cols && r < n_padded) cols[(size_t)c * stride + r] = tile[threadIdx.x][ty];
-    }
+    const uint64_t r = r0 + threadIdx.x;
+    if (r >= n_padded) return;
+    const bool real = threadIdx.x < have;
+    for (int c = 0; c < n_cols; ++c) cols[(size_t)c * stride + r] = real ? tp_sm[threadIdx.x * ncp + c] : pad.v[c];
 }
 
 cudaError_t transpose_pad(uint32_t* d_cols, size_t stride, const uint32_t* d_rows, uint64_t n_rows, int n_cols, int log,
@@ -578,9 +574,8 @@ cudaError_t transpose_pad(uint32_t* d_cols, size_t stride, const uint32_t* d_row
     PadRow pad{};
     for (int c = 0; c < n_cols; ++c) pad.v[c] = padding_value(kind, c);
     uint64_t n = (uint64_t)1 << log;
-    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((n_cols + 31) / 32));
-    dim3 block(32, 8);
-    transpose_pad_kernel<<<grid, block, 0, stream>>>(d_cols, stride, d_rows, n_rows, n_cols, n, pad);
+    size_t smem = (size_t)TP_ROWS * (n_cols | 1) * sizeof(uint32_t);
+    transpose_pad_kernel<<<(unsigned)((n + TP_ROWS - 1) / TP_ROWS), TP_ROWS, smem, stream>>>(d_cols, stride, d_rows, n_rows, n_cols, n, pad);
     return cudaGetLastError();
 }
 
