@@ -380,3 +380,30 @@ def test_cpp_caller_reproduces_fixture(golden_dir):
     out = subprocess.run([exe, os.path.join(golden_dir, "simple_current.proof.bin")], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "identical" in out.stdout
+
+
+@pytest.mark.parametrize("blowup,last_bound,n_queries", [(2, 0, 3), (3, 1, 5)])
+def test_larger_blowup_factor(be, blowup, last_bound, n_queries):
+    """log_blowup_factor > 1: the commitment domain is larger than the constraint evaluation domain, so the constraint
+    kernels read columns re-evaluated on CanonicCoset(log + 1) (the framework's `need_to_extend` path) and FRI starts higher."""
+    from luminair_b200.prover import PcsConfig, prove
+    from oracle.proof import PcsConfig as OPcs
+    pie = examples.graph_pie(6, seed=17)
+    lp, digests = _oracle_transcript(lambda: oprover.prove(pie, config=OPcs(5, blowup, last_bound, n_queries)))
+    got = prove(pie, backend=be, config=PcsConfig(5, blowup, last_bound, n_queries))
+    _assert_same_proof(be, got, to_bincode(lp), digests)
+    overifier.verify(from_bincode(got))
+
+
+def test_larger_blowup_factor_with_lookup_tables(be):
+    from luminair_b200 import pie as piemod
+    from luminair_b200.prover import PcsConfig, prove
+    from oracle.proof import PcsConfig as OPcs
+    g = piemod.GraphTrace()
+    x = g.input(np.random.Generator(np.random.PCG64(23)).integers(-40, 40, 20))  # Exp2 table of 2^7 rows over a 32-row trace
+    g.less_than(g.exp2(x), x)
+    pie, pre = g.finish()
+    lp, digests = _oracle_transcript(lambda: oprover.prove(pie, config=OPcs(5, 2, 0, 3), preprocessed=pre))
+    got = prove(pie, backend=be, config=PcsConfig(5, 2, 0, 3), preprocessed=pre)
+    _assert_same_proof(be, got, to_bincode(lp), digests)
+    overifier.verify(from_bincode(got), preprocessed=[(cid, len(v).bit_length() - 1) for cid, v in pre])
