@@ -407,3 +407,14 @@ def test_larger_blowup_factor_with_lookup_tables(be):
     got = prove(pie, backend=be, config=PcsConfig(5, 2, 0, 3), preprocessed=pre)
     _assert_same_proof(be, got, to_bincode(lp), digests)
     overifier.verify(from_bincode(got), preprocessed=[(cid, len(v).bit_length() - 1) for cid, v in pre])
+
+
+def test_large_proof_is_accepted(be):
+    """Add 2^22 rows + Inputs 2^23 rows (LDE 2^24, composition LDE 2^25): far beyond what the numpy oracle prover can follow;
+    the oracle verifier accepts the proof (it only touches the queried positions)."""
+    from luminair_b200.pie import synthetic_add_graph_pie
+    from luminair_b200.prover import prove
+    proof = prove(synthetic_add_graph_pie(22, seed=1), backend=be)
+    lp = from_bincode(proof)
+    assert lp.claim[0] == 22 and lp.claim[15] == 23
+    overifier.verify(lp)
