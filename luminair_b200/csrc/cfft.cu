@@ -446,6 +446,10 @@ __device__ __forceinline__ void low_round(uint32_t* sm, const PassParams& p, uin
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[c][j] = gbase + j < n_src ? srcc[gbase + j] : 0u;
                 }
+            } else if (p.log_src >= p.log_n) {
+                // full-size source (always the case when this is not the only pass): no zero-extension checks
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[c][j] = srcc[gbase + ((size_t)j << A)];
             } else {
                 const size_t n_src = (size_t)1 << p.log_src;
 #pragma unroll
