@@ -514,8 +514,15 @@ __device__ __forceinline__ void low_round(uint32_t* sm, const PassParams& p, uin
                                        finalize(v[c][4 * q + 2], p.final_mode, p.scale), finalize(v[c][4 * q + 3], p.final_mode, p.scale));
 #endif
             } else {
+                // inverse: the low pass is the first pass (lazy store) unless it is the only one (scale by 1/n)
+                auto st = [&](auto mode_tag) {
+                    constexpr int MODE = decltype(mode_tag)::value;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) dstc[gbase + ((size_t)j << A)] = finalize(v[c][j], p.final_mode, p.scale);
+                    for (int j = 0; j < 16; ++j) dstc[gbase + ((size_t)j << A)] = finalize_m<MODE>(v[c][j], p.scale);
+                };
+                if (p.final_mode == 0) st(std::integral_constant<int, 0>{});
+                else if (p.final_mode == 1) st(std::integral_constant<int, 1>{});
+                else st(std::integral_constant<int, 2>{});
             }
         } else {
             const int sb = low_pad(e0);
