@@ -45,3 +45,17 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.replace("no CPU fallback", ""), f"{f} mentions the oracle"
+
+
+def test_rust_ffi_file_is_in_sync_with_the_header():
+    """integration/rust/luminair_b200_sys.rs is generated from the header (scripts/gen_rust_ffi.py): it is up to date and
+    declares every function the library exports."""
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert subprocess.run([sys.executable, os.path.join(root, "scripts", "gen_rust_ffi.py"), "--check"]).returncode == 0
+    rs = open(os.path.join(root, "integration", "rust", "luminair_b200_sys.rs")).read()
+    declared = set(re.findall(r"pub fn (lb_\w+)\(", rs))
+    from luminair_b200._lib import SIGNATURES
+    assert declared == set(SIGNATURES)
