@@ -178,6 +178,8 @@ struct PassParams {
     int m;                 // layers in this pass
     int ts;                // log2(FFT elements per tile), ts >= m
     int final_mode;        // 0 lazy store, 1 canonical, 2 scale (interpolate) + canonical
+    size_t src_mask;       // ANDed into the source index of a high pass's first round: all ones, or 2^log_src - 1 when the
+                           // top layer of a blow-up-2 evaluate is taken as the duplication it is (see cfft_evaluate_scatter)
     uint2 scale;
     RedK redk;             // {2, -P}: opaque multipliers for red_fma
     // row-sharded scatter of the final (low) pass of an evaluate: tile rows [s*R/W, (s+1)*R/W) of column c go to
@@ -621,7 +623,7 @@ __device__ __forceinline__ void high_round(uint32_t* sm, const PassParams& p, ui
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         if (first) {
-            const uint32_t* sp = src + (size_t)c * p.src_stride + gb;
+            const uint32_t* sp = src + (size_t)c * p.src_stride + (gb & p.src_mask);
             if (ZEXT == 2) {
                 const size_t n_src = (size_t)1 << p.log_src;
 #pragma unroll
@@ -777,7 +779,7 @@ __device__ __forceinline__ void high_round_vec(uint32_t* sm, const PassParams& p
     uint32_t v[VW][16];
     constexpr bool HALF = (ZEXT == 1 && TOP && FWD);  // the upper half of the rows is the zero extension
     if (first) {
-        const uint32_t* sp = src + gb;
+        const uint32_t* sp = src + (gb & p.src_mask);
 #pragma unroll
         for (int j = 0; j < (HALF ? 8 : 16); ++j) {
             uint32_t t[VW];
@@ -913,6 +915,13 @@ static Plan make_plan(int n) {
     }
     return pl;
 }
+
+// passes for the lowest `layers` (>= 16) layers of a transform: the low pass and as many high passes as needed
+static Plan make_plan_layers(int layers) { return make_plan(layers); }
+
+#ifndef LB_LDE_DUP
+#define LB_LDE_DUP 1
+#endif
 
 static int pick_cols_per_block(size_t tiles, int n_cols, int sm_count) {
     int cpb = 1;
@@ -1095,6 +1104,7 @@ cudaError_t cfft_interpolate(const Twiddles* tw, uint32_t* data, size_t stride, 
         p.m = pl.m[k];
         p.ts = (k == 0) ? std::min(log_n, LOW_TS_MAX) : p.m;
         p.final_mode = (k == pl.n_pass - 1) ? 2 : 0;
+        p.src_mask = ~(size_t)0;
         p.scale = make_uint2(inv_n, shoup_companion(inv_n));
         for (int b = 0; b < p.m; ++b) p.tw[b] = layer_tw(tw, true, log_n, p.i_lo + b);
         cudaError_t e = launch_pass<false>(p, pl, k, sm_count, stream);
@@ -1119,7 +1129,11 @@ cudaError_t cfft_evaluate_scatter(const Twiddles* tw, const uint32_t* coeffs, si
         while ((1 << log_w) < n_peers) ++log_w;
         if (log_out - log_w < 12 || log_out < 16) return cudaErrorInvalidValue;  // whole 4096-row tiles per rank, multi-pass plan
     }
-    Plan pl = make_plan(log_out);
+    // Blow-up 2 (log_in = log_out - 1, the commit path): the top layer pairs every coefficient with a zero, i.e. it only
+    // copies the lower half into the upper half.  The plan then covers layers 0 .. log_out-2 and the top-most pass reads
+    // its source at (index mod 2^log_in): one layer and, for log_out = 23, one whole HBM pass less.
+    const bool dup = LB_LDE_DUP && log_in == log_out - 1 && log_out >= 17 && coeffs != out;
+    Plan pl = dup ? make_plan_layers(log_out - 1) : make_plan(log_out);
     for (int k = pl.n_pass - 1; k >= 0; --k) {
         PassParams p{};
         p.redk = RedK{2u, 0u - P};
@@ -1130,7 +1144,8 @@ cudaError_t cfft_evaluate_scatter(const Twiddles* tw, const uint32_t* coeffs, si
         p.dst_stride = dst_stride;
         p.n_cols = n_cols;
         p.log_n = log_out;
-        p.log_src = first ? log_in : log_out;
+        p.log_src = (first && !dup) ? log_in : log_out;
+        p.src_mask = (first && dup) ? (((size_t)1 << log_in) - 1) : ~(size_t)0;
         p.i_lo = pl.i_lo[k];
         p.m = pl.m[k];
         p.ts = (k == 0) ? std::min(log_out, LOW_TS_MAX) : p.m;
