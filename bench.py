@@ -307,7 +307,10 @@ def run_gpu(args):
         peak, peak_kind = load_peaks()
         n_launch_per_step = 4  # 2 passes per transform at log 20
         alg_bytes_launch = algorithmic_bytes_per_step() / n_launch_per_step
-        avg_launch_ms = (t_int + t_ev) / n_launch_per_step
+        # the timed region is K steps of exactly these four launches, back to back on one stream, bracketed by CUDA events:
+        # its per-launch average is the duration the roofline uses (the separately timed interpolate / evaluate calls below
+        # carry one event pair per call and are reported for the split only)
+        avg_launch_ms = ms_per_step / n_launch_per_step
         achieved = alg_bytes_launch / (avg_launch_ms * 1e-3) / 1e9
         line = {
             "metric": "cfft_roundtrip_m31_field_ops_per_s", "value": value, "unit": "M31 field-ops/s",
