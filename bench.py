@@ -195,6 +195,7 @@ def run_gpu(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     distributed = world > 1
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
     numa = pin_to_gpu_numa_node(local_rank)  # before any pinned allocation: first touch lands on the GPU's NUMA node
     if distributed:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -335,7 +336,8 @@ def run_gpu(args):
         if sharded_info:
             line["sharded_commit"] = sharded_info
         if world == 1 and not args.no_cpu:
-            threads = min(os.cpu_count() or 1, N_COLS)
+            os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every host core again, as in --impl reference
+            threads = min(len(all_cpus), N_COLS)
             sample_cols = min(N_COLS, max(threads, 8))
             dt = cpu_roundtrip(sample_cols, threads)
             line["cpu_baseline"] = {"value": field_ops_per_step(LOG_N, sample_cols) / dt, "unit": "M31 field-ops/s",
