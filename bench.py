@@ -537,7 +537,7 @@ def bench_prove(be, torch, args):
             buf = be.upload(rows.reshape(-1))
             keep.append(buf)
             wdev[name] = (buf.ptr, rows.shape[0], rows.shape[1])
-        meta = [(k, np.empty(v.shape, dtype=np.uint32)) for k, v in wpie]
+        meta = [(k, None) for k, v in wpie]
         for _ in range(2):
             prove(meta, backend=be, device_tables=wdev)
         t_w, st_w = [], None

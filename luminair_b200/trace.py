@@ -61,7 +61,7 @@ class DeviceGraphTrace:
         return self._binary("mul", a, b)
 
     def finish(self):
-        """Run the graph on the device.  -> (pie_meta, device_tables, values): ``pie_meta`` = [(name, None-rows placeholder)]
+        """Run the graph on the device.  -> (pie_meta, device_tables, values): ``pie_meta`` = [(name, None)]
         in claim-slot order for ``prove``, ``device_tables`` = {name: (ptr, n_rows, n_cols)}, ``values`` = device buffers of
         every node's tensor (int32 raw values)."""
         be, lib, ctx = self.be, self.be.lib, self.be.ctx
@@ -88,5 +88,5 @@ class DeviceGraphTrace:
         order = [k for k in ("add", "mul", "inputs") if rows_total[k]]
         device_tables = {k: (tables[k].ptr, rows_total[k], N_COLS[k]) for k in order}
         self.tables, self.values = tables, values  # the buffers must outlive the prove() call
-        pie_meta = [(k, np.empty((rows_total[k], N_COLS[k]), dtype=np.uint32)) for k in order]  # shapes only; rows live on the device
+        pie_meta = [(k, None) for k in order]  # table order for prove(); the rows live on the device (device_tables)
         return pie_meta, device_tables, values

@@ -103,7 +103,7 @@ def _commit_tree(be, cols_by_log):
     return root, layers
 
 
-@pytest.mark.parametrize("shape", [{5: 3}, {6: 31}, {4: 16}, {7: 17, 5: 4, 2: 1}, {3: 0, 2: 2}])
+@pytest.mark.parametrize("shape", [{5: 3}, {6: 31}, {4: 16}, {7: 17, 5: 4, 2: 1}, {3: 0, 2: 2}, {19: 17, 18: 33}, {18: 4}])
 def test_merkle_vs_oracle(be, shape):
     rng = np.random.Generator(np.random.PCG64(7))
     cols_by_log = {l: rng.integers(0, P, size=(n, 1 << l), dtype=np.uint64).astype(np.uint32) for l, n in shape.items()}
