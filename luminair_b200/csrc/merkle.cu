@@ -184,6 +184,82 @@ cudaError_t merkle_commit_top(const MerkleTopArgs& args, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+// ---- several levels per launch (narrow layers) ---------------------------------------------------------
+// CTA b hashes nodes [b * S, (b + 1) * S) of layer log_top (S = 512: two nodes per thread on the widest level), then
+// their S/2 parents, ... for `depth` levels.  Each level is written to its global buffer (the tree is kept for
+// decommitment) and read back by the same CTA after a block barrier.
+__global__ void __launch_bounds__(256, 2) merkle_subtree_kernel(const __grid_constant__ MerkleSubtreeArgs a, uint32_t one) {
+    const uint32_t n_top = 1u << a.log_top;
+    const uint32_t S = min(512u, n_top);  // nodes of layer log_top per CTA
+    const uint32_t base = blockIdx.x * S;
+    {
+        uint32_t h[2][8], m[2][16];
+        const uint32_t i0 = base + threadIdx.x, i1 = i0 + 256;
+        const bool on0 = threadIdx.x < S, on1 = threadIdx.x + 256 < S;
+        const uint32_t j0 = on0 ? i0 : base, j1 = on1 ? i1 : base;  // idle lanes recompute node `base` (never stored)
+        blake2s_init(h[0]);
+        blake2s_init(h[1]);
+        uint32_t t = 0;
+        if (a.prev) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const uint4* pp = reinterpret_cast<const uint4*>(a.prev + (size_t)(q ? j1 : j0) * 16);
+                uint4 x = pp[0], y = pp[1], z = pp[2], w = pp[3];
+                m[q][0] = x.x; m[q][1] = x.y; m[q][2] = x.z; m[q][3] = x.w;
+                m[q][4] = y.x; m[q][5] = y.y; m[q][6] = y.z; m[q][7] = y.w;
+                m[q][8] = z.x; m[q][9] = z.y; m[q][10] = z.z; m[q][11] = z.w;
+                m[q][12] = w.x; m[q][13] = w.y; m[q][14] = w.z; m[q][15] = w.w;
+            }
+            t = 64;
+            compress_dev(h[0], m[0], t, a.n_cols == 0 ? 0xFFFFFFFFu : 0u, one);
+            compress_dev(h[1], m[1], t, a.n_cols == 0 ? 0xFFFFFFFFu : 0u, one);
+        }
+        if (a.n_cols > 0 || !a.prev) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                m[0][j] = (j < a.n_cols) ? a.cols.p[j][j0] : 0u;
+                m[1][j] = (j < a.n_cols) ? a.cols.p[j][j1] : 0u;
+            }
+            t += 4u * a.n_cols;
+            compress_dev(h[0], m[0], t, 0xFFFFFFFFu, one);
+            compress_dev(h[1], m[1], t, 0xFFFFFFFFu, one);
+        }
+        if (on0) {
+            uint4* o = reinterpret_cast<uint4*>(a.layers[0] + (size_t)i0 * 8);
+            o[0] = make_uint4(h[0][0], h[0][1], h[0][2], h[0][3]);
+            o[1] = make_uint4(h[0][4], h[0][5], h[0][6], h[0][7]);
+        }
+        if (on1) {
+            uint4* o = reinterpret_cast<uint4*>(a.layers[0] + (size_t)i1 * 8);
+            o[0] = make_uint4(h[1][0], h[1][1], h[1][2], h[1][3]);
+            o[1] = make_uint4(h[1][4], h[1][5], h[1][6], h[1][7]);
+        }
+    }
+    for (int d = 1; d < a.depth; ++d) {
+        __syncthreads();  // level d-1 of this CTA's range is complete (global writes are visible block-wide after the barrier)
+        const uint32_t cnt = S >> d;
+        if (cnt == 0) break;
+        if (threadIdx.x < cnt) {
+            const uint32_t i = (base >> d) + threadIdx.x;
+            uint32_t h[8];
+            hash_node<true>(h, a.layers[d - 1], nullptr, 0, i, one);
+            uint4* o = reinterpret_cast<uint4*>(a.layers[d] + (size_t)i * 8);
+            o[0] = make_uint4(h[0], h[1], h[2], h[3]);
+            o[1] = make_uint4(h[4], h[5], h[6], h[7]);
+        }
+    }
+}
+
+cudaError_t merkle_commit_subtree(const MerkleSubtreeArgs& args, cudaStream_t stream) {
+    if (args.depth < 1 || args.depth > MERKLE_SUBTREE_MAX_DEPTH || args.depth > args.log_top + 1 || args.n_cols < 0 ||
+        args.n_cols > MERKLE_SMALL_COLS)
+        return cudaErrorInvalidValue;
+    uint32_t n_top = 1u << args.log_top;
+    uint32_t S = n_top < 512u ? n_top : 512u;
+    merkle_subtree_kernel<<<n_top / S, 256, 0, stream>>>(args, 1u);
+    return cudaGetLastError();
+}
+
 // out[k*n_cols + c] = cols[c][idx[k]]
 __global__ void gather_rows_kernel(uint32_t* out, const uint32_t* const* cols, int n_cols, const uint32_t* idx, int n_idx) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -19,6 +19,18 @@ struct MerkleTopArgs {
     int from_log;
 };
 cudaError_t merkle_commit_top(const MerkleTopArgs& args, cudaStream_t stream);
+// Several levels per launch for the narrow middle of a tree (2^11 .. 2^17 nodes), where one launch per layer is a chain of
+// latency-bound kernels: level 0 = layer `log_top` (children `prev` and / or <= MERKLE_SMALL_COLS columns), then `depth - 1`
+// column-less layers above it.  One CTA owns 512 adjacent nodes of layer log_top and what they reduce to.
+constexpr int MERKLE_SUBTREE_MAX_DEPTH = 10;
+constexpr int MERKLE_SUBTREE_MAX_LOG = 17;
+struct MerkleSubtreeArgs {
+    uint32_t* layers[MERKLE_SUBTREE_MAX_DEPTH];  // layers[d] = buffer of layer log_top - d
+    const uint32_t* prev;                        // digests of layer log_top + 1, or nullptr
+    MerkleColsArg cols;
+    int n_cols, log_top, depth;
+};
+cudaError_t merkle_commit_subtree(const MerkleSubtreeArgs& args, cudaStream_t stream);
 cudaError_t gather_rows(uint32_t* d_out, const uint32_t* const* d_cols, int n_cols, const uint32_t* d_idx, int n_idx,
                         cudaStream_t stream);
 }  // namespace lb

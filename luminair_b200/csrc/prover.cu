@@ -216,6 +216,9 @@ class Channel {
 // ------------------------------------------------------------------------------------
 // Merkle trees over mixed-height column sets (prover/vcs/prover.rs MerkleProver)
 // ------------------------------------------------------------------------------------
+#ifndef LB_MERKLE_SUBTREE
+#define LB_MERKLE_SUBTREE 1
+#endif
 struct ColRef {
     const uint32_t* ptr;
     int log;
@@ -285,6 +288,25 @@ void merkle_commit(lb_ctx* ctx, Arena& arena, const std::vector<ColRef>& cols, M
         for (int log = t.max_log; log >= 0; --log) t.layers[log] = all + 8 * (((size_t)1 << log) - 1);
     }
     for (int log = t.max_log; log >= fused_from; --log) {
+        if (LB_MERKLE_SUBTREE && small && log <= MERKLE_SUBTREE_MAX_LOG && log >= fused_from + 3) {
+            // narrow middle of the tree: this layer and the column-less layers above it, down to the layer the fused top
+            // starts from, in one launch (only when that saves at least two launches: small trees are faster layer by layer)
+            int depth = 1;
+            while (depth < MERKLE_SUBTREE_MAX_DEPTH && log - depth >= fused_from && count[log - depth] == 0) ++depth;
+            if (depth >= 2) {
+                MerkleSubtreeArgs a{};
+                for (int d = 0; d < depth; ++d) a.layers[d] = t.layers[log - d];
+                a.prev = prev;
+                for (int k = 0; k < count[log]; ++k) a.cols.p[k] = table[first[log] + k];
+                a.n_cols = count[log];
+                a.log_top = log;
+                a.depth = depth;
+                ck(merkle_commit_subtree(a, ctx->stream), "merkle subtree");
+                log -= depth - 1;
+                prev = t.layers[log];
+                continue;
+            }
+        }
         if (small) {
             MerkleColsArg ca{};
             for (int k = 0; k < count[log]; ++k) ca.p[k] = table[first[log] + k];
