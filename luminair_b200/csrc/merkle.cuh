@@ -23,7 +23,10 @@ cudaError_t merkle_commit_top(const MerkleTopArgs& args, cudaStream_t stream);
 // latency-bound kernels: level 0 = layer `log_top` (children `prev` and / or <= MERKLE_SMALL_COLS columns), then `depth - 1`
 // column-less layers above it.  One CTA owns 512 adjacent nodes of layer log_top and what they reduce to.
 constexpr int MERKLE_SUBTREE_MAX_DEPTH = 10;
-constexpr int MERKLE_SUBTREE_MAX_LOG = 17;
+#ifndef LB_MERKLE_SUBTREE_MAX_LOG
+#define LB_MERKLE_SUBTREE_MAX_LOG 17
+#endif
+constexpr int MERKLE_SUBTREE_MAX_LOG = LB_MERKLE_SUBTREE_MAX_LOG;
 struct MerkleSubtreeArgs {
     uint32_t* layers[MERKLE_SUBTREE_MAX_DEPTH];  // layers[d] = buffer of layer log_top - d
     const uint32_t* prev;                        // digests of layer log_top + 1, or nullptr
