@@ -1239,7 +1239,9 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             uint32_t dg[8];
             channel.digest_words(dg);
             uint64_t base = 0;
-            const uint64_t chunk = (uint64_t)1 << 22;
+            // a nonce works with probability 2^-pow_bits: the first launch tries 2^(pow_bits + 7) of them (it misses with
+            // probability e^-128), later ones grow 16-fold up to 2^24
+            uint64_t chunk = (uint64_t)1 << std::min<uint32_t>(24, cfg.pow_bits + 7);
             for (;;) {
                 ck(cudaMemsetAsync(d_found, 0xFF, 8, st), "grind memset");
                 ck(grind_range(dg, cfg.channel_variant, cfg.pow_bits, base, chunk, d_found, st), "grind");
@@ -1251,6 +1253,7 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                     break;
                 }
                 base += chunk;
+                chunk = std::min<uint64_t>(chunk << 4, (uint64_t)1 << 24);
             }
             channel.mix_u64(nonce);
         }
