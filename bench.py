@@ -513,8 +513,9 @@ def bench_prove(be, torch, args):
     h2d = sum(int(v.nbytes) for _, v in host_pie)
     # BASELINE configs[3] shape: the 2-64-64-1 tanh MLP of examples/black-schole-nn (synthetic weights), 7 components
     # including the Exp2 lookup table (2^17 rows) and the extended evaluation domain of its consumer
-    from luminair_b200.pie import mlp_graph
-    mlp_pie, mlp_pre = mlp_graph()
+    from luminair_b200.pie import GraphTrace, build_mlp, build_wide
+    mlp_host = build_mlp(GraphTrace())
+    mlp_pie, mlp_pre = mlp_host.finish()
     for _ in range(2):
         prove(mlp_pie, backend=be, preprocessed=mlp_pre)
     t_mlp = []
@@ -522,16 +523,35 @@ def bench_prove(be, torch, args):
         t0 = time.perf_counter()
         mlp_proof = prove(mlp_pie, backend=be, preprocessed=mlp_pre)
         t_mlp.append((time.perf_counter() - t0) * 1e3)
+
+    # the same proof with gen_trace on the device (lb_trace_op: Mul over broadcast operands, SumReduce, Add, Exp2 through the
+    # host-generated LUT, Recip): only the weights / input / constants cross PCIe
+    def mlp_from_tensors():
+        dg = build_mlp(DeviceGraphTrace(be))
+        meta, dev_tables, _ = dg.finish(mlp_host.layouts)
+        return prove(meta, backend=be, device_tables=dev_tables, preprocessed=dg.preprocessed)
+
+    if mlp_from_tensors() != mlp_proof:
+        raise SystemExit("bench: MLP proof from device-generated tables differs from the proof from host tables")
+    t_mlp_dev = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        mlp_from_tensors()
+        t_mlp_dev.append((time.perf_counter() - t0) * 1e3)
     mlp_info = {"workload": "prove(): Linear 2-64-64-1 with tanh (Mul/SumReduce/Add/Exp2+LUT/Recip/Inputs tables: "
                             + ", ".join(f"{k} {v.shape[0]}" for k, v in mlp_pie) + " rows), host tables (BASELINE configs[3] shape, "
                             "synthetic weights)",
-                "ms_e2e_host_tables": {"min": min(t_mlp), "median": statistics.median(t_mlp)}, "proof_bytes": len(mlp_proof)}
+                "ms_e2e_host_tables": {"min": min(t_mlp), "median": statistics.median(t_mlp)},
+                "ms_e2e_host_tensors": {"min": min(t_mlp_dev), "median": statistics.median(t_mlp_dev),
+                                        "how": "graph recording, LUT column generation (host libm, as the reference), gen_trace "
+                                               "on the device (lb_trace_op) and prove(); proof bytes identical to the host-table path"},
+                "proof_bytes": len(mlp_proof)}
     # BASELINE.json's headline trace shape: 2^log rows x 61 main-trace columns (Add + Mul + Rem + SumReduce tables over the same
     # two inputs) beside the Inputs table; device-resident tables
-    from luminair_b200.pie import wide_graph
     wide_info = None
     if log >= 12:
-        wpie = [(k, np.ascontiguousarray(v, dtype=np.uint32)) for k, v in wide_graph(log)]
+        whost = build_wide(GraphTrace(), log)
+        wpie = [(k, np.ascontiguousarray(v, dtype=np.uint32)) for k, v in whost.finish()[0]]
         wdev, keep = {}, []
         for name, rows in wpie:
             buf = be.upload(rows.reshape(-1))
@@ -548,11 +568,35 @@ def bench_prove(be, torch, args):
             if not t_w or dt < min(t_w):
                 st_w = last_stage_ms(be)
             t_w.append(dt)
+        # gen_trace of the same graph on the device from its two input tensors (pinned), then prove
+        wtens = []
+        for node in (0, 1):
+            t = torch.empty((1 << log,), dtype=torch.int32, pin_memory=True)
+            t.numpy()[:] = whost.values[node]
+            wtens.append(t)
+
+        def wide_from_tensors():
+            dg = DeviceGraphTrace(be)
+            a, b = dg.input(wtens[0].numpy()), dg.input(wtens[1].numpy())
+            dg.add(a, b), dg.mul(a, b), dg.rem(a, b), dg.sum_reduce(a, 1)
+            m, devt, _ = dg.finish()
+            return prove(m, backend=be, device_tables=devt)
+
+        if wide_from_tensors() != wproof:
+            raise SystemExit("bench: wide proof from device-generated tables differs from the proof from host-built tables")
+        t_wt = []
+        for _ in range(max(3, reps // 2)):
+            t0 = time.perf_counter()
+            wide_from_tensors()
+            t_wt.append((time.perf_counter() - t0) * 1e3)
         n_main_cols = sum(v.shape[1] for k, v in wpie if k != "inputs")
         wide_info = {"workload": f"prove(): 2^{log} rows x {n_main_cols} main-trace columns (" +
                                  ", ".join(f"{k} {v.shape[0]}x{v.shape[1]}" for k, v in wpie) + "), device-resident tables "
                                  "(the 2^20 x 64 trace shape of BASELINE.json's metric, built from real operator tables)",
                      "ms_device_resident": {"min": min(t_w), "median": statistics.median(t_w)},
+                     "ms_e2e_host_tensors": {"min": min(t_wt), "median": statistics.median(t_wt), "h2d_bytes": int(2 * 4 << log),
+                                             "how": "the two input tensors uploaded from pinned memory, all five tables "
+                                                    "generated on the device (lb_trace_*), proof bytes identical"},
                      "stages_ms": dict(zip(STAGE_NAMES, [round(x, 3) for x in st_w])), "proof_bytes": len(wproof)}
         del keep
     return {

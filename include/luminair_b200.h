@@ -254,6 +254,64 @@ int lb_trace_add(lb_ctx* ctx, uint32_t node_id, uint32_t lhs_id, uint32_t rhs_id
 int lb_trace_mul(lb_ctx* ctx, uint32_t node_id, uint32_t lhs_id, uint32_t rhs_id, const int32_t* d_lhs, const int32_t* d_rhs,
                  uint64_t n, uint32_t out_mult, int32_t* d_out, uint32_t* d_rows, uint64_t row0);
 
+/* ---- every operator of the graph: LuminairOperator::process_trace (crates/graph/src/op/prim.rs) -------------------------
+ * lb_trace_op is the general form of the three entry points above: operands are device tensors of raw Fixed<12> values plus an
+ * optional gather index (u32, one entry per row: the element the row reads - the operator's index expression for
+ * broadcasts / expands, flattened by the caller; NULL = identity).  The operator kind is named by the claim slot of its
+ * component.  Rows are appended at `row0` of a row-major device table in the component's *TraceTableRow column order
+ * (crates/air/src/components/<name>/table.rs); the node's output tensor is written to d_out.
+ *   LB_OP_INPUTS      CopyToStwo / LuminairConstant  prim.rs:52-84,151-188 (d_lhs = the tensor; d_out may be NULL)
+ *   LB_OP_CONTIGUOUS  prim.rs:229-298     LB_OP_RECIP  :388-428     LB_OP_SQRT :617-657     LB_OP_ADD :967-1013
+ *   LB_OP_MUL :1090-1136   LB_OP_REM :1372-1418   LB_OP_LESS_THAN :1225-1292 (counts its four 8-bit limbs in
+ *   lookup->d_multiplicities, 256 counters: the RangeCheckLookup<1> table)
+ *   LB_OP_SIN :496-543, LB_OP_EXP2 :725-772, LB_OP_LOG2 :840-887: f(x) is read from the LUT column the caller generated on the
+ *   host exactly as the reference does (preprocessed.rs:351-383) at LookupLayout::find_index(x) (preprocessed.rs:96-116), and
+ *   that entry's counter in lookup->d_multiplicities (the *_lookup table) is incremented; a value outside every range fails
+ *   with LB_ERR_BAD_ARG "Value should fit in range." (the reference panics with that text).
+ *   LB_OP_SUM_REDUCE :1517-1562, LB_OP_MAX_REDUCE :1685-1731: output element i folds the `group` gathered inputs
+ *   [i*group, (i+1)*group); one row per step, n * group rows.
+ * d_out_mult: per output element, the multiplicity the node yields it with = the number of rows that consume it
+ * (node_info.num_consumers, prim.rs:947-951; 0 for a graph output; NULL = all 0) - count it with lb_trace_count_uses. */
+#define LB_OP_ADD 0
+#define LB_OP_MUL 1
+#define LB_OP_RECIP 2
+#define LB_OP_SIN 3
+#define LB_OP_SUM_REDUCE 5
+#define LB_OP_MAX_REDUCE 6
+#define LB_OP_SQRT 7
+#define LB_OP_REM 8
+#define LB_OP_EXP2 9
+#define LB_OP_LOG2 11
+#define LB_OP_LESS_THAN 13
+#define LB_OP_INPUTS 15
+#define LB_OP_CONTIGUOUS 16
+#define LB_MAX_LOOKUP_RANGES 8
+typedef struct {
+    int n_ranges;                       /* LookupLayout.ranges (preprocessed.rs:41-60): sorted, disjoint, inclusive */
+    int32_t lo[8], hi[8];               /* LB_MAX_LOOKUP_RANGES entries, raw Fixed<12> values */
+    const uint32_t* d_values;           /* DEVICE: LUT column 1 (function values, canonical M31); unused by less_than */
+    uint32_t* d_multiplicities;         /* DEVICE: one counter per table entry, incremented */
+} lb_lookup;
+typedef struct {
+    int op;                             /* LB_OP_* */
+    uint32_t node_id, lhs_id, rhs_id;   /* rhs_id unused by unary operators */
+    const int32_t* d_lhs;
+    const uint32_t* d_lhs_idx;
+    const int32_t* d_rhs;
+    const uint32_t* d_rhs_idx;
+    uint64_t n;                         /* output elements */
+    uint32_t group;                     /* reductions: steps per output element; else ignored */
+    const uint32_t* d_out_mult;
+    int32_t* d_out;
+    uint32_t* d_rows;
+    uint64_t row0;
+    const lb_lookup* lookup;            /* sin / exp2 / log2 / less_than */
+} lb_trace_op_desc;
+int lb_trace_op(lb_ctx* ctx, const lb_trace_op_desc* op);
+/* d_uses[d_idx[i]] += 1 for i < n_reads (d_idx NULL: d_uses[i] += 1): one call per operand of every consumer gives the
+ * per-element multiplicities of a node (graph.rs:161-604 keeps the same count in node_info) */
+int lb_trace_count_uses(lb_ctx* ctx, uint32_t* d_uses, const uint32_t* d_idx, uint64_t n_reads);
+
 #ifdef __cplusplus
 }
 #endif

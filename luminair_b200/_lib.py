@@ -66,6 +66,20 @@ class PreprocessedColumn(C.Structure):
                 ("on_device", C.c_int)]
 
 
+class Lookup(C.Structure):
+    """lb_lookup"""
+    _fields_ = [("n_ranges", C.c_int), ("lo", C.c_int32 * 8), ("hi", C.c_int32 * 8), ("d_values", C.c_void_p),
+                ("d_multiplicities", C.c_void_p)]
+
+
+class TraceOpDesc(C.Structure):
+    """lb_trace_op_desc"""
+    _fields_ = [("op", C.c_int), ("node_id", C.c_uint32), ("lhs_id", C.c_uint32), ("rhs_id", C.c_uint32),
+                ("d_lhs", C.c_void_p), ("d_lhs_idx", C.c_void_p), ("d_rhs", C.c_void_p), ("d_rhs_idx", C.c_void_p),
+                ("n", C.c_uint64), ("group", C.c_uint32), ("d_out_mult", C.c_void_p), ("d_out", C.c_void_p),
+                ("d_rows", C.c_void_p), ("row0", C.c_uint64), ("lookup", C.POINTER(Lookup))]
+
+
 class Relation(C.Structure):
     """lb_relation"""
     _fields_ = [("z", C.c_uint32 * 4), ("alpha", C.c_uint32 * 4)]
@@ -116,6 +130,8 @@ SIGNATURES.update({
                                C.c_void_p, C.c_void_p, C.c_uint64]),
     "lb_trace_mul": (C.c_int, [ctxp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
                                C.c_void_p, C.c_void_p, C.c_uint64]),
+    "lb_trace_op": (C.c_int, [ctxp, C.POINTER(TraceOpDesc)]),
+    "lb_trace_count_uses": (C.c_int, [ctxp, C.c_void_p, C.c_void_p, C.c_uint64]),
     "lb_prove_transcript": (C.c_int, [ctxp, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "lb_prove_stage_ms": (C.c_int, [ctxp, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]),
 })

@@ -501,6 +501,73 @@ int lb_trace_mul(lb_ctx* ctx, uint32_t node_id, uint32_t lhs_id, uint32_t rhs_id
     return trace_binary_api(ctx, true, node_id, lhs_id, rhs_id, d_lhs, d_rhs, n, out_mult, d_out, d_rows, row0);
 }
 
+int lb_trace_count_uses(lb_ctx* ctx, uint32_t* d_uses, const uint32_t* d_idx, uint64_t n_reads) {
+    if (!ctx || !d_uses) return fail(ctx, LB_ERR_BAD_ARG, "trace_count_uses: bad args");
+    cudaSetDevice(ctx->device);
+    CK(lb::trace_count_uses(d_uses, d_idx, n_reads, ctx->stream), "trace_count_uses");
+    return LB_OK;
+}
+
+int lb_trace_op(lb_ctx* ctx, const lb_trace_op_desc* d) {
+    if (!ctx || !d || !d->d_rows || !d->d_lhs || d->node_id >= lb::P || d->lhs_id >= lb::P || d->rhs_id >= lb::P)
+        return fail(ctx, LB_ERR_BAD_ARG, "trace_op: bad args");
+    int n_cols = 0;
+    bool binary = false, lut = false, reduce = false;
+    switch (d->op) {
+        case LB_OP_ADD: n_cols = 15; binary = true; break;
+        case LB_OP_MUL: case LB_OP_REM: n_cols = 16; binary = true; break;
+        case LB_OP_LESS_THAN: n_cols = 22; binary = true; break;
+        case LB_OP_RECIP: case LB_OP_SQRT: n_cols = 13; break;
+        case LB_OP_SIN: case LB_OP_EXP2: case LB_OP_LOG2: n_cols = 12; lut = true; break;
+        case LB_OP_SUM_REDUCE: n_cols = 14; reduce = true; break;
+        case LB_OP_MAX_REDUCE: n_cols = 15; reduce = true; break;
+        case LB_OP_INPUTS: n_cols = 7; break;
+        case LB_OP_CONTIGUOUS: n_cols = 11; break;
+        default: return fail(ctx, LB_ERR_BAD_ARG, "trace_op: unknown operator");
+    }
+    if (binary && !d->d_rhs) return fail(ctx, LB_ERR_BAD_ARG, "trace_op: binary operator without a right operand");
+    if (d->op != LB_OP_INPUTS && !d->d_out) return fail(ctx, LB_ERR_BAD_ARG, "trace_op: no output tensor");
+    if (reduce && d->group == 0) return fail(ctx, LB_ERR_BAD_ARG, "trace_op: reduction over an empty group");
+    if ((lut || d->op == LB_OP_LESS_THAN) && (!d->lookup || !d->lookup->d_multiplicities))
+        return fail(ctx, LB_ERR_BAD_ARG, "trace_op: lookup operator without its table");
+    cudaSetDevice(ctx->device);
+    lb::TraceOp p{};
+    p.op = d->op;
+    p.node_id = d->node_id; p.lhs_id = d->lhs_id; p.rhs_id = d->rhs_id;
+    p.lhs = d->d_lhs; p.lhs_idx = d->d_lhs_idx; p.rhs = d->d_rhs; p.rhs_idx = d->d_rhs_idx;
+    p.n = d->n;
+    p.group = reduce ? d->group : 1;
+    p.out_mult = d->d_out_mult;
+    p.out = d->d_out;
+    p.rows = d->d_rows + d->row0 * (uint64_t)n_cols;
+    if (d->lookup) p.lut_mult = d->lookup->d_multiplicities;
+    if (lut) {
+        const lb_lookup& L = *d->lookup;
+        if (L.n_ranges < 1 || L.n_ranges > LB_MAX_LOOKUP_RANGES || !L.d_values)
+            return fail(ctx, LB_ERR_BAD_ARG, "trace_op: lookup layout must have 1..8 ranges and its value column");
+        uint32_t base = 0;
+        p.lut.n = L.n_ranges;
+        for (int k = 0; k < L.n_ranges; ++k) {
+            if (L.hi[k] < L.lo[k] || (k && L.lo[k] <= L.hi[k - 1]))
+                return fail(ctx, LB_ERR_BAD_ARG, "trace_op: lookup ranges must be sorted and disjoint");
+            p.lut.lo[k] = L.lo[k]; p.lut.hi[k] = L.hi[k]; p.lut.base[k] = base;
+            base += (uint32_t)((int64_t)L.hi[k] - L.lo[k] + 1);
+        }
+        p.lut_vals = L.d_values;
+        if (ensure_scratch(ctx, 64) != LB_OK) return LB_ERR_OOM;
+        p.err = (int*)ctx->d_scratch;
+        CK(cudaMemsetAsync(p.err, 0, sizeof(int), ctx->stream), "trace_op: flag reset");
+    }
+    CK(lb::trace_op(p, ctx->stream), "trace_op");
+    if (lut) {  // the reference panics on an input outside the table; surface it here (one 4-byte read-back)
+        int flag = 0;
+        CK(cudaMemcpyAsync(&flag, p.err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream), "trace_op: flag read");
+        CK(cudaStreamSynchronize(ctx->stream), "trace_op: sync");
+        if (flag) return fail(ctx, LB_ERR_BAD_ARG, "Value should fit in range.");
+    }
+    return LB_OK;
+}
+
 int lb_prove_transcript(lb_ctx* ctx, uint8_t* out, size_t cap_hashes, size_t* n_hashes) {
     if (!ctx || !n_hashes) return LB_ERR_BAD_ARG;
     *n_hashes = ctx->transcript.size();

@@ -1,6 +1,7 @@
 // Launchers of the streaming kernels behind the PCS / FRI / AIR stages (pcs_kernels.cu,
 // air_kernels.cu).  Everything takes device pointers and a stream; nothing synchronises.
 #pragma once
+#include "../../include/luminair_b200.h"
 #include "air.cuh"
 #include "cfft.cuh"
 
@@ -102,5 +103,32 @@ cudaError_t constraint_quotients(int kind, const ConstraintParams& p, cudaStream
 cudaError_t trace_inputs(uint32_t* rows, const int32_t* vals, uint64_t n, uint32_t node_id, uint32_t mult, cudaStream_t stream);
 cudaError_t trace_binary(bool mul, uint32_t* rows, const int32_t* lhs, const int32_t* rhs, int32_t* out, uint64_t n,
                          uint32_t node_id, uint32_t lhs_id, uint32_t rhs_id, uint32_t out_mult, cudaStream_t stream);
+
+
+// ---- every operator's process_trace (trace_kernels.cu; include/luminair_b200.h lb_trace_op) ---------------------------
+struct LookupRanges {
+    int n;
+    int32_t lo[LB_MAX_LOOKUP_RANGES], hi[LB_MAX_LOOKUP_RANGES];
+    uint32_t base[LB_MAX_LOOKUP_RANGES];  // table index of lo[k]
+};
+struct TraceOp {
+    int op;
+    uint32_t node_id, lhs_id, rhs_id;
+    const int32_t* lhs;
+    const uint32_t* lhs_idx;
+    const int32_t* rhs;
+    const uint32_t* rhs_idx;
+    uint64_t n;
+    uint32_t group;
+    const uint32_t* out_mult;
+    int32_t* out;
+    uint32_t* rows;  // already offset to the node's first row
+    LookupRanges lut;
+    const uint32_t* lut_vals;
+    uint32_t* lut_mult;
+    int* err;  // device flag: set when a lookup input is outside every range
+};
+cudaError_t trace_op(const TraceOp& p, cudaStream_t stream);
+cudaError_t trace_count_uses(uint32_t* uses, const uint32_t* idx, uint64_t n, cudaStream_t stream);
 
 }  // namespace lb

@@ -299,11 +299,12 @@ class GraphTrace:
 
         preprocessed = []
         lut_tables = {}
+        self.layouts = {}  # what the reference's calibration pass (gen_circuit_settings) would put in the settings
         for name in ("sin", "exp2", "log2"):
             if not self.lut_inputs[name]:
                 continue
             x = np.concatenate(self.lut_inputs[name])
-            layout = LookupLayout.covering(x, lut_pad)
+            layout = self.layouts[name] = LookupLayout.covering(x, lut_pad)
             preprocessed += lut_columns(name, layout)
             mult = np.zeros(1 << layout.log_size, dtype=np.int64)
             np.add.at(mult, layout.find_index(x), 1)
@@ -327,8 +328,12 @@ class GraphTrace:
 
 def all_components_graph(n: int = 24, seed: int = 3):
     """A graph that touches all 17 components (tests)."""
+    return build_all_components(GraphTrace(), n, seed).finish()
+
+
+def build_all_components(g, n: int = 24, seed: int = 3):
+    """Record the all-components graph on `g` (a GraphTrace or a trace.DeviceGraphTrace: same interface)."""
     rng = np.random.Generator(np.random.PCG64(seed))
-    g = GraphTrace()
     x = g.input(to_fixed(rng.uniform(0.25, 2.0, n)))
     y = g.input(to_fixed(rng.uniform(-1.0, 1.0, n)))
     s = g.add(x, y)
@@ -346,7 +351,7 @@ def all_components_graph(n: int = 24, seed: int = 3):
     g.contiguous(t)
     g.add(m, c)
     g.mul(sr, mr)
-    return g.finish()
+    return g
 
 
 def mlp_graph(widths=(2, 64, 64, 1), x=(15.0, 0.5), seed: int = 7, scale: float = 0.3):
@@ -354,8 +359,12 @@ def mlp_graph(widths=(2, 64, 64, 1), x=(15.0, 0.5), seed: int = 7, scale: float 
     [15.0, 0.5]); synthetic weights uniform(-scale, scale), PCG64(seed) (the reference's weights are git-ignored).
     Each Linear is Mul over the expanded [out, in] operands + SumReduce + bias Add; tanh(z) lowers the way luminal
     does it: 2 * sigmoid(2z) - 1 with sigmoid(v) = 1 / (1 + exp2(-v * log2 e))  ->  Mul, Exp2, Add, Recip."""
+    return build_mlp(GraphTrace(), widths, x, seed, scale).finish()
+
+
+def build_mlp(g, widths=(2, 64, 64, 1), x=(15.0, 0.5), seed: int = 7, scale: float = 0.3):
+    """Record the MLP of `mlp_graph` on `g` (a GraphTrace or a trace.DeviceGraphTrace)."""
     rng = np.random.Generator(np.random.PCG64(seed))
-    g = GraphTrace()
     act = g.input(to_fixed(np.asarray(x, dtype=np.float64)))
     n_layers = len(widths) - 1
     for li in range(n_layers):
@@ -374,7 +383,7 @@ def mlp_graph(widths=(2, 64, 64, 1), x=(15.0, 0.5), seed: int = 7, scale: float 
         e = g.exp2(g.mul(z, c_m2log2e))
         sig = g.recip(g.add(e, one))
         act = g.add(g.mul(sig, two), neg_one)
-    return g.finish()
+    return g
 
 
 def wide_graph(log_n: int, seed: int = 64):
@@ -382,15 +391,19 @@ def wide_graph(log_n: int, seed: int = 64):
     tensors - Add (15 columns), Mul (16), Rem (16), SumReduce with groups of one (14) = 61 main-trace columns of 2^log_n rows,
     beside the Inputs table (7 columns, 2^(log_n+1) rows).  Inputs are positive Fixed<12> values (Rem needs a non-zero
     divisor), uniform(0.25, 2), PCG64(seed)."""
+    pie, pre = build_wide(GraphTrace(), log_n, seed).finish()
+    assert not pre
+    return pie
+
+
+def build_wide(g, log_n: int, seed: int = 64):
+    """Record the graph of `wide_graph` on `g` (a GraphTrace or a trace.DeviceGraphTrace)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     n = 1 << log_n
-    g = GraphTrace()
     a = g.input(to_fixed(rng.uniform(0.25, 2.0, n)))
     b = g.input(to_fixed(rng.uniform(0.25, 2.0, n)))
     g.add(a, b)
     g.mul(a, b)
     g.rem(a, b)
     g.sum_reduce(a, 1)
-    pie, pre = g.finish()
-    assert not pre
-    return pie
+    return g
