@@ -293,80 +293,4 @@ cudaError_t constraint_quotients(int kind, const ConstraintParams& p, cudaStream
     return cudaGetLastError();
 }
 
-// ------------------------------------------------------------------------------------
-// Trace emitters (LuminairOperator::process_trace, crates/graph/src/op/prim.rs): one thread per row, rows written in
-// the *TraceTableRow column order (row-major; a warp writes one contiguous run of 32 rows).
-// ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t fixed_to_m31(int64_t v) {  // Fixed::to_m31: negative raw values map to p - |v|
-    return v < 0 ? (uint32_t)((int64_t)P + v) : (uint32_t)v;
-}
-
-__global__ void __launch_bounds__(256) trace_inputs_kernel(uint32_t* __restrict__ rows, const int32_t* __restrict__ vals,
-                                                           uint64_t n, uint32_t node_id, uint32_t mult) {
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t* r = rows + i * 7;  // inputs/table.rs: node_id, idx, is_last_idx, next_node_id, next_idx, val, multiplicity
-    r[0] = node_id;
-    r[1] = (uint32_t)i;
-    r[2] = (i == n - 1);
-    r[3] = node_id;
-    r[4] = (uint32_t)(i + 1);
-    r[5] = fixed_to_m31(vals[i]);
-    r[6] = mult;
-}
-
-template <bool MUL>
-__global__ void __launch_bounds__(256) trace_binary_kernel(uint32_t* __restrict__ rows, const int32_t* __restrict__ lhs,
-                                                           const int32_t* __restrict__ rhs, int32_t* __restrict__ out, uint64_t n,
-                                                           uint32_t node_id, uint32_t lhs_id, uint32_t rhs_id, uint32_t out_mult) {
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int64_t x = lhs[i], y = rhs[i];
-    int64_t o, rem = 0;
-    if (MUL) {
-        const int64_t prod = x * y;
-        o = prod >> 12;  // arithmetic shift: floor division by the scale
-        rem = prod - (o << 12);
-    } else {
-        o = x + y;
-    }
-    out[i] = (int32_t)o;
-    constexpr int NC = MUL ? 16 : 15;  // add/table.rs, mul/table.rs
-    uint32_t* r = rows + i * NC;
-    r[0] = node_id;
-    r[1] = lhs_id;
-    r[2] = rhs_id;
-    r[3] = (uint32_t)i;
-    r[4] = (i == n - 1);
-    r[5] = node_id;
-    r[6] = lhs_id;
-    r[7] = rhs_id;
-    r[8] = (uint32_t)(i + 1);
-    r[9] = fixed_to_m31(x);
-    r[10] = fixed_to_m31(y);
-    r[11] = fixed_to_m31(o);
-    int c = 12;
-    if (MUL) r[c++] = (uint32_t)rem;
-    r[c++] = P - 1;  // lhs_mult = -1
-    r[c++] = P - 1;  // rhs_mult = -1
-    r[c] = out_mult;
-}
-
-cudaError_t trace_inputs(uint32_t* rows, const int32_t* vals, uint64_t n, uint32_t node_id, uint32_t mult, cudaStream_t stream) {
-    if (n == 0) return cudaSuccess;
-    trace_inputs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(rows, vals, n, node_id, mult);
-    return cudaGetLastError();
-}
-
-cudaError_t trace_binary(bool mul, uint32_t* rows, const int32_t* lhs, const int32_t* rhs, int32_t* out, uint64_t n,
-                         uint32_t node_id, uint32_t lhs_id, uint32_t rhs_id, uint32_t out_mult, cudaStream_t stream) {
-    if (n == 0) return cudaSuccess;
-    unsigned blocks = (unsigned)((n + 255) / 256);
-    if (mul)
-        trace_binary_kernel<true><<<blocks, 256, 0, stream>>>(rows, lhs, rhs, out, n, node_id, lhs_id, rhs_id, out_mult);
-    else
-        trace_binary_kernel<false><<<blocks, 256, 0, stream>>>(rows, lhs, rhs, out, n, node_id, lhs_id, rhs_id, out_mult);
-    return cudaGetLastError();
-}
-
 }  // namespace lb

@@ -477,7 +477,15 @@ int lb_trace_inputs(lb_ctx* ctx, uint32_t node_id, const int32_t* d_vals, uint64
                     uint64_t row0) {
     if (!ctx || !d_vals || !d_rows || node_id >= lb::P || out_mult >= lb::P) return fail(ctx, LB_ERR_BAD_ARG, "trace_inputs: bad args");
     cudaSetDevice(ctx->device);
-    CK(lb::trace_inputs(d_rows + row0 * 7, d_vals, n, node_id, out_mult, ctx->stream), "trace_inputs");
+    lb::TraceOp p{};
+    p.op = LB_OP_INPUTS;
+    p.node_id = node_id;
+    p.lhs = d_vals;
+    p.n = n;
+    p.group = 1;
+    p.out_mult_all = out_mult;
+    p.rows = d_rows + row0 * 7;
+    CK(lb::trace_op(p, ctx->stream), "trace_inputs");
     return LB_OK;
 }
 
@@ -486,8 +494,16 @@ static int trace_binary_api(lb_ctx* ctx, bool mul, uint32_t node_id, uint32_t lh
     if (!ctx || !d_lhs || !d_rhs || !d_out || !d_rows || node_id >= lb::P || lhs_id >= lb::P || rhs_id >= lb::P || out_mult >= lb::P)
         return fail(ctx, LB_ERR_BAD_ARG, "trace_add/mul: bad args");
     cudaSetDevice(ctx->device);
-    CK(lb::trace_binary(mul, d_rows + row0 * (mul ? 16 : 15), d_lhs, d_rhs, d_out, n, node_id, lhs_id, rhs_id, out_mult, ctx->stream),
-       "trace_binary");
+    lb::TraceOp p{};
+    p.op = mul ? LB_OP_MUL : LB_OP_ADD;
+    p.node_id = node_id; p.lhs_id = lhs_id; p.rhs_id = rhs_id;
+    p.lhs = d_lhs; p.rhs = d_rhs;
+    p.n = n;
+    p.group = 1;
+    p.out_mult_all = out_mult;
+    p.out = d_out;
+    p.rows = d_rows + row0 * (mul ? 16 : 15);
+    CK(lb::trace_op(p, ctx->stream), "trace_binary");
     return LB_OK;
 }
 

@@ -99,10 +99,6 @@ struct ConstraintParams {
 };
 cudaError_t constraint_quotients(int kind, const ConstraintParams& p, cudaStream_t stream);
 
-// ---- trace emitters (process_trace on the device): row-major rows of Inputs / Add / Mul ---------------------------
-cudaError_t trace_inputs(uint32_t* rows, const int32_t* vals, uint64_t n, uint32_t node_id, uint32_t mult, cudaStream_t stream);
-cudaError_t trace_binary(bool mul, uint32_t* rows, const int32_t* lhs, const int32_t* rhs, int32_t* out, uint64_t n,
-                         uint32_t node_id, uint32_t lhs_id, uint32_t rhs_id, uint32_t out_mult, cudaStream_t stream);
 
 
 // ---- every operator's process_trace (trace_kernels.cu; include/luminair_b200.h lb_trace_op) ---------------------------
@@ -120,7 +116,8 @@ struct TraceOp {
     const uint32_t* rhs_idx;
     uint64_t n;
     uint32_t group;
-    const uint32_t* out_mult;
+    const uint32_t* out_mult;  // per output element, or NULL: out_mult_all for every element
+    uint32_t out_mult_all;
     int32_t* out;
     uint32_t* rows;  // already offset to the node's first row
     LookupRanges lut;

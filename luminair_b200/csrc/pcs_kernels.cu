@@ -557,7 +557,28 @@ __global__ void __launch_bounds__(TP_ROWS) transpose_pad_kernel(uint32_t* __rest
     const uint64_t have = r0 < n_rows ? min((uint64_t)TP_ROWS, n_rows - r0) : 0;  // real rows in this block
     const uint32_t words = (uint32_t)have * n_cols;
     const uint32_t* src = rows + r0 * n_cols;
-    for (uint32_t w = threadIdx.x; w < words; w += TP_ROWS) {
+    // the block's rows are one contiguous run of `words` words: 128-bit loads, (row, column) of each word kept incrementally
+    // (one division per thread instead of one per word)
+    const uint32_t nvec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) ? (words >> 2) : 0;
+    if (nvec) {
+        const uint32_t dr = (4 * TP_ROWS) / n_cols, dc = (4 * TP_ROWS) - dr * n_cols;
+        uint32_t r = (4 * threadIdx.x) / n_cols, c = 4 * threadIdx.x - r * n_cols;
+        for (uint32_t v = threadIdx.x; v < nvec; v += TP_ROWS) {
+            const uint4 x = reinterpret_cast<const uint4*>(src)[v];
+            uint32_t rr = r, cc = c;
+            tp_sm[rr * ncp + cc] = x.x;
+            if (++cc == (uint32_t)n_cols) { cc = 0; ++rr; }
+            tp_sm[rr * ncp + cc] = x.y;
+            if (++cc == (uint32_t)n_cols) { cc = 0; ++rr; }
+            tp_sm[rr * ncp + cc] = x.z;
+            if (++cc == (uint32_t)n_cols) { cc = 0; ++rr; }
+            tp_sm[rr * ncp + cc] = x.w;
+            r += dr;
+            c += dc;
+            if (c >= (uint32_t)n_cols) { c -= n_cols; ++r; }
+        }
+    }
+    for (uint32_t w = 4 * nvec + threadIdx.x; w < words; w += TP_ROWS) {
         uint32_t r = w / n_cols, c = w - r * n_cols;
         tp_sm[r * ncp + c] = src[w];
     }

@@ -4,7 +4,7 @@
 // already flattened by the caller).  Each kernel computes the node's output tensor and appends the node's rows, in the
 // column order of the component's *TraceTableRow (crates/air/src/components/*/table.rs), to a row-major device table -
 // the format lb_prove takes with rows_on_device = 1.  One thread per row (per output element for the reductions, whose
-// rows are a sequential recurrence); a warp writes one contiguous run of rows.
+// rows are a sequential recurrence); a CTA stages its run of rows in shared memory and stores it coalesced.
 //
 //   CopyToStwo / LuminairConstant  prim.rs:52-84, 151-188     LuminairContiguous  prim.rs:229-298
 //   LuminairRecip  :388-428   LuminairSin  :496-543   LuminairSqrt  :617-657   LuminairExp2  :725-772
@@ -53,19 +53,31 @@ __device__ __forceinline__ uint32_t* head1(uint32_t* r, const TraceOp& p, uint64
 }
 
 template <int OP>
+__host__ __device__ constexpr int op_cols() {  // columns of the component's *TraceTableRow (crates/air/src/components/*/table.rs)
+    return OP == LB_OP_INPUTS ? 7 : OP == LB_OP_ADD ? 15 : (OP == LB_OP_MUL || OP == LB_OP_REM) ? 16 : OP == LB_OP_LESS_THAN ? 22
+           : (OP == LB_OP_RECIP || OP == LB_OP_SQRT) ? 13 : OP == LB_OP_CONTIGUOUS ? 11 : 12;
+}
+
+// A thread's row is NC words at a stride of NC words in the table: stored straight from registers, a warp instruction would
+// touch 32 different sectors.  The CTA's 256 rows are one contiguous run of 256 * NC words, so each thread parks its row in
+// shared memory (odd pitch: conflict-free) and the CTA copies the run out with 128-bit, fully coalesced stores.
+template <int OP>
 __global__ void __launch_bounds__(256) trace_rows_kernel(const TraceOp p) {
-    __shared__ uint32_t hist[256];
+    constexpr int NC = op_cols<OP>(), NCP = NC | 1;
+    __shared__ uint32_t stage[256 * NCP];
+    __shared__ uint32_t hist[OP == LB_OP_LESS_THAN ? 256 : 1];
     if (OP == LB_OP_LESS_THAN) {
         hist[threadIdx.x] = 0;
         __syncthreads();
     }
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint32_t* const row = stage + threadIdx.x * NCP;
     if (i < p.n) {
-        const uint32_t mult = p.out_mult ? p.out_mult[i] : 0u;
+        const uint32_t mult = p.out_mult ? p.out_mult[i] : p.out_mult_all;
         const uint32_t M1 = P - 1;  // multiplicity -1 of a consumed operand
         if (OP == LB_OP_INPUTS) {
             const int64_t v = p.lhs[i];
-            uint32_t* r = p.rows + i * 7;  // inputs/table.rs
+            uint32_t* r = row;  // inputs/table.rs
             r[0] = p.node_id; r[1] = (uint32_t)i; r[2] = (i == p.n - 1); r[3] = p.node_id; r[4] = (uint32_t)(i + 1);
             r[5] = to_m31(v); r[6] = mult;
         } else if (OP == LB_OP_ADD || OP == LB_OP_MUL || OP == LB_OP_REM) {
@@ -82,8 +94,7 @@ __global__ void __launch_bounds__(256) trace_rows_kernel(const TraceOp p) {
                 o = x - aux * y;
             }
             p.out[i] = (int32_t)o;
-            constexpr int NC = OP == LB_OP_ADD ? 15 : 16;  // add/table.rs, mul/table.rs, rem/table.rs
-            uint32_t* r = head2(p.rows + i * NC, p, i);
+            uint32_t* r = head2(row, p, i);  // add/table.rs, mul/table.rs, rem/table.rs
             *r++ = to_m31(x); *r++ = to_m31(y); *r++ = to_m31(o);
             if (OP != LB_OP_ADD) *r++ = to_m31(aux);
             *r++ = M1; *r++ = M1; *r = mult;
@@ -93,7 +104,7 @@ __global__ void __launch_bounds__(256) trace_rows_kernel(const TraceOp p) {
             const int64_t diff = lt ? y - x : y - x + (int64_t)P;  // prim.rs:1209-1213
             const uint32_t d32 = (uint32_t)diff;
             p.out[i] = lt ? 4096 : 0;
-            uint32_t* r = head2(p.rows + i * 22, p, i);
+            uint32_t* r = head2(row, p, i);
             *r++ = to_m31(x); *r++ = to_m31(y); *r++ = lt ? 4096u : 0u;
             *r++ = (uint32_t)(((diff % (int64_t)P) + (int64_t)P) % (int64_t)P);
             *r++ = lt ? 0u : 1u;  // borrow
@@ -116,7 +127,7 @@ __global__ void __launch_bounds__(256) trace_rows_kernel(const TraceOp p) {
                 rem = t - o * o;
             }
             p.out[i] = (int32_t)o;
-            uint32_t* r = head1(p.rows + i * 13, p, i);
+            uint32_t* r = head1(row, p, i);
             *r++ = to_m31(x); *r++ = to_m31(o); *r++ = to_m31(rem); *r++ = 4096u; *r++ = M1; *r = mult;
         } else if (OP == LB_OP_SIN || OP == LB_OP_EXP2 || OP == LB_OP_LOG2) {  // sin/exp2/log2 table.rs: 12 columns
             const int64_t x = rd(p.lhs, p.lhs_idx, i);
@@ -133,19 +144,41 @@ __global__ void __launch_bounds__(256) trace_rows_kernel(const TraceOp p) {
                 atomicAdd(&p.lut_mult[at], 1u);
             }
             p.out[i] = fv > P / 2 ? (int32_t)((int64_t)fv - (int64_t)P) : (int32_t)fv;
-            uint32_t* r = head1(p.rows + i * 12, p, i);
+            uint32_t* r = head1(row, p, i);
             *r++ = to_m31(x); *r++ = fv; *r++ = M1; *r++ = mult; *r = 1u;
         } else if (OP == LB_OP_CONTIGUOUS) {  // contiguous/table.rs: 11 columns
             const int64_t x = rd(p.lhs, p.lhs_idx, i);
             p.out[i] = (int32_t)x;
-            uint32_t* r = head1(p.rows + i * 11, p, i);
+            uint32_t* r = head1(row, p, i);
             *r++ = to_m31(x); *r++ = to_m31(x); *r++ = M1; *r = mult;
         }
     }
+    __syncthreads();
     if (OP == LB_OP_LESS_THAN) {
-        __syncthreads();
         const uint32_t c = hist[threadIdx.x];
         if (c) atomicAdd(&p.lut_mult[threadIdx.x], c);
+    }
+    // copy-out of the CTA's run of rows
+    const uint64_t r0 = blockIdx.x * (uint64_t)blockDim.x;
+    const uint32_t have = (uint32_t)min((uint64_t)256, p.n - r0);
+    const uint32_t words = have * NC;
+    uint32_t* dst = p.rows + r0 * NC;
+    const uint32_t nvec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? (words >> 2) : 0;
+    for (uint32_t v = threadIdx.x; v < nvec; v += 256) {
+        uint32_t w = 4 * v, r = w / NC, c = w - r * NC;  // NC is a compile-time constant: no division instruction
+        uint4 x;
+        x.x = stage[r * NCP + c];
+        if (++c == NC) { c = 0; ++r; }
+        x.y = stage[r * NCP + c];
+        if (++c == NC) { c = 0; ++r; }
+        x.z = stage[r * NCP + c];
+        if (++c == NC) { c = 0; ++r; }
+        x.w = stage[r * NCP + c];
+        reinterpret_cast<uint4*>(dst)[v] = x;
+    }
+    for (uint32_t w = 4 * nvec + threadIdx.x; w < words; w += 256) {
+        const uint32_t r = w / NC, c = w - r * NC;
+        dst[w] = stage[r * NCP + c];
     }
 }
 
