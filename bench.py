@@ -543,7 +543,7 @@ def bench_prove(be, torch, args):
                             "synthetic weights)",
                 "ms_e2e_host_tables": {"min": min(t_mlp), "median": statistics.median(t_mlp)},
                 "ms_e2e_host_tensors": {"min": min(t_mlp_dev), "median": statistics.median(t_mlp_dev),
-                                        "how": "graph recording, LUT column generation (host libm, as the reference), gen_trace "
+                                        "how": "graph recording, LUT columns of the circuit settings (host libm as the reference; cached per layout), gen_trace "
                                                "on the device (lb_trace_op) and prove(); proof bytes identical to the host-table path"},
                 "proof_bytes": len(mlp_proof)}
     # BASELINE.json's headline trace shape: 2^log rows x 61 main-trace columns (Add + Mul + Rem + SumReduce tables over the same

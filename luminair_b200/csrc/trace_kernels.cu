@@ -184,30 +184,65 @@ __global__ void __launch_bounds__(256) trace_rows_kernel(const TraceOp p) {
 
 // reductions: output element i folds `group` gathered inputs; one row per step (sum_reduce/table.rs 14 columns,
 // max_reduce/table.rs 15 columns).  The finished value appears in every row, hence the two sweeps.
-template <bool MAX>
+// STAGED (group * NC words per thread fit the 48 KB of static-limit shared memory): the CTA's 256 * group rows are one
+// contiguous run, parked in shared memory and stored coalesced like trace_rows_kernel does.
+template <bool MAX, bool STAGED>
 __global__ void __launch_bounds__(256) trace_reduce_kernel(const TraceOp p) {
-    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= p.n) return;
-    const uint64_t g = p.group, base = i * g;
-    int64_t fin = MAX ? rd(p.lhs, p.lhs_idx, base) : 0;
-    for (uint64_t j = 0; j < g; ++j) {
-        const int64_t x = rd(p.lhs, p.lhs_idx, base + j);
-        fin = MAX ? (x > fin ? x : fin) : fin + x;
-    }
-    p.out[i] = (int32_t)fin;
-    const uint32_t mult = p.out_mult ? p.out_mult[i] : 0u;
+    extern __shared__ uint32_t rstage[];
     constexpr int NC = MAX ? 15 : 14;
-    int64_t acc = 0;  // running value before the step (0 before the first step, also for max: prim.rs:1703-1709)
-    for (uint64_t j = 0; j < g; ++j) {
-        const int64_t x = rd(p.lhs, p.lhs_idx, base + j);
-        const bool is_max = (j == 0) || x > acc;
-        const int64_t next = MAX ? (is_max ? x : acc) : acc + x;
-        const bool last_step = (j == g - 1);
-        uint32_t* r = head1(p.rows + (base + j) * NC, p, i);
-        *r++ = to_m31(x); *r++ = to_m31(fin); *r++ = to_m31(acc); *r++ = to_m31(next); *r++ = last_step;
-        if (MAX) *r++ = is_max;
-        *r++ = P - 1; *r = last_step ? mult : 0u;
-        acc = next;
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t g = p.group, base = i * g;
+    const uint32_t pitch = ((uint32_t)g * NC) | 1;
+    if (i < p.n) {
+        int64_t fin = MAX ? rd(p.lhs, p.lhs_idx, base) : 0;
+        for (uint64_t j = 0; j < g; ++j) {
+            const int64_t x = rd(p.lhs, p.lhs_idx, base + j);
+            fin = MAX ? (x > fin ? x : fin) : fin + x;
+        }
+        p.out[i] = (int32_t)fin;
+        const uint32_t mult = p.out_mult ? p.out_mult[i] : p.out_mult_all;
+        int64_t acc = 0;  // running value before the step (0 before the first step, also for max: prim.rs:1703-1709)
+        for (uint64_t j = 0; j < g; ++j) {
+            const int64_t x = rd(p.lhs, p.lhs_idx, base + j);
+            const bool is_max = (j == 0) || x > acc;
+            const int64_t next = MAX ? (is_max ? x : acc) : acc + x;
+            const bool last_step = (j == g - 1);
+            uint32_t* r = head1(STAGED ? rstage + threadIdx.x * pitch + (uint32_t)j * NC : p.rows + (base + j) * NC, p, i);
+            *r++ = to_m31(x); *r++ = to_m31(fin); *r++ = to_m31(acc); *r++ = to_m31(next); *r++ = last_step;
+            if (MAX) *r++ = is_max;
+            *r++ = P - 1; *r = last_step ? mult : 0u;
+            acc = next;
+        }
+    }
+    if (!STAGED) return;
+    __syncthreads();
+    const uint64_t o0 = blockIdx.x * (uint64_t)blockDim.x;
+    const uint32_t have = (uint32_t)min((uint64_t)256, p.n - o0);
+    const uint32_t per = (uint32_t)g * NC, words = have * per;
+    uint32_t* dst = p.rows + o0 * per;
+    const uint32_t nvec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? (words >> 2) : 0;
+    if (nvec) {
+        const uint32_t dt = 1024 / per, dc = 1024 - dt * per;
+        uint32_t t = (4 * threadIdx.x) / per, c = 4 * threadIdx.x - t * per;
+        for (uint32_t v = threadIdx.x; v < nvec; v += 256) {
+            uint32_t tt = t, cc = c;
+            uint4 x;
+            x.x = rstage[tt * pitch + cc];
+            if (++cc == per) { cc = 0; ++tt; }
+            x.y = rstage[tt * pitch + cc];
+            if (++cc == per) { cc = 0; ++tt; }
+            x.z = rstage[tt * pitch + cc];
+            if (++cc == per) { cc = 0; ++tt; }
+            x.w = rstage[tt * pitch + cc];
+            reinterpret_cast<uint4*>(dst)[v] = x;
+            t += dt;
+            c += dc;
+            if (c >= per) { c -= per; ++t; }
+        }
+    }
+    for (uint32_t w = 4 * nvec + threadIdx.x; w < words; w += 256) {
+        const uint32_t t = w / per, c = w - t * per;
+        dst[w] = rstage[t * pitch + c];
     }
 }
 
@@ -233,8 +268,19 @@ cudaError_t trace_op(const TraceOp& p, cudaStream_t stream) {
         LB_TRACE_CASE(LB_OP_ADD) LB_TRACE_CASE(LB_OP_MUL) LB_TRACE_CASE(LB_OP_REM) LB_TRACE_CASE(LB_OP_LESS_THAN)
         LB_TRACE_CASE(LB_OP_RECIP) LB_TRACE_CASE(LB_OP_SQRT) LB_TRACE_CASE(LB_OP_SIN) LB_TRACE_CASE(LB_OP_EXP2)
         LB_TRACE_CASE(LB_OP_LOG2) LB_TRACE_CASE(LB_OP_CONTIGUOUS) LB_TRACE_CASE(LB_OP_INPUTS)
-        case LB_OP_SUM_REDUCE: trace_reduce_kernel<false><<<blocks, 256, 0, stream>>>(p); break;
-        case LB_OP_MAX_REDUCE: trace_reduce_kernel<true><<<blocks, 256, 0, stream>>>(p); break;
+        case LB_OP_SUM_REDUCE:
+        case LB_OP_MAX_REDUCE: {
+            const bool mx = p.op == LB_OP_MAX_REDUCE;
+            const size_t smem = 256 * (size_t)((p.group * (mx ? 15 : 14)) | 1) * sizeof(uint32_t);
+            if (p.group <= 3 && smem <= 48 * 1024) {
+                if (mx) trace_reduce_kernel<true, true><<<blocks, 256, smem, stream>>>(p);
+                else trace_reduce_kernel<false, true><<<blocks, 256, smem, stream>>>(p);
+            } else {
+                if (mx) trace_reduce_kernel<true, false><<<blocks, 256, 0, stream>>>(p);
+                else trace_reduce_kernel<false, false><<<blocks, 256, 0, stream>>>(p);
+            }
+            break;
+        }
         default: return cudaErrorInvalidValue;
     }
 #undef LB_TRACE_CASE

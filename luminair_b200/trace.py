@@ -33,6 +33,7 @@ OP_CODE = {"add": 0, "mul": 1, "recip": 2, "sin": 3, "sum_reduce": 5, "max_reduc
 ORDER = ["add", "mul", "recip", "sin", "sin_lookup", "sum_reduce", "max_reduce", "sqrt", "rem", "exp2", "exp2_lookup", "log2",
          "log2_lookup", "less_than", "range_check_lookup", "inputs", "contiguous"]
 BINARY = ("add", "mul", "rem", "less_than")
+_LUT_HOST = {}  # (lut name, layout ranges) -> [(column id, values)]: pie.lut_columns of a circuit-settings layout
 LUT_OPS = ("sin", "exp2", "log2")
 
 
@@ -129,13 +130,20 @@ class DeviceGraphTrace:
             layout = layouts[name]
             if len(layout.ranges) > 8:
                 raise LuminairB200Error("at most 8 lookup ranges (LB_MAX_LOOKUP_RANGES)")
-            cols = lut_columns(name, layout)
+            # the columns depend only on the circuit settings: generated once per layout, the device copy once per backend
+            key = (name, tuple(layout.ranges))
+            cols = _LUT_HOST.get(key)
+            if cols is None:
+                cols = _LUT_HOST[key] = lut_columns(name, layout)
             self.preprocessed += cols
             lk = Lookup()
             lk.n_ranges = len(layout.ranges)
             for k, (lo, hi) in enumerate(layout.ranges):
                 lk.lo[k], lk.hi[k] = lo, hi
-            d_vals = be.upload(cols[1][1])
+            dev_cache = be.__dict__.setdefault("_lut_device_columns", {})
+            d_vals = dev_cache.get(key)
+            if d_vals is None:
+                d_vals = dev_cache[key] = be.upload(cols[1][1])
             d_mult = self._zeros(1 << layout.log_size)
             lk.d_values, lk.d_multiplicities = d_vals.ptr, d_mult.ptr
             lookups[name] = (lk, d_vals, d_mult, 1 << layout.log_size)

@@ -108,6 +108,8 @@ def test_gathers_broadcasts_and_signed_edge_cases(be):
         c = g.contiguous((mr, np.arange(3 * n // 7)[::-1]))
         g.add(sr, m)
         g.mul(c, c)
+        g.max_reduce((s, perm3[:2330]), 2)
+        g.sum_reduce((q, rep[:n]), 1)
     _compare(be, hg, dg)
 
 
