@@ -59,3 +59,40 @@ def test_rust_ffi_file_is_in_sync_with_the_header():
     declared = set(re.findall(r"pub fn (lb_\w+)\(", rs))
     from luminair_b200._lib import SIGNATURES
     assert declared == set(SIGNATURES)
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of every struct the ctypes mirror passes by pointer, computed by gcc from the header itself, and the
+    LB_OP_* / LB_REL_* constants the Python side hard-codes."""
+    import ctypes as C
+    import subprocess
+    from luminair_b200 import _lib, trace
+    structs = {"lb_trace_table": _lib.TraceTable, "lb_prove_config": _lib.ProveConfig,
+               "lb_preprocessed_column": _lib.PreprocessedColumn, "lb_relation": _lib.Relation,
+               "lb_batch_shard": _lib.BatchShard, "lb_sample_batch": _lib.SampleBatch, "lb_lookup": _lib.Lookup,
+               "lb_trace_op_desc": _lib.TraceOpDesc}
+    ops = {"add": "LB_OP_ADD", "mul": "LB_OP_MUL", "recip": "LB_OP_RECIP", "sin": "LB_OP_SIN", "sum_reduce": "LB_OP_SUM_REDUCE",
+           "max_reduce": "LB_OP_MAX_REDUCE", "sqrt": "LB_OP_SQRT", "rem": "LB_OP_REM", "exp2": "LB_OP_EXP2", "log2": "LB_OP_LOG2",
+           "less_than": "LB_OP_LESS_THAN", "inputs": "LB_OP_INPUTS", "contiguous": "LB_OP_CONTIGUOUS"}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "luminair_b200.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    for key, macro in ops.items():
+        lines.append(f'printf("op.{key} %d\\n", {macro});')
+    lines.append('return 0; }')
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+    for key in ops:
+        assert int(got[f"op.{key}"]) == trace.OP_CODE[key], key
+    # the operator code is the claim slot of the operator's component
+    from luminair_b200.prover import CLAIM_SLOT
+    assert all(trace.OP_CODE[k] == CLAIM_SLOT[k] for k in trace.OP_CODE)
