@@ -380,6 +380,11 @@ def test_cpp_caller_reproduces_fixture(golden_dir):
     out = subprocess.run([exe, os.path.join(golden_dir, "simple_current.proof.bin")], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "identical" in out.stdout
+    # the same caller with gen_trace on the device (lb_trace_count_uses + lb_trace_op): same bytes
+    out = subprocess.run([exe, os.path.join(golden_dir, "simple_current.proof.bin"), "--device-trace"], capture_output=True,
+                         text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "generated on the device" in out.stdout and "identical" in out.stdout
 
 
 @pytest.mark.parametrize("blowup,last_bound,n_queries", [(2, 0, 3), (3, 1, 5)])
