@@ -58,6 +58,19 @@ struct DevChannel {
 };
 cudaError_t channel_mix_root_draw(DevChannel* d_ch, const uint32_t* d_root, int variant, QM31* d_alpha_out, uint32_t* d_digest_log,
                                   cudaStream_t stream);
+// the last FRI layers (line layers of at most 2^FRI_TAIL_MAX_LOG values) in one launch: per layer lg = from_log .. last_log + 1:
+// Merkle tree of the layer -> mix_root -> draw -> fold_line into layer lg - 1
+constexpr int FRI_TAIL_MAX_LOG = 10;
+struct FriTailArgs {
+    uint32_t* vals[FRI_TAIL_MAX_LOG + 1];    // vals[lg]: the 4 coordinate columns of layer lg, 2^lg words apart
+    uint32_t* tree[FRI_TAIL_MAX_LOG + 1];    // tree[lg]: all levels of the tree over layer lg, level k at word 8 * (2^k - 1)
+    const uint2* itw[FRI_TAIL_MAX_LOG + 1];  // inverse twiddles of fold_line at layer lg
+    int from_log, last_log, variant;
+    DevChannel* ch;
+    QM31* alphas;       // alphas[0]: coefficient that produced layer from_log; alphas[s + 1] is drawn after layer from_log - s
+    uint32_t* digests;  // 8 words per layer: channel digest after each mix_root
+};
+cudaError_t fri_tail(const FriTailArgs& a, cudaStream_t stream);
 
 // ---- GrindOps ------------------------------------------------------------------------------------
 // tests nonces [base, base + count); *d_found = min nonce that works (or UINT64_MAX)

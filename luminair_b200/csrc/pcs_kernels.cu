@@ -412,9 +412,8 @@ cudaError_t fold_line_dev(uint32_t* const dst[4], const uint32_t* const src[4], 
 // on the stream without a host round trip per layer.  Same Blake2sChannel as prover.cu's host class
 // (core/channel/blake2s.rs; variant 0 "legacy" / 1 "v2").  One thread.
 // ------------------------------------------------------------------------------------
-__global__ void channel_mix_root_draw_kernel(DevChannel* ch, const uint32_t* __restrict__ root, int variant, QM31* alpha_out,
-                                             uint32_t* digest_log) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ void channel_mix_root_draw_dev(DevChannel* ch, const uint32_t* root, int variant, QM31* alpha_out,
+                                         uint32_t* digest_log) {
     uint32_t h[8], m[16];
     // mix_root: digest <- Blake2s(digest || root), one 64-byte final block
     blake2s_init(h);
@@ -457,6 +456,91 @@ __global__ void channel_mix_root_draw_kernel(DevChannel* ch, const uint32_t* __r
     ch->n_sent = n_sent;
     *alpha_out = q_make(h[0] >= P ? h[0] - P : h[0], h[1] >= P ? h[1] - P : h[1], h[2] >= P ? h[2] - P : h[2],
                         h[3] >= P ? h[3] - P : h[3]);
+}
+
+__global__ void channel_mix_root_draw_kernel(DevChannel* ch, const uint32_t* root, int variant, QM31* alpha_out,
+                                             uint32_t* digest_log) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    channel_mix_root_draw_dev(ch, root, variant, alpha_out, digest_log);
+}
+
+// ------------------------------------------------------------------------------------
+// The tail of the FRI commit loop in one launch.  Once a line layer has at most 2^FRI_TAIL_MAX_LOG values, every step of
+// FriProver::commit for it - Merkle tree of the layer's four coordinate columns, mix_root, draw the folding coefficient,
+// fold_line into the next layer - is a handful of dependent Blake2s compressions and a few hundred field operations: four
+// launches of 3-20 us per layer whose cost is launch and drain latency.  One CTA runs all of them for all remaining layers
+// with block barriers in between; every tree level and every folded layer is written to the same buffers the layer-by-layer
+// path uses (the decommitment reads them later).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) fri_tail_kernel(const __grid_constant__ FriTailArgs a) {
+    __shared__ QM31 s_alpha;
+    const uint32_t tid = threadIdx.x;
+    int step = 0;
+    for (int lg = a.from_log; lg > a.last_log; --lg, ++step) {
+        const uint32_t n = 1u << lg;
+        uint32_t* const T = a.tree[lg];  // layer k of this tree: 2^k digests at word offset 8 * (2^k - 1)
+        uint32_t* const V = a.vals[lg];  // coordinate c of this FRI layer at V + c * n
+        uint32_t h[8], m[16];
+        if (tid < n) {  // leaves: Blake2s-256 of the four coordinate words (one final 16-byte block)
+            blake2s_init(h);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) m[c] = __ldcg(V + (size_t)c * n + tid);
+#pragma unroll
+            for (int j = 4; j < 16; ++j) m[j] = 0;
+            blake2s_compress(h, m, 16, 0, 0xFFFFFFFFu);
+            uint4* o = reinterpret_cast<uint4*>(T + 8 * ((size_t)n - 1) + 8 * (size_t)tid);
+            o[0] = make_uint4(h[0], h[1], h[2], h[3]);
+            o[1] = make_uint4(h[4], h[5], h[6], h[7]);
+        }
+        __syncthreads();
+        for (int k = lg - 1; k >= 0; --k) {  // node = Blake2s-256(left || right)
+            if (tid < (1u << k)) {
+                const uint4* pp = reinterpret_cast<const uint4*>(T + 8 * (((size_t)2 << k) - 1) + 16 * (size_t)tid);
+                const uint4 x0 = __ldcg(pp), x1 = __ldcg(pp + 1), x2 = __ldcg(pp + 2), x3 = __ldcg(pp + 3);
+                m[0] = x0.x; m[1] = x0.y; m[2] = x0.z; m[3] = x0.w;
+                m[4] = x1.x; m[5] = x1.y; m[6] = x1.z; m[7] = x1.w;
+                m[8] = x2.x; m[9] = x2.y; m[10] = x2.z; m[11] = x2.w;
+                m[12] = x3.x; m[13] = x3.y; m[14] = x3.z; m[15] = x3.w;
+                blake2s_init(h);
+                blake2s_compress(h, m, 64, 0, 0xFFFFFFFFu);
+                uint4* o = reinterpret_cast<uint4*>(T + 8 * (((size_t)1 << k) - 1) + 8 * (size_t)tid);
+                o[0] = make_uint4(h[0], h[1], h[2], h[3]);
+                o[1] = make_uint4(h[4], h[5], h[6], h[7]);
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {  // the root was written by this thread
+            channel_mix_root_draw_dev(a.ch, T, a.variant, a.alphas + step + 1, a.digests + 8 * (size_t)step);
+            s_alpha = a.alphas[step + 1];
+        }
+        __syncthreads();
+        const uint32_t n_out = n >> 1;
+        if (tid < n_out) {  // FriOps::fold_line
+            const QM31 alpha = s_alpha;
+            uint32_t p[4], q[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint2 v = __ldcg(reinterpret_cast<const uint2*>(V + (size_t)c * n + 2 * (size_t)tid));
+                p[c] = v.x;
+                q[c] = v.y;
+            }
+            const uint32_t tinv = a.itw[lg][tid].x;
+            const QM31 f_p = q_make(p[0], p[1], p[2], p[3]), f_n = q_make(q[0], q[1], q[2], q[3]);
+            const QM31 r = q_add(q_mul(alpha, q_mul_m(q_sub(f_p, f_n), tinv)), q_add(f_p, f_n));
+            uint32_t* const W = a.vals[lg - 1];
+            W[tid] = r.a.a;
+            W[(size_t)n_out + tid] = r.a.b;
+            W[2 * (size_t)n_out + tid] = r.b.a;
+            W[3 * (size_t)n_out + tid] = r.b.b;
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t fri_tail(const FriTailArgs& a, cudaStream_t stream) {
+    if (a.from_log > FRI_TAIL_MAX_LOG || a.last_log < 0 || a.from_log <= a.last_log) return cudaErrorInvalidValue;
+    fri_tail_kernel<<<1, 1024, 0, stream>>>(a);
+    return cudaGetLastError();
 }
 
 cudaError_t channel_mix_root_draw(DevChannel* d_ch, const uint32_t* d_root, int variant, QM31* d_alpha_out, uint32_t* d_digest_log,

@@ -216,6 +216,9 @@ class Channel {
 // ------------------------------------------------------------------------------------
 // Merkle trees over mixed-height column sets (prover/vcs/prover.rs MerkleProver)
 // ------------------------------------------------------------------------------------
+#ifndef LB_FRI_TAIL
+#define LB_FRI_TAIL 1  // the last FRI layers (<= 2^FRI_TAIL_MAX_LOG values) in one single-CTA launch (pcs_kernels.cu fri_tail_kernel)
+#endif
 #ifndef LB_MERKLE_SUBTREE
 #define LB_MERKLE_SUBTREE 1
 #endif
@@ -1160,6 +1163,37 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                                                  quotients[qi].log, d_alphas + li, st),
                        "fold circle");
                     ++qi;
+                }
+                if (LB_FRI_TAIL && line_log <= FRI_TAIL_MAX_LOG && qi == quotients.size()) {
+                    // every remaining layer (tree, mix_root, draw, fold_line) in one single-CTA launch: fri_tail_kernel
+                    FriTailArgs a{};
+                    a.from_log = line_log;
+                    a.last_log = last_log;
+                    a.variant = cfg.channel_variant;
+                    a.ch = d_ch;
+                    a.alphas = d_alphas + li;
+                    a.digests = d_digests + 8 * (size_t)li;
+                    for (int lg = line_log; lg > last_log; --lg) {
+                        FriLayer L;
+                        L.log = lg;
+                        uint32_t* base = layer_at(lg);
+                        for (int k = 0; k < 4; ++k) L.coords[k] = base + ((size_t)k << lg);
+                        L.tree.empty = false;
+                        L.tree.max_log = lg;
+                        for (int k = 0; k < 4; ++k) L.tree.sorted.push_back({L.coords[k], lg});
+                        uint32_t* all = arena.alloc<uint32_t>((size_t)16 << lg);
+                        L.tree.layers.assign(lg + 1, nullptr);
+                        for (int k = 0; k <= lg; ++k) L.tree.layers[k] = all + 8 * (((size_t)1 << k) - 1);
+                        a.vals[lg] = base;
+                        a.tree[lg] = all;
+                        a.itw[lg] = inv_x_twiddles(tw, lg);
+                        inner.push_back(L);
+                    }
+                    a.vals[last_log] = layer_at(last_log);
+                    ck(fri_tail(a, st), "fri tail");
+                    cur = layer_at(last_log);
+                    line_log = last_log;
+                    break;
                 }
                 FriLayer L;
                 L.log = line_log;
