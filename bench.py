@@ -198,6 +198,8 @@ def run_gpu(args):
     all_cpus = os.sched_getaffinity(0)
     numa = pin_to_gpu_numa_node(local_rank)  # before any pinned allocation: first touch lands on the GPU's NUMA node
     if distributed:
+        # stdout carries the one JSON line only: NCCL's own log (version banner, NCCL_DEBUG output) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from luminair_b200.backend import ColumnBatch, CudaBackend
