@@ -14,6 +14,9 @@
 
 namespace lb {
 
+#ifndef LB_MERKLE_SUBTREE_LATENCY_FORM
+#define LB_MERKLE_SUBTREE_LATENCY_FORM 1  // upper levels of merkle_subtree_kernel: plain-add compression (few warps per CTA)
+#endif
 #ifndef LB_MERKLE_FMA
 #define LB_MERKLE_FMA 1
 #endif
@@ -164,17 +167,42 @@ cudaError_t merkle_commit_layer_small(uint32_t* out, const uint32_t* prev, const
 // The top of a tree in one launch: given layer `from_log` (<= MERKLE_TOP_MAX_LOG) already hashed, one CTA computes the
 // column-less layers from_log-1 .. 0, each into its own buffer, with a block barrier between levels.  Saves one
 // ~3 us dependent launch per level on every tree (the FRI layers make ~25 trees per proof).
+// These levels are a chain of dependent compressions on a handful of warps, so latency is what counts: children are handed
+// from level to level through shared memory (each level is still written to its global buffer for the decommitment) and the
+// compression is the plain-add form, whose three-input adds make a shorter dependent chain than the IMAD-forced throughput form.
+__device__ __forceinline__ void hash_children_latency(uint32_t h[8], const uint4 x0, const uint4 x1, const uint4 x2, const uint4 x3) {
+    uint32_t m[16] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w, x3.x, x3.y, x3.z, x3.w};
+    blake2s_init(h);
+    blake2s_compress(h, m, 64, 0, 0xFFFFFFFFu);
+}
+
 __global__ void __launch_bounds__(512) merkle_top_kernel(MerkleTopArgs a, uint32_t one) {
+    (void)one;
+    __shared__ uint4 sm[2 * 512];  // digest i of the level just hashed: sm[2 * i], sm[2 * i + 1]
+    const uint32_t tid = threadIdx.x;
     for (int log = a.from_log - 1; log >= 0; --log) {
-        uint32_t n = 1u << log;
-        if (threadIdx.x < n) {
-            uint32_t h[8];
-            hash_node<true>(h, a.layers[log + 1], nullptr, 0, threadIdx.x, one);
-            uint4* o = reinterpret_cast<uint4*>(a.layers[log] + (size_t)threadIdx.x * 8);
-            o[0] = make_uint4(h[0], h[1], h[2], h[3]);
-            o[1] = make_uint4(h[4], h[5], h[6], h[7]);
+        const uint32_t n = 1u << log;
+        uint4 x0, x1, x2, x3;
+        if (tid < n) {
+            if (log == a.from_log - 1) {  // written by the previous launch
+                const uint4* pp = reinterpret_cast<const uint4*>(a.layers[log + 1] + (size_t)tid * 16);
+                x0 = pp[0]; x1 = pp[1]; x2 = pp[2]; x3 = pp[3];
+            } else {
+                x0 = sm[4 * tid]; x1 = sm[4 * tid + 1]; x2 = sm[4 * tid + 2]; x3 = sm[4 * tid + 3];
+            }
         }
-        __syncthreads();  // the level just written is read by other threads of this CTA next
+        __syncthreads();  // every child has been read: the slots can be overwritten
+        if (tid < n) {
+            uint32_t h[8];
+            hash_children_latency(h, x0, x1, x2, x3);
+            const uint4 lo = make_uint4(h[0], h[1], h[2], h[3]), hi = make_uint4(h[4], h[5], h[6], h[7]);
+            uint4* o = reinterpret_cast<uint4*>(a.layers[log] + (size_t)tid * 8);
+            o[0] = lo;
+            o[1] = hi;
+            sm[2 * tid] = lo;
+            sm[2 * tid + 1] = hi;
+        }
+        __syncthreads();
     }
 }
 
@@ -242,7 +270,12 @@ __global__ void __launch_bounds__(256, 2) merkle_subtree_kernel(const __grid_con
         if (threadIdx.x < cnt) {
             const uint32_t i = (base >> d) + threadIdx.x;
             uint32_t h[8];
+#if LB_MERKLE_SUBTREE_LATENCY_FORM
+            const uint4* pp = reinterpret_cast<const uint4*>(a.layers[d - 1] + (size_t)i * 16);
+            hash_children_latency(h, __ldcg(pp), __ldcg(pp + 1), __ldcg(pp + 2), __ldcg(pp + 3));
+#else
             hash_node<true>(h, a.layers[d - 1], nullptr, 0, i, one);
+#endif
             uint4* o = reinterpret_cast<uint4*>(a.layers[d] + (size_t)i * 8);
             o[0] = make_uint4(h[0], h[1], h[2], h[3]);
             o[1] = make_uint4(h[4], h[5], h[6], h[7]);

@@ -474,6 +474,7 @@ __global__ void channel_mix_root_draw_kernel(DevChannel* ch, const uint32_t* roo
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) fri_tail_kernel(const __grid_constant__ FriTailArgs a) {
     __shared__ QM31 s_alpha;
+    __shared__ uint4 s_dig[2 * 1024];  // digest i of the tree level just hashed: s_dig[2 * i], s_dig[2 * i + 1]
     const uint32_t tid = threadIdx.x;
     int step = 0;
     for (int lg = a.from_log; lg > a.last_log; --lg, ++step) {
@@ -488,24 +489,34 @@ __global__ void __launch_bounds__(1024) fri_tail_kernel(const __grid_constant__ 
 #pragma unroll
             for (int j = 4; j < 16; ++j) m[j] = 0;
             blake2s_compress(h, m, 16, 0, 0xFFFFFFFFu);
+            const uint4 lo = make_uint4(h[0], h[1], h[2], h[3]), hi = make_uint4(h[4], h[5], h[6], h[7]);
             uint4* o = reinterpret_cast<uint4*>(T + 8 * ((size_t)n - 1) + 8 * (size_t)tid);
-            o[0] = make_uint4(h[0], h[1], h[2], h[3]);
-            o[1] = make_uint4(h[4], h[5], h[6], h[7]);
+            o[0] = lo;
+            o[1] = hi;
+            s_dig[2 * tid] = lo;
+            s_dig[2 * tid + 1] = hi;
         }
         __syncthreads();
-        for (int k = lg - 1; k >= 0; --k) {  // node = Blake2s-256(left || right)
-            if (tid < (1u << k)) {
-                const uint4* pp = reinterpret_cast<const uint4*>(T + 8 * (((size_t)2 << k) - 1) + 16 * (size_t)tid);
-                const uint4 x0 = __ldcg(pp), x1 = __ldcg(pp + 1), x2 = __ldcg(pp + 2), x3 = __ldcg(pp + 3);
+        for (int k = lg - 1; k >= 0; --k) {  // node = Blake2s-256(left || right); children handed over in shared memory
+            const bool on = tid < (1u << k);
+            uint4 x0, x1, x2, x3;
+            if (on) {
+                x0 = s_dig[4 * tid]; x1 = s_dig[4 * tid + 1]; x2 = s_dig[4 * tid + 2]; x3 = s_dig[4 * tid + 3];
+            }
+            __syncthreads();  // all children read: the slots can be overwritten
+            if (on) {
                 m[0] = x0.x; m[1] = x0.y; m[2] = x0.z; m[3] = x0.w;
                 m[4] = x1.x; m[5] = x1.y; m[6] = x1.z; m[7] = x1.w;
                 m[8] = x2.x; m[9] = x2.y; m[10] = x2.z; m[11] = x2.w;
                 m[12] = x3.x; m[13] = x3.y; m[14] = x3.z; m[15] = x3.w;
                 blake2s_init(h);
                 blake2s_compress(h, m, 64, 0, 0xFFFFFFFFu);
+                const uint4 lo = make_uint4(h[0], h[1], h[2], h[3]), hi = make_uint4(h[4], h[5], h[6], h[7]);
                 uint4* o = reinterpret_cast<uint4*>(T + 8 * (((size_t)1 << k) - 1) + 8 * (size_t)tid);
-                o[0] = make_uint4(h[0], h[1], h[2], h[3]);
-                o[1] = make_uint4(h[4], h[5], h[6], h[7]);
+                o[0] = lo;
+                o[1] = hi;
+                s_dig[2 * tid] = lo;
+                s_dig[2 * tid + 1] = hi;
             }
             __syncthreads();
         }
