@@ -88,6 +88,20 @@ int lb_ipc_close(lb_ctx* ctx, uint32_t* d_ptr);
 int lb_lde_host(lb_ctx* ctx, const uint32_t* h_values, uint32_t* h_evals, int n_cols, int log_in, int log_out,
                 uint32_t* h_coeffs, int chunk_cols);
 
+/* ---- ColumnOps / FieldOps / AccumulationOps: the small trait methods stwo::prover::prove and the LogUp generator reach ---- */
+/* ColumnOps<BaseField>::bit_reverse_column, in place (a SecureField column is its 4 coordinate columns: 4 calls) */
+int lb_bit_reverse(lb_ctx* ctx, uint32_t* d_col, int log_size);
+/* PolyOps::new_canonical_ordered: 2^log_size values in canonic-coset order -> bit-reversed circle-domain order (d_out != d_in) */
+int lb_new_canonical_ordered(lb_ctx* ctx, const uint32_t* d_in, uint32_t* d_out, int log_size);
+/* FieldOps<BaseField>::batch_inverse / FieldOps<SecureField>::batch_inverse (4 coordinate columns); d_out may equal d_in.
+ * A zero input fails with LB_ERR_BAD_ARG "0 has no inverse" (stwo panics with that text). */
+int lb_batch_inverse_m31(lb_ctx* ctx, const uint32_t* d_in, uint32_t* d_out, size_t n);
+int lb_batch_inverse_qm31(lb_ctx* ctx, const uint32_t* const d_in[4], uint32_t* const d_out[4], size_t n);
+/* AccumulationOps::accumulate: column += other, coordinate-wise over SecureColumnByCoords of n elements */
+int lb_accumulate(lb_ctx* ctx, uint32_t* const d_column[4], const uint32_t* const d_other[4], size_t n);
+/* AccumulationOps::generate_secure_powers: h_out[4 * k .. 4 * k + 3] = felt^k for k < n_powers (host; the sequence is serial) */
+int lb_generate_secure_powers(const uint32_t felt[4], int n_powers, uint32_t* h_out);
+
 /* ---- MerkleOps<Blake2sMerkleHasher> ------------------------------------------------------- */
 /* commit_on_layer: d_out = 2^log_size digests (8 u32 each); d_prev = child layer or NULL;
  * h_cols = HOST array of n_cols DEVICE column pointers (columns of exactly this log size) */

@@ -130,6 +130,12 @@ SIGNATURES.update({
                                C.c_void_p, C.c_void_p, C.c_uint64]),
     "lb_trace_mul": (C.c_int, [ctxp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
                                C.c_void_p, C.c_void_p, C.c_uint64]),
+    "lb_bit_reverse": (C.c_int, [ctxp, C.c_void_p, C.c_int]),
+    "lb_new_canonical_ordered": (C.c_int, [ctxp, C.c_void_p, C.c_void_p, C.c_int]),
+    "lb_batch_inverse_m31": (C.c_int, [ctxp, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "lb_batch_inverse_qm31": (C.c_int, [ctxp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t]),
+    "lb_accumulate": (C.c_int, [ctxp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t]),
+    "lb_generate_secure_powers": (C.c_int, [u32p, C.c_int, u32p]),
     "lb_trace_op": (C.c_int, [ctxp, C.POINTER(TraceOpDesc)]),
     "lb_trace_count_uses": (C.c_int, [ctxp, C.c_void_p, C.c_void_p, C.c_uint64]),
     "lb_prove_transcript": (C.c_int, [ctxp, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),

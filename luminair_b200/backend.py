@@ -224,6 +224,36 @@ class CudaBackend:
         check(self.ctx, self.lib.lb_grind(self.ctx, dg, channel_variant, pow_bits, C.byref(nonce)), "lb_grind")
         return int(nonce.value)
 
+    # ---- ColumnOps / FieldOps / AccumulationOps ---------------------------------------------------
+    @staticmethod
+    def _ptr4(ptrs):
+        return (C.c_void_p * 4)(*[C.c_void_p(int(p)) for p in ptrs])
+
+    def bit_reverse_column(self, ptr: int, log_size: int):
+        check(self.ctx, self.lib.lb_bit_reverse(self.ctx, C.c_void_p(ptr), log_size), "lb_bit_reverse")
+
+    def new_canonical_ordered(self, src_ptr: int, dst_ptr: int, log_size: int):
+        check(self.ctx, self.lib.lb_new_canonical_ordered(self.ctx, C.c_void_p(src_ptr), C.c_void_p(dst_ptr), log_size),
+              "lb_new_canonical_ordered")
+
+    def batch_inverse(self, src_ptr: int, dst_ptr: int, n: int):
+        check(self.ctx, self.lib.lb_batch_inverse_m31(self.ctx, C.c_void_p(src_ptr), C.c_void_p(dst_ptr), n), "lb_batch_inverse_m31")
+
+    def batch_inverse_secure(self, src_ptrs, dst_ptrs, n: int):
+        check(self.ctx, self.lib.lb_batch_inverse_qm31(self.ctx, self._ptr4(src_ptrs), self._ptr4(dst_ptrs), n),
+              "lb_batch_inverse_qm31")
+
+    def accumulate(self, column_ptrs, other_ptrs, n: int):
+        check(self.ctx, self.lib.lb_accumulate(self.ctx, self._ptr4(column_ptrs), self._ptr4(other_ptrs), n), "lb_accumulate")
+
+    def generate_secure_powers(self, felt, n_powers: int) -> np.ndarray:
+        f = (C.c_uint32 * 4)(*[int(x) for x in felt])
+        out = np.zeros((max(n_powers, 1), 4), dtype=np.uint32)
+        rc = self.lib.lb_generate_secure_powers(f, n_powers, out.ctypes.data_as(C.POINTER(C.c_uint32)))
+        if rc != 0:
+            raise LuminairB200Error(f"lb_generate_secure_powers: {rc}")
+        return out[:n_powers]
+
     # ---- AIR kernels -------------------------------------------------------------------------
     def logup_interaction_trace(self, component: int, main: ColumnBatch, inter: ColumnBatch, z, alpha) -> np.ndarray:
         zz = (C.c_uint32 * 4)(*[int(v) for v in z])

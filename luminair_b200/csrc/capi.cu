@@ -517,6 +517,71 @@ int lb_trace_mul(lb_ctx* ctx, uint32_t node_id, uint32_t lhs_id, uint32_t rhs_id
     return trace_binary_api(ctx, true, node_id, lhs_id, rhs_id, d_lhs, d_rhs, n, out_mult, d_out, d_rows, row0);
 }
 
+int lb_bit_reverse(lb_ctx* ctx, uint32_t* d_col, int log_size) {
+    if (!ctx || !d_col || log_size < 0 || log_size > 31) return fail(ctx, LB_ERR_BAD_ARG, "bit_reverse: bad args");
+    cudaSetDevice(ctx->device);
+    CK(lb::bit_reverse(d_col, log_size, ctx->stream), "bit_reverse");
+    return LB_OK;
+}
+
+int lb_new_canonical_ordered(lb_ctx* ctx, const uint32_t* d_in, uint32_t* d_out, int log_size) {
+    if (!ctx || !d_in || !d_out || d_in == d_out || log_size < 1 || log_size > 31)
+        return fail(ctx, LB_ERR_BAD_ARG, "new_canonical_ordered: bad args");
+    cudaSetDevice(ctx->device);
+    CK(lb::canonical_to_storage(d_out, d_in, log_size, ctx->stream), "new_canonical_ordered");
+    return LB_OK;
+}
+
+static int batch_inverse_api(lb_ctx* ctx, const uint32_t* const* in, uint32_t* const* out, int n_coords, size_t n) {
+    cudaSetDevice(ctx->device);
+    if (ensure_scratch(ctx, 64) != LB_OK) return LB_ERR_OOM;
+    int* d_flag = (int*)ctx->d_scratch;
+    CK(cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream), "batch_inverse: flag reset");
+    if (n_coords == 1)
+        CK(lb::batch_inverse_m31(out[0], in[0], n, d_flag, ctx->stream), "batch_inverse");
+    else
+        CK(lb::batch_inverse_qm31(out, in, n, d_flag, ctx->stream), "batch_inverse");
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream), "batch_inverse: flag read");
+    CK(cudaStreamSynchronize(ctx->stream), "batch_inverse: sync");
+    if (flag) return fail(ctx, LB_ERR_BAD_ARG, "0 has no inverse");
+    return LB_OK;
+}
+
+int lb_batch_inverse_m31(lb_ctx* ctx, const uint32_t* d_in, uint32_t* d_out, size_t n) {
+    if (!ctx || !d_in || !d_out) return fail(ctx, LB_ERR_BAD_ARG, "batch_inverse: bad args");
+    return batch_inverse_api(ctx, &d_in, &d_out, 1, n);
+}
+
+int lb_batch_inverse_qm31(lb_ctx* ctx, const uint32_t* const d_in[4], uint32_t* const d_out[4], size_t n) {
+    if (!ctx || !d_in || !d_out) return fail(ctx, LB_ERR_BAD_ARG, "batch_inverse: bad args");
+    for (int c = 0; c < 4; ++c)
+        if (!d_in[c] || !d_out[c]) return fail(ctx, LB_ERR_BAD_ARG, "batch_inverse: null coordinate column");
+    return batch_inverse_api(ctx, d_in, d_out, 4, n);
+}
+
+int lb_accumulate(lb_ctx* ctx, uint32_t* const d_column[4], const uint32_t* const d_other[4], size_t n) {
+    if (!ctx || !d_column || !d_other) return fail(ctx, LB_ERR_BAD_ARG, "accumulate: bad args");
+    cudaSetDevice(ctx->device);
+    for (int c = 0; c < 4; ++c) {
+        if (!d_column[c] || !d_other[c]) return fail(ctx, LB_ERR_BAD_ARG, "accumulate: null coordinate column");
+        CK(lb::add_inplace(d_column[c], d_other[c], n, ctx->stream), "accumulate");
+    }
+    return LB_OK;
+}
+
+int lb_generate_secure_powers(const uint32_t felt[4], int n_powers, uint32_t* h_out) {
+    if (!felt || n_powers < 0 || (n_powers && !h_out)) return LB_ERR_BAD_ARG;
+    for (int c = 0; c < 4; ++c)
+        if (felt[c] >= lb::P) return LB_ERR_BAD_ARG;
+    lb::QM31 f = lb::q_make(felt[0], felt[1], felt[2], felt[3]), acc = lb::q_from_m(1);
+    for (int k = 0; k < n_powers; ++k) {
+        h_out[4 * k] = acc.a.a; h_out[4 * k + 1] = acc.a.b; h_out[4 * k + 2] = acc.b.a; h_out[4 * k + 3] = acc.b.b;
+        acc = lb::q_mul(acc, f);
+    }
+    return LB_OK;
+}
+
 int lb_trace_count_uses(lb_ctx* ctx, uint32_t* d_uses, const uint32_t* d_idx, uint64_t n_reads) {
     if (!ctx || !d_uses) return fail(ctx, LB_ERR_BAD_ARG, "trace_count_uses: bad args");
     cudaSetDevice(ctx->device);

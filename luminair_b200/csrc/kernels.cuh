@@ -79,6 +79,11 @@ cudaError_t grind_range(const uint32_t digest[8], int variant, uint32_t pow_bits
 
 // ---- small column utilities -----------------------------------------------------------------------
 cudaError_t add_inplace(uint32_t* dst, const uint32_t* src, size_t n, cudaStream_t stream);  // dst += src (M31)
+cudaError_t bit_reverse(uint32_t* col, int log, cudaStream_t stream);  // in place
+cudaError_t canonical_to_storage(uint32_t* out, const uint32_t* in, int log, cudaStream_t stream);
+// out = 1 / in element-wise; *d_flag is set to 1 when an input is zero (its output is then unspecified)
+cudaError_t batch_inverse_m31(uint32_t* out, const uint32_t* in, size_t n, int* d_flag, cudaStream_t stream);
+cudaError_t batch_inverse_qm31(uint32_t* const out[4], const uint32_t* const in[4], size_t n, int* d_flag, cudaStream_t stream);
 cudaError_t gather_words(uint32_t* d_out, const uint32_t* const* d_addrs, int n, cudaStream_t stream);
 // rows (row-major n_rows x n_cols) -> n_cols columns of 2^log at `stride`, padded with the component's
 // `padding()` row (write_trace, e.g. add/witness.rs:43-46; air.cuh padding_value)

@@ -626,6 +626,110 @@ cudaError_t add_inplace(uint32_t* dst, const uint32_t* src, size_t n, cudaStream
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------
+// Column utilities behind the remaining backend-trait methods (ColumnOps::bit_reverse_column, PolyOps::new_canonical_ordered,
+// FieldOps::batch_inverse for BaseField and SecureField columns).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bit_reverse_kernel(uint32_t* __restrict__ col, int log) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >> log) return;
+    const uint32_t j = log ? __brev(i) >> (32 - log) : 0;
+    if (i < j) {
+        const uint32_t a = col[i], b = col[j];
+        col[i] = b;
+        col[j] = a;
+    }
+}
+cudaError_t bit_reverse(uint32_t* col, int log, cudaStream_t stream) {
+    const uint32_t n = 1u << log;
+    bit_reverse_kernel<<<(n + 255) / 256, 256, 0, stream>>>(col, log);
+    return cudaGetLastError();
+}
+
+// values in canonic-coset order -> the bit-reversed circle-domain order every other entry point uses
+// (CircleEvaluation::new_canonical_ordered: coset point k is circle-domain point k/2 for even k, n/2 + (n-1-k)/2 for odd k)
+__global__ void __launch_bounds__(256) canonical_to_storage_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ in,
+                                                                   int log) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >> log) return;
+    const uint32_t n = 1u << log;
+    const uint32_t dom = (k & 1) ? (n >> 1) + ((n - 1 - k) >> 1) : (k >> 1);
+    out[log ? __brev(dom) >> (32 - log) : 0] = in[k];
+}
+cudaError_t canonical_to_storage(uint32_t* out, const uint32_t* in, int log, cudaStream_t stream) {
+    const uint32_t n = 1u << log;
+    canonical_to_storage_kernel<<<(n + 255) / 256, 256, 0, stream>>>(out, in, log);
+    return cudaGetLastError();
+}
+
+// four consecutive elements per thread share one field inversion (Montgomery's trick); a zero input raises *flag
+__global__ void __launch_bounds__(256) batch_inverse_m31_kernel(uint32_t* out, const uint32_t* in, size_t n, int* flag) {
+    const size_t i0 = 4 * (blockIdx.x * (size_t)blockDim.x + threadIdx.x);
+    if (i0 >= n) return;
+    uint32_t x[4], pre[4];
+    uint32_t acc = 1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        x[k] = (i0 + k < n) ? in[i0 + k] : 1u;
+        if (x[k] == 0) {
+            atomicExch(flag, 1);
+            x[k] = 1;
+        }
+        pre[k] = acc;
+        acc = m_mul(acc, x[k]);
+    }
+    uint32_t inv = m_inv(acc);
+#pragma unroll
+    for (int k = 3; k >= 0; --k) {
+        if (i0 + k < n) out[i0 + k] = m_mul(inv, pre[k]);
+        inv = m_mul(inv, x[k]);
+    }
+}
+__global__ void __launch_bounds__(256) batch_inverse_qm31_kernel(Coords4 out, CCoords4 in, size_t n, int* flag) {
+    const size_t i0 = 4 * (blockIdx.x * (size_t)blockDim.x + threadIdx.x);
+    if (i0 >= n) return;
+    QM31 x[4], pre[4];
+    QM31 acc = q_from_m(1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        x[k] = (i0 + k < n) ? q_make(in.p[0][i0 + k], in.p[1][i0 + k], in.p[2][i0 + k], in.p[3][i0 + k]) : q_from_m(1);
+        if (q_eq(x[k], q_zero())) {
+            atomicExch(flag, 1);
+            x[k] = q_from_m(1);
+        }
+        pre[k] = acc;
+        acc = q_mul(acc, x[k]);
+    }
+    QM31 inv = q_inv(acc);
+#pragma unroll
+    for (int k = 3; k >= 0; --k) {
+        if (i0 + k < n) {
+            const QM31 r = q_mul(inv, pre[k]);
+            out.p[0][i0 + k] = r.a.a;
+            out.p[1][i0 + k] = r.a.b;
+            out.p[2][i0 + k] = r.b.a;
+            out.p[3][i0 + k] = r.b.b;
+        }
+        inv = q_mul(inv, x[k]);
+    }
+}
+cudaError_t batch_inverse_m31(uint32_t* out, const uint32_t* in, size_t n, int* d_flag, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    batch_inverse_m31_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, stream>>>(out, in, n, d_flag);
+    return cudaGetLastError();
+}
+cudaError_t batch_inverse_qm31(uint32_t* const out[4], const uint32_t* const in[4], size_t n, int* d_flag, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    Coords4 o;
+    CCoords4 s;
+    for (int c = 0; c < 4; ++c) {
+        o.p[c] = out[c];
+        s.p[c] = in[c];
+    }
+    batch_inverse_qm31_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, stream>>>(o, s, n, d_flag);
+    return cudaGetLastError();
+}
+
 __global__ void gather_words_kernel(uint32_t* out, const uint32_t* const* addrs, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = *addrs[i];

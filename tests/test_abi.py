@@ -96,3 +96,21 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
     # the operator code is the claim slot of the operator's component
     from luminair_b200.prover import CLAIM_SLOT
     assert all(trace.OP_CODE[k] == CLAIM_SLOT[k] for k in trace.OP_CODE)
+
+
+def test_generate_secure_powers_on_the_host():
+    """AccumulationOps::generate_secure_powers needs no device: [1, f, f^2, ...] against the CPU restatement's QM31."""
+    import ctypes as C
+    import numpy as np
+    from luminair_b200._lib import load_library
+    from oracle.fields import QM31
+    lib = load_library()
+    felt = (123456789, 987654321, 5, 2147483646)
+    out = np.zeros((9, 4), dtype=np.uint32)
+    rc = lib.lb_generate_secure_powers((C.c_uint32 * 4)(*felt), 9, out.ctypes.data_as(C.POINTER(C.c_uint32)))
+    assert rc == 0
+    acc, f = QM31(1, 0, 0, 0), QM31(*felt)
+    for k in range(9):
+        assert tuple(int(x) for x in out[k]) == acc.tup()
+        acc = acc * f
+    assert lib.lb_generate_secure_powers((C.c_uint32 * 4)(2147483647, 0, 0, 0), 1, out.ctypes.data_as(C.POINTER(C.c_uint32))) == -3
