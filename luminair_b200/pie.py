@@ -250,10 +250,11 @@ class GraphTrace:
         return self._reduce("max_reduce", a, group)
 
     # -- tables ------------------------------------------------------------------------------
-    def finish(self, lut_pad: int = 0):
+    def finish(self, lut_pad: int = 0, layouts=None):
         """-> (pie, preprocessed): trace tables in claim-slot order (graph.rs:502-593) and the LUT columns in
         ``lookups_to_preprocessed_column`` order (preprocessed.rs:181-206).  Nodes nobody reads are the graph's
-        final outputs (multiplicity 0)."""
+        final outputs (multiplicity 0).  ``layouts``: {lut name: LookupLayout} of given circuit settings (default: one range
+        covering the values seen, as a calibration run would produce)."""
         rows = {}
 
         def emit(kind, cols, n):
@@ -304,7 +305,7 @@ class GraphTrace:
             if not self.lut_inputs[name]:
                 continue
             x = np.concatenate(self.lut_inputs[name])
-            layout = self.layouts[name] = LookupLayout.covering(x, lut_pad)
+            layout = self.layouts[name] = (layouts or {}).get(name) or LookupLayout.covering(x, lut_pad)
             preprocessed += lut_columns(name, layout)
             mult = np.zeros(1 << layout.log_size, dtype=np.int64)
             np.add.at(mult, layout.find_index(x), 1)

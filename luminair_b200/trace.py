@@ -44,6 +44,7 @@ class DeviceGraphTrace:
         self.sizes = []   # node -> elements
         self.reads = []   # node -> [(device idx buffer | None, n_reads)] of its consumers
         self._keep = []
+        self._program = None  # after the first finish(): the emission calls, replayed by later finish() calls
 
     # -- nodes ------------------------------------------------------------------------------------------------
     def input(self, raw_values) -> int:
@@ -54,6 +55,15 @@ class DeviceGraphTrace:
         arr = arr.reshape(-1)
         buf = self.be.upload(arr.view(np.uint32), self.be.alloc(arr.size, pooled=True))
         return self._node("inputs", buf, arr.size)
+
+    def set_input(self, node: int, raw_values):
+        """New values for an input tensor of a recorded graph (same size); the next ``finish()`` re-runs the graph with them -
+        the reference's compile-once / ``gen_trace``-per-execution split (StwoCompiler, then graph.rs:161-604 per run)."""
+        kind, buf = self.nodes[node]
+        arr = np.ascontiguousarray(np.asarray(raw_values).astype(np.int64).astype(np.int32)).reshape(-1)
+        if kind != "inputs" or arr.size != self.sizes[node]:
+            raise LuminairB200Error("set_input: not an input node, or a different number of elements")
+        self.be.upload(arr.view(np.uint32), buf)
 
     def input_device(self, buf, n: int) -> int:
         """An input tensor already resident in HBM (int32 raw values)."""
@@ -113,6 +123,22 @@ class DeviceGraphTrace:
         ``device_tables`` = {name: (ptr, n_rows, n_cols)}, ``values`` = device buffers of every node's tensor (int32 raw
         values).  ``self.preprocessed`` holds the LUT columns for ``prove(preprocessed=...)``."""
         be, lib, ctx = self.be, self.be.lib, self.be.ctx
+        if self._program is not None:
+            # the graph was planned by an earlier call (buffers, consumer counts, gather indices, descriptors): clear the lookup
+            # counters and replay the emission calls on the current input values
+            for _, _, d_mult, n_entries in self.lookups.values():
+                check(ctx, lib.lb_memset_zero(ctx, C.c_void_p(d_mult.ptr), n_entries), "lb_memset_zero")
+            for call in self._program:
+                call()
+            return self._result
+        program = []
+
+        def emit(fn, args, what):
+            def call():
+                check(ctx, fn(ctx, *args), what)
+            program.append(call)
+            call()
+
         layouts = layouts or {}
         rows_total = {}
         for (kind, payload), n in zip(self.nodes, self.sizes):
@@ -166,14 +192,14 @@ class DeviceGraphTrace:
                 mult = len(reads) % P
                 if kind == "inputs":
                     buf = payload
-                    check(ctx, lib.lb_trace_inputs(ctx, node, C.c_void_p(buf.ptr), n, mult, C.c_void_p(tables[kind].ptr), at[kind]),
-                          "lb_trace_inputs")
+                    emit(lib.lb_trace_inputs, (node, C.c_void_p(buf.ptr), n, mult, C.c_void_p(tables[kind].ptr), at[kind]),
+                         "lb_trace_inputs")
                 else:
                     (a, _), (b, _) = payload[0]
                     buf = be.alloc(max(n, 1), pooled=True)
                     fn = lib.lb_trace_add if kind == "add" else lib.lb_trace_mul
-                    check(ctx, fn(ctx, node, a, b, C.c_void_p(values[a].ptr), C.c_void_p(values[b].ptr), n, mult,
-                                  C.c_void_p(buf.ptr), C.c_void_p(tables[kind].ptr), at[kind]), "lb_trace_" + kind)
+                    emit(fn, (node, a, b, C.c_void_p(values[a].ptr), C.c_void_p(values[b].ptr), n, mult, C.c_void_p(buf.ptr),
+                              C.c_void_p(tables[kind].ptr), at[kind]), "lb_trace_" + kind)
                 values.append(buf)
                 at[kind] += n
                 continue
@@ -202,7 +228,8 @@ class DeviceGraphTrace:
                     d.d_rhs_idx = srcs[1][1].ptr if srcs[1][1] else None
                 if kind in lookups:
                     d.lookup = C.pointer(lookups[kind][0])
-            check(ctx, lib.lb_trace_op(ctx, C.byref(d)), "lb_trace_op(" + kind + ")")
+            self._keep.append(d)
+            emit(lib.lb_trace_op, (C.byref(d),), "lb_trace_op(" + kind + ")")
             values.append(buf)
             at[kind] += n * (payload[1] if kind != "inputs" else 1)
 
@@ -214,4 +241,6 @@ class DeviceGraphTrace:
         order = [k for k in ORDER if k in device_tables]
         self.tables, self.values, self.lookups = tables, values, lookups  # the buffers must outlive the prove() call
         pie_meta = [(k, None) for k in order]  # table order for prove(); the rows live on the device (device_tables)
-        return pie_meta, {k: device_tables[k] for k in order}, values
+        self._program = program
+        self._result = (pie_meta, {k: device_tables[k] for k in order}, values)
+        return self._result

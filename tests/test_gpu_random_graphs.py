@@ -20,9 +20,23 @@ def be():
     b.close()
 
 
-def random_graph(seed: int):
+class _Both:
+    """Records every node on the host builder and on a second builder with the same interface (same node ids)."""
+
+    def __init__(self, host, other):
+        self.host, self.other, self.values = host, other, host.values
+
+    def __getattr__(self, name):
+        def call(*args):
+            node = getattr(self.host, name)(*args)
+            assert getattr(self.other, name)(*args) == node
+            return node
+        return call
+
+
+def random_graph(seed: int, builder=None):
     rng = np.random.Generator(np.random.PCG64(seed))
-    g = piemod.GraphTrace()
+    g = builder or piemod.GraphTrace()
     n = int(rng.integers(5, 90))
     pos = [g.input(piemod.to_fixed(rng.uniform(0.3, 3.0, n)))]   # strictly positive tensors (recip, sqrt, log2, rem divisor)
     any_ = [g.input(piemod.to_fixed(rng.uniform(-2.0, 2.0, n)))]  # any sign
@@ -64,7 +78,7 @@ def random_graph(seed: int):
             size = g.values[a].size
             idx = np.arange(size, dtype=np.int64) % g.values[p].size
             any_.append(g.mul(a, (p, idx)))
-    return g.finish()
+    return g if builder is not None else g.finish()
 
 
 @pytest.mark.parametrize("seed", [101, 102, 103, 104, 105, 106, 107, 108])
@@ -75,3 +89,17 @@ def test_random_graph_proof_bytes(be, seed):
     got = prove(pie, backend=be, preprocessed=pre)
     _assert_same_proof(be, got, to_bincode(lp), digests)
     overifier.verify(from_bincode(got), preprocessed=[(cid, len(v).bit_length() - 1) for cid, v in pre])
+
+
+@pytest.mark.parametrize("seed", [101, 102, 103, 104, 105, 106, 107, 108, 201, 202, 203, 204])
+def test_random_graph_device_gen_trace(be, seed):
+    """The same random graphs with gen_trace on the device (lb_trace_op): every table, lookup multiplicity table and node tensor
+    equals the host builder's, and the proof from the device-generated tables has the same bytes."""
+    from luminair_b200.prover import prove
+    from luminair_b200.trace import DeviceGraphTrace
+    from test_gpu_trace import _compare
+    hg, dg = piemod.GraphTrace(), DeviceGraphTrace(be)
+    random_graph(seed, _Both(hg, dg))
+    host_pie, host_pre, meta, dev = _compare(be, hg, dg)
+    assert prove(meta, backend=be, device_tables=dev, preprocessed=dg.preprocessed) == \
+        prove(host_pie, backend=be, preprocessed=host_pre)

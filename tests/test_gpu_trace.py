@@ -56,7 +56,7 @@ def test_proof_from_device_generated_tables(be):
 
 # ---- every operator (lb_trace_op): device tables vs the host builder, proofs from device-generated tables -----------------
 def _compare(be, hg, dg, layouts=None):
-    host_pie, host_pre = hg.finish()
+    host_pie, host_pre = hg.finish(layouts=layouts)
     meta, dev, values = dg.finish(layouts if layouts is not None else hg.layouts)
     assert [k for k, _ in host_pie] == [k for k, _ in meta]
     for name, rows in host_pie:
@@ -165,5 +165,31 @@ def test_full_mlp_device_tables_prove_equals_host_tables_prove(be):
     hg = piemod.build_mlp(piemod.GraphTrace())
     dg = piemod.build_mlp(DeviceGraphTrace(be))
     host_pie, host_pre, meta, dev = _compare(be, hg, dg)
+    assert prove(meta, backend=be, device_tables=dev, preprocessed=dg.preprocessed) == \
+        prove(host_pie, backend=be, preprocessed=host_pre)
+
+
+def test_replay_a_recorded_graph_with_new_inputs(be):
+    """Record once, run per execution (the reference compiles the graph once and calls gen_trace per run): the second run
+    uploads only the two input tensors and replays the emission; tables and lookup counters equal a fresh host build."""
+    from luminair_b200.prover import prove
+    from luminair_b200.trace import DeviceGraphTrace
+    n = 600
+    hg1 = piemod.build_all_components(piemod.GraphTrace(), n, 3)
+    hg2 = piemod.build_all_components(piemod.GraphTrace(), n, 4)
+    hg1.finish()
+    hg2.finish()
+    layouts = {}
+    for name in hg1.layouts:  # settings that cover both executions
+        (lo1, hi1), (lo2, hi2) = hg1.layouts[name].ranges[0], hg2.layouts[name].ranges[0]
+        layouts[name] = piemod.LookupLayout([(min(lo1, lo2), max(hi1, hi2))])
+    dg = piemod.build_all_components(DeviceGraphTrace(be), n, 3)
+    hg1 = piemod.build_all_components(piemod.GraphTrace(), n, 3)
+    _compare(be, hg1, dg, layouts)
+    # second execution: new values for the two graph inputs (nodes 0 and 1)
+    hg2 = piemod.build_all_components(piemod.GraphTrace(), n, 4)
+    dg.set_input(0, hg2.values[0])
+    dg.set_input(1, hg2.values[1])
+    host_pie, host_pre, meta, dev = _compare(be, hg2, dg, layouts)
     assert prove(meta, backend=be, device_tables=dev, preprocessed=dg.preprocessed) == \
         prove(host_pie, backend=be, preprocessed=host_pre)
