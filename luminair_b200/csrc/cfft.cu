@@ -737,6 +737,9 @@ __global__ void __launch_bounds__(HighGeom<M>::THREADS, NC == 1 ? HighGeom<M>::M
 #ifndef LB_HIGH_VEC
 #define LB_HIGH_VEC 1
 #endif
+#ifndef LB_HIGH_VEC_MAX_M
+#define LB_HIGH_VEC_MAX_M 10  // 8: only the n = 20 high pass is vectorised; 9 / 10: also the single high pass of n = 21 / 22
+#endif
 #ifndef LB_HIGH_VW
 #define LB_HIGH_VW 2  // measured: 2 -> 0.592 ms round trip, 4 -> 0.605 ms (128 registers, half the resident warps)
 #endif
@@ -832,8 +835,8 @@ __device__ __forceinline__ void high_round_vec(uint32_t* sm, const PassParams& p
 }
 
 template <bool FWD, int M, int ILO, int ZEXT, int VW>
-__global__ void __launch_bounds__((1 << (M - 4)) * 16, VW == 4 ? 2 : 4) cfft_high_vec(PassParams p) {
-    static_assert(M == 8, "two rounds of four layers");
+__global__ void __launch_bounds__((1 << (M - 4)) * 16, M == 8 ? (VW == 4 ? 2 : 4) : (M == 9 && VW == 2 ? 2 : 1)) cfft_high_vec(PassParams p) {
+    static_assert(M >= 8 && M <= 10, "two or three rounds of up to four layers");
     extern __shared__ __align__(16) uint32_t smv[];
     constexpr uint32_t W = 16 * VW;
     constexpr uint32_t l_tiles = (1u << ILO) / W;
@@ -841,14 +844,23 @@ __global__ void __launch_bounds__((1 << (M - 4)) * 16, VW == 4 ? 2 : 4) cfft_hig
     const size_t g_base = ((size_t)tile_h << (ILO + M)) + (size_t)lt * W;
     const uint32_t* src = p.src + (size_t)blockIdx.y * p.src_stride;
     uint32_t* dst = p.dst + (size_t)blockIdx.y * p.dst_stride;
+    constexpr bool THREE = (M > 8);  // M = 9, 10: a third round for the one or two layers above the first eight
     if constexpr (FWD) {
-        high_round_vec<FWD, M, 1, ILO, ZEXT, VW>(smv, p, tile_h, g_base, src, dst, true, false);
+        if constexpr (THREE) {
+            high_round_vec<FWD, M, 2, ILO, ZEXT, VW>(smv, p, tile_h, g_base, src, dst, true, false);
+            __syncthreads();
+        }
+        high_round_vec<FWD, M, 1, ILO, ZEXT, VW>(smv, p, tile_h, g_base, src, dst, !THREE, false);
         __syncthreads();
         high_round_vec<FWD, M, 0, ILO, ZEXT, VW>(smv, p, tile_h, g_base, src, dst, false, true);
     } else {
         high_round_vec<FWD, M, 0, ILO, 0, VW>(smv, p, tile_h, g_base, src, dst, true, false);
         __syncthreads();
-        high_round_vec<FWD, M, 1, ILO, 0, VW>(smv, p, tile_h, g_base, src, dst, false, true);
+        high_round_vec<FWD, M, 1, ILO, 0, VW>(smv, p, tile_h, g_base, src, dst, false, !THREE);
+        if constexpr (THREE) {
+            __syncthreads();
+            high_round_vec<FWD, M, 2, ILO, 0, VW>(smv, p, tile_h, g_base, src, dst, false, true);
+        }
     }
 }
 
@@ -1044,7 +1056,7 @@ static cudaError_t launch_high_m(const PassParams& p, int sm_count, cudaStream_t
         bool top = (p.i_lo + M == p.log_n);
         zext = (top && p.log_src == p.log_n - 1 && M >= 4) ? 1 : 2;
     }
-    if constexpr (M == 8 && LB_HIGH_VEC) {
+    if constexpr (M >= 8 && M <= LB_HIGH_VEC_MAX_M && LB_HIGH_VEC) {
         // the vectorised kernel needs whole 64-offset tiles below the pass (i_lo = 12) and no ragged zero extension
         if (p.i_lo == 12 && zext != 2) {
             if (FWD && zext == 1) return launch_high_vec<FWD, M, 12, 1>(p, stream);
