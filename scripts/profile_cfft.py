@@ -7,7 +7,7 @@ import numpy as np
 from luminair_b200.backend import ColumnBatch, CudaBackend
 
 P = (1 << 31) - 1
-log, ncols = 20, 64
+log, ncols = int(os.environ.get("LOG", 20)), int(os.environ.get("NCOLS", 64))
 be = CudaBackend(0)
 rng = np.random.Generator(np.random.PCG64(20260101))
 host = rng.integers(0, P, size=(ncols, 1 << log), dtype=np.uint64).astype(np.uint32)
