@@ -197,9 +197,12 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     all_cpus = os.sched_getaffinity(0)
     numa = pin_to_gpu_numa_node(local_rank)  # before any pinned allocation: first touch lands on the GPU's NUMA node
+    # stdout carries the one JSON line only: whatever native libraries write to fd 1 on the way (the "NCCL version ..." banner
+    # of the first collective, NCCL_DEBUG output) is sent to stderr; the saved descriptor is restored for the final print
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if distributed:
-        # stdout carries the one JSON line only: NCCL's own log (version banner, NCCL_DEBUG output) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from luminair_b200.backend import ColumnBatch, CudaBackend
@@ -348,6 +351,8 @@ def run_gpu(args):
                                               "round trip, C restatement (oracle/c) with OpenMP over columns"}
             if prove_info:
                 line["cpu_baseline"]["prove"] = cpu_prove_baseline()
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if distributed:
         dist.destroy_process_group()
