@@ -32,7 +32,6 @@ OP_CODE = {"add": 0, "mul": 1, "recip": 2, "sin": 3, "sum_reduce": 5, "max_reduc
            "log2": 11, "less_than": 13, "inputs": 15, "contiguous": 16}
 ORDER = ["add", "mul", "recip", "sin", "sin_lookup", "sum_reduce", "max_reduce", "sqrt", "rem", "exp2", "exp2_lookup", "log2",
          "log2_lookup", "less_than", "range_check_lookup", "inputs", "contiguous"]
-BINARY = ("add", "mul", "rem", "less_than")
 _LUT_HOST = {}  # (lut name, layout ranges) -> [(column id, values)]: pie.lut_columns of a circuit-settings layout
 LUT_OPS = ("sin", "exp2", "log2")
 
