@@ -23,7 +23,7 @@ from typing import List, Optional, Tuple
 
 import numpy as np
 
-from .pie import RANGE_CHECK_BITS, LookupLayout, lut_columns, range_check_column
+from .lookups import RANGE_CHECK_BITS, LookupLayout, lut_columns, range_check_column
 
 LUT_ORDER = ("sin", "exp2", "log2")  # field order of `Lookups`, then range_check
 

@@ -7,12 +7,12 @@ tables (15x more bytes for a + b).
 
 The graph is recorded first and emitted in ``finish()``, because the multiplicity a node yields an element with is the number
 of rows that consume it (``node_info.num_consumers``, op/prim.rs:947-951), known only once the graph is complete.  Same
-interface, node numbering, row order and table order as the host builder ``luminair_b200.pie.GraphTrace`` (creation order;
+interface, node numbering, row order and table order as the host builder used by the tests (a numpy ``GraphTrace`` kept with the test infrastructure) (creation order;
 tables in claim-slot order), which the tests compare against: operands are ``node`` or ``(node, gather index)``.
 
 Lookup operators (sin / exp2 / log2) need the ``LookupLayout`` of the circuit settings (crates/air/src/preprocessed.rs:41-116,
 produced by the reference's calibration pass ``gen_circuit_settings``): the LUT columns are generated on the host exactly as
-the reference does (``pie.lut_columns``: f64 libm + Fixed::from_f64), uploaded once, and the device reads ``f(x)`` from them.
+the reference does (``lookups.lut_columns``: f64 libm + Fixed::from_f64), uploaded once, and the device reads ``f(x)`` from them.
 """
 from __future__ import annotations
 
@@ -22,7 +22,7 @@ import numpy as np
 
 from ._lib import Lookup, LuminairB200Error, TraceOpDesc, check
 from .backend import CudaBackend
-from .pie import RANGE_CHECK_BITS, lut_columns, range_check_column
+from .lookups import RANGE_CHECK_BITS, lut_columns, range_check_column
 
 P = (1 << 31) - 1
 N_COLS = {"add": 15, "mul": 16, "recip": 13, "sin": 12, "sum_reduce": 14, "max_reduce": 15, "sqrt": 13, "rem": 16,
@@ -32,7 +32,7 @@ OP_CODE = {"add": 0, "mul": 1, "recip": 2, "sin": 3, "sum_reduce": 5, "max_reduc
            "log2": 11, "less_than": 13, "inputs": 15, "contiguous": 16}
 ORDER = ["add", "mul", "recip", "sin", "sin_lookup", "sum_reduce", "max_reduce", "sqrt", "rem", "exp2", "exp2_lookup", "log2",
          "log2_lookup", "less_than", "range_check_lookup", "inputs", "contiguous"]
-_LUT_HOST = {}  # (lut name, layout ranges) -> [(column id, values)]: pie.lut_columns of a circuit-settings layout
+_LUT_HOST = {}  # (lut name, layout ranges) -> [(column id, values)]: lookups.lut_columns of a circuit-settings layout
 LUT_OPS = ("sin", "exp2", "log2")
 
 

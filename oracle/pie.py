@@ -1,21 +1,47 @@
-"""Trace tables (the ``LuminairPie`` of crates/air/src/pie.rs:143-148) for element-wise graphs,
-laid out the way ``LuminairGraph::gen_trace`` emits them (crates/graph/src/graph.rs:161-604):
-one row per element with the columns of ``AddTraceTableRow`` (components/add/table.rs),
-``MulTraceTableRow`` and ``InputsTraceTableRow``, multiplicities as the consumers dictate.
-
-Host-side helper for benchmarks and tests: it only builds inputs for ``prove``.
+"""numpy restatement of ``LuminairGraph::gen_trace`` (oracle; TEST INFRASTRUCTURE ONLY): the trace tables (the
+``LuminairPie`` of crates/air/src/pie.rs:143-148) of an operator graph over Fixed<12> tensors, laid out the way
+/root/reference/crates/graph/src/graph.rs:161-604 emits them with the row emitters of crates/graph/src/op/prim.rs
+(``process_trace`` of every operator).  It is the checker ``luminair_b200.trace.DeviceGraphTrace`` (gen_trace on the device) is
+compared with, and the table builder of the oracle-side fixtures.  Self-contained: LUT columns are generated here with host
+libm (``math``), independently of ``luminair_b200.lookups`` (tests/test_settings.py checks the two agree).
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
+
+# workload definitions (pure recorders against the GraphTrace interface; shared with the device trace)
+from luminair_b200.workloads import build_add_graph, build_all_components, build_mlp, build_wide, synthetic_add_graph_inputs  # noqa: F401,E501
 
 P = (1 << 31) - 1
 FP_SCALE = 1 << 12  # numerair Fixed<12>, crates/air/src/lib.rs:23
+RANGE_CHECK_BITS = 8
 
 
-def to_fixed(x: np.ndarray) -> np.ndarray:
-    """f32/f64 -> Fixed<12> raw value (round to nearest), as int64."""
-    return np.round(np.asarray(x, dtype=np.float64) * FP_SCALE).astype(np.int64)
+def _round_half_away(x) -> np.ndarray:
+    """Rust f64::round (ties away from zero) - numerair Fixed::from_f64 restated as (v * 2^12).round(); parity unpinned."""
+    x = np.asarray(x, dtype=np.float64)
+    return (np.sign(x) * np.floor(np.abs(x) + 0.5)).astype(np.int64)
+
+
+def to_fixed(x) -> np.ndarray:
+    return _round_half_away(np.asarray(x, dtype=np.float64) * FP_SCALE)
+
+
+def _apply_libm(name: str, raw) -> np.ndarray:
+    """f(raw / 2^12) through the platform libm one element at a time (Rust's f64::sin/exp2/log2 are libm calls;
+    preprocessed.rs:374,457,540), back to raw Fixed<12>; NaN / -inf -> 0."""
+    fn = {"sin": math.sin, "exp2": lambda v: 2.0 ** v if not hasattr(math, "exp2") else math.exp2(v), "log2": math.log2}[name]
+    vals = np.asarray(raw, dtype=np.int64).reshape(-1).tolist()
+    out = np.empty(len(vals), dtype=np.float64)
+    for i, v in enumerate(vals):
+        try:
+            out[i] = fn(v / FP_SCALE)
+        except (ValueError, OverflowError):
+            out[i] = 0.0
+    out = np.nan_to_num(out, nan=0.0, neginf=0.0)
+    return _round_half_away(out * FP_SCALE).reshape(np.shape(raw))
 
 
 def _table(n, cols):
@@ -38,33 +64,9 @@ def add_graph_pie(a_fixed: np.ndarray, b_fixed: np.ndarray):
     return [("add", add), ("inputs", inp)]
 
 
-def synthetic_add_graph_inputs(log_n: int, seed: int = 42):
-    """The two input tensors of BASELINE cfg 3 as raw Fixed<12> values: f32 uniform(-0.5, 0.5), PCG64(seed)."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    n = 1 << log_n
-    a = to_fixed(rng.uniform(-0.5, 0.5, n))
-    b = to_fixed(rng.uniform(-0.5, 0.5, n))
-    return a, b
-
-
 def synthetic_add_graph_pie(log_n: int, seed: int = 42):
     """BASELINE cfg 3: 2^log_n-element a + b with f32 uniform(-0.5, 0.5) inputs, PCG64(seed)."""
     return add_graph_pie(*synthetic_add_graph_inputs(log_n, seed))
-
-
-# ---------------------------------------------------------------------------------------------
-# Trace tables of arbitrary operator graphs (all 17 components)
-# ---------------------------------------------------------------------------------------------
-def _round_fixed(x) -> np.ndarray:
-    return np.round(np.asarray(x, dtype=np.float64) * FP_SCALE).astype(np.int64)
-
-
-def _from_fixed(v) -> np.ndarray:
-    return np.asarray(v, dtype=np.float64) / FP_SCALE
-
-
-LUT_FUNCS = {"sin": np.sin, "exp2": np.exp2, "log2": np.log2}
-RANGE_CHECK_BITS = 8  # RangeCheckLookup<1> over the 8-bit limbs of less_than (less_than/component.rs:105-133)
 
 
 class LookupLayout:
@@ -100,8 +102,7 @@ def lut_columns(name: str, layout: LookupLayout):
     c0 = np.zeros(n, dtype=np.int64)
     c1 = np.zeros(n, dtype=np.int64)
     c0[: layout.values.size] = layout.values
-    with np.errstate(divide="ignore", invalid="ignore"):
-        c1[: layout.values.size] = _round_fixed(np.nan_to_num(LUT_FUNCS[name](_from_fixed(layout.values)), neginf=0.0))
+    c1[: layout.values.size] = _apply_libm(name, layout.values)
     return [(f"{name}_lut_0", (c0 % P).astype(np.uint32)), (f"{name}_lut_1", (c1 % P).astype(np.uint32))]
 
 
@@ -211,8 +212,7 @@ class GraphTrace:
     def _lut(self, name, a):
         def f(x):
             self.lut_inputs[name].append(x)
-            with np.errstate(divide="ignore", invalid="ignore"):
-                return _round_fixed(LUT_FUNCS[name](_from_fixed(x))), {}
+            return _apply_libm(name, x), {}
         return self._unary(name, a, f)
 
     def sin(self, a):
@@ -332,79 +332,13 @@ def all_components_graph(n: int = 24, seed: int = 3):
     return build_all_components(GraphTrace(), n, seed).finish()
 
 
-def build_all_components(g, n: int = 24, seed: int = 3):
-    """Record the all-components graph on `g` (a GraphTrace or a trace.DeviceGraphTrace: same interface)."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    x = g.input(to_fixed(rng.uniform(0.25, 2.0, n)))
-    y = g.input(to_fixed(rng.uniform(-1.0, 1.0, n)))
-    s = g.add(x, y)
-    p = g.mul(s, x)
-    r = g.recip(x)
-    q = g.sqrt(x)
-    e = g.exp2(y)
-    l = g.log2(x)
-    t = g.sin(p)
-    m = g.rem(x, q)
-    c = g.less_than(y, r)
-    k = 4
-    sr = g.sum_reduce(e, k)
-    mr = g.max_reduce(l, k)
-    g.contiguous(t)
-    g.add(m, c)
-    g.mul(sr, mr)
-    return g
-
-
 def mlp_graph(widths=(2, 64, 64, 1), x=(15.0, 0.5), seed: int = 7, scale: float = 0.3):
-    """BASELINE cfg 4 shape (examples/black-schole-nn/src/main.rs: Linear 2-64-64-1 with tanh between, input
-    [15.0, 0.5]); synthetic weights uniform(-scale, scale), PCG64(seed) (the reference's weights are git-ignored).
-    Each Linear is Mul over the expanded [out, in] operands + SumReduce + bias Add; tanh(z) lowers the way luminal
-    does it: 2 * sigmoid(2z) - 1 with sigmoid(v) = 1 / (1 + exp2(-v * log2 e))  ->  Mul, Exp2, Add, Recip."""
+    """BASELINE cfg 4 shape: see luminair_b200.workloads.build_mlp."""
     return build_mlp(GraphTrace(), widths, x, seed, scale).finish()
 
 
-def build_mlp(g, widths=(2, 64, 64, 1), x=(15.0, 0.5), seed: int = 7, scale: float = 0.3):
-    """Record the MLP of `mlp_graph` on `g` (a GraphTrace or a trace.DeviceGraphTrace)."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    act = g.input(to_fixed(np.asarray(x, dtype=np.float64)))
-    n_layers = len(widths) - 1
-    for li in range(n_layers):
-        d_in, d_out = widths[li], widths[li + 1]
-        w = g.input(to_fixed(rng.uniform(-scale, scale, d_out * d_in)))
-        b = g.input(to_fixed(rng.uniform(-scale, scale, d_out)))
-        prod = g.mul(w, (act, np.tile(np.arange(d_in, dtype=np.int64), d_out)))
-        z = g.add(g.sum_reduce(prod, d_in), b) if d_in > 1 else g.add(prod, b)
-        if li == n_layers - 1:
-            act = z
-            break
-        c_m2log2e = g.input(np.full(d_out, int(round(-2.0 * np.log2(np.e) * FP_SCALE))))
-        one = g.input(np.full(d_out, FP_SCALE))
-        two = g.input(np.full(d_out, 2 * FP_SCALE))
-        neg_one = g.input(np.full(d_out, -FP_SCALE))
-        e = g.exp2(g.mul(z, c_m2log2e))
-        sig = g.recip(g.add(e, one))
-        act = g.add(g.mul(sig, two), neg_one)
-    return g
-
-
 def wide_graph(log_n: int, seed: int = 64):
-    """The headline trace shape of BASELINE.json ("2^20 x 64"): four 2^log_n-row operator tables over the same two input
-    tensors - Add (15 columns), Mul (16), Rem (16), SumReduce with groups of one (14) = 61 main-trace columns of 2^log_n rows,
-    beside the Inputs table (7 columns, 2^(log_n+1) rows).  Inputs are positive Fixed<12> values (Rem needs a non-zero
-    divisor), uniform(0.25, 2), PCG64(seed)."""
+    """The headline trace shape ("2^20 x 64"): see luminair_b200.workloads.build_wide."""
     pie, pre = build_wide(GraphTrace(), log_n, seed).finish()
     assert not pre
     return pie
-
-
-def build_wide(g, log_n: int, seed: int = 64):
-    """Record the graph of `wide_graph` on `g` (a GraphTrace or a trace.DeviceGraphTrace)."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    n = 1 << log_n
-    a = g.input(to_fixed(rng.uniform(0.25, 2.0, n)))
-    b = g.input(to_fixed(rng.uniform(0.25, 2.0, n)))
-    g.add(a, b)
-    g.mul(a, b)
-    g.rem(a, b)
-    g.sum_reduce(a, 1)
-    return g

@@ -5,7 +5,7 @@ the ncu launch list / captures of the trace emitters:
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from luminair_b200 import pie as piemod
+from oracle import pie as piemod
 from luminair_b200.backend import CudaBackend
 from luminair_b200.prover import prove
 from luminair_b200.trace import DeviceGraphTrace

@@ -2,7 +2,7 @@ import sys, os, time
 sys.path.insert(0, os.getcwd())
 import numpy as np
 from luminair_b200.backend import CudaBackend
-from luminair_b200.pie import synthetic_add_graph_pie
+from oracle.pie import synthetic_add_graph_pie
 from luminair_b200.prover import prove, last_stage_ms, STAGE_NAMES
 from oracle import verifier as ov
 from oracle.proof import from_bincode

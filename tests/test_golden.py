@@ -6,7 +6,7 @@ import os
 
 import pytest
 
-from luminair_b200 import pie as piemod
+from oracle import pie as piemod
 from oracle import examples
 
 # name -> (pie, preprocessed LUT columns)
@@ -48,3 +48,24 @@ def test_cuda_prover_reproduces_fixture(golden_dir, name):
     want = open(os.path.join(golden_dir, name), "rb").read()
     pie, pre = CASES[name]()
     assert prove(pie, preprocessed=pre) == want
+
+
+# fixtures at the benchmark sizes (tests/golden/large.json), made by the compiled CPU prover (scripts/make_golden.py --large;
+# tests/test_cpu_prover.py pins that prover): whole-proof byte parity of lb_prove on BASELINE configs[2] at 2^20, on the
+# headline 2^20 x 61-column trace shape and on a 2^16-element graph with all 17 components - no oracle run on the GPU box
+LARGE = {
+    "cfg3_add_log20.proof.bin": lambda: (piemod.synthetic_add_graph_pie(20, seed=42), ()),
+    "wide_log20.proof.bin": lambda: (piemod.wide_graph(20), ()),
+    "all_components_log16.proof.bin": lambda: piemod.all_components_graph(n=1 << 16, seed=3),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(LARGE))
+def test_cuda_prover_reproduces_large_fixture(golden_dir, name):
+    from luminair_b200.prover import prove
+    want = open(os.path.join(golden_dir, name), "rb").read()
+    pie, pre = LARGE[name]()
+    got = prove(pie, preprocessed=pre)
+    assert len(got) == len(want)
+    assert got == want

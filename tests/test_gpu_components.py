@@ -7,7 +7,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-from luminair_b200 import pie as piemod
+from oracle import pie as piemod
 from oracle import air, cfft as ocfft, prover as oprover, verifier as overifier
 from oracle.circle import CanonicCoset
 from oracle.fields import P, QM31

@@ -401,7 +401,7 @@ def test_larger_blowup_factor(be, blowup, last_bound, n_queries):
 
 
 def test_larger_blowup_factor_with_lookup_tables(be):
-    from luminair_b200 import pie as piemod
+    from oracle import pie as piemod
     from luminair_b200.prover import PcsConfig, prove
     from oracle.proof import PcsConfig as OPcs
     g = piemod.GraphTrace()
@@ -417,7 +417,7 @@ def test_larger_blowup_factor_with_lookup_tables(be):
 def test_large_proof_is_accepted(be):
     """Add 2^22 rows + Inputs 2^23 rows (LDE 2^24, composition LDE 2^25): far beyond what the numpy oracle prover can follow;
     the oracle verifier accepts the proof (it only touches the queried positions)."""
-    from luminair_b200.pie import synthetic_add_graph_pie
+    from oracle.pie import synthetic_add_graph_pie
     from luminair_b200.prover import prove
     proof = prove(synthetic_add_graph_pie(22, seed=1), backend=be)
     lp = from_bincode(proof)

@@ -6,7 +6,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-from luminair_b200 import pie as piemod
+from oracle import pie as piemod
 from oracle import prover as oprover, verifier as overifier
 from oracle.proof import from_bincode, to_bincode
 from test_gpu_prover import _assert_same_proof, _oracle_transcript

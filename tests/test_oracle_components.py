@@ -8,7 +8,7 @@ Parity note: Recip/Sqrt/Rem use numerair helpers that the reference's committed 
 import numpy as np
 import pytest
 
-from luminair_b200 import pie as piemod
+from oracle import pie as piemod
 from oracle import prover as oprover
 from oracle import verifier as overifier
 from oracle.proof import from_bincode, to_bincode

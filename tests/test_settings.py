@@ -3,7 +3,7 @@ settings file the reference commits (ui/demo/public/settings: a single 0x00 byte
 import numpy as np
 import pytest
 
-from luminair_b200 import pie as piemod
+from oracle import pie as piemod
 from luminair_b200.settings import CircuitSettings, Lookup, RangeCheckLookup
 
 
