@@ -93,60 +93,77 @@ def gen_inputs(n_cols, log_n, seed):
 
 
 # ---------------------------------------------------------------------------------------
-def cpu_roundtrip(sample_cols, threads, reps=1):
-    """Time the C oracle on `sample_cols` columns. Returns (seconds per round trip, cores)."""
-    from oracle import cbind
-    c = cbind.CpuCfft(LOG_N)
+def cpu_roundtrip(sample_cols, threads, reps=3):
+    """Time the packed (AVX-512 / AVX2) + OpenMP CFFT of the CPU prover (oracle/c/cpu_prover) on `sample_cols` columns.
+    Returns seconds per interpolate + evaluate round trip (best of `reps`)."""
+    from oracle import cpu_prover as cp
     v = gen_inputs(sample_cols, LOG_N, SEED)
-    c.interpolate(v, threads)  # warm (page-in, thread pool)
-    c.evaluate(v, threads)
+    ref = v.copy()
+    cp.cfft(v, forward=False, n_threads=threads)  # warm (page-in, thread pool, twiddles)
+    cp.cfft(v, forward=True, n_threads=threads)
+    if not np.array_equal(v, ref):
+        raise SystemExit("bench: CPU CFFT round trip did not reproduce its input")
     best = None
     for _ in range(reps):
         t0 = time.perf_counter()
-        c.interpolate(v, threads)
-        c.evaluate(v, threads)
+        cp.cfft(v, forward=False, n_threads=threads)
+        cp.cfft(v, forward=True, n_threads=threads)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return best
 
 
-def cpu_prove_baseline(log=14):
-    """The CPU restatement of prove() (oracle/, numpy, 1 core) on a bounded sample of the cfg-3 graph, and on the
-    whole cfg-4 MLP graph."""
-    from luminair_b200.pie import mlp_graph
-    from oracle import examples, prover as oprover
-    pie = examples.graph_pie(log, seed=42, with_mul=False)
-    t0 = time.perf_counter()
-    oprover.prove(pie)
-    dt = time.perf_counter() - t0
-    mlp_pie, mlp_pre = mlp_graph()
-    t0 = time.perf_counter()
-    oprover.prove(mlp_pie, preprocessed=mlp_pre)
-    dt_mlp = time.perf_counter() - t0
-    return {"value": dt * 1e3, "unit": "ms per proof", "cores": 1, "kind": "port",
-            "sample": f"a+b graph at 2^{log} elements (64x smaller than the GPU workload), numpy restatement (oracle/prover.py); "
-                      "not stwo SimdBackend (Rust toolchain absent)",
-            "mlp_ms_per_proof": dt_mlp * 1e3, "mlp_sample": "the same 2-64-64-1 MLP graph as prove.mlp (whole workload)"}
+def cpu_prove_baseline(log, threads, gpu_proof=None, wide=True):
+    """The compiled CPU prover (oracle/c/cpu_prover: packed M31 arithmetic, OpenMP; the restatement of the reference's
+    SimdBackend + rayon path) on the WHOLE cfg-3 workload (and the 2^log x 61-column wide trace), all host cores."""
+    from oracle import cpu_prover as cp
+    from oracle import pie as opie
+    pie = opie.synthetic_add_graph_pie(log, seed=42)
+    cp.prove(pie, n_threads=threads)  # warm: domain tables, buffer pool
+    ts, stages, proof = [], None, None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        proof, st = cp.prove(pie, n_threads=threads, return_stages=True)
+        dt = (time.perf_counter() - t0) * 1e3
+        if not ts or dt < min(ts):
+            stages = st
+        ts.append(dt)
+    out = {"value": min(ts), "unit": "ms per proof", "median_ms": statistics.median(ts), "proofs_per_s": 1e3 / min(ts),
+           "cores": threads, "kind": "port", "lanes": cp.lanes(),
+           "sample": f"the whole GPU workload: a+b graph at 2^{log} elements (Add 2^{log} x 15 + Inputs 2^{log + 1} x 7), "
+                     f"{threads} threads, {cp.lanes()}-lane packed M31 (oracle/c/cpu_prover, C++/OpenMP); a restatement of the "
+                     "reference's SimdBackend path, not stwo itself (Rust toolchain absent)",
+           "stages_ms": {k: round(v, 2) for k, v in stages.items()}}
+    if gpu_proof is not None:
+        out["proof_bytes_equal_gpu"] = proof == gpu_proof
+    if wide:
+        wpie = opie.wide_graph(log)
+        cp.prove(wpie, n_threads=threads)
+        t0 = time.perf_counter()
+        cp.prove(wpie, n_threads=threads)
+        out["wide_ms_per_proof"] = (time.perf_counter() - t0) * 1e3
+        out["wide_sample"] = f"the whole wide workload (2^{log} rows x 61 main-trace columns + Inputs), one timed proof after one warm-up"
+    return out
 
 
 def run_reference(args):
+    """The reference arm: the CPU implementation of the same path (the packed + OpenMP CFFT of oracle/c/cpu_prover; the Rust
+    reference cannot be built here) on ALL host cores - the thread count is taken from the affinity mask, not from
+    OMP_NUM_THREADS (torchrun sets that to 1) - on the same 64 x 2^20 round trip per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import cbind
-    cores = os.cpu_count() or 1
-    threads = min(cores, cbind.max_threads(), N_COLS)
-    sample_cols = min(N_COLS, max(threads, 16))
-    # each step: one round trip over `sample_cols` columns (bounded sample of the 64-column job)
-    c = cbind.CpuCfft(LOG_N)
+    from oracle import cpu_prover as cp
+    threads = cp.host_cores()
+    sample_cols = N_COLS  # the whole per-GPU workload every step (about 0.1-0.2 s of CPU work per step)
     v = gen_inputs(sample_cols, LOG_N, SEED)
     for _ in range(max(args.warmup, 1)):
-        c.interpolate(v, threads)
-        c.evaluate(v, threads)
+        cp.cfft(v, forward=False, n_threads=threads)
+        cp.cfft(v, forward=True, n_threads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        c.interpolate(v, threads)
-        c.evaluate(v, threads)
+        cp.cfft(v, forward=False, n_threads=threads)
+        cp.cfft(v, forward=True, n_threads=threads)
     dt = (time.perf_counter() - t0) / args.steps
     ops = field_ops_per_step(LOG_N, sample_cols)
     value = ops / dt
@@ -154,13 +171,14 @@ def run_reference(args):
         "impl": "reference",
         "metric": "cfft_roundtrip_m31_field_ops_per_s", "value": value, "unit": "M31 field-ops/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt * 1e3 * (N_COLS / sample_cols), "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32 (M31)", "data": "synthetic",
-        "config": {"workload": "cfft_roundtrip 2^20 rows x 64 M31 columns (BASELINE configs[1])",
-                   "log_rows": LOG_N, "n_cols": N_COLS},
-        "cpu_baseline": {"value": value, "unit": "M31 field-ops/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample_cols} of {N_COLS} columns x 2^{LOG_N}, interpolate+evaluate, OpenMP over columns; "
-                                   "CPU restatement (oracle/c), not stwo SimdBackend (Rust toolchain absent)"},
+        "config": {"workload": "cfft_roundtrip 2^20 rows x 64 M31 columns per GPU (BASELINE configs[1])",
+                   "log_rows": LOG_N, "n_cols_per_gpu": N_COLS},
+        "cpu_baseline": {"value": value, "unit": "M31 field-ops/s", "cores": threads, "kind": "port", "lanes": cp.lanes(),
+                         "sample": f"all {N_COLS} columns x 2^{LOG_N} per step, interpolate+evaluate, {threads} threads "
+                                   f"(affinity mask; OMP_NUM_THREADS ignored), {cp.lanes()}-lane packed M31 butterflies, "
+                                   "cache-blocked; CPU restatement (oracle/c/cpu_prover), not stwo SimdBackend (Rust toolchain absent)"},
         "e2e": {"value": value, "unit": "M31 field-ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -342,15 +360,25 @@ def run_gpu(args):
             line["sharded_commit"] = sharded_info
         if world == 1 and not args.no_cpu:
             os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every host core again, as in --impl reference
-            threads = min(len(all_cpus), N_COLS)
-            sample_cols = min(N_COLS, max(threads, 8))
+            threads = len(all_cpus)
+            sample_cols = N_COLS
             dt = cpu_roundtrip(sample_cols, threads)
+            from oracle import cpu_prover as _cp
             line["cpu_baseline"] = {"value": field_ops_per_step(LOG_N, sample_cols) / dt, "unit": "M31 field-ops/s",
-                                    "cores": threads, "kind": "port",
-                                    "sample": f"{sample_cols} of {N_COLS} columns x 2^{LOG_N}, one interpolate+evaluate "
-                                              "round trip, C restatement (oracle/c) with OpenMP over columns"}
+                                    "cores": threads, "kind": "port", "lanes": _cp.lanes(),
+                                    "sample": f"all {N_COLS} columns x 2^{LOG_N}, interpolate+evaluate round trip, best of 3, "
+                                              f"{_cp.lanes()}-lane packed M31 + OpenMP, cache-blocked (oracle/c/cpu_prover)"}
             if prove_info:
-                line["cpu_baseline"]["prove"] = cpu_prove_baseline()
+                cpu_p = cpu_prove_baseline(args.prove_log, threads, gpu_proof=prove_info.pop("_proof_bytes", None))
+                line["cpu_baseline"]["prove"] = cpu_p
+                prove_info["speedup_vs_cpu_prover"] = {
+                    "device_resident": cpu_p["value"] / prove_info["ms_device_resident"]["median"],
+                    "e2e_host_tensors": cpu_p["value"] / prove_info["ms_e2e_host_tensors"]["median"],
+                    "cpu_cores": threads,
+                    "note": "proofs/s of lb_prove on 1 x B200 over proofs/s of the compiled CPU prover on all host cores, same "
+                            "2^%d workload, proof bytes equal: %s (north-star target >= 10x)" % (args.prove_log, cpu_p.get("proof_bytes_equal_gpu"))}
+        if prove_info:
+            prove_info.pop("_proof_bytes", None)
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
@@ -449,23 +477,32 @@ def bench_sharded_commit(be, torch, dist, args, rank, world, local_rank):
             "timer": "host wall clock between stream synchronisations, max over ranks"}
 
 
-def bench_prove(be, torch, args):
-    """luminair_prover::prover::prove on the cfg-3 graph (a + b over 2^log elements): device-resident
-    tables (value) and host tables in pinned memory (e2e: H2D of the trace + proof bytes back)."""
-    from luminair_b200.pie import synthetic_add_graph_pie
-    from luminair_b200.prover import STAGE_NAMES, last_stage_ms, prove
-    log = args.prove_log
-    pie = synthetic_add_graph_pie(log, seed=42)
-    pinned, host_pie, dev = [], [], {}
-    for name, rows in pie:
-        t = torch.empty(rows.shape, dtype=torch.int32, pin_memory=True)
+def _device_tables_to_host(be, torch, meta, dev_tables):
+    """Download device-generated trace tables into pinned host arrays: the `host tables` legs prove from these."""
+    pinned, host_pie = [], []
+    for name, _ in meta:
+        ptr, n_rows, n_cols = dev_tables[name]
+        t = torch.empty((n_rows, n_cols), dtype=torch.int32, pin_memory=True)
         v = t.numpy().view(np.uint32)
-        v[:] = rows
+        v[:] = be.download_ptr(ptr, n_rows * n_cols).reshape(n_rows, n_cols)
         pinned.append(t)
         host_pie.append((name, v))
-        buf = be.upload(v.reshape(-1))
-        dev[name] = (buf.ptr, rows.shape[0], rows.shape[1])
-        pinned.append(buf)
+    return host_pie, pinned
+
+
+def bench_prove(be, torch, args):
+    """luminair_prover::prover::prove on the cfg-3 graph (a + b over 2^log elements): device-resident tables (value), host
+    tables in pinned memory (H2D of the trace + proof bytes back) and from the two input tensors (gen_trace on the device).
+    Every table is produced by the product's own gen_trace (lb_trace_*); nothing here touches oracle/."""
+    from luminair_b200.lookups import LookupLayout
+    from luminair_b200.prover import STAGE_NAMES, last_stage_ms, prove
+    from luminair_b200.trace import DeviceGraphTrace
+    from luminair_b200.workloads import MLP_EXP2_RANGE, build_add_graph, build_mlp, build_wide, synthetic_add_graph_inputs
+    log = args.prove_log
+    a_raw, b_raw = synthetic_add_graph_inputs(log, seed=42)
+    dg0 = build_add_graph(DeviceGraphTrace(be), a_raw, b_raw)
+    meta0, dev, _ = dg0.finish()
+    host_pie, pinned = _device_tables_to_host(be, torch, meta0, dev)
     reps = max(3, min(args.steps, 10))
 
     def run(device_tables):
@@ -485,9 +522,6 @@ def bench_prove(be, torch, args):
     ts_dev, st_dev, nbytes = run(dev)
     ts_host, st_host, _ = run(None)
     # the same proof from the two input TENSORS: upload a and b (pinned), gen_trace on the device (lb_trace_*), prove
-    from luminair_b200.pie import synthetic_add_graph_inputs
-    from luminair_b200.trace import DeviceGraphTrace
-    a_raw, b_raw = synthetic_add_graph_inputs(log, seed=42)
     tens = []
     for x in (a_raw, b_raw):
         t = torch.empty(x.shape, dtype=torch.int32, pin_memory=True)
@@ -503,6 +537,12 @@ def bench_prove(be, torch, args):
     ref_proof = prove(host_pie, backend=be)
     if prove_from_tensors() != ref_proof:
         raise SystemExit("bench: proof from device-generated tables differs from the proof from host tables")
+    fixture = os.path.join(ROOT, "tests", "golden", "cfg3_add_log20.proof.bin")
+    equals_fixture = None
+    if log == 20 and os.path.exists(fixture):
+        equals_fixture = open(fixture, "rb").read() == ref_proof
+        if not equals_fixture:
+            raise SystemExit("bench: the cfg-3 proof differs from the committed CPU-prover fixture")
     prove_from_tensors()
     ts_tens = []
     for _ in range(reps):
@@ -510,7 +550,9 @@ def bench_prove(be, torch, args):
         prove_from_tensors()
         ts_tens.append((time.perf_counter() - t0) * 1e3)
     # the reference's one published prove() figure: Add 32x32 (docs/snippets/benchmark-component.mdx:173)
-    small = synthetic_add_graph_pie(10, seed=42)
+    sa, sb = synthetic_add_graph_inputs(10, seed=42)
+    sm_meta, sm_dev, _ = build_add_graph(DeviceGraphTrace(be), sa, sb).finish()
+    small, small_keep = _device_tables_to_host(be, torch, sm_meta, sm_dev)
     for _ in range(3):
         prove(small, backend=be)
     t0 = time.perf_counter()
@@ -519,10 +561,13 @@ def bench_prove(be, torch, args):
     small_ms = (time.perf_counter() - t0) * 1e2
     h2d = sum(int(v.nbytes) for _, v in host_pie)
     # BASELINE configs[3] shape: the 2-64-64-1 tanh MLP of examples/black-schole-nn (synthetic weights), 7 components
-    # including the Exp2 lookup table (2^17 rows) and the extended evaluation domain of its consumer
-    from luminair_b200.pie import GraphTrace, build_mlp, build_wide
-    mlp_host = build_mlp(GraphTrace())
-    mlp_pie, mlp_pre = mlp_host.finish()
+    # including the Exp2 lookup table (2^17 rows) and the extended evaluation domain of its consumer.  The Exp2 layout is
+    # the circuit setting a calibration run of this network yields (workloads.MLP_EXP2_RANGE)
+    mlp_layouts = {"exp2": LookupLayout([MLP_EXP2_RANGE])}
+    mlp_rec = build_mlp(DeviceGraphTrace(be))
+    mlp_meta, mlp_dev_tables, _ = mlp_rec.finish(mlp_layouts)
+    mlp_pre = mlp_rec.preprocessed
+    mlp_pie, mlp_keep = _device_tables_to_host(be, torch, mlp_meta, mlp_dev_tables)
     for _ in range(2):
         prove(mlp_pie, backend=be, preprocessed=mlp_pre)
     t_mlp = []
@@ -535,7 +580,7 @@ def bench_prove(be, torch, args):
     # host-generated LUT, Recip): only the weights / input / constants cross PCIe
     def mlp_from_tensors():
         dg = build_mlp(DeviceGraphTrace(be))
-        meta, dev_tables, _ = dg.finish(mlp_host.layouts)
+        meta, dev_tables, _ = dg.finish(mlp_layouts)
         return prove(meta, backend=be, device_tables=dev_tables, preprocessed=dg.preprocessed)
 
     if mlp_from_tensors() != mlp_proof:
@@ -547,14 +592,13 @@ def bench_prove(be, torch, args):
         t_mlp_dev.append((time.perf_counter() - t0) * 1e3)
     # compile once, run per execution (StwoCompiler once, gen_trace + prove per input): the recorded device graph is replayed
     # with a new network input; weights, gather indices, consumer counts and LUT columns stay resident
-    mlp_dev = build_mlp(DeviceGraphTrace(be))
-    mlp_dev.finish(mlp_host.layouts)
-    x_raw = mlp_host.values[0]
+    from luminair_b200.lookups import to_fixed
+    x_raw = to_fixed(np.asarray((15.0, 0.5), dtype=np.float64))
 
     def mlp_replay():
-        mlp_dev.set_input(0, x_raw)
-        meta, dev_tables, _ = mlp_dev.finish()
-        return prove(meta, backend=be, device_tables=dev_tables, preprocessed=mlp_dev.preprocessed)
+        mlp_rec.set_input(0, x_raw)
+        meta, dev_tables, _ = mlp_rec.finish()
+        return prove(meta, backend=be, device_tables=dev_tables, preprocessed=mlp_rec.preprocessed)
 
     if mlp_replay() != mlp_proof:
         raise SystemExit("bench: MLP proof from the replayed device graph differs from the proof from host tables")
@@ -578,14 +622,9 @@ def bench_prove(be, torch, args):
     # two inputs) beside the Inputs table; device-resident tables
     wide_info = None
     if log >= 12:
-        whost = build_wide(GraphTrace(), log)
-        wpie = [(k, np.ascontiguousarray(v, dtype=np.uint32)) for k, v in whost.finish()[0]]
-        wdev, keep = {}, []
-        for name, rows in wpie:
-            buf = be.upload(rows.reshape(-1))
-            keep.append(buf)
-            wdev[name] = (buf.ptr, rows.shape[0], rows.shape[1])
-        meta = [(k, None) for k, v in wpie]
+        wrec = build_wide(DeviceGraphTrace(be), log)
+        meta, wdev, wvalues = wrec.finish()
+        shapes = {k: (wdev[k][1], wdev[k][2]) for k, _ in meta}
         for _ in range(2):
             prove(meta, backend=be, device_tables=wdev)
         t_w, st_w = [], None
@@ -596,11 +635,15 @@ def bench_prove(be, torch, args):
             if not t_w or dt < min(t_w):
                 st_w = last_stage_ms(be)
             t_w.append(dt)
+        wfix = os.path.join(ROOT, "tests", "golden", "wide_log20.proof.bin")
+        wide_equals_fixture = (open(wfix, "rb").read() == wproof) if (log == 20 and os.path.exists(wfix)) else None
+        if wide_equals_fixture is False:
+            raise SystemExit("bench: the wide proof differs from the committed CPU-prover fixture")
         # gen_trace of the same graph on the device from its two input tensors (pinned), then prove
         wtens = []
         for node in (0, 1):
             t = torch.empty((1 << log,), dtype=torch.int32, pin_memory=True)
-            t.numpy()[:] = whost.values[node]
+            t.numpy().view(np.uint32)[:] = be.download_ptr(wvalues[node].ptr, 1 << log)
             wtens.append(t)
 
         def wide_from_tensors():
@@ -611,27 +654,29 @@ def bench_prove(be, torch, args):
             return prove(m, backend=be, device_tables=devt)
 
         if wide_from_tensors() != wproof:
-            raise SystemExit("bench: wide proof from device-generated tables differs from the proof from host-built tables")
+            raise SystemExit("bench: wide proof from device-generated tables differs from the proof from the recorded graph's tables")
         t_wt = []
         for _ in range(max(3, reps // 2)):
             t0 = time.perf_counter()
             wide_from_tensors()
             t_wt.append((time.perf_counter() - t0) * 1e3)
-        n_main_cols = sum(v.shape[1] for k, v in wpie if k != "inputs")
+        n_main_cols = sum(c for k, (r, c) in shapes.items() if k != "inputs")
         wide_info = {"workload": f"prove(): 2^{log} rows x {n_main_cols} main-trace columns (" +
-                                 ", ".join(f"{k} {v.shape[0]}x{v.shape[1]}" for k, v in wpie) + "), device-resident tables "
+                                 ", ".join(f"{k} {r}x{c}" for k, (r, c) in shapes.items()) + "), device-resident tables "
                                  "(the 2^20 x 64 trace shape of BASELINE.json's metric, built from real operator tables)",
                      "ms_device_resident": {"min": min(t_w), "median": statistics.median(t_w)},
                      "ms_e2e_host_tensors": {"min": min(t_wt), "median": statistics.median(t_wt), "h2d_bytes": int(2 * 4 << log),
                                              "how": "the two input tensors uploaded from pinned memory, all five tables "
                                                     "generated on the device (lb_trace_*), proof bytes identical"},
+                     "proof_equals_cpu_prover_fixture": wide_equals_fixture,
                      "stages_ms": dict(zip(STAGE_NAMES, [round(x, 3) for x in st_w])), "proof_bytes": len(wproof)}
-        del keep
     return {
         "wide": wide_info,
         "mlp": mlp_info,
         "workload": f"prove(): a+b graph, Add 2^{log} rows x 15 cols + Inputs 2^{log + 1} rows x 7 cols, blow-up 2, Blake2s Merkle, FRI "
-                    "(BASELINE configs[2]); proof bytes bit-exact vs the CPU restatement at test sizes, verifier-accepted at this size",
+                    "(BASELINE configs[2]); proof bytes equal to the compiled CPU prover's at this size (tests/golden/cfg3_add_log20.proof.bin)",
+        "proof_equals_cpu_prover_fixture": equals_fixture,
+        "_proof_bytes": ref_proof,
         "ms_device_resident": {"min": min(ts_dev), "median": statistics.median(ts_dev)},
         "ms_e2e_host_tables": {"min": min(ts_host), "median": statistics.median(ts_host), "h2d_bytes": h2d, "d2h_bytes": nbytes},
         "ms_e2e_host_tensors": {"min": min(ts_tens), "median": statistics.median(ts_tens), "h2d_bytes": int(2 * 4 << log),

@@ -18,6 +18,11 @@ def synthetic_add_graph_inputs(log_n: int, seed: int = 42):
     return a, b
 
 
+# The Exp2 lookup range a calibration run (the reference's gen_circuit_settings) of the default cfg-4 MLP below yields: the raw
+# Fixed<12> inputs its Exp2 nodes see (tests/test_settings.py checks it against the values the numpy checker records)
+MLP_EXP2_RANGE = (-57162, 54948)
+
+
 def build_add_graph(g, a_fixed, b_fixed):
     """BASELINE cfg 3: c = a + b over n elements (nodes: a = 0, b = 1, add = 2) -> Add table n rows, Inputs table 2n rows."""
     a = g.input(a_fixed)

@@ -52,3 +52,21 @@ def test_prove_with_settings_equals_prove_with_columns():
     pie, pre = piemod.mlp_graph(widths=(2, 8, 8, 1))
     s = CircuitSettings.from_bincode(CircuitSettings.from_graph_trace(pie, pre).to_bincode())
     assert prove(pie, settings=s) == prove(pie, preprocessed=pre)
+
+
+def test_mlp_exp2_range_is_the_calibrated_one():
+    """workloads.MLP_EXP2_RANGE (the circuit setting bench.py proves the cfg-4 MLP with) is the covering range a calibration
+    run records, and the product's LUT columns equal the checker's own (both through host libm)."""
+    from luminair_b200 import lookups, workloads
+    g = piemod.build_mlp(piemod.GraphTrace())
+    _, pre = g.finish()
+    assert g.layouts["exp2"].ranges == [workloads.MLP_EXP2_RANGE]
+    mine = lookups.lut_columns("exp2", lookups.LookupLayout([workloads.MLP_EXP2_RANGE]))
+    for (cid, want), (cid2, got) in zip(pre, mine):
+        assert cid == cid2 and np.array_equal(want, got)
+    for name in ("sin", "log2"):
+        lay = lookups.LookupLayout([(1, 5000)])
+        olay = piemod.LookupLayout([(1, 5000)])
+        for (_, a), (_, b) in zip(lookups.lut_columns(name, lay), piemod.lut_columns(name, olay)):
+            assert np.array_equal(a, b)
+    assert int(lookups.to_fixed(2.0 ** -13)) == 1 and int(lookups.to_fixed(-(2.0 ** -13))) == -1  # ties away from zero
