@@ -551,7 +551,8 @@ def bench_prove(be, torch, args):
         ts_tens.append((time.perf_counter() - t0) * 1e3)
     # the reference's one published prove() figure: Add 32x32 (docs/snippets/benchmark-component.mdx:173)
     sa, sb = synthetic_add_graph_inputs(10, seed=42)
-    sm_meta, sm_dev, _ = build_add_graph(DeviceGraphTrace(be), sa, sb).finish()
+    sm_rec = build_add_graph(DeviceGraphTrace(be), sa, sb)  # the recorder owns the device tables
+    sm_meta, sm_dev, _ = sm_rec.finish()
     small, small_keep = _device_tables_to_host(be, torch, sm_meta, sm_dev)
     for _ in range(3):
         prove(small, backend=be)
