@@ -41,6 +41,14 @@ int lb_ctx_create(int device, lb_ctx** out) {
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return LB_ERR_CUDA;
     lb_ctx* ctx = new lb_ctx();
     ctx->device = device;
+    int caller_device = -1;
+    cudaGetDevice(&caller_device);
+    struct Restore {
+        int d;
+        ~Restore() {
+            if (d >= 0) cudaSetDevice(d);
+        }
+    } restore{caller_device};  // the calling thread keeps its current device
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
@@ -67,7 +75,7 @@ int lb_ctx_create(int device, lb_ctx** out) {
 
 void lb_ctx_destroy(lb_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    lb::DeviceGuard _dg(ctx);
     cudaStreamSynchronize(ctx->stream);
     lb::twiddles_destroy(&ctx->tw);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
@@ -88,12 +96,14 @@ void lb_ctx_destroy(lb_ctx* ctx) {
 const char* lb_last_error(lb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 int lb_sync(lb_ctx* ctx) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx) return LB_ERR_BAD_ARG;
     CK(cudaStreamSynchronize(ctx->stream), "sync");
     return LB_OK;
 }
 
 int lb_alloc(lb_ctx* ctx, size_t n_u32, uint32_t** d_out) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !d_out) return LB_ERR_BAD_ARG;
     cudaSetDevice(ctx->device);
     void* p = nullptr;
@@ -103,6 +113,7 @@ int lb_alloc(lb_ctx* ctx, size_t n_u32, uint32_t** d_out) {
 }
 
 int lb_free(lb_ctx* ctx, uint32_t* d_ptr) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx) return LB_ERR_BAD_ARG;
     cudaSetDevice(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream), "free/sync");
@@ -113,6 +124,7 @@ int lb_free(lb_ctx* ctx, uint32_t* d_ptr) {
 // stream-ordered variants (cudaMallocAsync on the context's stream, memory kept in the device pool): no device-wide
 // synchronisation, for short-lived buffers such as the tensors and tables of a device-side gen_trace.  Not for lb_ipc_export.
 int lb_alloc_pooled(lb_ctx* ctx, size_t n_u32, uint32_t** d_out) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !d_out) return LB_ERR_BAD_ARG;
     cudaSetDevice(ctx->device);
     void* p = nullptr;
@@ -122,6 +134,7 @@ int lb_alloc_pooled(lb_ctx* ctx, size_t n_u32, uint32_t** d_out) {
 }
 
 int lb_free_pooled(lb_ctx* ctx, uint32_t* d_ptr) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx) return LB_ERR_BAD_ARG;
     cudaSetDevice(ctx->device);
     CK(cudaFreeAsync(d_ptr, ctx->stream), "free_pooled");
@@ -129,12 +142,14 @@ int lb_free_pooled(lb_ctx* ctx, uint32_t* d_ptr) {
 }
 
 int lb_memset_zero(lb_ctx* ctx, uint32_t* d_ptr, size_t n_u32) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx) return LB_ERR_BAD_ARG;
     CK(cudaMemsetAsync(d_ptr, 0, n_u32 * sizeof(uint32_t), ctx->stream), "memset");
     return LB_OK;
 }
 
 int lb_upload(lb_ctx* ctx, uint32_t* d_dst, const uint32_t* h_src, size_t n_u32) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || (!h_src && n_u32)) return LB_ERR_BAD_ARG;
     CK(cudaMemcpyAsync(d_dst, h_src, n_u32 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream), "upload");
     CK(cudaStreamSynchronize(ctx->stream), "upload/sync");
@@ -142,6 +157,7 @@ int lb_upload(lb_ctx* ctx, uint32_t* d_dst, const uint32_t* h_src, size_t n_u32)
 }
 
 int lb_download(lb_ctx* ctx, uint32_t* h_dst, const uint32_t* d_src, size_t n_u32) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || (!h_dst && n_u32)) return LB_ERR_BAD_ARG;
     CK(cudaMemcpyAsync(h_dst, d_src, n_u32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream), "download");
     CK(cudaStreamSynchronize(ctx->stream), "download/sync");
@@ -149,18 +165,21 @@ int lb_download(lb_ctx* ctx, uint32_t* h_dst, const uint32_t* d_src, size_t n_u3
 }
 
 int lb_copy(lb_ctx* ctx, uint32_t* d_dst, const uint32_t* d_src, size_t n_u32) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx) return LB_ERR_BAD_ARG;
     CK(cudaMemcpyAsync(d_dst, d_src, n_u32 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream), "copy");
     return LB_OK;
 }
 
 int lb_timer_start(lb_ctx* ctx) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx) return LB_ERR_BAD_ARG;
     CK(cudaEventRecord(ctx->ev0, ctx->stream), "timer start");
     return LB_OK;
 }
 
 int lb_timer_stop_ms(lb_ctx* ctx, float* ms_out) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !ms_out) return LB_ERR_BAD_ARG;
     CK(cudaEventRecord(ctx->ev1, ctx->stream), "timer stop");
     CK(cudaEventSynchronize(ctx->ev1), "timer sync");
@@ -169,6 +188,7 @@ int lb_timer_stop_ms(lb_ctx* ctx, float* ms_out) {
 }
 
 int lb_device_info(lb_ctx* ctx, int* sm_count, size_t* total_mem_bytes) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx) return LB_ERR_BAD_ARG;
     if (sm_count) *sm_count = ctx->sm_count;
     if (total_mem_bytes) *total_mem_bytes = ctx->total_mem;
@@ -176,6 +196,7 @@ int lb_device_info(lb_ctx* ctx, int* sm_count, size_t* total_mem_bytes) {
 }
 
 int lb_twiddles_ensure(lb_ctx* ctx, int max_log) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || max_log < 1 || max_log > 28) return fail(ctx, LB_ERR_BAD_ARG, "twiddles: max_log out of range");
     if (max_log < 2) max_log = 2;
     if (ctx->tw.max_log >= max_log) return LB_OK;
@@ -188,6 +209,7 @@ int lb_twiddles_ensure(lb_ctx* ctx, int max_log) {
 }
 
 int lb_twiddles_export(lb_ctx* ctx, int root_log, uint32_t* d_out) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !d_out) return LB_ERR_BAD_ARG;
     if (ctx->tw.max_log < root_log + 1) return fail(ctx, LB_ERR_BAD_ARG, "twiddles_export: tables too small");
     CK(lb::twiddles_export_stwo(&ctx->tw, root_log, d_out, ctx->stream), "twiddles export");
@@ -195,6 +217,7 @@ int lb_twiddles_export(lb_ctx* ctx, int root_log, uint32_t* d_out) {
 }
 
 int lb_interpolate_batch(lb_ctx* ctx, uint32_t* d_cols, size_t stride, int n_cols, int log_size) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || n_cols < 0 || log_size < 1) return fail(ctx, LB_ERR_BAD_ARG, "interpolate: bad args");
     if (stride < ((size_t)1 << log_size) && n_cols > 1) return fail(ctx, LB_ERR_BAD_ARG, "interpolate: stride < column size");
     int r = lb_twiddles_ensure(ctx, log_size);
@@ -205,6 +228,7 @@ int lb_interpolate_batch(lb_ctx* ctx, uint32_t* d_cols, size_t stride, int n_col
 
 int lb_evaluate_batch(lb_ctx* ctx, const uint32_t* d_coeffs, size_t src_stride, int log_in, uint32_t* d_out,
                       size_t dst_stride, int log_out, int n_cols) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || n_cols < 0 || log_out < 1 || log_in < 0 || log_in > log_out)
         return fail(ctx, LB_ERR_BAD_ARG, "evaluate: bad args");
     int r = lb_twiddles_ensure(ctx, log_out);
@@ -217,6 +241,7 @@ int lb_evaluate_batch(lb_ctx* ctx, const uint32_t* d_coeffs, size_t src_stride, 
 
 int lb_merkle_commit_layer(lb_ctx* ctx, int log_size, const uint32_t* d_prev, const uint32_t* const* h_cols,
                            int n_cols, uint32_t* d_out) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !d_out || log_size < 0 || log_size > 30 || n_cols < 0 || (n_cols && !h_cols))
         return fail(ctx, LB_ERR_BAD_ARG, "merkle: bad args");
     const uint32_t* const* d_cols = nullptr;
@@ -235,8 +260,10 @@ int lb_merkle_commit_layer(lb_ctx* ctx, int log_size, const uint32_t* d_prev, co
 
 int lb_gather_rows(lb_ctx* ctx, const uint32_t* const* h_cols, int n_cols, const uint32_t* h_idx, int n_idx,
                    uint32_t* h_out) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || n_cols < 0 || n_idx < 0) return fail(ctx, LB_ERR_BAD_ARG, "gather: bad args");
     if (n_cols == 0 || n_idx == 0) return LB_OK;
+    if (!h_cols || !h_idx || !h_out) return fail(ctx, LB_ERR_BAD_ARG, "gather: null pointer");
     size_t pb = (size_t)n_cols * sizeof(void*), ib = (size_t)n_idx * 4, ob = (size_t)n_cols * n_idx * 4;
     size_t pb_al = (pb + 255) & ~(size_t)255, ib_al = (ib + 255) & ~(size_t)255;
     int r = ensure_scratch(ctx, pb_al + ib_al + ob);
@@ -255,6 +282,7 @@ int lb_gather_rows(lb_ctx* ctx, const uint32_t* const* h_cols, int n_cols, const
 
 int lb_eval_at_point(lb_ctx* ctx, const uint32_t* const* h_cols, int n_cols, int log_size, const uint32_t point[8],
                      uint32_t* h_out) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || n_cols < 0 || log_size < 0 || log_size > 30 || (n_cols && (!h_cols || !h_out)) || !point)
         return fail(ctx, LB_ERR_BAD_ARG, "eval_at_point: bad args");
     if (n_cols == 0) return LB_OK;
@@ -264,6 +292,7 @@ int lb_eval_at_point(lb_ctx* ctx, const uint32_t* const* h_cols, int n_cols, int
 int lb_accumulate_quotients(lb_ctx* ctx, int log_size, const uint32_t* const* h_cols, int n_cols,
                             const lb_sample_batch* batches, int n_batches, const uint32_t random_coeff[4],
                             uint32_t* const d_out[4]) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !h_cols || !batches || !random_coeff || !d_out || n_cols < 1 || n_batches < 1 || log_size < 1 || log_size > 30)
         return fail(ctx, LB_ERR_BAD_ARG, "accumulate_quotients: bad args");
     return lb::accumulate_quotients_impl(ctx, log_size, h_cols, n_cols, batches, nullptr, n_batches, random_coeff, d_out);
@@ -272,6 +301,7 @@ int lb_accumulate_quotients(lb_ctx* ctx, int log_size, const uint32_t* const* h_
 int lb_accumulate_quotients_shard(lb_ctx* ctx, int log_size, const uint32_t* const* h_cols, int n_cols,
                                   const lb_sample_batch* batches, const lb_batch_shard* shards, int n_batches,
                                   const uint32_t random_coeff[4], uint32_t* const d_out[4]) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !h_cols || !batches || !shards || !random_coeff || !d_out || n_cols < 1 || n_batches < 1 || log_size < 1 ||
         log_size > 30)
         return fail(ctx, LB_ERR_BAD_ARG, "accumulate_quotients_shard: bad args");
@@ -280,16 +310,19 @@ int lb_accumulate_quotients_shard(lb_ctx* ctx, int log_size, const uint32_t* con
 
 int lb_fold_circle_into_line(lb_ctx* ctx, uint32_t* const d_dst[4], const uint32_t* const d_src[4], int log_size,
                              const uint32_t alpha[4]) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !d_dst || !d_src || !alpha) return fail(ctx, LB_ERR_BAD_ARG, "fold_circle_into_line: bad args");
     return lb::fold_impl(ctx, 1, d_dst, d_src, log_size, alpha);
 }
 
 int lb_fold_line(lb_ctx* ctx, uint32_t* const d_dst[4], const uint32_t* const d_src[4], int log_size, const uint32_t alpha[4]) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !d_dst || !d_src || !alpha) return fail(ctx, LB_ERR_BAD_ARG, "fold_line: bad args");
     return lb::fold_impl(ctx, 0, d_dst, d_src, log_size, alpha);
 }
 
 int lb_grind(lb_ctx* ctx, const uint32_t digest[8], int channel_variant, uint32_t pow_bits, uint64_t* nonce_out) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !digest || !nonce_out || channel_variant < 0 || channel_variant > 1)
         return fail(ctx, LB_ERR_BAD_ARG, "grind: bad args");
     return lb::grind_impl(ctx, digest, channel_variant, pow_bits, nonce_out);
@@ -298,6 +331,7 @@ int lb_grind(lb_ctx* ctx, const uint32_t digest[8], int channel_variant, uint32_
 int lb_logup_interaction_trace(lb_ctx* ctx, int component, const uint32_t* d_main, size_t main_stride, uint32_t* d_inter,
                                size_t inter_stride, int log_size, const uint32_t z[4], const uint32_t alpha[4],
                                uint32_t claimed_out[4]) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !d_main || !d_inter || !z || !alpha || !claimed_out || log_size < 1 || log_size > 30)
         return fail(ctx, LB_ERR_BAD_ARG, "logup: bad args");
     lb_relation node;
@@ -309,6 +343,7 @@ int lb_logup_interaction_trace(lb_ctx* ctx, int component, const uint32_t* d_mai
 int lb_logup_interaction_trace_lut(lb_ctx* ctx, int component, const uint32_t* d_main, size_t main_stride,
                                    const uint32_t* const d_lut[2], uint32_t* d_inter, size_t inter_stride, int log_size,
                                    const lb_relation rels[LB_REL_COUNT], uint32_t claimed_out[4]) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !d_main || !d_inter || !rels || !claimed_out || log_size < 1 || log_size > 30)
         return fail(ctx, LB_ERR_BAD_ARG, "logup: bad args");
     return lb::logup_impl(ctx, component, d_main, main_stride, d_lut, d_inter, inter_stride, log_size, rels, LB_REL_COUNT,
@@ -319,6 +354,7 @@ int lb_constraint_quotients(lb_ctx* ctx, int component, const uint32_t* d_main, 
                             size_t inter_stride, int log_size, const uint32_t z[4], const uint32_t alpha[4],
                             const uint32_t claimed_sum[4], const uint32_t* pows, int n_pows, uint32_t* const d_acc[4],
                             int accumulate) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !d_main || !d_inter || !z || !alpha || !claimed_sum || !pows || !d_acc || log_size < 1 || log_size > 29)
         return fail(ctx, LB_ERR_BAD_ARG, "constraint_quotients: bad args");
     lb_relation node;
@@ -332,6 +368,7 @@ int lb_constraint_quotients_lut(lb_ctx* ctx, int component, const uint32_t* d_ma
                                 size_t inter_stride, const uint32_t* const d_lut[2], int log_size, int eval_log_size,
                                 const lb_relation rels[LB_REL_COUNT], const uint32_t claimed_sum[4], const uint32_t* pows,
                                 int n_pows, uint32_t* const d_acc[4], int accumulate) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !d_main || !d_inter || !rels || !claimed_sum || !pows || !d_acc || log_size < 1 || log_size > 29)
         return fail(ctx, LB_ERR_BAD_ARG, "constraint_quotients: bad args");
     return lb::constraint_quotients_impl(ctx, component, d_main, main_stride, d_inter, inter_stride, d_lut, log_size,
@@ -341,6 +378,7 @@ int lb_constraint_quotients_lut(lb_ctx* ctx, int component, const uint32_t* d_ma
 int lb_evaluate_batch_scatter(lb_ctx* ctx, const uint32_t* d_coeffs, size_t src_stride, int log_in, uint32_t* d_scratch,
                               size_t dst_stride, int log_out, int n_cols, uint32_t* const* h_peers, int n_peers,
                               size_t peer_col0) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || n_cols < 0 || log_out < 1 || log_in < 0 || log_in > log_out || n_peers < 1 || n_peers > 8 || !h_peers)
         return fail(ctx, LB_ERR_BAD_ARG, "evaluate_scatter: bad args");
     int r = lb_twiddles_ensure(ctx, log_out);
@@ -352,6 +390,7 @@ int lb_evaluate_batch_scatter(lb_ctx* ctx, const uint32_t* d_coeffs, size_t src_
 }
 
 int lb_ipc_export(lb_ctx* ctx, const uint32_t* d_ptr, uint8_t handle_out[64]) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !d_ptr || !handle_out) return fail(ctx, LB_ERR_BAD_ARG, "ipc_export: bad args");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
     cudaSetDevice(ctx->device);
@@ -362,6 +401,7 @@ int lb_ipc_export(lb_ctx* ctx, const uint32_t* d_ptr, uint8_t handle_out[64]) {
 }
 
 int lb_ipc_open(lb_ctx* ctx, const uint8_t handle[64], uint32_t** d_ptr_out) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !handle || !d_ptr_out) return fail(ctx, LB_ERR_BAD_ARG, "ipc_open: bad args");
     cudaSetDevice(ctx->device);
     cudaIpcMemHandle_t h;
@@ -373,6 +413,7 @@ int lb_ipc_open(lb_ctx* ctx, const uint8_t handle[64], uint32_t** d_ptr_out) {
 }
 
 int lb_ipc_close(lb_ctx* ctx, uint32_t* d_ptr) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx) return LB_ERR_BAD_ARG;
     cudaSetDevice(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream), "ipc close/sync");
@@ -382,6 +423,7 @@ int lb_ipc_close(lb_ctx* ctx, uint32_t* d_ptr) {
 
 int lb_lde_host(lb_ctx* ctx, const uint32_t* h_values, uint32_t* h_evals, int n_cols, int log_in, int log_out,
                 uint32_t* h_coeffs, int chunk_cols) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !h_values || !h_evals || n_cols < 0 || log_in < 1 || log_out < log_in || log_out > 28)
         return fail(ctx, LB_ERR_BAD_ARG, "lde_host: bad args");
     if (n_cols == 0) return LB_OK;
@@ -452,6 +494,7 @@ int lb_lde_host(lb_ctx* ctx, const uint32_t* h_values, uint32_t* h_evals, int n_
 
 int lb_prove_with_lookups(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_preprocessed_column* lut_columns,
                           int n_lut_columns, const lb_prove_config* cfg, uint8_t** proof_out, size_t* proof_len) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !proof_out || !proof_len) return fail(ctx, LB_ERR_BAD_ARG, "prove: bad args");
     *proof_out = nullptr;
     *proof_len = 0;
@@ -468,6 +511,7 @@ int lb_prove_with_lookups(lb_ctx* ctx, const lb_trace_table* tables, int n_table
 
 int lb_prove(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_prove_config* cfg, uint8_t** proof_out,
              size_t* proof_len) {
+    lb::DeviceGuard _dg(ctx);
     return lb_prove_with_lookups(ctx, tables, n_tables, nullptr, 0, cfg, proof_out, proof_len);
 }
 
@@ -475,6 +519,7 @@ void lb_free_host(void* p) { std::free(p); }
 
 int lb_trace_inputs(lb_ctx* ctx, uint32_t node_id, const int32_t* d_vals, uint64_t n, uint32_t out_mult, uint32_t* d_rows,
                     uint64_t row0) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !d_vals || !d_rows || node_id >= lb::P || out_mult >= lb::P) return fail(ctx, LB_ERR_BAD_ARG, "trace_inputs: bad args");
     cudaSetDevice(ctx->device);
     lb::TraceOp p{};
@@ -509,15 +554,18 @@ static int trace_binary_api(lb_ctx* ctx, bool mul, uint32_t node_id, uint32_t lh
 
 int lb_trace_add(lb_ctx* ctx, uint32_t node_id, uint32_t lhs_id, uint32_t rhs_id, const int32_t* d_lhs, const int32_t* d_rhs,
                  uint64_t n, uint32_t out_mult, int32_t* d_out, uint32_t* d_rows, uint64_t row0) {
+    lb::DeviceGuard _dg(ctx);
     return trace_binary_api(ctx, false, node_id, lhs_id, rhs_id, d_lhs, d_rhs, n, out_mult, d_out, d_rows, row0);
 }
 
 int lb_trace_mul(lb_ctx* ctx, uint32_t node_id, uint32_t lhs_id, uint32_t rhs_id, const int32_t* d_lhs, const int32_t* d_rhs,
                  uint64_t n, uint32_t out_mult, int32_t* d_out, uint32_t* d_rows, uint64_t row0) {
+    lb::DeviceGuard _dg(ctx);
     return trace_binary_api(ctx, true, node_id, lhs_id, rhs_id, d_lhs, d_rhs, n, out_mult, d_out, d_rows, row0);
 }
 
 int lb_bit_reverse(lb_ctx* ctx, uint32_t* d_col, int log_size) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !d_col || log_size < 0 || log_size > 31) return fail(ctx, LB_ERR_BAD_ARG, "bit_reverse: bad args");
     cudaSetDevice(ctx->device);
     CK(lb::bit_reverse(d_col, log_size, ctx->stream), "bit_reverse");
@@ -525,6 +573,7 @@ int lb_bit_reverse(lb_ctx* ctx, uint32_t* d_col, int log_size) {
 }
 
 int lb_new_canonical_ordered(lb_ctx* ctx, const uint32_t* d_in, uint32_t* d_out, int log_size) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !d_in || !d_out || d_in == d_out || log_size < 1 || log_size > 31)
         return fail(ctx, LB_ERR_BAD_ARG, "new_canonical_ordered: bad args");
     cudaSetDevice(ctx->device);
@@ -549,11 +598,13 @@ static int batch_inverse_api(lb_ctx* ctx, const uint32_t* const* in, uint32_t* c
 }
 
 int lb_batch_inverse_m31(lb_ctx* ctx, const uint32_t* d_in, uint32_t* d_out, size_t n) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !d_in || !d_out) return fail(ctx, LB_ERR_BAD_ARG, "batch_inverse: bad args");
     return batch_inverse_api(ctx, &d_in, &d_out, 1, n);
 }
 
 int lb_batch_inverse_qm31(lb_ctx* ctx, const uint32_t* const d_in[4], uint32_t* const d_out[4], size_t n) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !d_in || !d_out) return fail(ctx, LB_ERR_BAD_ARG, "batch_inverse: bad args");
     for (int c = 0; c < 4; ++c)
         if (!d_in[c] || !d_out[c]) return fail(ctx, LB_ERR_BAD_ARG, "batch_inverse: null coordinate column");
@@ -561,6 +612,7 @@ int lb_batch_inverse_qm31(lb_ctx* ctx, const uint32_t* const d_in[4], uint32_t* 
 }
 
 int lb_accumulate(lb_ctx* ctx, uint32_t* const d_column[4], const uint32_t* const d_other[4], size_t n) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !d_column || !d_other) return fail(ctx, LB_ERR_BAD_ARG, "accumulate: bad args");
     cudaSetDevice(ctx->device);
     for (int c = 0; c < 4; ++c) {
@@ -583,6 +635,7 @@ int lb_generate_secure_powers(const uint32_t felt[4], int n_powers, uint32_t* h_
 }
 
 int lb_trace_count_uses(lb_ctx* ctx, uint32_t* d_uses, const uint32_t* d_idx, uint64_t n_reads) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !d_uses) return fail(ctx, LB_ERR_BAD_ARG, "trace_count_uses: bad args");
     cudaSetDevice(ctx->device);
     CK(lb::trace_count_uses(d_uses, d_idx, n_reads, ctx->stream), "trace_count_uses");
@@ -590,6 +643,7 @@ int lb_trace_count_uses(lb_ctx* ctx, uint32_t* d_uses, const uint32_t* d_idx, ui
 }
 
 int lb_trace_op(lb_ctx* ctx, const lb_trace_op_desc* d) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !d || !d->d_rows || !d->d_lhs || d->node_id >= lb::P || d->lhs_id >= lb::P || d->rhs_id >= lb::P)
         return fail(ctx, LB_ERR_BAD_ARG, "trace_op: bad args");
     int n_cols = 0;
@@ -650,6 +704,7 @@ int lb_trace_op(lb_ctx* ctx, const lb_trace_op_desc* d) {
 }
 
 int lb_prove_transcript(lb_ctx* ctx, uint8_t* out, size_t cap_hashes, size_t* n_hashes) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !n_hashes) return LB_ERR_BAD_ARG;
     *n_hashes = ctx->transcript.size();
     size_t n = ctx->transcript.size() < cap_hashes ? ctx->transcript.size() : cap_hashes;
@@ -658,6 +713,7 @@ int lb_prove_transcript(lb_ctx* ctx, uint8_t* out, size_t cap_hashes, size_t* n_
 }
 
 int lb_prove_stage_ms(lb_ctx* ctx, float* out, int cap, int* n) {
+    lb::DeviceGuard _dg(ctx);
     if (!ctx || !n) return LB_ERR_BAD_ARG;
     *n = (int)ctx->stage_ms.size();
     for (int i = 0; i < cap && i < *n && out; ++i) out[i] = ctx->stage_ms[i];

@@ -31,6 +31,22 @@ struct lb_ctx {
 };
 
 namespace lb {
+// Every extern "C" entry point runs with the context's device current and puts the caller's device back on return: two
+// contexts (two GPUs) in one process, or a host that has another device current, must not launch on the wrong device.
+struct DeviceGuard {
+    int prev = -1;
+    bool armed = false;
+    explicit DeviceGuard(const lb_ctx* ctx) {
+        if (!ctx) return;
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        if (prev != ctx->device) armed = cudaSetDevice(ctx->device) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (armed) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 inline int ctx_fail(lb_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
     if (ctx) {
         ctx->err = what;

@@ -674,6 +674,12 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
         if (n_tables < 1 || !tables) fail(LB_ERR_BAD_ARG, "prove: no trace tables");
         if (cfg.n_slots < 2 || cfg.n_slots > 64) fail(LB_ERR_BAD_ARG, "prove: bad n_slots");
         if (cfg.log_blowup_factor < 1 || cfg.log_blowup_factor > 4) fail(LB_ERR_BAD_ARG, "prove: bad blow-up");
+        // the grind loop below ends only when a nonce exists: a 64-bit nonce cannot be asked for more than 64 zero bits, and
+        // anything near that never finishes; stwo's own configurations stay below 32
+        if (cfg.pow_bits > 40) fail(LB_ERR_BAD_ARG, "prove: pow_bits > 40");
+        if (cfg.channel_variant != 0 && cfg.channel_variant != 1) fail(LB_ERR_BAD_ARG, "prove: unknown channel variant");
+        if (cfg.log_last_layer_degree_bound > 16 || cfg.n_queries < 1 || cfg.n_queries > 4096)
+            fail(LB_ERR_BAD_ARG, "prove: bad FRI configuration");
         const int blowup = (int)cfg.log_blowup_factor;
         cudaStream_t st = ctx->stream;
         ck(cudaSetDevice(ctx->device), "set device");
@@ -1424,6 +1430,18 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
         cudaStreamSynchronize(ctx->stream);
         ctx->err = e.msg;
         return e.code;
+    } catch (const std::bad_alloc&) {  // nothing may unwind through the extern "C" boundary
+        cudaStreamSynchronize(ctx->stream);
+        ctx->err = "prove: host allocation failed";
+        return LB_ERR_OOM;
+    } catch (const std::exception& e) {
+        cudaStreamSynchronize(ctx->stream);
+        ctx->err = std::string("prove: ") + e.what();
+        return LB_ERR_BAD_ARG;
+    } catch (...) {
+        cudaStreamSynchronize(ctx->stream);
+        ctx->err = "prove: unknown exception";
+        return LB_ERR_CUDA;
     }
 }
 
@@ -1448,6 +1466,18 @@ int guarded(lb_ctx* ctx, Fn&& fn) {
         cudaStreamSynchronize(ctx->stream);
         ctx->err = e.msg;
         return e.code;
+    } catch (const std::bad_alloc&) {
+        cudaStreamSynchronize(ctx->stream);
+        ctx->err = "host allocation failed";
+        return LB_ERR_OOM;
+    } catch (const std::exception& e) {
+        cudaStreamSynchronize(ctx->stream);
+        ctx->err = e.what();
+        return LB_ERR_BAD_ARG;
+    } catch (...) {
+        cudaStreamSynchronize(ctx->stream);
+        ctx->err = "unknown exception";
+        return LB_ERR_CUDA;
     }
 }
 }  // namespace

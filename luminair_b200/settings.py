@@ -153,6 +153,45 @@ class CircuitSettings:
         return s
 
 
+    # ---- JSON (serde_json of the same structs, settings.rs:64-122) -----------------------------------
+    def to_json(self) -> str:
+        """``CircuitSettings::to_json``: {"lookups": {"sin" | "exp2" | "log2": null | {"layout": {"ranges": [[lo, hi], ..],
+        "log_size": k}, "multiplicities": {"data": [..]}}, "range_check": null | {"layout": {"ranges": [n_bits], "log_size": k},
+        "multiplicities": {"data": [..]}}}}.  ``Range(Fixed, Fixed)`` is a tuple struct of two newtypes over i64
+        (preprocessed.rs:35) - a pair of numbers; ``AtomicU32`` serialises as its value.  Parity unpinned (no JSON settings
+        file in the reference)."""
+        import json
+
+        def lut(lk):
+            if lk is None:
+                return None
+            return {"layout": {"ranges": [[int(lo), int(hi)] for lo, hi in lk.ranges], "log_size": int(lk.log_size)},
+                    "multiplicities": {"data": [int(x) for x in np.asarray(lk.multiplicities).reshape(-1)]}}
+
+        rc = self.range_check
+        doc = {"lookups": {"sin": lut(self.sin), "exp2": lut(self.exp2), "log2": lut(self.log2),
+                           "range_check": None if rc is None else {
+                               "layout": {"ranges": [int(rc.n_bits)], "log_size": int(rc.log_size)},
+                               "multiplicities": {"data": [int(x) for x in np.asarray(rc.multiplicities).reshape(-1)]}}}}
+        return json.dumps(doc, indent=2)
+
+    @staticmethod
+    def from_json(text: str) -> "CircuitSettings":
+        import json
+        lk = json.loads(text)["lookups"]
+        s = CircuitSettings()
+        for name in LUT_ORDER:
+            j = lk.get(name)
+            if j is not None:
+                setattr(s, name, Lookup([(int(a), int(b)) for a, b in j["layout"]["ranges"]], int(j["layout"]["log_size"]),
+                                        np.asarray(j["multiplicities"]["data"], dtype=np.uint32)))
+        j = lk.get("range_check")
+        if j is not None:
+            s.range_check = RangeCheckLookup(int(j["layout"]["ranges"][0]), int(j["layout"]["log_size"]),
+                                             np.asarray(j["multiplicities"]["data"], dtype=np.uint32))
+        return s
+
+
 def _covering_count(lut0_values: np.ndarray) -> int:
     """Number of enumerated values of a one-range table: entries are consecutive raw values, the padding is zeros."""
     P = (1 << 31) - 1
