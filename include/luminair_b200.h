@@ -250,6 +250,36 @@ int lb_prove(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_p
 int lb_prove_with_lookups(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_preprocessed_column* lut_columns,
                           int n_lut_columns, const lb_prove_config* cfg, uint8_t** proof_out, size_t* proof_len);
 void lb_free_host(void* p);
+
+/* ---- multi-GPU prove(): one rank (process or thread) per GPU, NCCL over NVLink / NVSwitch ----------------------
+ * The reference has ONE tree per phase holding every column (crates/prover/src/prover.rs:56-59,68,179,298) and one
+ * stwo::prover::prove (prover.rs:311-312); lb_prove_sharded runs that same protocol over `world` GPUs and returns, on every
+ * rank, the SAME bytes lb_prove returns on one GPU:
+ *   - column-wise steps (interpolate, LDE, eval_at_point) are split by column: every column has one owner rank;
+ *   - one grouped exchange per tree turns the owners' LDE columns into row shards (rank r holds rows [r R/W, (r+1) R/W) of
+ *     every column); everything row-wise - Merkle leaves and sub-trees, constraint quotients, DEEP quotients, FRI folds and
+ *     layer trees - then runs on the row shard with no further data exchange, only the 32-byte sub-tree roots are
+ *     all-gathered (the top log2 W tree levels are hashed from them);
+ *   - the composition polynomial goes rows -> columns once (16 B per row), sampled values and the decommitted words are
+ *     summed over the ranks (each has exactly one owner); the last, latency-bound FRI layers are all-gathered and replicated;
+ *   - the Fiat-Shamir channel runs replicated on every rank.
+ * Every rank passes the same tables / LUT columns / configuration (the trace is replicated input: on the device it is
+ * generated by lb_trace_* in microseconds).  NCCL is bound at run time (libnccl.so.2); without it these entry points return
+ * LB_ERR_NCCL and the single-GPU entry points are unaffected.  Limitation: a component evaluated on a domain larger than
+ * its committed one (a lookup table larger than its consumer's trace) is rejected with LB_ERR_BAD_ARG for world > 1. */
+#define LB_COMM_ID_BYTES 128
+typedef struct lb_comm lb_comm;
+/* rank 0 creates the id (ncclGetUniqueId); the host hands it to the other ranks by its own means (MPI, a file, a socket) */
+int lb_comm_unique_id(uint8_t id_out[LB_COMM_ID_BYTES]);
+/* collective: every rank calls it with its own context (one GPU each); world must be a power of two */
+int lb_comm_init(lb_ctx* ctx, const uint8_t id[LB_COMM_ID_BYTES], int rank, int world, lb_comm** out);
+void lb_comm_destroy(lb_comm* comm);
+/* rank / world and the NCCL traffic of the last lb_prove_sharded on this rank (any pointer may be NULL) */
+int lb_comm_stats(const lb_comm* comm, int* rank, int* world, uint64_t* bytes_sent, uint64_t* bytes_received,
+                  int* n_collectives);
+int lb_prove_sharded(lb_ctx* ctx, lb_comm* comm, const lb_trace_table* tables, int n_tables,
+                     const lb_preprocessed_column* lut_columns, int n_lut_columns, const lb_prove_config* cfg,
+                     uint8_t** proof_out, size_t* proof_len);
 /* diagnostics of the last lb_prove: channel digest after every mix (32 B each) and per-stage wall-clock ms */
 int lb_prove_transcript(lb_ctx* ctx, uint8_t* out, size_t cap_hashes, size_t* n_hashes);
 int lb_prove_stage_ms(lb_ctx* ctx, float* out, int cap, int* n);

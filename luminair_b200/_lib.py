@@ -125,6 +125,13 @@ SIGNATURES.update({
     "lb_prove": (C.c_int, [ctxp, C.POINTER(TraceTable), C.c_int, C.POINTER(ProveConfig), C.POINTER(C.c_void_p),
                            C.POINTER(C.c_size_t)]),
     "lb_free_host": (None, [C.c_void_p]),
+    "lb_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "lb_comm_init": (C.c_int, [ctxp, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "lb_comm_destroy": (None, [C.c_void_p]),
+    "lb_comm_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                C.POINTER(C.c_int)]),
+    "lb_prove_sharded": (C.c_int, [ctxp, C.c_void_p, C.POINTER(TraceTable), C.c_int, C.POINTER(PreprocessedColumn), C.c_int,
+                                   C.POINTER(ProveConfig), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "lb_trace_inputs": (C.c_int, [ctxp, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64]),
     "lb_trace_add": (C.c_int, [ctxp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
                                C.c_void_p, C.c_void_p, C.c_uint64]),

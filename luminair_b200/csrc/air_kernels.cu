@@ -230,7 +230,12 @@ struct DomainEval : LogupMixin<DomainEval, FM, FQ> {
         return v;
     }
     __device__ __forceinline__ void next_ext_mask_prev_cur(FQ& prev, FQ& cur) {
-        prev = read_ext(row_prev);
+        if (p.inter_prev) {
+            const uint32_t* b = p.inter_prev + row;
+            prev = {q_make(b[0], b[p.inter_stride], b[2 * p.inter_stride], b[3 * p.inter_stride])};
+        } else {
+            prev = read_ext(row_prev);
+        }
         cur = read_ext(row);
         ic += 4;
     }
@@ -259,12 +264,12 @@ __device__ __forceinline__ uint32_t prev_row_index(uint32_t j, int domain_log, i
 
 template <int KIND>
 __global__ void __launch_bounds__(256) constraint_quotients_kernel(const __grid_constant__ ConstraintParams p) {
-    uint32_t n = 1u << p.eval_log;
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = p.n_rows ? p.n_rows : (1u << p.eval_log);
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;  // local row; the global row is row0 + j
     if (j >= n) return;
-    DomainEval ev(p, j, prev_row_index(j, p.log_size, p.eval_log));
+    DomainEval ev(p, j, p.inter_prev ? 0u : prev_row_index(j, p.log_size, p.eval_log));
     eval_kind<KIND>(ev, p.rels);
-    QM31 r = q_mul_m(ev.res, p.denom_inv[j >> p.log_size]);
+    QM31 r = q_mul_m(ev.res, p.denom_inv[(p.row0 + j) >> p.log_size]);
     if (p.accumulate) r = q_add(r, q_make(p.acc[0][j], p.acc[1][j], p.acc[2][j], p.acc[3][j]));
     p.acc[0][j] = r.a.a;
     p.acc[1][j] = r.a.b;
@@ -278,14 +283,27 @@ struct ConstraintLaunch {
     cudaStream_t stream;
     template <int KIND>
     void operator()() {
-        uint32_t n = 1u << p.eval_log;
+        uint32_t n = p.n_rows ? p.n_rows : (1u << p.eval_log);
         constraint_quotients_kernel<KIND><<<(n + 255) / 256, 256, 0, stream>>>(p);
     }
 };
 }  // namespace
 
+__global__ void __launch_bounds__(256) shifted_prev_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ col,
+                                                           int domain_log, int eval_log) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < (1u << eval_log)) out[j] = col[prev_row_index(j, domain_log, eval_log)];
+}
+cudaError_t shifted_prev_column(uint32_t* out, const uint32_t* col, int domain_log, int eval_log, cudaStream_t stream) {
+    if (eval_log - domain_log < 1 || eval_log > 30) return cudaErrorInvalidValue;
+    uint32_t n = 1u << eval_log;
+    shifted_prev_kernel<<<(n + 255) / 256, 256, 0, stream>>>(out, col, domain_log, eval_log);
+    return cudaGetLastError();
+}
+
 cudaError_t constraint_quotients(int kind, const ConstraintParams& p, cudaStream_t stream) {
     if (p.eval_log - p.log_size < 1 || p.eval_log > 30 || !p.denom_inv) return cudaErrorInvalidValue;
+    if (p.n_rows && ((uint64_t)p.row0 + p.n_rows > ((uint64_t)1 << p.eval_log) || !p.inter_prev)) return cudaErrorInvalidValue;
     if (kind < 0 || kind >= COMP_KIND_COUNT) return cudaErrorInvalidValue;
     if (component_shape(kind).n_pre > 0 && !p.pre.p[0]) return cudaErrorInvalidValue;
     ConstraintLaunch launch{p, stream};

@@ -5,6 +5,7 @@
 #include <string>
 #include <vector>
 
+#include "comm.h"
 #include "ctx.h"
 #include "kernels.cuh"
 #include "merkle.cuh"
@@ -500,6 +501,79 @@ int lb_prove_with_lookups(lb_ctx* ctx, const lb_trace_table* tables, int n_table
     *proof_len = 0;
     std::vector<uint8_t> bytes;
     int r = lb::prove_impl(ctx, tables, n_tables, lut_columns, n_lut_columns, cfg, bytes);
+    if (r) return r;
+    uint8_t* p = (uint8_t*)std::malloc(bytes.size() ? bytes.size() : 1);
+    if (!p) return fail(ctx, LB_ERR_OOM, "prove: host malloc");
+    std::memcpy(p, bytes.data(), bytes.size());
+    *proof_out = p;
+    *proof_len = bytes.size();
+    return LB_OK;
+}
+
+// ---- multi-GPU: one rank per GPU, NCCL over NVLink (SURVEY 8b lb_comm_init / 8e) --------------------------------------
+int lb_comm_unique_id(uint8_t id_out[LB_COMM_ID_BYTES]) {
+    if (!id_out) return LB_ERR_BAD_ARG;
+    lb::NcclApi& api = lb::nccl_api();
+    if (!api.load()) return LB_ERR_NCCL;
+    static_assert(sizeof(ncclUniqueId) == LB_COMM_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    if (api.GetUniqueId(&id) != ncclSuccess) return LB_ERR_NCCL;
+    std::memcpy(id_out, &id, sizeof(id));
+    return LB_OK;
+}
+
+int lb_comm_init(lb_ctx* ctx, const uint8_t id[LB_COMM_ID_BYTES], int rank, int world, lb_comm** out) {
+    lb::DeviceGuard _dg(ctx);
+    if (!ctx || !id || !out || world < 1 || world > 64 || rank < 0 || rank >= world || (world & (world - 1)))
+        return fail(ctx, LB_ERR_BAD_ARG, "comm: bad args (the world size must be a power of two)");
+    *out = nullptr;
+    lb::NcclApi& api = lb::nccl_api();
+    if (!api.load()) return fail(ctx, LB_ERR_NCCL, api.error.c_str());
+    cudaSetDevice(ctx->device);
+    ncclUniqueId nid;
+    std::memcpy(&nid, id, sizeof(nid));
+    lb_comm* c = new lb_comm();
+    c->rank = rank;
+    c->world = world;
+    while ((1 << c->log_world) < world) ++c->log_world;
+    c->ctx = ctx;
+    ncclResult_t r = api.CommInitRank(&c->comm, world, nid, rank);
+    if (r != ncclSuccess) {
+        std::string msg = std::string("ncclCommInitRank: ") + api.GetErrorString(r);
+        delete c;
+        return fail(ctx, LB_ERR_NCCL, msg.c_str());
+    }
+    *out = c;
+    return LB_OK;
+}
+
+void lb_comm_destroy(lb_comm* comm) {
+    if (!comm) return;
+    lb::DeviceGuard _dg(comm->ctx);
+    if (comm->ctx) cudaStreamSynchronize(comm->ctx->stream);
+    if (comm->comm) lb::nccl_api().CommDestroy(comm->comm);
+    delete comm;
+}
+
+int lb_comm_stats(const lb_comm* comm, int* rank, int* world, uint64_t* bytes_sent, uint64_t* bytes_received, int* n_collectives) {
+    if (!comm) return LB_ERR_BAD_ARG;
+    if (rank) *rank = comm->rank;
+    if (world) *world = comm->world;
+    if (bytes_sent) *bytes_sent = comm->bytes_sent;
+    if (bytes_received) *bytes_received = comm->bytes_received;
+    if (n_collectives) *n_collectives = comm->n_collectives;
+    return LB_OK;
+}
+
+int lb_prove_sharded(lb_ctx* ctx, lb_comm* comm, const lb_trace_table* tables, int n_tables,
+                     const lb_preprocessed_column* lut_columns, int n_lut_columns, const lb_prove_config* cfg,
+                     uint8_t** proof_out, size_t* proof_len) {
+    lb::DeviceGuard _dg(ctx);
+    if (!ctx || !comm || !proof_out || !proof_len) return fail(ctx, LB_ERR_BAD_ARG, "prove_sharded: bad args");
+    *proof_out = nullptr;
+    *proof_len = 0;
+    std::vector<uint8_t> bytes;
+    int r = lb::prove_impl(ctx, tables, n_tables, lut_columns, n_lut_columns, cfg, bytes, comm);
     if (r) return r;
     uint8_t* p = (uint8_t*)std::malloc(bytes.size() ? bytes.size() : 1);
     if (!p) return fail(ctx, LB_ERR_OOM, "prove: host malloc");

@@ -7,6 +7,8 @@
 #include "blake2s.cuh"
 #include "cfft.cuh"
 
+struct lb_comm;
+
 struct lb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -59,7 +61,7 @@ inline int ctx_fail(lb_ctx* ctx, int code, const char* what, cudaError_t e = cud
 }
 // the prover proper (prover.cu)
 int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_preprocessed_column* pre, int n_pre,
-               const lb_prove_config* cfg, std::vector<uint8_t>& out);
+               const lb_prove_config* cfg, std::vector<uint8_t>& out, lb_comm* comm = nullptr);
 int eval_at_point_impl(lb_ctx* ctx, const uint32_t* const* h_cols, int n_cols, int log, const uint32_t point[8],
                        uint32_t* h_out);
 int accumulate_quotients_impl(lb_ctx* ctx, int log, const uint32_t* const* h_cols, int n_cols,

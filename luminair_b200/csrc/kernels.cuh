@@ -33,8 +33,10 @@ struct QuotientParams {
     int n_batches;
     QuotientBatch b[MAX_QUOTIENT_BATCHES];
 };
+// row0 / n_rows: the row range [row0, row0 + n_rows) of the domain the columns and outputs hold (n_rows = 0: all 2^log rows)
 cudaError_t accumulate_quotients(uint32_t* const out[4], const uint32_t* const* d_cols, const QuotientEntry* d_entries,
-                                 const QuotientParams& qp, const Twiddles* tw, int log, cudaStream_t stream);
+                                 const QuotientParams& qp, const Twiddles* tw, int log, cudaStream_t stream, uint32_t row0 = 0,
+                                 uint32_t n_rows = 0);
 
 // ---- FriOps -------------------------------------------------------------------------------------
 // dst (4 coords, n/2) = dst * alpha^2 + fold(src (4 coords, n = 2^log));  itw = inverse y twiddles of the domain
@@ -114,8 +116,16 @@ struct ConstraintParams {
     QM31 cumsum_shift;
     QM31 pows[MAX_CONSTRAINTS];  // this component's random-coefficient powers, first constraint first
     const uint32_t* denom_inv;   // DEVICE: 1 / Z_H at eval_domain.at(bitrev(i)), i < 2^(eval_log - log_size)
+    // row range [row0, row0 + n_rows) of the evaluation domain held by main / inter / pre / acc (n_rows = 0: the whole
+    // domain).  inter_prev: for a row shard, the [-1]-offset mask values of the last LogUp column as 4 coordinate columns
+    // at inter_stride (the predecessor rows live on other ranks; the column's owner ships them, see shifted_prev_column);
+    // NULL: read them from `inter` at the predecessor row.
+    uint32_t row0, n_rows;
+    const uint32_t* inter_prev;
 };
 cudaError_t constraint_quotients(int kind, const ConstraintParams& p, cudaStream_t stream);
+// out[j] = col[offset_bit_reversed_circle_domain_index(j, domain_log, eval_log, -1)], j < 2^eval_log
+cudaError_t shifted_prev_column(uint32_t* out, const uint32_t* col, int domain_log, int eval_log, cudaStream_t stream);
 
 
 

@@ -160,7 +160,9 @@ __global__ void __launch_bounds__(256, 2) quotients_kernel(uint32_t* __restrict_
                                                         const QuotientEntry* __restrict__ entries,
                                                         const __grid_constant__ QuotientParams qp,
                                                         const uint2* __restrict__ tw_x, const uint2* __restrict__ tw_y,
-                                                        uint32_t n) {
+                                                        uint32_t n, uint32_t row0) {
+    // rows [row0, row0 + n) of the domain: the columns and the outputs are this row range (the whole domain on one GPU;
+    // a rank's row shard in the sharded prover), the domain points are those of the global rows
     const uint32_t j0 = blockIdx.x * (256 * QROWS) + threadIdx.x;
     uint32_t ys[QROWS];
     CM31 den[QROWS * NB], pre[QROWS * NB];
@@ -169,6 +171,7 @@ __global__ void __launch_bounds__(256, 2) quotients_kernel(uint32_t* __restrict_
     for (int r = 0; r < QROWS; ++r) {
         uint32_t j = j0 + r * 256;
         if (j >= n) j = n - 1;  // clamp (results of clamped rows are not stored)
+        j += row0;
         uint32_t h = j >> 1;
         uint32_t x = tw_x[h >> 1].x;
         if (h & 1) x = m_neg(x);
@@ -269,15 +272,17 @@ __global__ void __launch_bounds__(256, 2) quotients_kernel(uint32_t* __restrict_
 }
 
 cudaError_t accumulate_quotients(uint32_t* const out[4], const uint32_t* const* d_cols, const QuotientEntry* d_entries,
-                                 const QuotientParams& qp, const Twiddles* tw, int log, cudaStream_t stream) {
+                                 const QuotientParams& qp, const Twiddles* tw, int log, cudaStream_t stream, uint32_t row0,
+                                 uint32_t n_rows) {
     if (qp.n_batches < 1 || qp.n_batches > MAX_QUOTIENT_BATCHES) return cudaErrorInvalidValue;
     if (log < 2 || log > tw->max_log) return cudaErrorInvalidValue;
-    uint32_t n = 1u << log;
+    uint32_t n = n_rows ? n_rows : (1u << log);
+    if ((uint64_t)row0 + n > ((uint64_t)1 << log) || (row0 & 1) || (n & 1)) return cudaErrorInvalidValue;
     const uint2* tw_x = tw->fwd + ((size_t)1 << (log - 2));              // X[log-1]
     const uint2* tw_y = tw->fwd + tw->y_off + ((size_t)1 << (log - 1));  // Y[log-1]
     unsigned blocks = (n + 256 * QROWS - 1) / (256 * QROWS);
 #define LB_Q_LAUNCH(NB) \
-    quotients_kernel<NB><<<blocks, 256, 0, stream>>>(out[0], out[1], out[2], out[3], d_cols, d_entries, qp, tw_x, tw_y, n)
+    quotients_kernel<NB><<<blocks, 256, 0, stream>>>(out[0], out[1], out[2], out[3], d_cols, d_entries, qp, tw_x, tw_y, n, row0)
     switch (qp.n_batches) {
         case 1: LB_Q_LAUNCH(1); break;
         case 2: LB_Q_LAUNCH(2); break;
@@ -732,7 +737,7 @@ cudaError_t batch_inverse_qm31(uint32_t* const out[4], const uint32_t* const in[
 
 __global__ void gather_words_kernel(uint32_t* out, const uint32_t* const* addrs, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = *addrs[i];
+    if (i < n) out[i] = addrs[i] ? *addrs[i] : 0u;  // a null address = a word another rank owns (sharded prover)
 }
 cudaError_t gather_words(uint32_t* d_out, const uint32_t* const* d_addrs, int n, cudaStream_t stream) {
     if (!n) return cudaSuccess;

@@ -16,6 +16,7 @@
 #include <string>
 #include <vector>
 
+#include "comm.h"
 #include "ctx.h"
 #include "host_util.h"
 #include "kernels.cuh"
@@ -233,22 +234,55 @@ struct MerkleTree {
     std::vector<uint32_t*> layers;  // layers[k]: 2^k digests (8 u32 each), device
     std::vector<ColRef> sorted;     // stable sort by size, descending
     Hash32 root;
+    // Row-sharded tree (sharded prover): this rank holds the sub-tree over its row range - `layers` / `sorted` / `max_log`
+    // describe that local sub-tree, whose root is node `rank` of level `logw` of the whole tree; the levels above it
+    // (top[k], k <= logw, 2^k digests) are hashed on the host from the all-gathered sub-tree roots.  logw = 0: whole tree.
+    int logw = 0, rank = 0;
+    std::vector<std::vector<Hash32>> top;
+    int global_max_log() const { return max_log + logw; }
 };
 
 // collects device word addresses; one gather kernel + one D2H serves the whole decommitment
 struct Gatherer {
-    std::vector<const uint32_t*> addrs;
+    std::vector<const uint32_t*> addrs;  // null: a word held by another rank (its value arrives through the all-reduce)
     std::vector<uint32_t> values;
+    std::vector<std::pair<size_t, uint32_t>> consts;  // words known on the host (upper levels of a sharded tree)
     size_t add(const uint32_t* a) {
         addrs.push_back(a);
+        return addrs.size() - 1;
+    }
+    size_t add_const(uint32_t v) {
+        consts.push_back({addrs.size(), v});
+        addrs.push_back(nullptr);
         return addrs.size() - 1;
     }
 };
 
 inline size_t add_hash(Gatherer& g, const uint32_t* h) {
     size_t first = g.add(h);
-    for (int i = 1; i < 8; ++i) g.add(h + i);
+    for (int i = 1; i < 8; ++i) g.add(h ? h + i : nullptr);
     return first;
+}
+// word `row` (global) of a column held as row shards of 2^local_log rows per rank (logw = 0: replicated, rank 0 reports it)
+inline size_t add_col_word(Gatherer& g, const uint32_t* local, int local_log, int logw, int rank, uint32_t row) {
+    if (logw == 0) return g.add(rank == 0 ? local + row : nullptr);
+    uint32_t owner = row >> local_log;
+    return g.add((int)owner == rank ? local + (row & ((1u << local_log) - 1)) : nullptr);
+}
+// digest `idx` of global level `level` of a (possibly row-sharded) tree
+inline size_t add_tree_hash(Gatherer& g, const MerkleTree& t, int level, uint32_t idx, int rank) {
+    if (level < t.logw) {
+        const Hash32& h = t.top[level][idx];
+        uint32_t w[8];
+        std::memcpy(w, h.b, 32);
+        size_t first = g.add_const(w[0]);
+        for (int i = 1; i < 8; ++i) g.add_const(w[i]);
+        return first;
+    }
+    int local_level = level - t.logw;
+    if (t.logw == 0) return add_hash(g, rank == 0 ? t.layers[local_level] + (size_t)idx * 8 : nullptr);
+    uint32_t owner = idx >> local_level;
+    return add_hash(g, (int)owner == t.rank ? t.layers[local_level] + (size_t)(idx & ((1u << local_level) - 1)) * 8 : nullptr);
 }
 
 struct DecommitIdx {
@@ -332,10 +366,11 @@ void merkle_commit(lb_ctx* ctx, Arena& arena, const std::vector<ColRef>& cols, M
 
 // MerkleProver::decommit: emits, in proof order, what must be gathered
 void merkle_decommit_plan(const MerkleTree& t, const std::map<int, std::vector<uint32_t>>& queries_per_log, Gatherer& g,
-                          DecommitIdx& out) {
+                          DecommitIdx& out, int rank = 0) {
     std::vector<uint32_t> last;
-    for (int log = t.max_log; log >= 0; --log) {
-        const uint32_t* prev_hashes = (!t.empty && log + 1 <= t.max_log) ? t.layers[log + 1] : nullptr;
+    const int gmax = t.empty ? 0 : t.global_max_log();
+    for (int log = gmax; log >= 0; --log) {
+        const bool prev_hashes = !t.empty && log + 1 <= gmax;
         std::vector<uint32_t> col_q;
         auto it = queries_per_log.find(log);
         if (it != queries_per_log.end()) col_q = it->second;
@@ -350,17 +385,17 @@ void merkle_decommit_plan(const MerkleTree& t, const std::map<int, std::vector<u
                 if (pi < prev_q.size() && prev_q[pi] == 2 * node)
                     ++pi;
                 else
-                    out.hash_witness.push_back(add_hash(g, prev_hashes + (size_t)(2 * node) * 8));
+                    out.hash_witness.push_back(add_tree_hash(g, t, log + 1, 2 * node, rank));
                 if (pi < prev_q.size() && prev_q[pi] == 2 * node + 1)
                     ++pi;
                 else
-                    out.hash_witness.push_back(add_hash(g, prev_hashes + (size_t)(2 * node + 1) * 8));
+                    out.hash_witness.push_back(add_tree_hash(g, t, log + 1, 2 * node + 1, rank));
             }
             bool queried = ci < col_q.size() && col_q[ci] == node;
             if (queried) ++ci;
             for (const ColRef& c : t.sorted) {
-                if (c.log != log) continue;
-                size_t idx = g.add(c.ptr + node);
+                if (c.log + t.logw != log) continue;
+                size_t idx = add_col_word(g, c.ptr, c.log, t.logw, rank, node);
                 (queried ? out.queried_values : out.column_witness).push_back(idx);
             }
             total.push_back(node);
@@ -438,7 +473,8 @@ std::vector<uint32_t> fold_queries(const std::vector<uint32_t>& pos, int n_folds
 
 // compute_decommitment_positions_and_witness_evals with fold_step = 1
 void fri_positions_and_witness(uint32_t* const coords[4], const std::vector<uint32_t>& queries, Gatherer& g,
-                               std::vector<uint32_t>& positions, std::vector<size_t>& witness) {
+                               std::vector<uint32_t>& positions, std::vector<size_t>& witness, int local_log = 0, int logw = 0,
+                               int rank = 0) {
     size_t i = 0;
     while (i < queries.size()) {
         size_t j = i;
@@ -451,8 +487,8 @@ void fri_positions_and_witness(uint32_t* const coords[4], const std::vector<uint
                 ++k;
                 continue;
             }
-            size_t first = g.add(coords[0] + pos);
-            for (int c = 1; c < 4; ++c) g.add(coords[c] + pos);
+            size_t first = add_col_word(g, coords[0], local_log, logw, rank, pos);
+            for (int c = 1; c < 4; ++c) add_col_word(g, coords[c], local_log, logw, rank, pos);
             witness.push_back(first);
         }
         i = j;
@@ -555,7 +591,8 @@ void launch_eval_at_point(lb_ctx* ctx, Arena& arena, const std::vector<const uin
 // QuotientOps::accumulate_quotients: quotient_constants (core/pcs/quotients.rs) on the host,
 // the row loop on the device
 void launch_quotients(lb_ctx* ctx, Arena& arena, int lg, const std::vector<const uint32_t*>& colptrs,
-                      std::vector<HostBatch>& batches, QM31 rc_q, uint32_t* const out[4]) {
+                      std::vector<HostBatch>& batches, QM31 rc_q, uint32_t* const out[4], uint32_t row0 = 0,
+                      uint32_t n_rows = 0) {
     std::sort(batches.begin(), batches.end(), [](const HostBatch& a, const HostBatch& b) { return qpt_less(a.pt, b.pt); });
     if (batches.empty() || batches.size() > (size_t)MAX_QUOTIENT_BATCHES) fail(LB_ERR_BAD_ARG, "quotients: bad number of sample batches");
     QuotientParams qp{};
@@ -594,21 +631,117 @@ void launch_quotients(lb_ctx* ctx, Arena& arena, int lg, const std::vector<const
         int r = lb_twiddles_ensure(ctx, lg);  // domain points are read from the twiddle tables
         if (r) fail(r, ctx->err);
     }
-    ck(accumulate_quotients(out, d_cols, d_entries, qp, &ctx->tw, lg, ctx->stream), "accumulate quotients");
+    ck(accumulate_quotients(out, d_cols, d_entries, qp, &ctx->tw, lg, ctx->stream, row0, n_rows), "accumulate quotients");
 }
 
 // ------------------------------------------------------------------------------------
 // commitment scheme state
 // ------------------------------------------------------------------------------------
 struct PolyCol {
-    uint32_t* coeffs;  // 2^log
-    uint32_t* lde;     // 2^(log + blowup), filled by commit
+    uint32_t* coeffs;  // 2^log (sharded prover: valid on the owner rank only)
+    uint32_t* lde;     // 2^(log + blowup), filled by commit (sharded prover: this rank's row shard, 2^(log + blowup - logw))
     int log;
+    int owner = 0;     // rank that interpolates / extends / samples this column
+};
+// columns pushed together (same size, contiguous coefficients): the unit of the batched transforms and of the ownership split
+struct ColRun {
+    size_t first;
+    int n, log;
 };
 struct CommitTree {
     std::vector<PolyCol> cols;
+    std::vector<ColRun> runs;
     MerkleTree merkle;
 };
+
+// ---- sharded prover plumbing (one rank per GPU; world = 1: everything below degenerates to the single-GPU path) -------
+struct Shard {
+    lb_comm* comm = nullptr;
+    int rank = 0, world = 1, logw = 0;
+    int next_start = 0;  // rotating first rank of the ownership split, so that remainders spread over the ranks
+    bool on() const { return world > 1; }
+};
+inline void nck(ncclResult_t r, const char* what) {
+    if (r != ncclSuccess) fail(LB_ERR_NCCL, std::string(what) + ": " + nccl_api().GetErrorString(r));
+}
+// contiguous, balanced split of a run of n columns over the ranks: out[k] = owner of column k
+std::vector<int> split_run(Shard& sh, int n) {
+    std::vector<int> owner(n, 0);
+    if (!sh.on()) return owner;
+    int base = n / sh.world, extra = n % sh.world, k = 0;
+    for (int i = 0; i < sh.world; ++i) {
+        int r = (sh.next_start + i) % sh.world;
+        int cnt = base + (i < extra ? 1 : 0);
+        for (int c = 0; c < cnt; ++c) owner[k++] = r;
+    }
+    sh.next_start = (sh.next_start + extra) % sh.world;
+    return owner;
+}
+// [a, b) = this rank's columns of a run (they are contiguous by construction)
+inline void own_range(const CommitTree& t, const ColRun& run, int rank, int& a, int& b) {
+    a = b = 0;
+    bool found = false;
+    for (int k = 0; k < run.n; ++k)
+        if (t.cols[run.first + k].owner == rank) {
+            if (!found) a = k;
+            b = k + 1;
+            found = true;
+        }
+}
+struct Xfer {
+    const uint32_t* src;
+    uint32_t* dst;
+    size_t n;
+    int peer;
+    bool send;
+};
+// one grouped exchange; a transfer whose peer is this rank is a device copy.  Both sides of a pair list their transfers in
+// the same (column) order, which is the order NCCL matches sends with receives.
+void run_exchange(lb_ctx* ctx, Shard& sh, const std::vector<Xfer>& xs) {
+    NcclApi& api = nccl_api();
+    nck(api.GroupStart(), "ncclGroupStart");
+    for (const Xfer& x : xs) {
+        if (x.peer == sh.rank) {
+            if (x.send) ck(cudaMemcpyAsync(x.dst, x.src, x.n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream), "self copy");
+            continue;
+        }
+        if (x.send) {
+            nck(api.Send(x.src, x.n, ncclUint32, x.peer, sh.comm->comm, ctx->stream), "ncclSend");
+            sh.comm->bytes_sent += x.n * 4;
+        } else {
+            nck(api.Recv(x.dst, x.n, ncclUint32, x.peer, sh.comm->comm, ctx->stream), "ncclRecv");
+            sh.comm->bytes_received += x.n * 4;
+        }
+    }
+    nck(api.GroupEnd(), "ncclGroupEnd");
+    sh.comm->n_collectives++;
+}
+// root of a row-sharded tree: all-gather the sub-tree roots, hash the log2(world) levels above them on the host
+void finish_sharded_root(lb_ctx* ctx, Arena& arena, Shard& sh, MerkleTree& t) {
+    t.logw = sh.logw;
+    t.rank = sh.rank;
+    NcclApi& api = nccl_api();
+    uint32_t* d_roots = arena.alloc<uint32_t>(8 * (size_t)sh.world);
+    nck(api.AllGather(t.layers[0], d_roots, 8, ncclUint32, sh.comm->comm, ctx->stream), "ncclAllGather(roots)");
+    sh.comm->n_collectives++;
+    sh.comm->bytes_sent += 32;
+    sh.comm->bytes_received += 32 * (size_t)(sh.world - 1);
+    std::vector<Hash32> lvl(sh.world);
+    ck(cudaMemcpyAsync(lvl.data(), d_roots, 32 * (size_t)sh.world, cudaMemcpyDeviceToHost, ctx->stream), "roots d2h");
+    ck(cudaStreamSynchronize(ctx->stream), "roots sync");
+    t.top.assign(sh.logw + 1, {});
+    t.top[sh.logw] = lvl;
+    for (int k = sh.logw - 1; k >= 0; --k) {
+        t.top[k].resize((size_t)1 << k);
+        for (size_t i = 0; i < t.top[k].size(); ++i) {
+            uint8_t buf[64];
+            std::memcpy(buf, t.top[k + 1][2 * i].b, 32);
+            std::memcpy(buf + 32, t.top[k + 1][2 * i + 1].b, 32);
+            t.top[k][i] = blake2s_hash(buf, 64);
+        }
+    }
+    t.root = t.top[0][0];
+}
 
 struct Component {
     int kind, slot, log;
@@ -617,6 +750,7 @@ struct Component {
     QM31 claimed_sum;
     int pre_idx[2] = {-1, -1};   // preprocessed columns read by a lookup-table component (index into tree 0)
     int eval_log = 0;            // max_constraint_log_degree_bound
+    uint32_t* inter_prev = nullptr;  // sharded prover: row shard of the [-1]-shifted last LogUp column (4 coordinate columns)
 };
 
 // one preprocessed column as committed in tree 0
@@ -656,8 +790,18 @@ struct StageTimer {
 
 // ======================================================================================
 int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_preprocessed_column* pre_in, int n_pre,
-               const lb_prove_config* cfg_in, std::vector<uint8_t>& out) {
+               const lb_prove_config* cfg_in, std::vector<uint8_t>& out, lb_comm* comm) {
     try {
+        Shard sh;
+        if (comm && comm->world > 1) {
+            if (comm->ctx != ctx) fail(LB_ERR_BAD_ARG, "prove: the communicator belongs to another context");
+            sh.comm = comm;
+            sh.rank = comm->rank;
+            sh.world = comm->world;
+            sh.logw = comm->log_world;
+            comm->bytes_sent = comm->bytes_received = 0;
+            comm->n_collectives = 0;
+        }
         lb_prove_config cfg;
         if (cfg_in)
             cfg = *cfg_in;
@@ -717,30 +861,92 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
         }
         const Twiddles& tw = ctx->tw;
 
-        auto commit_tree = [&](CommitTree& tree) {
-            // evaluate every polynomial on CanonicCoset(log + blowup), Merkle-commit, mix the root
-            std::vector<ColRef> refs;
-            size_t i = 0;
-            while (i < tree.cols.size()) {
-                // consecutive columns allocated as one batch share stride: detect runs
-                size_t j = i;
-                int lg = tree.cols[i].log;
-                size_t stride = (size_t)1 << lg;
-                while (j + 1 < tree.cols.size() && tree.cols[j + 1].log == lg &&
-                       tree.cols[j + 1].coeffs == tree.cols[j].coeffs + stride)
-                    ++j;
-                int n = (int)(j - i + 1);
-                size_t out_stride = (size_t)1 << (lg + blowup);
-                uint32_t* lde = arena.alloc<uint32_t>(out_stride * n);
-                ck(cfft_evaluate(&tw, tree.cols[i].coeffs, stride, lg, lde, out_stride, lg + blowup, n, ctx->sm_count, st),
-                   "LDE evaluate");
-                for (int k = 0; k < n; ++k) {
-                    tree.cols[i + k].lde = lde + (size_t)k * out_stride;
-                    refs.push_back({tree.cols[i + k].lde, lg + blowup});
-                }
-                i = j + 1;
+        if (sh.on()) {
+            if (!nccl_api().load()) fail(LB_ERR_NCCL, nccl_api().error);
+            if (blowup + 4 - sh.logw < 4) fail(LB_ERR_BAD_ARG, "prove: too many ranks for the smallest column");
+        }
+        struct AuxReq {  // a non-committed column shipped with a tree's exchange: the [-1]-shifted copy of column `col`
+            size_t col;
+            int domain_log;
+            uint32_t* dst;  // this rank's row shard of it
+        };
+        auto push_run = [&](CommitTree& tree, uint32_t* coeffs, int n, int lg) {
+            // n columns of 2^lg coefficients, contiguous; returns this rank's sub-range [a, b) of them
+            std::vector<int> owner = split_run(sh, n);
+            ColRun run{tree.cols.size(), n, lg};
+            for (int k = 0; k < n; ++k) {
+                PolyCol pc{coeffs ? coeffs + ((size_t)k << lg) : nullptr, nullptr, lg};
+                pc.owner = owner[k];
+                tree.cols.push_back(pc);
             }
-            merkle_commit(ctx, arena, refs, tree.merkle);
+            tree.runs.push_back(run);
+            return run;
+        };
+        auto commit_tree = [&](CommitTree& tree, const std::vector<AuxReq>* aux = nullptr) {
+            // evaluate every polynomial on CanonicCoset(log + blowup), Merkle-commit, mix the root.  Sharded: every rank
+            // extends the columns it owns, one grouped exchange turns the column shards into row shards (rank r gets rows
+            // [r R/W, (r+1) R/W) of EVERY column), each rank hashes the sub-tree over its rows, the roots are all-gathered.
+            std::vector<ColRef> refs;
+            std::vector<Xfer> xs;
+            std::vector<uint32_t*> to_free;
+            for (const ColRun& run : tree.runs) {
+                const int lg = run.log, L = lg + blowup;
+                const size_t stride = (size_t)1 << lg, out_stride = (size_t)1 << L;
+                if (!sh.on()) {
+                    uint32_t* lde = arena.alloc<uint32_t>(out_stride * run.n);
+                    ck(cfft_evaluate(&tw, tree.cols[run.first].coeffs, stride, lg, lde, out_stride, L, run.n, ctx->sm_count, st),
+                       "LDE evaluate");
+                    for (int k = 0; k < run.n; ++k) {
+                        tree.cols[run.first + k].lde = lde + (size_t)k * out_stride;
+                        refs.push_back({tree.cols[run.first + k].lde, L});
+                    }
+                    continue;
+                }
+                int a, b;
+                own_range(tree, run, sh.rank, a, b);
+                const size_t rl = out_stride >> sh.logw;
+                uint32_t* own = nullptr;
+                if (b > a) {
+                    own = arena.alloc<uint32_t>(out_stride * (b - a));
+                    to_free.push_back(own);
+                    ck(cfft_evaluate(&tw, tree.cols[run.first + a].coeffs, stride, lg, own, out_stride, L, b - a, ctx->sm_count, st),
+                       "LDE evaluate (own columns)");
+                }
+                uint32_t* local = arena.alloc<uint32_t>(rl * run.n);
+                for (int k = 0; k < run.n; ++k) {
+                    PolyCol& pc = tree.cols[run.first + k];
+                    uint32_t* mine = local + (size_t)k * rl;
+                    if (pc.owner == sh.rank) {
+                        const uint32_t* full = own + (size_t)(k - a) * out_stride;
+                        for (int r = 0; r < sh.world; ++r) xs.push_back({full + (size_t)r * rl, r == sh.rank ? mine : nullptr, rl, r, true});
+                    } else {
+                        xs.push_back({nullptr, mine, rl, pc.owner, false});
+                    }
+                    pc.lde = mine;
+                    refs.push_back({mine, L - sh.logw});
+                }
+                if (aux)
+                    for (const AuxReq& rq : *aux) {
+                        if (rq.col < run.first || rq.col >= run.first + (size_t)run.n) continue;
+                        int k = (int)(rq.col - run.first);
+                        const PolyCol& pc = tree.cols[rq.col];
+                        if (pc.owner == sh.rank) {
+                            uint32_t* shifted = arena.alloc<uint32_t>(out_stride);
+                            to_free.push_back(shifted);
+                            ck(shifted_prev_column(shifted, own + (size_t)(k - a) * out_stride, rq.domain_log, L, st), "shifted column");
+                            for (int r = 0; r < sh.world; ++r)
+                                xs.push_back({shifted + (size_t)r * rl, r == sh.rank ? rq.dst : nullptr, rl, r, true});
+                        } else {
+                            xs.push_back({nullptr, rq.dst, rl, pc.owner, false});
+                        }
+                    }
+            }
+            if (sh.on()) {
+                if (!xs.empty()) run_exchange(ctx, sh, xs);
+                for (uint32_t* f : to_free) arena.release(f);  // stream-ordered: freed after the sends have read them
+            }
+            merkle_commit(ctx, arena, refs, tree.merkle, /*fetch_root=*/!sh.on());
+            if (sh.on() && !tree.merkle.empty) finish_sharded_root(ctx, arena, sh, tree.merkle);
             channel.mix_root(tree.merkle.root);
         };
 
@@ -761,9 +967,11 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                 ck(cudaMemcpyAsync(evals, pc.values, n * sizeof(uint32_t), pc.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st),
                    "LUT upload");
                 uint32_t* coeffs = arena.alloc<uint32_t>(n);
-                ck(cudaMemcpyAsync(coeffs, evals, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st), "copy");
-                ck(cfft_interpolate(&tw, coeffs, n, 1, pc.log_size, ctx->sm_count, st), "interpolate LUT");
-                trees[0].cols.push_back({coeffs, nullptr, pc.log_size});
+                ColRun run = push_run(trees[0], coeffs, 1, pc.log_size);
+                if (trees[0].cols[run.first].owner == sh.rank) {
+                    ck(cudaMemcpyAsync(coeffs, evals, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st), "copy");
+                    ck(cfft_interpolate(&tw, coeffs, n, 1, pc.log_size, ctx->sm_count, st), "interpolate LUT");
+                }
                 pre_cols.push_back({pc.lut, pc.col_index, pc.log_size, evals});
                 if (lut_log[pc.lut] >= 0 && lut_log[pc.lut] != pc.log_size) fail(LB_ERR_BAD_ARG, "prove: LUT columns of one table differ in size");
                 lut_log[pc.lut] = pc.log_size;
@@ -780,8 +988,8 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             if (tb.slot < 0 || tb.slot >= cfg.n_slots) fail(LB_ERR_BAD_ARG, "prove: slot out of range");
             int kind = kind_of_slot(tb.slot, cfg.n_slots, cfg.air_era);
             if (kind < 0) fail(LB_ERR_BAD_ARG, "prove: component not supported by this backend yet");
-            ComponentShape sh = component_shape(kind);
-            if (tb.n_cols != sh.n_main) fail(LB_ERR_BAD_ARG, "prove: wrong column count for component");
+            ComponentShape shp = component_shape(kind);
+            if (tb.n_cols != shp.n_main) fail(LB_ERR_BAD_ARG, "prove: wrong column count for component");
             if (claim[tb.slot] >= 0) fail(LB_ERR_BAD_ARG, "prove: duplicate table for slot");
             // LuminairGraph::gen_trace emits tables in claim-slot order (graph.rs:502-593); the column spans the
             // components read (TraceLocationAllocator) only line up with the committed order in that case
@@ -800,11 +1008,21 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                    "trace upload");
                 d_rows = staged;
             }
-            uint32_t* evals = arena.alloc<uint32_t>(n * sh.n_main);
-            ck(transpose_pad(evals, n, d_rows, tb.n_rows, sh.n_main, lg, kind, st), "transpose");
-            uint32_t* coeffs = arena.alloc<uint32_t>(n * sh.n_main);
-            ck(cudaMemcpyAsync(coeffs, evals, n * sh.n_main * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st), "copy");
-            ck(cfft_interpolate(&tw, coeffs, n, sh.n_main, lg, ctx->sm_count, st), "interpolate");
+            uint32_t* evals = arena.alloc<uint32_t>(n * shp.n_main);
+            ck(transpose_pad(evals, n, d_rows, tb.n_rows, shp.n_main, lg, kind, st), "transpose");
+            uint32_t* coeffs = arena.alloc<uint32_t>(n * shp.n_main);
+            size_t main_first = trees[1].cols.size();
+            {
+                // every rank has the whole table (the trace is replicated input); it interpolates the columns it owns
+                ColRun run = push_run(trees[1], coeffs, shp.n_main, lg);
+                int a, b;
+                own_range(trees[1], run, sh.rank, a, b);
+                if (b > a) {
+                    ck(cudaMemcpyAsync(coeffs + (size_t)a * n, evals + (size_t)a * n, n * (size_t)(b - a) * sizeof(uint32_t),
+                                       cudaMemcpyDeviceToDevice, st), "copy");
+                    ck(cfft_interpolate(&tw, coeffs + (size_t)a * n, n, b - a, lg, ctx->sm_count, st), "interpolate");
+                }
+            }
             if (staged) {
                 ck(cudaStreamSynchronize(st), "upload sync");  // host rows may be pageable
                 arena.release(staged);
@@ -814,19 +1032,18 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             c.slot = tb.slot;
             c.log = lg;
             c.main_evals = evals;
-            if (sh.lut) {
-                if (lut_log[sh.lut] < 0) fail(LB_ERR_BAD_ARG, "prove: component needs a lookup table that was not supplied");
-                for (int q = 0; q < sh.n_pre; ++q) {
+            if (shp.lut) {
+                if (lut_log[shp.lut] < 0) fail(LB_ERR_BAD_ARG, "prove: component needs a lookup table that was not supplied");
+                for (int q = 0; q < shp.n_pre; ++q) {
                     for (size_t i = 0; i < pre_cols.size(); ++i)
-                        if (pre_cols[i].lut == sh.lut && pre_cols[i].col_index == q) c.pre_idx[q] = (int)i;
+                        if (pre_cols[i].lut == shp.lut && pre_cols[i].col_index == q) c.pre_idx[q] = (int)i;
                     if (c.pre_idx[q] < 0) fail(LB_ERR_BAD_ARG, "prove: missing LUT column");
                     if (pre_cols[c.pre_idx[q]].log != lg) fail(LB_ERR_BAD_ARG, "prove: lookup-table component and LUT column differ in size");
                 }
             }
             // max_constraint_log_degree_bound (add/component.rs:33-35; LUT consumers exp2/component.rs:41-43)
-            c.eval_log = (consumes_lut(kind) ? std::max(lg, lut_log[sh.lut]) : lg) + 1;
-            c.main_loc = trees[1].cols.size();  // location by pie order; components use slot order (see below)
-            for (int k = 0; k < sh.n_main; ++k) trees[1].cols.push_back({coeffs + (size_t)k * n, nullptr, lg});
+            c.eval_log = (consumes_lut(kind) ? std::max(lg, lut_log[shp.lut]) : lg) + 1;
+            c.main_loc = main_first;  // location by pie order; components use slot order (see below)
             claim[tb.slot] = lg;
             by_slot[tb.slot] = c;
         }
@@ -850,40 +1067,57 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
         if (!cfg.draw_lookup_elements && n_pre) fail(LB_ERR_BAD_ARG, "prove: LUT columns need draw_lookup_elements");
 
         std::vector<Component> comps;  // slot order = LuminairComponents order
+        std::vector<AuxReq> inter_aux;
         {
             // TraceLocationAllocator hands out spans in component (slot) order
             size_t main_next = 0;
             for (int s = 0; s < cfg.n_slots; ++s) {
                 if (claim[s] < 0) continue;
                 Component c = by_slot[s];
-                ComponentShape sh = component_shape(c.kind);
+                ComponentShape shp = component_shape(c.kind);
                 size_t n = (size_t)1 << c.log;
-                int n_ic = 4 * sh.n_fracs;
+                int n_ic = 4 * shp.n_fracs;
                 uint32_t* inter = arena.alloc<uint32_t>(n * n_ic);
                 uint32_t* scan_tmp = arena.alloc<uint32_t>(4 * n);
                 uint32_t* block_sums = arena.alloc<uint32_t>(4 * (n / 1024 + 1));
                 uint32_t* d_claimed = arena.alloc<uint32_t>(4);
                 PreCols pc{};
-                for (int q = 0; q < sh.n_pre; ++q) pc.p[q] = pre_cols[c.pre_idx[q]].evals;
+                for (int q = 0; q < shp.n_pre; ++q) pc.p[q] = pre_cols[c.pre_idx[q]].evals;
                 ck(logup_interaction_trace(c.kind, c.main_evals, n, pc, inter, n, c.log, rels, scan_tmp, block_sums, d_claimed, st),
                    "logup");
                 uint32_t cl[4];
                 ck(cudaMemcpyAsync(cl, d_claimed, 16, cudaMemcpyDeviceToHost, st), "claimed d2h");
-                ck(cfft_interpolate(&tw, inter, n, n_ic, c.log, ctx->sm_count, st), "interpolate interaction");
+                // sharded: the LogUp columns are computed on every rank (replicated input, no exchange); each rank interpolates
+                // the ones it owns
+                c.inter_loc = trees[2].cols.size();
+                {
+                    ColRun run = push_run(trees[2], inter, n_ic, c.log);
+                    int a, b;
+                    own_range(trees[2], run, sh.rank, a, b);
+                    if (b > a) ck(cfft_interpolate(&tw, inter + (size_t)a * n, n, b - a, c.log, ctx->sm_count, st), "interpolate interaction");
+                }
+                if (sh.on()) {
+                    // the [-1] mask of the last LogUp column reads a predecessor row that lives in another rank's row shard:
+                    // the column's owner ships a shifted copy with the exchange of this tree
+                    if (c.eval_log != c.log + blowup)
+                        fail(LB_ERR_BAD_ARG, "prove (sharded): a component evaluated on a domain other than its committed one "
+                                             "(lookup table larger than its consumer's trace) is not supported yet");
+                    size_t rl = ((size_t)1 << (c.log + blowup)) >> sh.logw;
+                    c.inter_prev = arena.alloc<uint32_t>(4 * rl);
+                    for (int k = 0; k < 4; ++k) inter_aux.push_back({c.inter_loc + (size_t)(n_ic - 4 + k), c.log, c.inter_prev + (size_t)k * rl});
+                }
                 ck(cudaStreamSynchronize(st), "claimed sync");
                 c.claimed_sum = q_make(cl[0], cl[1], cl[2], cl[3]);
                 arena.release(scan_tmp);
                 arena.release(c.main_evals);
                 c.main_evals = nullptr;
-                c.inter_loc = trees[2].cols.size();
-                for (int k = 0; k < n_ic; ++k) trees[2].cols.push_back({inter + (size_t)k * n, nullptr, c.log});
                 c.main_loc = main_next;  // span in slot order (equals the pie-order location when the pie is slot-ordered)
-                main_next += sh.n_main;
+                main_next += shp.n_main;
                 comps.push_back(c);
             }
         }
         for (const Component& c : comps) channel.mix_felts({c.claimed_sum});  // LuminairInteractionClaim::mix_into
-        commit_tree(trees[2]);
+        commit_tree(trees[2], sh.on() ? &inter_aux : nullptr);
         timer.lap();  // stage 1: LogUp + interpolate + LDE + Merkle of the interaction trace
 
         // ---- stwo::prover::prove -------------------------------------------------------------
@@ -894,9 +1128,9 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
         for (const Component& c : comps) {
             InfoEval info;
             eval_component(c.kind, info, rels);
-            ComponentShape sh = component_shape(c.kind);
-            if (info.n_main != sh.n_main || info.n_inter != 4 * sh.n_fracs || info.n_constraints != sh.n_constraints ||
-                info.n_pre != sh.n_pre || sh.n_constraints > MAX_CONSTRAINTS || sh.n_main > MAX_MAIN_COLS)
+            ComponentShape shp = component_shape(c.kind);
+            if (info.n_main != shp.n_main || info.n_inter != 4 * shp.n_fracs || info.n_constraints != shp.n_constraints ||
+                info.n_pre != shp.n_pre || shp.n_constraints > MAX_CONSTRAINTS || shp.n_main > MAX_MAIN_COLS)
                 fail(LB_ERR_BAD_ARG, "internal: component shape table out of date");
             n_constraints.push_back(info.n_constraints);
             total_constraints += info.n_constraints;
@@ -917,7 +1151,7 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                 const Component& c = comps[ci];
                 int nc = n_constraints[ci];
                 int eval_log = c.eval_log;
-                ComponentShape sh = component_shape(c.kind);
+                ComponentShape shp = component_shape(c.kind);
                 ConstraintParams p{};
                 size_t ne = (size_t)1 << eval_log;
                 // constraint-framework `need_to_extend`: columns not committed on the evaluation domain are
@@ -925,6 +1159,7 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                 std::vector<uint32_t*> scratch;
                 auto on_eval_domain = [&](CommitTree& tree, size_t first, int n_cols) -> const uint32_t* {
                     if (tree.cols[first].log + blowup == eval_log) return tree.cols[first].lde;
+                    if (sh.on()) fail(LB_ERR_BAD_ARG, "prove (sharded): evaluation-domain extension is not supported yet");
                     uint32_t* ext = arena.alloc<uint32_t>(ne * n_cols);
                     scratch.push_back(ext);
                     int lg = tree.cols[first].log;
@@ -932,14 +1167,20 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                        "extend to evaluation domain");
                     return ext;
                 };
-                p.main = on_eval_domain(trees[1], c.main_loc, sh.n_main);
-                p.main_stride = ne;
-                p.inter = on_eval_domain(trees[2], c.inter_loc, 4 * sh.n_fracs);
-                p.inter_stride = ne;
-                for (int q = 0; q < sh.n_pre; ++q) p.pre.p[q] = on_eval_domain(trees[0], (size_t)c.pre_idx[q], 1);
+                const size_t ne_local = ne >> sh.logw;  // rows of the evaluation domain this rank holds
+                p.main = on_eval_domain(trees[1], c.main_loc, shp.n_main);
+                p.main_stride = ne_local;
+                p.inter = on_eval_domain(trees[2], c.inter_loc, 4 * shp.n_fracs);
+                p.inter_stride = ne_local;
+                for (int q = 0; q < shp.n_pre; ++q) p.pre.p[q] = on_eval_domain(trees[0], (size_t)c.pre_idx[q], 1);
+                if (sh.on()) {
+                    p.row0 = (uint32_t)(ne_local * sh.rank);
+                    p.n_rows = (uint32_t)ne_local;
+                    p.inter_prev = c.inter_prev;
+                }
                 bool fresh = acc.find(eval_log) == acc.end();
-                if (fresh) acc[eval_log] = arena.alloc<uint32_t>((size_t)4 << eval_log);
-                for (int k = 0; k < 4; ++k) p.acc[k] = acc[eval_log] + ((size_t)k << eval_log);
+                if (fresh) acc[eval_log] = arena.alloc<uint32_t>(4 * ne_local);
+                for (int k = 0; k < 4; ++k) p.acc[k] = acc[eval_log] + (size_t)k * ne_local;
                 p.accumulate = fresh ? 0 : 1;
                 p.log_size = c.log;
                 p.eval_log = eval_log;
@@ -967,21 +1208,76 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
         // finalize: lift smaller accumulators into larger ones, interpolate -> composition coefficients
         uint32_t* comp_coeffs = nullptr;
         int comp_log = 0;
-        for (auto& kv : acc) {  // ascending eval_log
-            int lg = kv.first;
-            uint32_t* vals = kv.second;
-            size_t n = (size_t)1 << lg;
-            if (comp_coeffs) {
-                uint32_t* lifted = arena.alloc<uint32_t>(4 * n);
-                ck(cfft_evaluate(&tw, comp_coeffs, (size_t)1 << comp_log, comp_log, lifted, n, lg, 4, ctx->sm_count, st),
-                   "lift composition");
-                ck(add_inplace(vals, lifted, 4 * n, st), "accumulate");
+        if (!sh.on()) {
+            for (auto& kv : acc) {  // ascending eval_log
+                int lg = kv.first;
+                uint32_t* vals = kv.second;
+                size_t n = (size_t)1 << lg;
+                if (comp_coeffs) {
+                    uint32_t* lifted = arena.alloc<uint32_t>(4 * n);
+                    ck(cfft_evaluate(&tw, comp_coeffs, (size_t)1 << comp_log, comp_log, lifted, n, lg, 4, ctx->sm_count, st),
+                       "lift composition");
+                    ck(add_inplace(vals, lifted, 4 * n, st), "accumulate");
+                }
+                ck(cfft_interpolate(&tw, vals, n, 4, lg, ctx->sm_count, st), "interpolate composition");
+                comp_coeffs = vals;
+                comp_log = lg;
             }
-            ck(cfft_interpolate(&tw, vals, n, 4, lg, ctx->sm_count, st), "interpolate composition");
-            comp_coeffs = vals;
-            comp_log = lg;
+            push_run(trees[3], comp_coeffs, 4, comp_log);
+        } else {
+            // the accumulators are row-sharded; interpolation is column-wise: coordinate column k of every size class goes
+            // to the rank that owns composition column k (a rows -> columns exchange of 16 B per row), which lifts, adds and
+            // interpolates it
+            std::vector<int> owner = split_run(sh, 4);
+            int a = 4, b = 0;
+            for (int k = 0; k < 4; ++k)
+                if (owner[k] == sh.rank) {
+                    a = std::min(a, k);
+                    b = std::max(b, k + 1);
+                }
+            std::map<int, uint32_t*> full;  // eval_log -> this rank's coordinate columns, whole domain
+            std::vector<Xfer> xs;
+            for (auto& kv : acc) {
+                const int lg = kv.first;
+                const size_t n = (size_t)1 << lg, rl = n >> sh.logw;
+                uint32_t* f = b > a ? arena.alloc<uint32_t>(n * (size_t)(b - a)) : nullptr;
+                full[lg] = f;
+                for (int k = 0; k < 4; ++k) {
+                    const int o = owner[k];
+                    uint32_t* slot = o == sh.rank ? f + (size_t)(k - a) * n : nullptr;
+                    xs.push_back({kv.second + (size_t)k * rl, slot ? slot + rl * sh.rank : nullptr, rl, o, true});
+                    if (o == sh.rank)
+                        for (int r = 0; r < sh.world; ++r)
+                            if (r != sh.rank) xs.push_back({nullptr, slot + rl * r, rl, r, false});
+                }
+                comp_log = lg;
+            }
+            run_exchange(ctx, sh, xs);
+            if (b > a) {
+                int prev_log = 0;
+                for (auto& kv : full) {
+                    const int lg = kv.first;
+                    const size_t n = (size_t)1 << lg;
+                    uint32_t* vals = kv.second;
+                    if (comp_coeffs) {
+                        uint32_t* lifted = arena.alloc<uint32_t>(n * (size_t)(b - a));
+                        ck(cfft_evaluate(&tw, comp_coeffs, (size_t)1 << prev_log, prev_log, lifted, n, lg, b - a, ctx->sm_count, st),
+                           "lift composition");
+                        ck(add_inplace(vals, lifted, n * (size_t)(b - a), st), "accumulate");
+                    }
+                    ck(cfft_interpolate(&tw, vals, n, b - a, lg, ctx->sm_count, st), "interpolate composition");
+                    comp_coeffs = vals;
+                    prev_log = lg;
+                }
+            }
+            ColRun run{trees[3].cols.size(), 4, comp_log};
+            for (int k = 0; k < 4; ++k) {
+                PolyCol pc{owner[k] == sh.rank ? comp_coeffs + ((size_t)(k - a) << comp_log) : nullptr, nullptr, comp_log};
+                pc.owner = owner[k];
+                trees[3].cols.push_back(pc);
+            }
+            trees[3].runs.push_back(run);
         }
-        for (int k = 0; k < 4; ++k) trees[3].cols.push_back({comp_coeffs + ((size_t)k << comp_log), nullptr, comp_log});
         commit_tree(trees[3]);
         timer.lap();  // stage 2: constraint quotients + composition commit
 
@@ -1000,10 +1296,10 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
         sample_points[1].resize(trees[1].cols.size());
         sample_points[2].resize(trees[2].cols.size());
         for (const Component& c : comps) {
-            ComponentShape sh = component_shape(c.kind);
-            for (int q = 0; q < sh.n_pre; ++q) sample_points[0][c.pre_idx[q]] = {oods};
-            for (int k = 0; k < sh.n_main; ++k) sample_points[1][c.main_loc + k] = {oods};
-            int n_ic = 4 * sh.n_fracs;
+            ComponentShape shp = component_shape(c.kind);
+            for (int q = 0; q < shp.n_pre; ++q) sample_points[0][c.pre_idx[q]] = {oods};
+            for (int k = 0; k < shp.n_main; ++k) sample_points[1][c.main_loc + k] = {oods};
+            int n_ic = 4 * shp.n_fracs;
             QPt prev = qpt_add(oods, qpt_lift(host_index_to_point((0u - subgroup_gen(c.log)) & CIRCLE_ORDER_MASK)));
             for (int k = 0; k < n_ic; ++k) {
                 if (k >= n_ic - 4)
@@ -1031,6 +1327,7 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             for (int t = 0; t < 4; ++t)
                 for (size_t c = 0; c < trees[t].cols.size(); ++c)
                     for (size_t s = 0; s < sample_points[t][c].size(); ++s) {
+                        if (sh.on() && trees[t].cols[c].owner != sh.rank) continue;  // sampled by its owner, all-reduced below
                         const QPt& pt = sample_points[t][c][s];
                         int lg = trees[t].cols[c].log;
                         Job* job = nullptr;
@@ -1058,6 +1355,31 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             ck(cudaStreamSynchronize(st), "samples sync");
             for (size_t ji = 0; ji < jobs.size(); ++ji)
                 for (size_t k = 0; k < jobs[ji].dst.size(); ++k) *jobs[ji].dst[k] = results[ji][k];
+            if (sh.on()) {
+                // every sample has exactly one owner: a sum over the ranks (zeros elsewhere) hands all of them to everybody
+                std::vector<uint32_t> flat;
+                for (int t = 0; t < 4; ++t)
+                    for (size_t c = 0; c < trees[t].cols.size(); ++c)
+                        for (QM31 v : sampled[t][c]) {
+                            bool mine = trees[t].cols[c].owner == sh.rank;
+                            uint32_t w[4] = {v.a.a, v.a.b, v.b.a, v.b.b};
+                            for (int q = 0; q < 4; ++q) flat.push_back(mine ? w[q] : 0u);
+                        }
+                uint32_t* d_flat = arena.upload(flat);
+                nck(nccl_api().AllReduce(d_flat, d_flat, flat.size(), ncclUint32, ncclSum, sh.comm->comm, st), "ncclAllReduce(samples)");
+                sh.comm->n_collectives++;
+                sh.comm->bytes_sent += flat.size() * 4;
+                sh.comm->bytes_received += flat.size() * 4;
+                ck(cudaMemcpyAsync(flat.data(), d_flat, flat.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "samples d2h");
+                ck(cudaStreamSynchronize(st), "samples sync");
+                size_t at = 0;
+                for (int t = 0; t < 4; ++t)
+                    for (size_t c = 0; c < trees[t].cols.size(); ++c)
+                        for (QM31& v : sampled[t][c]) {
+                            v = q_make(flat[at], flat[at + 1], flat[at + 2], flat[at + 3]);
+                            at += 4;
+                        }
+            }
         }
         {
             std::vector<QM31> flat;
@@ -1071,8 +1393,9 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
 
         // ---- DEEP quotients (compute_fri_quotients) -----------------------------------------------
         struct QuotCol {
-            int log;
-            uint32_t* coords[4];
+            int log;               // of the whole column
+            uint32_t* coords[4];   // sharded: this rank's rows [rank * 2^(log - logw), ...)
+            uint32_t* full[4];     // sharded: the whole column once it was all-gathered for the replicated FRI layers (else null)
         };
         std::vector<QuotCol> quotients;
         {
@@ -1111,11 +1434,13 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                     }
                 std::vector<const uint32_t*> colptrs;
                 for (auto* f : grp) colptrs.push_back(f->lde);
-                QuotCol qc;
+                QuotCol qc{};
                 qc.log = lg;
-                uint32_t* buf = arena.alloc<uint32_t>((size_t)4 << lg);
-                for (int k = 0; k < 4; ++k) qc.coords[k] = buf + ((size_t)k << lg);
-                launch_quotients(ctx, arena, lg, colptrs, batches, rc_q, qc.coords);
+                const size_t rl = ((size_t)1 << lg) >> sh.logw;
+                uint32_t* buf = arena.alloc<uint32_t>(4 * rl);
+                for (int k = 0; k < 4; ++k) qc.coords[k] = buf + (size_t)k * rl;
+                launch_quotients(ctx, arena, lg, colptrs, batches, rc_q, qc.coords, sh.on() ? (uint32_t)(rl * sh.rank) : 0u,
+                                 sh.on() ? (uint32_t)rl : 0u);
                 quotients.push_back(qc);
             }
         }
@@ -1123,16 +1448,18 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
 
         // ---- FRI commit (FriProver::commit) ----------------------------------------------------------
         struct FriLayer {
-            int log;
-            uint32_t* coords[4];
+            int log;               // of the whole layer
+            uint32_t* coords[4];   // row shard when logw > 0
             MerkleTree tree;
+            int logw = 0;
         };
         MerkleTree fri_first_tree;
         {
             std::vector<ColRef> refs;
             for (auto& q : quotients)
-                for (int k = 0; k < 4; ++k) refs.push_back({q.coords[k], q.log});
-            merkle_commit(ctx, arena, refs, fri_first_tree);
+                for (int k = 0; k < 4; ++k) refs.push_back({q.coords[k], q.log - sh.logw});
+            merkle_commit(ctx, arena, refs, fri_first_tree, /*fetch_root=*/!sh.on());
+            if (sh.on()) finish_sharded_root(ctx, arena, sh, fri_first_tree);
             channel.mix_root(fri_first_tree.root);
         }
         std::vector<FriLayer> inner;
@@ -1141,14 +1468,93 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             QM31 folding_alpha = channel.draw_secure_felt();
             int line_log = quotients[0].log - 1;
             int last_log = (int)(cfg.log_last_layer_degree_bound + cfg.log_blowup_factor);
+            size_t qi = 0;
+            uint32_t* gathered = nullptr;  // sharded: the first replicated layer, all-gathered from the row shards
+            if (sh.on()) {
+                // Row-sharded layers: a fold pairs adjacent rows, so it stays inside a rank's row range; the layer tree is a
+                // sub-tree per rank plus an all-gather of the roots; the Fiat-Shamir step runs on the host of every rank
+                // (identical inputs, identical state).  Once a layer is down to 2^FRI_SHARD_MIN_LOG rows per rank it is
+                // all-gathered and the remaining (latency-bound) layers run replicated on every rank.
+                constexpr int FRI_SHARD_MIN_LOG = 12;
+                uint32_t* cur = nullptr;  // current layer, row shard: 4 coordinate columns of 2^(line_log - logw)
+                auto local_rows = [&](int lg) { return ((size_t)1 << lg) >> sh.logw; };
+                while (line_log > last_log && line_log - sh.logw > FRI_SHARD_MIN_LOG) {
+                    const size_t rl = local_rows(line_log);
+                    if (!cur) {
+                        cur = arena.alloc<uint32_t>(4 * rl);
+                        ck(cudaMemsetAsync(cur, 0, 4 * rl * sizeof(uint32_t), st), "memset");
+                    }
+                    uint32_t* coords[4];
+                    for (int k = 0; k < 4; ++k) coords[k] = cur + (size_t)k * rl;
+                    while (qi < quotients.size() && quotients[qi].log - 1 == line_log) {
+                        // inverse y twiddles of this rank's rows: entry i of the whole table belongs to rows 2i, 2i + 1
+                        ck(fold_circle_into_line(coords, quotients[qi].coords, inv_y_twiddles(tw, quotients[qi].log) + rl * sh.rank,
+                                                 quotients[qi].log - sh.logw, folding_alpha, st),
+                           "fold circle");
+                        ++qi;
+                    }
+                    FriLayer L;
+                    L.log = line_log;
+                    L.logw = sh.logw;
+                    for (int k = 0; k < 4; ++k) L.coords[k] = coords[k];
+                    std::vector<ColRef> refs;
+                    for (int k = 0; k < 4; ++k) refs.push_back({coords[k], line_log - sh.logw});
+                    merkle_commit(ctx, arena, refs, L.tree, /*fetch_root=*/false);
+                    finish_sharded_root(ctx, arena, sh, L.tree);
+                    channel.mix_root(L.tree.root);
+                    folding_alpha = channel.draw_secure_felt();
+                    inner.push_back(L);
+                    const size_t rl_next = local_rows(line_log - 1);
+                    uint32_t* next = arena.alloc<uint32_t>(4 * rl_next);
+                    uint32_t* ncoords[4];
+                    for (int k = 0; k < 4; ++k) ncoords[k] = next + (size_t)k * rl_next;
+                    ck(fold_line(ncoords, coords, inv_x_twiddles(tw, line_log) + rl_next * sh.rank, line_log - sh.logw, folding_alpha, st),
+                       "fold line");
+                    cur = next;
+                    --line_log;
+                }
+                // hand over to the replicated path: the current layer (if any fold happened) and the quotient columns that are
+                // still to be folded in, all-gathered coordinate by coordinate (rank order = row order)
+                NcclApi& api = nccl_api();
+                if (cur) {
+                    const size_t rl = local_rows(line_log);
+                    gathered = arena.alloc<uint32_t>((size_t)4 << line_log);
+                    nck(api.GroupStart(), "ncclGroupStart");
+                    for (int k = 0; k < 4; ++k)
+                        nck(api.AllGather(cur + (size_t)k * rl, gathered + ((size_t)k << line_log), rl, ncclUint32, sh.comm->comm, st),
+                            "ncclAllGather(fri layer)");
+                    nck(api.GroupEnd(), "ncclGroupEnd");
+                    sh.comm->n_collectives++;
+                    sh.comm->bytes_sent += 16 * rl;
+                    sh.comm->bytes_received += 16 * rl * (size_t)(sh.world - 1);
+                }
+                for (size_t q = qi; q < quotients.size(); ++q) {
+                    const size_t n = (size_t)1 << quotients[q].log, rl = n >> sh.logw;
+                    uint32_t* f = arena.alloc<uint32_t>(4 * n);
+                    nck(api.GroupStart(), "ncclGroupStart");
+                    for (int k = 0; k < 4; ++k) {
+                        quotients[q].full[k] = f + (size_t)k * n;
+                        nck(api.AllGather(quotients[q].coords[k], quotients[q].full[k], rl, ncclUint32, sh.comm->comm, st),
+                            "ncclAllGather(quotient column)");
+                    }
+                    nck(api.GroupEnd(), "ncclGroupEnd");
+                    sh.comm->n_collectives++;
+                    sh.comm->bytes_sent += 16 * rl;
+                    sh.comm->bytes_received += 16 * rl * (size_t)(sh.world - 1);
+                }
+            }
             // all line-layer evaluations in one allocation: layer of log k (4 coordinate columns) at word offset 4 * (2^k - 1)
             uint32_t* fri_buf = arena.alloc<uint32_t>((size_t)8 << line_log);
             auto layer_at = [&](int lg) { return fri_buf + 4 * (((size_t)1 << lg) - 1); };
             uint32_t* cur = layer_at(line_log);
-            ck(cudaMemsetAsync(cur, 0, ((size_t)4 << line_log) * sizeof(uint32_t), st), "memset");
+            if (gathered)
+                ck(cudaMemcpyAsync(cur, gathered, ((size_t)4 << line_log) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st), "copy");
+            else
+                ck(cudaMemsetAsync(cur, 0, ((size_t)4 << line_log) * sizeof(uint32_t), st), "memset");
             // The per-layer Fiat-Shamir step (mix_root, draw the next folding coefficient) runs on the device
             // (channel_mix_root_draw), so fold -> Merkle -> mix -> draw -> fold is enqueued for every layer without a host
             // round trip; roots, digests and the final channel state come back in one copy after the loop.
+            const size_t first_dev_layer = inner.size();
             int n_layers = std::max(0, line_log - last_log);
             DevChannel h_ch{};
             channel.digest_words(h_ch.digest);
@@ -1159,13 +1565,13 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             ck(cudaMemcpyAsync(d_ch, &h_ch, sizeof(h_ch), cudaMemcpyHostToDevice, st), "channel h2d");
             ck(cudaMemcpyAsync(d_alphas, &folding_alpha, sizeof(QM31), cudaMemcpyHostToDevice, st), "alpha h2d");
             ck(cudaStreamSynchronize(st), "channel h2d sync");  // h_ch / folding_alpha are stack objects
-            size_t qi = 0;
             int li = 0;
             while (line_log > last_log) {
                 uint32_t* coords[4];
                 for (int k = 0; k < 4; ++k) coords[k] = cur + ((size_t)k << line_log);
                 while (qi < quotients.size() && quotients[qi].log - 1 == line_log) {
-                    ck(fold_circle_into_line_dev(coords, quotients[qi].coords, inv_y_twiddles(tw, quotients[qi].log),
+                    uint32_t* const* src = quotients[qi].full[0] ? quotients[qi].full : quotients[qi].coords;
+                    ck(fold_circle_into_line_dev(coords, src, inv_y_twiddles(tw, quotients[qi].log),
                                                  quotients[qi].log, d_alphas + li, st),
                        "fold circle");
                     ++qi;
@@ -1221,7 +1627,8 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             if (n_layers > 0) {
                 std::vector<uint32_t> h_digests(8 * (size_t)n_layers);
                 for (int k = 0; k < n_layers; ++k)
-                    ck(cudaMemcpyAsync(inner[k].tree.root.b, inner[k].tree.layers[0], 32, cudaMemcpyDeviceToHost, st), "root d2h");
+                    ck(cudaMemcpyAsync(inner[first_dev_layer + k].tree.root.b, inner[first_dev_layer + k].tree.layers[0], 32,
+                                       cudaMemcpyDeviceToHost, st), "root d2h");
                 ck(cudaMemcpyAsync(h_digests.data(), d_digests, h_digests.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "digests d2h");
                 ck(cudaMemcpyAsync(&h_ch, d_ch, sizeof(h_ch), cudaMemcpyDeviceToHost, st), "channel d2h");
                 ck(cudaStreamSynchronize(st), "fri loop sync");
@@ -1312,10 +1719,10 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             for (auto& q : quotients) {
                 std::vector<uint32_t> cq = fold_queries(queries, max_lde_log - q.log);
                 std::vector<uint32_t> positions;
-                fri_positions_and_witness(q.coords, cq, g, positions, first_out.witness);
+                fri_positions_and_witness(q.coords, cq, g, positions, first_out.witness, q.log - sh.logw, sh.logw, sh.rank);
                 pos_by_size[q.log] = positions;
             }
-            merkle_decommit_plan(fri_first_tree, pos_by_size, g, first_out.decommit);
+            merkle_decommit_plan(fri_first_tree, pos_by_size, g, first_out.decommit, sh.rank);
             first_out.decommit.queried_values.clear();
         }
         std::vector<FriLayerOut> inner_out(inner.size());
@@ -1323,17 +1730,18 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             std::vector<uint32_t> lq = fold_queries(queries, 1);
             for (size_t li = 0; li < inner.size(); ++li) {
                 std::vector<uint32_t> positions;
-                fri_positions_and_witness(inner[li].coords, lq, g, positions, inner_out[li].witness);
+                fri_positions_and_witness(inner[li].coords, lq, g, positions, inner_out[li].witness, inner[li].log - inner[li].logw,
+                                          inner[li].logw, sh.rank);
                 std::map<int, std::vector<uint32_t>> m;
                 m[inner[li].log] = positions;
-                merkle_decommit_plan(inner[li].tree, m, g, inner_out[li].decommit);
+                merkle_decommit_plan(inner[li].tree, m, g, inner_out[li].decommit, sh.rank);
                 inner_out[li].decommit.queried_values.clear();
                 inner_out[li].commitment = inner[li].tree.root;
                 lq = fold_queries(lq, 1);
             }
         }
         std::vector<DecommitIdx> tree_dec(4);
-        for (int t = 0; t < 4; ++t) merkle_decommit_plan(trees[t].merkle, qpos, g, tree_dec[t]);
+        for (int t = 0; t < 4; ++t) merkle_decommit_plan(trees[t].merkle, qpos, g, tree_dec[t], sh.rank);
 
         // one gather for everything
         g.values.resize(g.addrs.size());
@@ -1341,8 +1749,16 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             const uint32_t** d_addrs = arena.upload(g.addrs);
             uint32_t* d_vals = arena.alloc<uint32_t>(g.addrs.size());
             ck(gather_words(d_vals, d_addrs, (int)g.addrs.size(), st), "gather");
+            if (sh.on()) {
+                // every word has one owner (null addresses read as 0): the sum over the ranks is the decommitment
+                nck(nccl_api().AllReduce(d_vals, d_vals, g.addrs.size(), ncclUint32, ncclSum, sh.comm->comm, st), "ncclAllReduce(decommitment)");
+                sh.comm->n_collectives++;
+                sh.comm->bytes_sent += g.addrs.size() * 4;
+                sh.comm->bytes_received += g.addrs.size() * 4;
+            }
             ck(cudaMemcpyAsync(g.values.data(), d_vals, g.values.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "gather d2h");
             ck(cudaStreamSynchronize(st), "gather sync");
+            for (auto& kv : g.consts) g.values[kv.first] = kv.second;
         }
         timer.lap();  // stage 6: grind + queries + decommitment
 

@@ -50,14 +50,44 @@ class PcsConfig:
     n_queries: int = 3
 
 
+class Comm:
+    """``lb_comm``: this rank's handle of the multi-GPU prover (one process per GPU, NCCL over NVLink).  ``unique_id()`` is
+    created on rank 0 and handed to the other ranks by the host's own means (``torch.distributed`` broadcast, MPI, a file)."""
+
+    def __init__(self, backend: CudaBackend, unique_id: bytes, rank: int, world: int):
+        self.be = backend
+        h = C.c_void_p()
+        check(backend.ctx, backend.lib.lb_comm_init(backend.ctx, unique_id, rank, world, C.byref(h)), "lb_comm_init")
+        self.handle, self.rank, self.world = h, rank, world
+
+    @staticmethod
+    def unique_id(backend: CudaBackend) -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = backend.lib.lb_comm_unique_id(buf)
+        if rc != 0:
+            raise LuminairB200Error(f"lb_comm_unique_id failed ({rc}): NCCL not available")
+        return buf.raw
+
+    def stats(self):
+        sent, recv, n = C.c_uint64(), C.c_uint64(), C.c_int()
+        self.be.lib.lb_comm_stats(self.handle, None, None, C.byref(sent), C.byref(recv), C.byref(n))
+        return {"bytes_sent": sent.value, "bytes_received": recv.value, "n_collectives": n.value}
+
+    def close(self):
+        if self.handle:
+            self.be.lib.lb_comm_destroy(self.handle)
+            self.handle = None
+
+
 def prove(pie, backend: CudaBackend | None = None, config: PcsConfig | None = None, channel_variant: str = "legacy",
           claim_slots=CLAIM_SLOT, n_slots: int = N_CLAIM_SLOTS, device_tables=None, air_era: str = "current",
-          preprocessed=(), settings=None) -> bytes:
+          preprocessed=(), settings=None, comm: Comm | None = None) -> bytes:
     """pie: [(name, rows[n_rows, n_cols])].  device_tables: optional {name: (device_ptr, n_rows, n_cols)} to prove
     from tables already resident in HBM (bench.py's device-resident leg).  preprocessed: [(id, values[2^k])] LUT
     columns of the circuit settings in ``lookups_to_preprocessed_column`` order (preprocessed.rs:181-206); or pass
     ``settings`` (``luminair_b200.settings.CircuitSettings``), as the reference's ``prove(pie, settings)`` does
-    (prover.rs:28-31), and the columns are derived from its lookup layouts."""
+    (prover.rs:28-31), and the columns are derived from its lookup layouts.  comm: a ``Comm`` - the proof is then made by
+    all its ranks together (``lb_prove_sharded``; every rank passes the same arguments and receives the same bytes)."""
     if settings is not None:
         if preprocessed:
             raise LuminairB200Error("pass either `settings` or `preprocessed`, not both")
@@ -103,7 +133,10 @@ def prove(pie, backend: CudaBackend | None = None, config: PcsConfig | None = No
             pre[i].on_device = 0
         out = C.c_void_p()
         out_len = C.c_size_t()
-        rc = be.lib.lb_prove_with_lookups(be.ctx, tables, n, pre, n_pre, C.byref(cfg), C.byref(out), C.byref(out_len))
+        if comm is not None:  # every rank calls this with the same pie; every rank gets the same bytes (lb_prove_sharded)
+            rc = be.lib.lb_prove_sharded(be.ctx, comm.handle, tables, n, pre, n_pre, C.byref(cfg), C.byref(out), C.byref(out_len))
+        else:
+            rc = be.lib.lb_prove_with_lookups(be.ctx, tables, n, pre, n_pre, C.byref(cfg), C.byref(out), C.byref(out_len))
         if rc == -5:
             raise ProvingError(be.lib.lb_last_error(be.ctx).decode())
         check(be.ctx, rc, "lb_prove")
