@@ -863,7 +863,6 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
 
         if (sh.on()) {
             if (!nccl_api().load()) fail(LB_ERR_NCCL, nccl_api().error);
-            if (blowup + 4 - sh.logw < 4) fail(LB_ERR_BAD_ARG, "prove: too many ranks for the smallest column");
         }
         struct AuxReq {  // a non-committed column shipped with a tree's exchange: the [-1]-shifted copy of column `col`
             size_t col;
@@ -902,6 +901,7 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                     }
                     continue;
                 }
+                if (L - sh.logw < 2) fail(LB_ERR_BAD_ARG, "prove (sharded): a committed column has fewer than 4 rows per rank");
                 int a, b;
                 own_range(tree, run, sh.rank, a, b);
                 const size_t rl = out_stride >> sh.logw;

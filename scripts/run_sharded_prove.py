@@ -26,6 +26,14 @@ out = {"world": world, "log": log}
 
 
 def bench(name, rec, fixture):
+    try:
+        return _bench(name, rec, fixture)
+    except Exception as e:  # show it: torchrun hides child tracebacks
+        print(f"rank {rank}: {name}: {type(e).__name__}: {e}", file=sys.stderr, flush=True)
+        raise
+
+
+def _bench(name, rec, fixture):
     meta, dev, _ = rec.finish()
     single = prove(meta, backend=be, device_tables=dev)
     dist.barrier()
