@@ -314,7 +314,9 @@ def run_gpu(args):
 
     # ---- N > 1: the column-sharded commit of BASELINE cfg 5 (the one place the path has a real exchange)
     sharded_info = None
+    sharded_prove_info = None
     if distributed and not args.no_sharded:
+        sharded_prove_info = bench_sharded_prove(be, torch, dist, args, rank, world)
         sharded_info = bench_sharded_commit(be, torch, dist, args, rank, world, local_rank)
 
     # ---- reduce over ranks (max time)
@@ -356,6 +358,8 @@ def run_gpu(args):
         }
         if prove_info:
             line["prove"] = prove_info
+        if sharded_prove_info:
+            line["sharded_prove"] = sharded_prove_info
         if sharded_info:
             line["sharded_commit"] = sharded_info
         if world == 1 and not args.no_cpu:
@@ -385,6 +389,62 @@ def run_gpu(args):
     if distributed:
         dist.destroy_process_group()
     be.close()
+
+
+def bench_sharded_prove(be, torch, dist, args, rank, world):
+    """prove() of ONE proof by all N GPUs together (lb_prove_sharded: strong scaling; the total work is that of the 1-GPU
+    proof): BASELINE configs[2] (a + b at 2^log) and the 2^log x 61-column wide trace.  Every rank checks that the bytes equal
+    its own single-GPU lb_prove of the same tables and, at log 20, the committed CPU-prover fixture."""
+    from luminair_b200.prover import STAGE_NAMES, Comm, last_stage_ms, prove
+    from luminair_b200.trace import DeviceGraphTrace
+    from luminair_b200.workloads import build_add_graph, build_wide, synthetic_add_graph_inputs
+    log = args.prove_log
+    ids = [Comm.unique_id(be) if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    comm = Comm(be, ids[0], rank, world)
+    out = {"how": "lb_prove_sharded: column-owned interpolate / LDE / sampling, one grouped NCCL exchange per tree into row shards, "
+                  "row-sharded Merkle sub-trees (all-gather of 32-byte roots), constraint quotients, DEEP quotients and FRI layers; "
+                  "replicated Fiat-Shamir channel; device-resident (replicated) trace tables",
+           "n_gpus": world, "scaling": "strong"}
+    a, b = synthetic_add_graph_inputs(log, seed=42)
+    for name, rec, fixture in (("cfg3_add", build_add_graph(DeviceGraphTrace(be), a, b), "cfg3_add_log20.proof.bin"),
+                               ("wide", build_wide(DeviceGraphTrace(be), log), "wide_log20.proof.bin")):
+        meta, dev, _ = rec.finish()
+        single = prove(meta, backend=be, device_tables=dev)
+        t1 = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            prove(meta, backend=be, device_tables=dev)
+            t1.append((time.perf_counter() - t0) * 1e3)
+        dist.barrier()
+        sharded = prove(meta, backend=be, device_tables=dev, comm=comm)
+        ts = []
+        for _ in range(6):
+            be.sync()
+            dist.barrier()
+            t0 = time.perf_counter()
+            prove(meta, backend=be, device_tables=dev, comm=comm)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        stages, stats = last_stage_ms(be), comm.stats()
+        t = torch.tensor([min(ts), statistics.median(ts), -min(t1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # slowest rank of the sharded proof, fastest single-GPU proof
+        fx = os.path.join(ROOT, "tests", "golden", fixture)
+        eq_fix = (open(fx, "rb").read() == sharded) if (log == 20 and os.path.exists(fx)) else None
+        ok = torch.tensor([1 if (sharded == single and eq_fix is not False) else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        ms_n, ms_1 = float(t[0]), -float(t[2])
+        out[name] = {"proof_equals_single_device": bool(ok[0]), "proof_equals_cpu_prover_fixture": eq_fix,
+                     "ms_per_proof_max_over_ranks": {"min": ms_n, "median": float(t[1])}, "ms_per_proof_1gpu": ms_1,
+                     "speedup_vs_1gpu": ms_1 / ms_n, "strong_scaling_efficiency": ms_1 / ms_n / world,
+                     "stages_ms_rank0": dict(zip(STAGE_NAMES, [round(x, 3) for x in stages])),
+                     "nccl_bytes_sent_per_rank": stats["bytes_sent"], "nccl_bytes_received_per_rank": stats["bytes_received"],
+                     "nccl_grouped_calls": stats["n_collectives"], "proof_bytes": len(sharded),
+                     "timer": "host wall clock around lb_prove_sharded after a barrier, max over ranks"}
+        if not bool(ok[0]):
+            raise SystemExit(f"bench: sharded proof of {name} differs from the single-GPU proof")
+        del rec
+    comm.close()
+    return out
 
 
 def bench_sharded_commit(be, torch, dist, args, rank, world, local_rank):

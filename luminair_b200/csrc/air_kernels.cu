@@ -289,15 +289,37 @@ struct ConstraintLaunch {
 };
 }  // namespace
 
-__global__ void __launch_bounds__(256) shifted_prev_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ col,
+// out[j] = col[prev(j)], j < 2^eval_log, prev = offset_bit_reversed_circle_domain_index(., domain_log, eval_log, -1); source
+// and destination are each held as 2^logw equal row ranges (logw = 0: one plain column)
+struct ShardPtrs {
+    const uint32_t* p[8];
+};
+struct ShardOut {
+    uint32_t* p[8];
+};
+__global__ void __launch_bounds__(256) shifted_prev_kernel(ShardOut out, ShardPtrs col, int src_shard_log, int dst_shard_log,
                                                            int domain_log, int eval_log) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < (1u << eval_log)) out[j] = col[prev_row_index(j, domain_log, eval_log)];
+    if (j >= (1u << eval_log)) return;
+    uint32_t q = prev_row_index(j, domain_log, eval_log);
+    out.p[j >> dst_shard_log][j & ((1u << dst_shard_log) - 1)] = col.p[q >> src_shard_log][q & ((1u << src_shard_log) - 1)];
 }
-cudaError_t shifted_prev_column(uint32_t* out, const uint32_t* col, int domain_log, int eval_log, cudaStream_t stream) {
-    if (eval_log - domain_log < 1 || eval_log > 30) return cudaErrorInvalidValue;
+cudaError_t shifted_prev_column(uint32_t* const out_shards[8], int n_out, const uint32_t* const src_shards[8], int n_src,
+                                int domain_log, int eval_log, cudaStream_t stream) {
+    auto lg = [](int n) {
+        int l = 0;
+        while ((1 << l) < n) ++l;
+        return l;
+    };
+    if (eval_log - domain_log < 1 || eval_log > 30 || n_out < 1 || n_out > 8 || n_src < 1 || n_src > 8 || (n_out & (n_out - 1)) ||
+        (n_src & (n_src - 1)))
+        return cudaErrorInvalidValue;
+    ShardPtrs sp{};
+    ShardOut so{};
+    for (int k = 0; k < n_src; ++k) sp.p[k] = src_shards[k];
+    for (int k = 0; k < n_out; ++k) so.p[k] = out_shards[k];
     uint32_t n = 1u << eval_log;
-    shifted_prev_kernel<<<(n + 255) / 256, 256, 0, stream>>>(out, col, domain_log, eval_log);
+    shifted_prev_kernel<<<(n + 255) / 256, 256, 0, stream>>>(so, sp, eval_log - lg(n_src), eval_log - lg(n_out), domain_log, eval_log);
     return cudaGetLastError();
 }
 

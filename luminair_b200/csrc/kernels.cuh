@@ -60,6 +60,10 @@ struct DevChannel {
 };
 cudaError_t channel_mix_root_draw(DevChannel* d_ch, const uint32_t* d_root, int variant, QM31* d_alpha_out, uint32_t* d_digest_log,
                                   cudaStream_t stream);
+// the same for a row-sharded layer: d_roots = the all-gathered sub-tree roots (2^logw x 8 words); hashes the top logw levels
+// into d_top_out (level k at word 8 * (2^k - 1); 8 * (2^(logw+1) - 1) words), mixes the root, draws
+cudaError_t channel_mix_sharded_root_draw(DevChannel* d_ch, const uint32_t* d_roots, int logw, int variant, QM31* d_alpha_out,
+                                          uint32_t* d_digest_log, uint32_t* d_top_out, cudaStream_t stream);
 // the last FRI layers (line layers of at most 2^FRI_TAIL_MAX_LOG values) in one launch: per layer lg = from_log .. last_log + 1:
 // Merkle tree of the layer -> mix_root -> draw -> fold_line into layer lg - 1
 constexpr int FRI_TAIL_MAX_LOG = 10;
@@ -124,8 +128,11 @@ struct ConstraintParams {
     const uint32_t* inter_prev;
 };
 cudaError_t constraint_quotients(int kind, const ConstraintParams& p, cudaStream_t stream);
-// out[j] = col[offset_bit_reversed_circle_domain_index(j, domain_log, eval_log, -1)], j < 2^eval_log
-cudaError_t shifted_prev_column(uint32_t* out, const uint32_t* col, int domain_log, int eval_log, cudaStream_t stream);
+// out[j] = col[offset_bit_reversed_circle_domain_index(j, domain_log, eval_log, -1)], j < 2^eval_log; the source column is held
+// as n_src equal row ranges (src_shards[s] = rows [s R/n_src, ...)), the result is written as n_out equal row ranges; both
+// counts are powers of two <= 8 (1 = one plain column)
+cudaError_t shifted_prev_column(uint32_t* const out_shards[8], int n_out, const uint32_t* const src_shards[8], int n_src,
+                                int domain_log, int eval_log, cudaStream_t stream);
 
 
 

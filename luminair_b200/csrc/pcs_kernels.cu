@@ -469,6 +469,34 @@ __global__ void channel_mix_root_draw_kernel(DevChannel* ch, const uint32_t* roo
     channel_mix_root_draw_dev(ch, root, variant, alpha_out, digest_log);
 }
 
+// Row-sharded layer (sharded prover): `roots` holds the all-gathered sub-tree roots of the W = 2^logw ranks; the top logw
+// levels of the layer tree are hashed here (node = Blake2s(left || right)), then mix_root + draw as above.  `top_out`
+// receives every level: level k (2^k digests) at word 8 * (2^k - 1), level logw = the gathered roots themselves.
+__global__ void channel_mix_sharded_root_draw_kernel(DevChannel* ch, const uint32_t* roots, int logw, int variant,
+                                                     QM31* alpha_out, uint32_t* digest_log, uint32_t* top_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int w = 1 << logw;
+    for (int i = 0; i < 8 * w; ++i) top_out[8 * (w - 1) + i] = roots[i];
+    for (int k = logw - 1; k >= 0; --k) {
+        const uint32_t* child = top_out + 8 * ((2 << k) - 1);
+        uint32_t* lvl = top_out + 8 * ((1 << k) - 1);
+        for (int i = 0; i < (1 << k); ++i) {
+            uint32_t h[8], m[16];
+            blake2s_init(h);
+            for (int q = 0; q < 16; ++q) m[q] = child[16 * i + q];
+            blake2s_compress(h, m, 64, 0, 0xFFFFFFFFu);
+            for (int q = 0; q < 8; ++q) lvl[8 * i + q] = h[q];
+        }
+    }
+    channel_mix_root_draw_dev(ch, top_out, variant, alpha_out, digest_log);
+}
+cudaError_t channel_mix_sharded_root_draw(DevChannel* d_ch, const uint32_t* d_roots, int logw, int variant, QM31* d_alpha_out,
+                                          uint32_t* d_digest_log, uint32_t* d_top_out, cudaStream_t stream) {
+    if (logw < 1 || logw > 6) return cudaErrorInvalidValue;
+    channel_mix_sharded_root_draw_kernel<<<1, 32, 0, stream>>>(d_ch, d_roots, logw, variant, d_alpha_out, d_digest_log, d_top_out);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------
 // The tail of the FRI commit loop in one launch.  Once a line layer has at most 2^FRI_TAIL_MAX_LOG values, every step of
 // FriProver::commit for it - Merkle tree of the layer's four coordinate columns, mix_root, draw the folding coefficient,

@@ -11,6 +11,8 @@
 // one by one.
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -699,6 +701,29 @@ struct Xfer {
 // the same (column) order, which is the order NCCL matches sends with receives.
 void run_exchange(lb_ctx* ctx, Shard& sh, const std::vector<Xfer>& xs) {
     NcclApi& api = nccl_api();
+    static const bool trace = getenv("LB_SHARD_TRACE") != nullptr;  // diagnostics: time every exchange (adds two syncs)
+    std::chrono::steady_clock::time_point t0;
+    unsigned long long sent0 = sh.comm->bytes_sent;
+    if (trace) {
+        cudaStreamSynchronize(ctx->stream);
+        t0 = std::chrono::steady_clock::now();
+    }
+    struct TraceEnd {
+        bool on;
+        lb_ctx* ctx;
+        Shard& sh;
+        std::chrono::steady_clock::time_point& t0;
+        unsigned long long& sent0;
+        size_t n;
+        ~TraceEnd() {
+            if (!on) return;
+            cudaStreamSynchronize(ctx->stream);
+            double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            unsigned long long b = sh.comm->bytes_sent - sent0;
+            fprintf(stderr, "[lb shard %d] exchange: %zu transfers, %.1f MB sent, %.3f ms (%.0f GB/s out)\n", sh.rank, n, b / 1e6, ms,
+                    ms > 0 ? b / ms / 1e6 : 0.0);
+        }
+    } trace_end{trace, ctx, sh, t0, sent0, xs.size()};
     nck(api.GroupStart(), "ncclGroupStart");
     for (const Xfer& x : xs) {
         if (x.peer == sh.rank) {
@@ -864,10 +889,10 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
         if (sh.on()) {
             if (!nccl_api().load()) fail(LB_ERR_NCCL, nccl_api().error);
         }
-        struct AuxReq {  // a non-committed column shipped with a tree's exchange: the [-1]-shifted copy of column `col`
-            size_t col;
+        struct AuxReq {  // non-committed columns shipped with a tree's exchange: the [-1]-shifted copies of the 4 coordinate
+            size_t col;  // columns col .. col + 3 (the last LogUp column of a component)
             int domain_log;
-            uint32_t* dst;  // this rank's row shard of it
+            uint32_t* dst;  // this rank's row shards of them: 4 x rl, contiguous
         };
         auto push_run = [&](CommitTree& tree, uint32_t* coeffs, int n, int lg) {
             // n columns of 2^lg coefficients, contiguous; returns this rank's sub-range [a, b) of them
@@ -905,22 +930,51 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                 int a, b;
                 own_range(tree, run, sh.rank, a, b);
                 const size_t rl = out_stride >> sh.logw;
-                uint32_t* own = nullptr;
+                uint32_t* local = arena.alloc<uint32_t>(rl * run.n);
+                // Large columns: the last pass of the transform writes every 4096-row tile straight into a per-destination
+                // staging block (cfft_evaluate_scatter; this rank's own rows go directly to their final place), so the
+                // exchange is ONE contiguous message per peer and run - received in place, because an owner's columns are
+                // contiguous in the run.  Small columns: plain transform, one message per column and peer.
+                const bool packed = L >= 16 && L - sh.logw >= 12 && sh.world <= 8;
+                uint32_t* own = nullptr;   // !packed: the owned columns, whole
+                uint32_t* pack = nullptr;  // packed: [peer][owned column][rl] (this rank's slot unused)
                 if (b > a) {
                     own = arena.alloc<uint32_t>(out_stride * (b - a));
                     to_free.push_back(own);
-                    ck(cfft_evaluate(&tw, tree.cols[run.first + a].coeffs, stride, lg, own, out_stride, L, b - a, ctx->sm_count, st),
-                       "LDE evaluate (own columns)");
+                    if (packed) {
+                        pack = arena.alloc<uint32_t>(out_stride * (b - a));
+                        to_free.push_back(pack);
+                        uint32_t* peers[8];
+                        for (int r = 0; r < sh.world; ++r)
+                            peers[r] = r == sh.rank ? local + (size_t)a * rl : pack + (size_t)r * (b - a) * rl;
+                        ck(cfft_evaluate_scatter(&tw, tree.cols[run.first + a].coeffs, stride, lg, own, out_stride, L, b - a, peers,
+                                                 sh.world, 0, ctx->sm_count, st),
+                           "LDE evaluate + scatter (own columns)");
+                        for (int r = 0; r < sh.world; ++r)
+                            if (r != sh.rank) xs.push_back({peers[r], nullptr, (size_t)(b - a) * rl, r, true});
+                    } else {
+                        ck(cfft_evaluate(&tw, tree.cols[run.first + a].coeffs, stride, lg, own, out_stride, L, b - a, ctx->sm_count, st),
+                           "LDE evaluate (own columns)");
+                    }
                 }
-                uint32_t* local = arena.alloc<uint32_t>(rl * run.n);
+                if (packed) {
+                    for (int r = 0; r < sh.world; ++r) {
+                        if (r == sh.rank) continue;
+                        int ra, rb;
+                        own_range(tree, run, r, ra, rb);
+                        if (rb > ra) xs.push_back({nullptr, local + (size_t)ra * rl, (size_t)(rb - ra) * rl, r, false});
+                    }
+                }
                 for (int k = 0; k < run.n; ++k) {
                     PolyCol& pc = tree.cols[run.first + k];
                     uint32_t* mine = local + (size_t)k * rl;
-                    if (pc.owner == sh.rank) {
-                        const uint32_t* full = own + (size_t)(k - a) * out_stride;
-                        for (int r = 0; r < sh.world; ++r) xs.push_back({full + (size_t)r * rl, r == sh.rank ? mine : nullptr, rl, r, true});
-                    } else {
-                        xs.push_back({nullptr, mine, rl, pc.owner, false});
+                    if (!packed) {
+                        if (pc.owner == sh.rank) {
+                            const uint32_t* full = own + (size_t)(k - a) * out_stride;
+                            for (int r = 0; r < sh.world; ++r) xs.push_back({full + (size_t)r * rl, r == sh.rank ? mine : nullptr, rl, r, true});
+                        } else {
+                            xs.push_back({nullptr, mine, rl, pc.owner, false});
+                        }
                     }
                     pc.lde = mine;
                     refs.push_back({mine, L - sh.logw});
@@ -928,16 +982,39 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                 if (aux)
                     for (const AuxReq& rq : *aux) {
                         if (rq.col < run.first || rq.col >= run.first + (size_t)run.n) continue;
-                        int k = (int)(rq.col - run.first);
-                        const PolyCol& pc = tree.cols[rq.col];
-                        if (pc.owner == sh.rank) {
-                            uint32_t* shifted = arena.alloc<uint32_t>(out_stride);
-                            to_free.push_back(shifted);
-                            ck(shifted_prev_column(shifted, own + (size_t)(k - a) * out_stride, rq.domain_log, L, st), "shifted column");
-                            for (int r = 0; r < sh.world; ++r)
-                                xs.push_back({shifted + (size_t)r * rl, r == sh.rank ? rq.dst : nullptr, rl, r, true});
-                        } else {
-                            xs.push_back({nullptr, rq.dst, rl, pc.owner, false});
+                        // the four columns may have different owners; each owner's share is contiguous: one message per
+                        // owner and peer, written by the shift kernel straight into per-destination staging blocks
+                        const int k0 = (int)(rq.col - run.first);
+                        for (int r = 0; r < sh.world; ++r) {
+                            int q0 = 4, q1 = 0;  // columns k0 + q0 .. k0 + q1 - 1 are owned by rank r
+                            for (int q = 0; q < 4; ++q)
+                                if (tree.cols[rq.col + q].owner == r) {
+                                    q0 = std::min(q0, q);
+                                    q1 = std::max(q1, q + 1);
+                                }
+                            if (q1 <= q0) continue;
+                            const size_t cnt = (size_t)(q1 - q0) * rl;
+                            if (r != sh.rank) {
+                                xs.push_back({nullptr, rq.dst + (size_t)q0 * rl, cnt, r, false});
+                                continue;
+                            }
+                            uint32_t* stage = arena.alloc<uint32_t>(cnt * sh.world);  // [peer][owned shifted column][rl]
+                            to_free.push_back(stage);
+                            for (int q = q0; q < q1; ++q) {
+                                const int k = k0 + q;
+                                const uint32_t* src[8];
+                                uint32_t* dst[8];
+                                for (int t = 0; t < sh.world; ++t) {
+                                    if (packed)
+                                        src[t] = (t == sh.rank ? local + (size_t)a * rl : pack + (size_t)t * (b - a) * rl) + (size_t)(k - a) * rl;
+                                    else
+                                        src[t] = own + (size_t)(k - a) * out_stride + (size_t)t * rl;
+                                    dst[t] = (t == sh.rank ? rq.dst + (size_t)q * rl : stage + (size_t)t * cnt + (size_t)(q - q0) * rl);
+                                }
+                                ck(shifted_prev_column(dst, sh.world, src, sh.world, rq.domain_log, L, st), "shifted column");
+                            }
+                            for (int t = 0; t < sh.world; ++t)
+                                if (t != sh.rank) xs.push_back({stage + (size_t)t * cnt, nullptr, cnt, t, true});
                         }
                     }
             }
@@ -1104,7 +1181,7 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                                              "(lookup table larger than its consumer's trace) is not supported yet");
                     size_t rl = ((size_t)1 << (c.log + blowup)) >> sh.logw;
                     c.inter_prev = arena.alloc<uint32_t>(4 * rl);
-                    for (int k = 0; k < 4; ++k) inter_aux.push_back({c.inter_loc + (size_t)(n_ic - 4 + k), c.log, c.inter_prev + (size_t)k * rl});
+                    inter_aux.push_back({c.inter_loc + (size_t)(n_ic - 4), c.log, c.inter_prev});
                 }
                 ck(cudaStreamSynchronize(st), "claimed sync");
                 c.claimed_sum = q_make(cl[0], cl[1], cl[2], cl[3]);
@@ -1469,15 +1546,36 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             int line_log = quotients[0].log - 1;
             int last_log = (int)(cfg.log_last_layer_degree_bound + cfg.log_blowup_factor);
             size_t qi = 0;
+            // The per-layer Fiat-Shamir step (mix_root, draw the next folding coefficient) runs on the device
+            // (channel_mix_root_draw), so fold -> Merkle -> mix -> draw -> fold is enqueued for every layer without a host
+            // round trip; roots, digests and the final channel state come back in one copy after the loop.
+            const int n_layers = std::max(0, line_log - last_log);
+            DevChannel h_ch{};
+            channel.digest_words(h_ch.digest);
+            h_ch.n_sent = channel.n_sent();
+            DevChannel* d_ch = arena.alloc<DevChannel>(1);
+            QM31* d_alphas = arena.alloc<QM31>(n_layers + 1);
+            uint32_t* d_digests = arena.alloc<uint32_t>(8 * (size_t)std::max(n_layers, 1));
+            ck(cudaMemcpyAsync(d_ch, &h_ch, sizeof(h_ch), cudaMemcpyHostToDevice, st), "channel h2d");
+            ck(cudaMemcpyAsync(d_alphas, &folding_alpha, sizeof(QM31), cudaMemcpyHostToDevice, st), "alpha h2d");
+            ck(cudaStreamSynchronize(st), "channel h2d sync");  // h_ch / folding_alpha are stack objects
+            int li = 0;
             uint32_t* gathered = nullptr;  // sharded: the first replicated layer, all-gathered from the row shards
+            const size_t top_words = 8 * (((size_t)2 << sh.logw) - 1);
+            uint32_t* d_tops = nullptr;    // sharded: per row-sharded layer, the top levels of its tree (device)
+            int n_sharded_layers = 0;
             if (sh.on()) {
                 // Row-sharded layers: a fold pairs adjacent rows, so it stays inside a rank's row range; the layer tree is a
-                // sub-tree per rank plus an all-gather of the roots; the Fiat-Shamir step runs on the host of every rank
-                // (identical inputs, identical state).  Once a layer is down to 2^FRI_SHARD_MIN_LOG rows per rank it is
-                // all-gathered and the remaining (latency-bound) layers run replicated on every rank.
-                constexpr int FRI_SHARD_MIN_LOG = 12;
+                // sub-tree per rank plus an all-gather of the 32-byte roots, from which every rank hashes the top levels and
+                // runs the Fiat-Shamir step on the device (identical inputs, identical state on every rank).  Once a layer is
+                // down to 2^FRI_SHARD_MIN_LOG rows per rank it is all-gathered and the remaining (latency-bound) layers run
+                // replicated on every rank.
+                static const int FRI_SHARD_MIN_LOG = getenv("LB_FRI_SHARD_MIN_LOG") ? atoi(getenv("LB_FRI_SHARD_MIN_LOG")) : 15;
+                NcclApi& api = nccl_api();
                 uint32_t* cur = nullptr;  // current layer, row shard: 4 coordinate columns of 2^(line_log - logw)
                 auto local_rows = [&](int lg) { return ((size_t)1 << lg) >> sh.logw; };
+                d_tops = arena.alloc<uint32_t>(top_words * (size_t)std::max(n_layers, 1));
+                uint32_t* d_roots = arena.alloc<uint32_t>(8 * (size_t)sh.world * (size_t)std::max(n_layers, 1));
                 while (line_log > last_log && line_log - sh.logw > FRI_SHARD_MIN_LOG) {
                     const size_t rl = local_rows(line_log);
                     if (!cur) {
@@ -1488,8 +1586,8 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                     for (int k = 0; k < 4; ++k) coords[k] = cur + (size_t)k * rl;
                     while (qi < quotients.size() && quotients[qi].log - 1 == line_log) {
                         // inverse y twiddles of this rank's rows: entry i of the whole table belongs to rows 2i, 2i + 1
-                        ck(fold_circle_into_line(coords, quotients[qi].coords, inv_y_twiddles(tw, quotients[qi].log) + rl * sh.rank,
-                                                 quotients[qi].log - sh.logw, folding_alpha, st),
+                        ck(fold_circle_into_line_dev(coords, quotients[qi].coords, inv_y_twiddles(tw, quotients[qi].log) + rl * sh.rank,
+                                                     quotients[qi].log - sh.logw, d_alphas + li, st),
                            "fold circle");
                         ++qi;
                     }
@@ -1500,22 +1598,31 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                     std::vector<ColRef> refs;
                     for (int k = 0; k < 4; ++k) refs.push_back({coords[k], line_log - sh.logw});
                     merkle_commit(ctx, arena, refs, L.tree, /*fetch_root=*/false);
-                    finish_sharded_root(ctx, arena, sh, L.tree);
-                    channel.mix_root(L.tree.root);
-                    folding_alpha = channel.draw_secure_felt();
+                    L.tree.logw = sh.logw;
+                    L.tree.rank = sh.rank;
+                    uint32_t* roots = d_roots + 8 * (size_t)sh.world * (size_t)li;
+                    nck(api.AllGather(L.tree.layers[0], roots, 8, ncclUint32, sh.comm->comm, st), "ncclAllGather(layer roots)");
+                    sh.comm->n_collectives++;
+                    sh.comm->bytes_sent += 32;
+                    sh.comm->bytes_received += 32 * (size_t)(sh.world - 1);
+                    ck(channel_mix_sharded_root_draw(d_ch, roots, sh.logw, cfg.channel_variant, d_alphas + li + 1,
+                                                     d_digests + 8 * (size_t)li, d_tops + top_words * (size_t)li, st),
+                       "channel mix/draw (sharded layer)");
                     inner.push_back(L);
                     const size_t rl_next = local_rows(line_log - 1);
                     uint32_t* next = arena.alloc<uint32_t>(4 * rl_next);
                     uint32_t* ncoords[4];
                     for (int k = 0; k < 4; ++k) ncoords[k] = next + (size_t)k * rl_next;
-                    ck(fold_line(ncoords, coords, inv_x_twiddles(tw, line_log) + rl_next * sh.rank, line_log - sh.logw, folding_alpha, st),
+                    ck(fold_line_dev(ncoords, coords, inv_x_twiddles(tw, line_log) + rl_next * sh.rank, line_log - sh.logw,
+                                     d_alphas + li + 1, st),
                        "fold line");
                     cur = next;
                     --line_log;
+                    ++li;
                 }
+                n_sharded_layers = li;
                 // hand over to the replicated path: the current layer (if any fold happened) and the quotient columns that are
                 // still to be folded in, all-gathered coordinate by coordinate (rank order = row order)
-                NcclApi& api = nccl_api();
                 if (cur) {
                     const size_t rl = local_rows(line_log);
                     gathered = arena.alloc<uint32_t>((size_t)4 << line_log);
@@ -1551,21 +1658,6 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                 ck(cudaMemcpyAsync(cur, gathered, ((size_t)4 << line_log) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st), "copy");
             else
                 ck(cudaMemsetAsync(cur, 0, ((size_t)4 << line_log) * sizeof(uint32_t), st), "memset");
-            // The per-layer Fiat-Shamir step (mix_root, draw the next folding coefficient) runs on the device
-            // (channel_mix_root_draw), so fold -> Merkle -> mix -> draw -> fold is enqueued for every layer without a host
-            // round trip; roots, digests and the final channel state come back in one copy after the loop.
-            const size_t first_dev_layer = inner.size();
-            int n_layers = std::max(0, line_log - last_log);
-            DevChannel h_ch{};
-            channel.digest_words(h_ch.digest);
-            h_ch.n_sent = channel.n_sent();
-            DevChannel* d_ch = arena.alloc<DevChannel>(1);
-            QM31* d_alphas = arena.alloc<QM31>(n_layers + 1);
-            uint32_t* d_digests = arena.alloc<uint32_t>(8 * (size_t)std::max(n_layers, 1));
-            ck(cudaMemcpyAsync(d_ch, &h_ch, sizeof(h_ch), cudaMemcpyHostToDevice, st), "channel h2d");
-            ck(cudaMemcpyAsync(d_alphas, &folding_alpha, sizeof(QM31), cudaMemcpyHostToDevice, st), "alpha h2d");
-            ck(cudaStreamSynchronize(st), "channel h2d sync");  // h_ch / folding_alpha are stack objects
-            int li = 0;
             while (line_log > last_log) {
                 uint32_t* coords[4];
                 for (int k = 0; k < 4; ++k) coords[k] = cur + ((size_t)k << line_log);
@@ -1626,12 +1718,24 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             }
             if (n_layers > 0) {
                 std::vector<uint32_t> h_digests(8 * (size_t)n_layers);
-                for (int k = 0; k < n_layers; ++k)
-                    ck(cudaMemcpyAsync(inner[first_dev_layer + k].tree.root.b, inner[first_dev_layer + k].tree.layers[0], 32,
-                                       cudaMemcpyDeviceToHost, st), "root d2h");
+                std::vector<uint32_t> h_tops(top_words * (size_t)n_sharded_layers);
+                if (n_sharded_layers)
+                    ck(cudaMemcpyAsync(h_tops.data(), d_tops, h_tops.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "tops d2h");
+                for (int k = n_sharded_layers; k < n_layers; ++k)
+                    ck(cudaMemcpyAsync(inner[k].tree.root.b, inner[k].tree.layers[0], 32, cudaMemcpyDeviceToHost, st), "root d2h");
                 ck(cudaMemcpyAsync(h_digests.data(), d_digests, h_digests.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "digests d2h");
                 ck(cudaMemcpyAsync(&h_ch, d_ch, sizeof(h_ch), cudaMemcpyDeviceToHost, st), "channel d2h");
                 ck(cudaStreamSynchronize(st), "fri loop sync");
+                for (int k = 0; k < n_sharded_layers; ++k) {
+                    // top levels of the row-sharded layer trees (hashed on the device): level j at word 8 * (2^j - 1)
+                    MerkleTree& t = inner[k].tree;
+                    t.top.assign(sh.logw + 1, {});
+                    for (int j = 0; j <= sh.logw; ++j) {
+                        t.top[j].resize((size_t)1 << j);
+                        std::memcpy(t.top[j].data(), h_tops.data() + top_words * (size_t)k + 8 * (((size_t)1 << j) - 1), 32 * ((size_t)1 << j));
+                    }
+                    t.root = t.top[0][0];
+                }
                 for (int k = 0; k < n_layers; ++k) {
                     Hash32 d;
                     std::memcpy(d.b, h_digests.data() + 8 * (size_t)k, 32);
