@@ -572,22 +572,50 @@ struct HostBatch {  // ColumnSampleBatch: one sample point and the (column, valu
     int n_cols_global = -1;  // -1: cols.size()
 };
 
-// PolyOps::eval_at_point for a set of equally sized coefficient columns
+// PolyOps::eval_at_point for several sets of equally sized coefficient columns (one set per (size, point) pair): every
+// argument table of every set goes to the device in ONE staged upload, then the kernels are queued back to back
+struct EvalJob {
+    int log;
+    QPt pt;
+    std::vector<const uint32_t*> cols;
+    QM31* d_out;  // cols.size() results
+};
+void launch_eval_jobs(lb_ctx* ctx, Arena& arena, const std::vector<EvalJob>& jobs) {
+    if (jobs.empty()) return;
+    // one byte blob: per job the fold factors [y, x, pi(x), ...] then the column pointer table
+    std::vector<uint8_t> blob;
+    std::vector<size_t> off_map(jobs.size()), off_cols(jobs.size());
+    auto append = [&](const void* p, size_t n) {
+        size_t at = (blob.size() + 15) & ~(size_t)15;
+        blob.resize(at + n);
+        std::memcpy(blob.data() + at, p, n);
+        return at;
+    };
+    for (size_t j = 0; j < jobs.size(); ++j) {
+        std::vector<QM31> mappings;
+        mappings.push_back(jobs[j].pt.y);
+        QM31 x = jobs[j].pt.x;
+        for (int i = 1; i < jobs[j].log; ++i) {
+            mappings.push_back(x);
+            x = q_double_x(x);
+        }
+        off_map[j] = append(mappings.data(), mappings.size() * sizeof(QM31));
+        off_cols[j] = append(jobs[j].cols.data(), jobs[j].cols.size() * sizeof(const uint32_t*));
+    }
+    uint8_t* d_blob = arena.upload(blob);
+    for (size_t j = 0; j < jobs.size(); ++j) {
+        const EvalJob& job = jobs[j];
+        int m = std::min(job.log, 12);
+        QM31* d_basis = arena.alloc<QM31>((size_t)1 << m);
+        QM31* d_part = arena.alloc<QM31>(job.cols.size() << (job.log - m));
+        ck(eval_at_point((const uint32_t* const*)(d_blob + off_cols[j]), (int)job.cols.size(), job.log, (const QM31*)(d_blob + off_map[j]),
+                         d_basis, d_part, job.d_out, ctx->stream),
+           "eval_at_point");
+    }
+}
 void launch_eval_at_point(lb_ctx* ctx, Arena& arena, const std::vector<const uint32_t*>& cols, int log, const QPt& pt,
                           QM31* d_out) {
-    std::vector<QM31> mappings;
-    mappings.push_back(pt.y);
-    QM31 x = pt.x;
-    for (int i = 1; i < log; ++i) {
-        mappings.push_back(x);
-        x = q_double_x(x);
-    }
-    int m = std::min(log, 12);
-    QM31* d_map = arena.upload(mappings);
-    const uint32_t** d_cols = arena.upload(cols);
-    QM31* d_basis = arena.alloc<QM31>((size_t)1 << m);
-    QM31* d_part = arena.alloc<QM31>(cols.size() << (log - m));
-    ck(eval_at_point(d_cols, (int)cols.size(), log, d_map, d_basis, d_part, d_out, ctx->stream), "eval_at_point");
+    launch_eval_jobs(ctx, arena, {EvalJob{log, pt, cols, d_out}});
 }
 
 // QuotientOps::accumulate_quotients: quotient_constants (core/pcs/quotients.rs) on the host,
@@ -1419,10 +1447,13 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                     }
             std::vector<std::vector<QM31>> results(jobs.size());
             std::vector<QM31*> d_results(jobs.size());
-            for (size_t ji = 0; ji < jobs.size(); ++ji) {
-                Job& j = jobs[ji];
-                d_results[ji] = arena.alloc<QM31>(j.cols.size());
-                launch_eval_at_point(ctx, arena, j.cols, j.log, j.pt, d_results[ji]);
+            {
+                std::vector<EvalJob> ej;
+                for (size_t ji = 0; ji < jobs.size(); ++ji) {
+                    d_results[ji] = arena.alloc<QM31>(jobs[ji].cols.size());
+                    ej.push_back(EvalJob{jobs[ji].log, jobs[ji].pt, jobs[ji].cols, d_results[ji]});
+                }
+                launch_eval_jobs(ctx, arena, ej);
             }
             for (size_t ji = 0; ji < jobs.size(); ++ji) {
                 results[ji].resize(jobs[ji].cols.size());
