@@ -1176,6 +1176,15 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
         {
             // TraceLocationAllocator hands out spans in component (slot) order
             size_t main_next = 0;
+            int n_present = 0;
+            for (int s = 0; s < cfg.n_slots; ++s) n_present += claim[s] >= 0;
+            // claimed sums of all components: one device array, one copy back, one synchronisation
+            uint32_t* d_claimed = arena.alloc<uint32_t>(4 * (size_t)std::max(n_present, 1));
+            ck(cudaMemsetAsync(d_claimed, 0, 4 * (size_t)std::max(n_present, 1) * sizeof(uint32_t), st), "memset");
+            std::vector<Xfer> xs;
+            std::vector<ColRun> inter_runs;
+            std::vector<uint32_t*> inter_bufs;
+            int ci = 0;
             for (int s = 0; s < cfg.n_slots; ++s) {
                 if (claim[s] < 0) continue;
                 Component c = by_slot[s];
@@ -1183,25 +1192,36 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                 size_t n = (size_t)1 << c.log;
                 int n_ic = 4 * shp.n_fracs;
                 uint32_t* inter = arena.alloc<uint32_t>(n * n_ic);
-                uint32_t* scan_tmp = arena.alloc<uint32_t>(4 * n);
-                uint32_t* block_sums = arena.alloc<uint32_t>(4 * (n / 1024 + 1));
-                uint32_t* d_claimed = arena.alloc<uint32_t>(4);
-                PreCols pc{};
-                for (int q = 0; q < shp.n_pre; ++q) pc.p[q] = pre_cols[c.pre_idx[q]].evals;
-                ck(logup_interaction_trace(c.kind, c.main_evals, n, pc, inter, n, c.log, rels, scan_tmp, block_sums, d_claimed, st),
-                   "logup");
-                uint32_t cl[4];
-                ck(cudaMemcpyAsync(cl, d_claimed, 16, cudaMemcpyDeviceToHost, st), "claimed d2h");
-                // sharded: the LogUp columns are computed on every rank (replicated input, no exchange); each rank interpolates
-                // the ones it owns
-                c.inter_loc = trees[2].cols.size();
-                {
-                    ColRun run = push_run(trees[2], inter, n_ic, c.log);
-                    int a, b;
-                    own_range(trees[2], run, sh.rank, a, b);
-                    if (b > a) ck(cfft_interpolate(&tw, inter + (size_t)a * n, n, b - a, c.log, ctx->sm_count, st), "interpolate interaction");
+                // Sharded: the LogUp columns of component i are generated by rank i mod W (the trace is replicated input) and
+                // every column is sent, whole, to the rank that owns it for interpolation / LDE; the claimed sums are summed
+                // over the ranks (one contributor each)
+                const int compute_rank = sh.on() ? ci % sh.world : 0;
+                if (compute_rank == sh.rank) {
+                    uint32_t* scan_tmp = arena.alloc<uint32_t>(4 * n);
+                    uint32_t* block_sums = arena.alloc<uint32_t>(4 * (n / 1024 + 1));
+                    PreCols pc{};
+                    for (int q = 0; q < shp.n_pre; ++q) pc.p[q] = pre_cols[c.pre_idx[q]].evals;
+                    ck(logup_interaction_trace(c.kind, c.main_evals, n, pc, inter, n, c.log, rels, scan_tmp, block_sums,
+                                               d_claimed + 4 * (size_t)ci, st),
+                       "logup");
+                    arena.release(scan_tmp);  // stream-ordered
+                    arena.release(block_sums);
                 }
+                arena.release(c.main_evals);
+                c.main_evals = nullptr;
+                c.inter_loc = trees[2].cols.size();
+                ColRun run = push_run(trees[2], inter, n_ic, c.log);
+                inter_runs.push_back(run);
+                inter_bufs.push_back(inter);
                 if (sh.on()) {
+                    for (int o = 0; o < sh.world; ++o) {
+                        if (o == compute_rank) continue;
+                        int oa, ob;
+                        own_range(trees[2], run, o, oa, ob);
+                        if (ob <= oa) continue;
+                        if (sh.rank == compute_rank) xs.push_back({inter + (size_t)oa * n, nullptr, (size_t)(ob - oa) * n, o, true});
+                        if (sh.rank == o) xs.push_back({nullptr, inter + (size_t)oa * n, (size_t)(ob - oa) * n, compute_rank, false});
+                    }
                     // the [-1] mask of the last LogUp column reads a predecessor row that lives in another rank's row shard:
                     // the column's owner ships a shifted copy with the exchange of this tree
                     if (c.eval_log != c.log + blowup)
@@ -1211,15 +1231,29 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                     c.inter_prev = arena.alloc<uint32_t>(4 * rl);
                     inter_aux.push_back({c.inter_loc + (size_t)(n_ic - 4), c.log, c.inter_prev});
                 }
-                ck(cudaStreamSynchronize(st), "claimed sync");
-                c.claimed_sum = q_make(cl[0], cl[1], cl[2], cl[3]);
-                arena.release(scan_tmp);
-                arena.release(c.main_evals);
-                c.main_evals = nullptr;
                 c.main_loc = main_next;  // span in slot order (equals the pie-order location when the pie is slot-ordered)
                 main_next += shp.n_main;
                 comps.push_back(c);
+                ++ci;
             }
+            if (sh.on()) {
+                if (!xs.empty()) run_exchange(ctx, sh, xs);
+                nck(nccl_api().AllReduce(d_claimed, d_claimed, 4 * (size_t)n_present, ncclUint32, ncclSum, sh.comm->comm, st),
+                    "ncclAllReduce(claimed sums)");
+                sh.comm->n_collectives++;
+            }
+            std::vector<uint32_t> cl(4 * (size_t)std::max(n_present, 1));
+            ck(cudaMemcpyAsync(cl.data(), d_claimed, cl.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "claimed d2h");
+            for (size_t k = 0; k < inter_runs.size(); ++k) {
+                int a, b;
+                own_range(trees[2], inter_runs[k], sh.rank, a, b);
+                size_t n = (size_t)1 << inter_runs[k].log;
+                if (b > a)
+                    ck(cfft_interpolate(&tw, inter_bufs[k] + (size_t)a * n, n, b - a, inter_runs[k].log, ctx->sm_count, st),
+                       "interpolate interaction");
+            }
+            ck(cudaStreamSynchronize(st), "claimed sync");
+            for (size_t k = 0; k < comps.size(); ++k) comps[k].claimed_sum = q_make(cl[4 * k], cl[4 * k + 1], cl[4 * k + 2], cl[4 * k + 3]);
         }
         for (const Component& c : comps) channel.mix_felts({c.claimed_sum});  // LuminairInteractionClaim::mix_into
         commit_tree(trees[2], sh.on() ? &inter_aux : nullptr);
