@@ -15,7 +15,7 @@ from luminair_b200.workloads import build_add_graph, build_wide, synthetic_add_g
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-log = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+log = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 20
 torch.cuda.set_device(local)
 dist.init_process_group("gloo")  # only carries the 128-byte NCCL id and the barriers of this script
 be = CudaBackend(local)
@@ -61,6 +61,23 @@ def _bench(name, rec, fixture):
 a, b = synthetic_add_graph_inputs(log, seed=42)
 ok1 = bench("cfg3_add", build_add_graph(DeviceGraphTrace(be), a, b), "cfg3_add_log20.proof.bin")
 ok2 = bench("wide", build_wide(DeviceGraphTrace(be), log), "wide_log20.proof.bin")
+if "--all-components" in sys.argv:
+    # every component incl. the four lookup tables (test infrastructure: host tables and LUT layouts from the numpy checker),
+    # non-default PcsConfig and the "v2" channel: sharded bytes == single-GPU bytes
+    from luminair_b200.prover import PcsConfig
+    from oracle import pie as opie
+    pie, pre = opie.all_components_graph(n=1 << 16, seed=3)  # lookup tables (2^8 .. 2^15) no larger than their consumers
+    ok3 = True
+    for cfg, variant in ((None, "legacy"), (PcsConfig(7, 1, 1, 9), "v2")):  # blow-up 2 (the reference's): see DESIGN section 6
+        single = prove(pie, backend=be, preprocessed=pre, config=cfg, channel_variant=variant)
+        dist.barrier()
+        sharded = prove(pie, backend=be, preprocessed=pre, config=cfg, channel_variant=variant, comm=comm)
+        ok3 = ok3 and sharded == single
+    flag = torch.tensor([1 if ok3 else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["all_components"] = {"proof_equals_single_device": bool(flag[0]), "tables": {k: list(v.shape) for k, v in pie},
+                             "configs": ["default / legacy channel", "pow 7, last-layer bound 2, 9 queries / v2 channel"]}
+    ok2 = ok2 and bool(flag[0])
 if rank == 0:
     print(json.dumps(out), flush=True)
 comm.close()

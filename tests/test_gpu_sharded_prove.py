@@ -25,7 +25,7 @@ def test_sharded_proof_equals_single_gpu_proof(world):
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(29530 + world), os.path.join(ROOT, "scripts", "run_sharded_prove.py"), "14"]
+           "--master-port", str(29530 + world), os.path.join(ROOT, "scripts", "run_sharded_prove.py"), "14", "--all-components"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
@@ -34,6 +34,7 @@ def test_sharded_proof_equals_single_gpu_proof(world):
     for name in ("cfg3_add", "wide"):
         assert out[name]["proof_equals_single_device"] is True
         assert out[name]["nccl"]["bytes_sent"] > 0
+    assert out["all_components"]["proof_equals_single_device"] is True  # 17 components, LUT tree, two PcsConfigs / channels
 
 
 def test_comm_entry_points_fail_cleanly_without_a_gpu():
