@@ -207,10 +207,16 @@ cudaError_t eval_at_point(const uint32_t* const* d_cols, int n_cols, int log, co
 // x_h = +-X[log-1][h >> 1] (sign by the low bit of h: adjacent half-coset points differ by the order-2 point),
 // row 2h+1 is the conjugate.  Each thread handles QROWS rows 256 apart so that all QROWS * n_batches
 // denominators share ONE field inversion.
-constexpr int QROWS = 4;
+#ifndef LB_QROWS
+#define LB_QROWS 4
+#endif
+#ifndef LB_Q_MINBLOCKS
+#define LB_Q_MINBLOCKS 3  // measured r2 (cfg 3 DEEP stage): 2 -> 0.670 ms, 3 -> 0.632 ms, 4 rows x 3 CTAs; 2 rows x 4 CTAs 0.645, 8 rows x 1 CTA 0.791
+#endif
+constexpr int QROWS = LB_QROWS;
 
 template <int NB>
-__global__ void __launch_bounds__(256, 2) quotients_kernel(uint32_t* __restrict__ o0, uint32_t* __restrict__ o1,
+__global__ void __launch_bounds__(256, LB_Q_MINBLOCKS) quotients_kernel(uint32_t* __restrict__ o0, uint32_t* __restrict__ o1,
                                                         uint32_t* __restrict__ o2, uint32_t* __restrict__ o3,
                                                         const uint32_t* const* __restrict__ cols,
                                                         const QuotientEntry* __restrict__ entries,

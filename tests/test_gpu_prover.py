@@ -423,3 +423,47 @@ def test_large_proof_is_accepted(be):
     lp = from_bincode(proof)
     assert lp.claim[0] == 22 and lp.claim[15] == 23
     overifier.verify(lp)
+
+
+def test_bad_prove_configs_are_rejected_not_looped_on(be):
+    """a pow_bits no 64-bit nonce can satisfy must be an error, not an endless grind; unknown channel variants and
+    absurd FRI parameters likewise.  Nothing crosses the C ABI but a return code."""
+    from luminair_b200._lib import LuminairB200Error
+    from luminair_b200.prover import PcsConfig, prove
+    pie = examples.simple_pie("current")
+    for cfg in (PcsConfig(41, 1, 0, 3), PcsConfig(5, 1, 17, 3), PcsConfig(5, 1, 0, 0), PcsConfig(5, 7, 0, 3)):
+        with pytest.raises(LuminairB200Error, match="LB_ERR_BAD_ARG"):
+            prove(pie, backend=be, config=cfg)
+    import ctypes as C
+    from luminair_b200._lib import ProveConfig, TraceTable
+    t = (TraceTable * 1)()
+    rows = np.ascontiguousarray(pie[0][1], dtype=np.uint32)
+    t[0].slot, t[0].n_cols, t[0].n_rows, t[0].rows = 0, 15, rows.shape[0], rows.ctypes.data
+    cfg = ProveConfig(5, 1, 0, 3, 7, 17, 0, 1)  # channel_variant 7
+    out, n = C.c_void_p(), C.c_size_t()
+    assert be.lib.lb_prove(be.ctx, t, 1, C.byref(cfg), C.byref(out), C.byref(n)) == -3
+    assert be.lib.lb_gather_rows(be.ctx, None, 3, None, 2, None) == -3  # null pointers with non-zero counts
+    # the backend still works afterwards
+    assert len(prove(pie, backend=be)) > 1000
+
+
+def test_two_contexts_interleave(be):
+    """every entry point makes its context's device current and restores the caller's; two contexts used
+    alternately from one thread (same or different GPUs) must not disturb each other."""
+    import torch
+    from luminair_b200.backend import ColumnBatch, CudaBackend
+    other = CudaBackend(1 if torch.cuda.device_count() > 1 else 0)
+    before = torch.cuda.current_device()
+    try:
+        rng = np.random.Generator(np.random.PCG64(2))
+        vals = rng.integers(0, (1 << 31) - 1, size=(2, 1 << 12), dtype=np.uint64).astype(np.uint32)
+        a = ColumnBatch(be.upload(vals.reshape(-1)), 2, 12)
+        b = ColumnBatch(other.upload(vals.reshape(-1)), 2, 12)
+        be.interpolate(a)
+        other.interpolate(b)
+        be.evaluate(a, a)
+        other.evaluate(b, b)
+        assert np.array_equal(be.download(a.buf), vals.reshape(-1)) and np.array_equal(other.download(b.buf), vals.reshape(-1))
+        assert torch.cuda.current_device() == before  # the calls left the caller's device alone
+    finally:
+        other.close()
