@@ -551,6 +551,7 @@ void lb_comm_destroy(lb_comm* comm) {
     if (!comm) return;
     lb::DeviceGuard _dg(comm->ctx);
     if (comm->ctx) cudaStreamSynchronize(comm->ctx->stream);
+    lb::release_symmetric(comm);  // peers' mappings first, then this rank's buffer (callers destroy collectively)
     if (comm->comm) lb::nccl_api().CommDestroy(comm->comm);
     delete comm;
 }
@@ -559,7 +560,7 @@ int lb_comm_stats(const lb_comm* comm, int* rank, int* world, uint64_t* bytes_se
     if (!comm) return LB_ERR_BAD_ARG;
     if (rank) *rank = comm->rank;
     if (world) *world = comm->world;
-    if (bytes_sent) *bytes_sent = comm->bytes_sent;
+    if (bytes_sent) *bytes_sent = comm->bytes_sent + comm->bytes_peer_stored;  // NCCL sends + direct NVLink peer stores
     if (bytes_received) *bytes_received = comm->bytes_received;
     if (n_collectives) *n_collectives = comm->n_collectives;
     return LB_OK;

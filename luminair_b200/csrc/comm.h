@@ -6,6 +6,7 @@
 #include <nccl.h>
 
 #include <string>
+#include <vector>
 
 #include "ctx.h"
 
@@ -71,4 +72,24 @@ struct lb_comm {
     // traffic of the last lb_prove_sharded on this rank
     unsigned long long bytes_sent = 0, bytes_received = 0;
     int n_collectives = 0;
+    // Symmetric heap for the fused exchange: every rank allocates the same-sized buffer and maps every peer's copy (CUDA IPC,
+    // NVLink peer access), so a kernel on rank a can store straight into rank b's buffer at the same offset.  sym_peer[r] is
+    // this process's mapping of rank r's buffer (sym_peer[rank] == sym_base).  ipc: 1 usable, 0 unavailable (same-process
+    // ranks, IPC refused, LB_SHARD_IPC=0): the exchange then goes through NCCL send/recv.
+    uint32_t* sym_base = nullptr;
+    size_t sym_words = 0, sym_used = 0;
+    std::vector<uint32_t*> sym_peer;
+    int ipc = -1;
+    unsigned long long bytes_peer_stored = 0;  // written into peers' memory by the fused LDE / shift kernels
 };
+
+namespace lb {
+inline void release_symmetric(lb_comm* c) {
+    for (int r = 0; r < (int)c->sym_peer.size(); ++r)
+        if (r != c->rank && c->sym_peer[r]) cudaIpcCloseMemHandle(c->sym_peer[r]);
+    c->sym_peer.clear();
+    if (c->sym_base) cudaFree(c->sym_base);
+    c->sym_base = nullptr;
+    c->sym_words = 0;
+}
+}  // namespace lb

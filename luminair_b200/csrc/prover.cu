@@ -769,6 +769,84 @@ void run_exchange(lb_ctx* ctx, Shard& sh, const std::vector<Xfer>& xs) {
     nck(api.GroupEnd(), "ncclGroupEnd");
     sh.comm->n_collectives++;
 }
+// stream-ordered barrier over the ranks: when it completes on this stream, every rank's stream has passed the same point
+void shard_barrier(lb_ctx* ctx, Shard& sh, uint32_t* d_word) {
+    nck(nccl_api().AllReduce(d_word, d_word, 1, ncclUint32, ncclSum, sh.comm->comm, ctx->stream), "ncclAllReduce(barrier)");
+    sh.comm->n_collectives++;
+}
+// (collective) make the symmetric heap at least `words` large and mapped on every rank; false: IPC is not usable here
+bool ensure_symmetric(lb_ctx* ctx, Arena& arena, Shard& sh, size_t words) {
+    lb_comm* c = sh.comm;
+    if (c->ipc == 0) return false;
+    if (c->ipc < 0 && getenv("LB_SHARD_IPC") && atoi(getenv("LB_SHARD_IPC")) == 0) {
+        c->ipc = 0;
+        return false;
+    }
+    if (c->sym_words >= words) return true;
+    NcclApi& api = nccl_api();
+    uint32_t* d_word = arena.alloc<uint32_t>(1);
+    ck(cudaMemsetAsync(d_word, 0, 4, ctx->stream), "memset");
+    shard_barrier(ctx, sh, d_word);  // nobody still reads or writes the old heap
+    ck(cudaStreamSynchronize(ctx->stream), "sym sync");
+    release_symmetric(c);
+    size_t want = words + words / 4 + 4096;
+    int ok = cudaMalloc(&c->sym_base, want * sizeof(uint32_t)) == cudaSuccess;
+    cudaIpcMemHandle_t mine;
+    std::memset(&mine, 0, sizeof(mine));
+    if (ok) ok = cudaIpcGetMemHandle(&mine, c->sym_base) == cudaSuccess;
+    // all-gather the handles (+ an ok flag per rank)
+    struct Slot {
+        cudaIpcMemHandle_t h;
+        int ok;
+        int pad[15];
+    };
+    static_assert(sizeof(Slot) == 128, "slot size");
+    std::vector<Slot> all(sh.world);
+    Slot me{};
+    me.h = mine;
+    me.ok = ok;
+    Slot* d_all = arena.alloc<Slot>(sh.world);
+    ck(cudaMemcpyAsync(d_all + sh.rank, &me, sizeof(Slot), cudaMemcpyHostToDevice, ctx->stream), "handle h2d");
+    nck(api.AllGather(d_all + sh.rank, d_all, sizeof(Slot), ncclChar, c->comm, ctx->stream), "ncclAllGather(ipc handles)");
+    ck(cudaMemcpyAsync(all.data(), d_all, sizeof(Slot) * sh.world, cudaMemcpyDeviceToHost, ctx->stream), "handle d2h");
+    ck(cudaStreamSynchronize(ctx->stream), "handle sync");
+    for (auto& sl : all) ok = ok && sl.ok;
+    c->sym_peer.assign(sh.world, nullptr);
+    if (ok) {
+        for (int r = 0; r < sh.world && ok; ++r) {
+            if (r == sh.rank) {
+                c->sym_peer[r] = c->sym_base;
+                continue;
+            }
+            void* ptr = nullptr;
+            ok = cudaIpcOpenMemHandle(&ptr, all[r].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            c->sym_peer[r] = (uint32_t*)ptr;
+        }
+        cudaGetLastError();  // clear a refused mapping (same-process ranks, no peer access)
+    }
+    // agree: one refusal anywhere switches every rank to the NCCL exchange
+    uint32_t flag = ok ? 0u : 1u;
+    ck(cudaMemcpyAsync(d_word, &flag, 4, cudaMemcpyHostToDevice, ctx->stream), "flag h2d");
+    shard_barrier(ctx, sh, d_word);
+    ck(cudaMemcpyAsync(&flag, d_word, 4, cudaMemcpyDeviceToHost, ctx->stream), "flag d2h");
+    ck(cudaStreamSynchronize(ctx->stream), "flag sync");
+    if (flag != 0) {
+        release_symmetric(c);
+        c->ipc = 0;
+        return false;
+    }
+    c->sym_words = want;
+    c->ipc = 1;
+    return true;
+}
+inline uint32_t* sym_alloc(lb_comm* c, size_t words) {
+    size_t off = (c->sym_used + 63) & ~(size_t)63;
+    if (off + words > c->sym_words) fail(LB_ERR_OOM, "sharded prove: symmetric heap too small (internal size estimate)");
+    c->sym_used = off + words;
+    return c->sym_base + off;
+}
+inline uint32_t* peer_ptr(const lb_comm* c, int r, const uint32_t* local) { return c->sym_peer[r] + (local - c->sym_base); }
+
 // root of a row-sharded tree: all-gather the sub-tree roots, hash the log2(world) levels above them on the host
 void finish_sharded_root(lb_ctx* ctx, Arena& arena, Shard& sh, MerkleTree& t) {
     t.logw = sh.logw;
@@ -914,8 +992,33 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
         }
         const Twiddles& tw = ctx->tw;
 
+        bool use_ipc = false;  // fused exchange: LDE tiles stored straight into the owner rank's row-shard buffer (NVLink)
+        uint32_t* d_barrier = nullptr;
         if (sh.on()) {
             if (!nccl_api().load()) fail(LB_ERR_NCCL, nccl_api().error);
+            // symmetric heap: the row shards of every committed column + the shifted LogUp copies, the same layout on all ranks
+            size_t words = 0;
+            auto shard_words = [&](int lg, size_t n_cols) { return ((((size_t)n_cols << (lg + blowup)) >> sh.logw) + 64); };
+            int top = 0;
+            for (int t = 0; t < n_tables; ++t) {
+                int lg = 0;
+                while (((uint64_t)1 << lg) < tables[t].n_rows) ++lg;
+                if (lg < 4) lg = 4;
+                top = std::max(top, lg);
+                int kind = kind_of_slot(tables[t].slot, cfg.n_slots, cfg.air_era);
+                if (kind < 0) continue;
+                ComponentShape shp = component_shape(kind);
+                words += shard_words(lg, shp.n_main) + shard_words(lg, 4 * shp.n_fracs) + shard_words(lg, 4);
+            }
+            for (int k = 0; k < n_pre; ++k) words += shard_words(pre_in[k].log_size, 1);
+            words += shard_words(top + blowup, 4);  // composition: log = max evaluation domain = top + blowup (no extension)
+            d_barrier = arena.alloc<uint32_t>(1);
+            ck(cudaMemsetAsync(d_barrier, 0, 4, st), "memset");
+            use_ipc = ensure_symmetric(ctx, arena, sh, words);
+            sh.comm->sym_used = 0;
+            sh.comm->bytes_peer_stored = 0;
+            // no rank may store into a peer's heap before that peer is done with the previous proof
+            if (use_ipc) shard_barrier(ctx, sh, d_barrier);
         }
         struct AuxReq {  // non-committed columns shipped with a tree's exchange: the [-1]-shifted copies of the 4 coordinate
             size_t col;  // columns col .. col + 3 (the last LogUp column of a component)
@@ -958,11 +1061,13 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                 int a, b;
                 own_range(tree, run, sh.rank, a, b);
                 const size_t rl = out_stride >> sh.logw;
-                uint32_t* local = arena.alloc<uint32_t>(rl * run.n);
-                // Large columns: the last pass of the transform writes every 4096-row tile straight into a per-destination
-                // staging block (cfft_evaluate_scatter; this rank's own rows go directly to their final place), so the
-                // exchange is ONE contiguous message per peer and run - received in place, because an owner's columns are
-                // contiguous in the run.  Small columns: plain transform, one message per column and peer.
+                uint32_t* local = use_ipc ? sym_alloc(sh.comm, rl * run.n) : arena.alloc<uint32_t>(rl * run.n);
+                // Large columns: the last pass of the transform (cfft_evaluate_scatter) writes every 4096-row tile straight
+                // to where it belongs.  Fused exchange (use_ipc): that is the owner rank's row-shard buffer itself, mapped over
+                // NVLink - no staging, no message, the transfer overlaps the butterflies tile by tile.  Otherwise: a
+                // per-destination staging block, so the exchange is ONE contiguous NCCL message per peer and run, received in
+                // place (an owner's columns are contiguous in the run).  Small columns: plain transform, one message per column
+                // and peer.
                 const bool packed = L >= 16 && L - sh.logw >= 12 && sh.world <= 8;
                 uint32_t* own = nullptr;   // !packed: the owned columns, whole
                 uint32_t* pack = nullptr;  // packed: [peer][owned column][rl] (this rank's slot unused)
@@ -970,22 +1075,28 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                     own = arena.alloc<uint32_t>(out_stride * (b - a));
                     to_free.push_back(own);
                     if (packed) {
-                        pack = arena.alloc<uint32_t>(out_stride * (b - a));
-                        to_free.push_back(pack);
                         uint32_t* peers[8];
-                        for (int r = 0; r < sh.world; ++r)
-                            peers[r] = r == sh.rank ? local + (size_t)a * rl : pack + (size_t)r * (b - a) * rl;
+                        if (use_ipc) {
+                            for (int r = 0; r < sh.world; ++r) peers[r] = peer_ptr(sh.comm, r, local) + (size_t)a * rl;
+                            sh.comm->bytes_peer_stored += (size_t)(b - a) * rl * 4 * (size_t)(sh.world - 1);
+                        } else {
+                            pack = arena.alloc<uint32_t>(out_stride * (b - a));
+                            to_free.push_back(pack);
+                            for (int r = 0; r < sh.world; ++r)
+                                peers[r] = r == sh.rank ? local + (size_t)a * rl : pack + (size_t)r * (b - a) * rl;
+                        }
                         ck(cfft_evaluate_scatter(&tw, tree.cols[run.first + a].coeffs, stride, lg, own, out_stride, L, b - a, peers,
                                                  sh.world, 0, ctx->sm_count, st),
                            "LDE evaluate + scatter (own columns)");
-                        for (int r = 0; r < sh.world; ++r)
-                            if (r != sh.rank) xs.push_back({peers[r], nullptr, (size_t)(b - a) * rl, r, true});
+                        if (!use_ipc)
+                            for (int r = 0; r < sh.world; ++r)
+                                if (r != sh.rank) xs.push_back({peers[r], nullptr, (size_t)(b - a) * rl, r, true});
                     } else {
                         ck(cfft_evaluate(&tw, tree.cols[run.first + a].coeffs, stride, lg, own, out_stride, L, b - a, ctx->sm_count, st),
                            "LDE evaluate (own columns)");
                     }
                 }
-                if (packed) {
+                if (packed && !use_ipc) {
                     for (int r = 0; r < sh.world; ++r) {
                         if (r == sh.rank) continue;
                         int ra, rb;
@@ -1023,31 +1134,44 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                             if (q1 <= q0) continue;
                             const size_t cnt = (size_t)(q1 - q0) * rl;
                             if (r != sh.rank) {
-                                xs.push_back({nullptr, rq.dst + (size_t)q0 * rl, cnt, r, false});
+                                if (!use_ipc) xs.push_back({nullptr, rq.dst + (size_t)q0 * rl, cnt, r, false});
                                 continue;
                             }
-                            uint32_t* stage = arena.alloc<uint32_t>(cnt * sh.world);  // [peer][owned shifted column][rl]
-                            to_free.push_back(stage);
+                            uint32_t* stage = nullptr;  // [peer][owned shifted column][rl]; fused exchange: not needed
+                            if (!use_ipc) {
+                                stage = arena.alloc<uint32_t>(cnt * sh.world);
+                                to_free.push_back(stage);
+                            } else {
+                                sh.comm->bytes_peer_stored += cnt * 4 * (size_t)(sh.world - 1);
+                            }
                             for (int q = q0; q < q1; ++q) {
                                 const int k = k0 + q;
                                 const uint32_t* src[8];
                                 uint32_t* dst[8];
                                 for (int t = 0; t < sh.world; ++t) {
-                                    if (packed)
+                                    if (packed && use_ipc)  // the column's shards already sit in their owners' buffers
+                                        src[t] = peer_ptr(sh.comm, t, local) + (size_t)k * rl;
+                                    else if (packed)
                                         src[t] = (t == sh.rank ? local + (size_t)a * rl : pack + (size_t)t * (b - a) * rl) + (size_t)(k - a) * rl;
                                     else
                                         src[t] = own + (size_t)(k - a) * out_stride + (size_t)t * rl;
-                                    dst[t] = (t == sh.rank ? rq.dst + (size_t)q * rl : stage + (size_t)t * cnt + (size_t)(q - q0) * rl);
+                                    if (use_ipc)
+                                        dst[t] = peer_ptr(sh.comm, t, rq.dst) + (size_t)q * rl;
+                                    else
+                                        dst[t] = (t == sh.rank ? rq.dst + (size_t)q * rl : stage + (size_t)t * cnt + (size_t)(q - q0) * rl);
                                 }
                                 ck(shifted_prev_column(dst, sh.world, src, sh.world, rq.domain_log, L, st), "shifted column");
                             }
-                            for (int t = 0; t < sh.world; ++t)
-                                if (t != sh.rank) xs.push_back({stage + (size_t)t * cnt, nullptr, cnt, t, true});
+                            if (!use_ipc)
+                                for (int t = 0; t < sh.world; ++t)
+                                    if (t != sh.rank) xs.push_back({stage + (size_t)t * cnt, nullptr, cnt, t, true});
                         }
                     }
             }
             if (sh.on()) {
                 if (!xs.empty()) run_exchange(ctx, sh, xs);
+                // fused exchange: my rows are complete once EVERY rank's kernels have run - a stream-ordered barrier
+                if (use_ipc) shard_barrier(ctx, sh, d_barrier);
                 for (uint32_t* f : to_free) arena.release(f);  // stream-ordered: freed after the sends have read them
             }
             merkle_commit(ctx, arena, refs, tree.merkle, /*fetch_root=*/!sh.on());
@@ -1228,7 +1352,7 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                         fail(LB_ERR_BAD_ARG, "prove (sharded): a component evaluated on a domain other than its committed one "
                                              "(lookup table larger than its consumer's trace) is not supported yet");
                     size_t rl = ((size_t)1 << (c.log + blowup)) >> sh.logw;
-                    c.inter_prev = arena.alloc<uint32_t>(4 * rl);
+                    c.inter_prev = use_ipc ? sym_alloc(sh.comm, 4 * rl) : arena.alloc<uint32_t>(4 * rl);
                     inter_aux.push_back({c.inter_loc + (size_t)(n_ic - 4), c.log, c.inter_prev});
                 }
                 c.main_loc = main_next;  // span in slot order (equals the pie-order location when the pie is slot-ordered)
