@@ -355,7 +355,7 @@ def run_gpu(args):
             "gpu_launches": args.steps * n_launch_per_step,
             "roofline": {"bound": "hbm", "kernel": "cfft_low_fast / cfft_high_vec (the 4 CFFT passes of a step)", "achieved": achieved, "peak": peak,
                          "peak_source": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, mean of the 4 passes, profiles/r1_cfft_v8_ncu_full_summary.csv",
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, mean of the 4 passes, profiles/r2_cfft_ncu_full_summary.csv (same kernels as profiles/r1_cfft_v8_ncu_full_summary.csv)",
                          "algorithmic_bytes_per_launch": alg_bytes_launch, "avg_launch_ms": avg_launch_ms,
                          "interpolate_ms": t_int, "evaluate_ms": t_ev},
         }

@@ -106,3 +106,12 @@ def test_large_fixtures_are_what_the_cpu_prover_produces(golden_dir):
     # a 2^16 cross-check of the two CPU restatements themselves (numpy takes ~15 s)
     pie = piemod.synthetic_add_graph_pie(16, seed=42)
     assert cp.prove(pie) == to_bincode(oprover.prove(pie))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_graphs_equal_numpy(seed):
+    """Random operator graphs over all component kinds (the generator of tests/test_gpu_random_graphs.py): the two CPU
+    restatements - numpy and the compiled prover - produce the same proof bytes."""
+    from test_gpu_random_graphs import random_graph
+    pie, pre = random_graph(100 + seed)
+    assert cp.prove(pie, preprocessed=pre) == to_bincode(oprover.prove(pie, preprocessed=pre))
