@@ -267,9 +267,7 @@ void lb_free_host(void* p);
  *   - the Fiat-Shamir channel runs replicated on every rank.
  * Every rank passes the same tables / LUT columns / configuration (the trace is replicated input: on the device it is
  * generated by lb_trace_* in microseconds).  NCCL is bound at run time (libnccl.so.2); without it these entry points return
- * LB_ERR_NCCL and the single-GPU entry points are unaffected.  Limitation: a component evaluated on a domain other than
- * its committed one (a lookup table larger than its consumer's trace, or log_blowup_factor != 1) is rejected with
- * LB_ERR_BAD_ARG for world > 1. */
+ * LB_ERR_NCCL and the single-GPU entry points are unaffected.  Every committed column needs at least 4 rows per rank. */
 #define LB_COMM_ID_BYTES 128
 typedef struct lb_comm lb_comm;
 /* rank 0 creates the id (ncclGetUniqueId); the host hands it to the other ranks by its own means (MPI, a file, a socket) */

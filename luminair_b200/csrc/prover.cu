@@ -998,20 +998,27 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             if (!nccl_api().load()) fail(LB_ERR_NCCL, nccl_api().error);
             // symmetric heap: the row shards of every committed column + the shifted LogUp copies, the same layout on all ranks
             size_t words = 0;
-            auto shard_words = [&](int lg, size_t n_cols) { return ((((size_t)n_cols << (lg + blowup)) >> sh.logw) + 64); };
-            int top = 0;
+            auto shard_words = [&](int lde_log, size_t n_cols) { return ((((size_t)n_cols << lde_log) >> sh.logw) + 64); };
+            int lut_sz[REL_COUNT];
+            for (int k = 0; k < REL_COUNT; ++k) lut_sz[k] = -1;
+            for (int k = 0; k < n_pre; ++k)
+                if (pre_in[k].lut >= 0 && pre_in[k].lut < REL_COUNT) lut_sz[pre_in[k].lut] = pre_in[k].log_size;
+            int top_eval = 0;
             for (int t = 0; t < n_tables; ++t) {
                 int lg = 0;
                 while (((uint64_t)1 << lg) < tables[t].n_rows) ++lg;
                 if (lg < 4) lg = 4;
-                top = std::max(top, lg);
                 int kind = kind_of_slot(tables[t].slot, cfg.n_slots, cfg.air_era);
                 if (kind < 0) continue;
                 ComponentShape shp = component_shape(kind);
-                words += shard_words(lg, shp.n_main) + shard_words(lg, 4 * shp.n_fracs) + shard_words(lg, 4);
+                int ev = ((consumes_lut(kind) && shp.lut && lut_sz[shp.lut] >= 0) ? std::max(lg, lut_sz[shp.lut]) : lg) + 1;
+                top_eval = std::max(top_eval, ev);
+                words += shard_words(lg + blowup, shp.n_main) + shard_words(lg + blowup, 4 * shp.n_fracs) + shard_words(lg + blowup, 4);
+                // constraint evaluation on another domain than the committed one: the columns are sharded a second time
+                if (ev != lg + blowup) words += shard_words(ev, shp.n_main) + shard_words(ev, 4 * shp.n_fracs) + shard_words(ev, 4 + 2);
             }
-            for (int k = 0; k < n_pre; ++k) words += shard_words(pre_in[k].log_size, 1);
-            words += shard_words(top + blowup, 4);  // composition: log = max evaluation domain = top + blowup (no extension)
+            for (int k = 0; k < n_pre; ++k) words += shard_words(pre_in[k].log_size + blowup, 1) + shard_words(top_eval, 1);
+            words += shard_words(top_eval + blowup, 4);  // composition: log = the largest evaluation domain
             d_barrier = arena.alloc<uint32_t>(1);
             ck(cudaMemsetAsync(d_barrier, 0, 4, st), "memset");
             use_ipc = ensure_symmetric(ctx, arena, sh, words);
@@ -1037,6 +1044,124 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             tree.runs.push_back(run);
             return run;
         };
+        // Sharded: evaluate the polynomials of one run (each on its owner rank) on CanonicCoset(L) and leave every rank with
+        // its row shard [rank R/W, (rank+1) R/W) of ALL of them (run.n columns at stride R/W; returned).  Transfers that need
+        // NCCL are appended to `xs` (the caller runs ONE grouped exchange for everything it shards), temporaries to `to_free`.
+        // `aux`: [-1]-shifted copies of columns of this run to ship along (constraint evaluation on row shards).
+        auto shard_run = [&](CommitTree& tree, const ColRun& run, int L, const std::vector<AuxReq>* aux, std::vector<Xfer>& xs,
+                             std::vector<uint32_t*>& to_free) -> uint32_t* {
+            const int lg = run.log;
+            const size_t stride = (size_t)1 << lg, out_stride = (size_t)1 << L;
+            if (L - sh.logw < 2) fail(LB_ERR_BAD_ARG, "prove (sharded): a committed column has fewer than 4 rows per rank");
+            int a, b;
+            own_range(tree, run, sh.rank, a, b);
+            const size_t rl = out_stride >> sh.logw;
+            uint32_t* local = use_ipc ? sym_alloc(sh.comm, rl * run.n) : arena.alloc<uint32_t>(rl * run.n);
+            // Large columns: the last pass of the transform (cfft_evaluate_scatter) writes every 4096-row tile straight
+            // to where it belongs.  Fused exchange (use_ipc): that is the owner rank's row-shard buffer itself, mapped over
+            // NVLink - no staging, no message, the transfer overlaps the butterflies tile by tile.  Otherwise: a
+            // per-destination staging block, so the exchange is ONE contiguous NCCL message per peer and run, received in
+            // place (an owner's columns are contiguous in the run).  Small columns: plain transform, one message per column
+            // and peer.
+            const bool packed = L >= 16 && L - sh.logw >= 12 && sh.world <= 8;
+            uint32_t* own = nullptr;   // !packed: the owned columns, whole
+            uint32_t* pack = nullptr;  // packed: [peer][owned column][rl] (this rank's slot unused)
+            if (b > a) {
+                own = arena.alloc<uint32_t>(out_stride * (b - a));
+                to_free.push_back(own);
+                if (packed) {
+                    uint32_t* peers[8];
+                    if (use_ipc) {
+                        for (int r = 0; r < sh.world; ++r) peers[r] = peer_ptr(sh.comm, r, local) + (size_t)a * rl;
+                        sh.comm->bytes_peer_stored += (size_t)(b - a) * rl * 4 * (size_t)(sh.world - 1);
+                    } else {
+                        pack = arena.alloc<uint32_t>(out_stride * (b - a));
+                        to_free.push_back(pack);
+                        for (int r = 0; r < sh.world; ++r)
+                            peers[r] = r == sh.rank ? local + (size_t)a * rl : pack + (size_t)r * (b - a) * rl;
+                    }
+                    ck(cfft_evaluate_scatter(&tw, tree.cols[run.first + a].coeffs, stride, lg, own, out_stride, L, b - a, peers,
+                                             sh.world, 0, ctx->sm_count, st),
+                       "LDE evaluate + scatter (own columns)");
+                    if (!use_ipc)
+                        for (int r = 0; r < sh.world; ++r)
+                            if (r != sh.rank) xs.push_back({peers[r], nullptr, (size_t)(b - a) * rl, r, true});
+                } else {
+                    ck(cfft_evaluate(&tw, tree.cols[run.first + a].coeffs, stride, lg, own, out_stride, L, b - a, ctx->sm_count, st),
+                       "LDE evaluate (own columns)");
+                }
+            }
+            if (packed && !use_ipc) {
+                for (int r = 0; r < sh.world; ++r) {
+                    if (r == sh.rank) continue;
+                    int ra, rb;
+                    own_range(tree, run, r, ra, rb);
+                    if (rb > ra) xs.push_back({nullptr, local + (size_t)ra * rl, (size_t)(rb - ra) * rl, r, false});
+                }
+            }
+            for (int k = 0; k < run.n; ++k) {
+                const PolyCol& pc = tree.cols[run.first + k];
+                uint32_t* mine = local + (size_t)k * rl;
+                if (!packed) {
+                    if (pc.owner == sh.rank) {
+                        const uint32_t* full = own + (size_t)(k - a) * out_stride;
+                        for (int r = 0; r < sh.world; ++r) xs.push_back({full + (size_t)r * rl, r == sh.rank ? mine : nullptr, rl, r, true});
+                    } else {
+                        xs.push_back({nullptr, mine, rl, pc.owner, false});
+                    }
+                }
+            }
+            if (aux)
+                for (const AuxReq& rq : *aux) {
+                    if (rq.col < run.first || rq.col >= run.first + (size_t)run.n) continue;
+                    // the four columns may have different owners; each owner's share is contiguous: one message per
+                    // owner and peer, written by the shift kernel straight into per-destination staging blocks
+                    const int k0 = (int)(rq.col - run.first);
+                    for (int r = 0; r < sh.world; ++r) {
+                        int q0 = 4, q1 = 0;  // columns k0 + q0 .. k0 + q1 - 1 are owned by rank r
+                        for (int q = 0; q < 4; ++q)
+                            if (tree.cols[rq.col + q].owner == r) {
+                                q0 = std::min(q0, q);
+                                q1 = std::max(q1, q + 1);
+                            }
+                        if (q1 <= q0) continue;
+                        const size_t cnt = (size_t)(q1 - q0) * rl;
+                        if (r != sh.rank) {
+                            if (!use_ipc) xs.push_back({nullptr, rq.dst + (size_t)q0 * rl, cnt, r, false});
+                            continue;
+                        }
+                        uint32_t* stage = nullptr;  // [peer][owned shifted column][rl]; fused exchange: not needed
+                        if (!use_ipc) {
+                            stage = arena.alloc<uint32_t>(cnt * sh.world);
+                            to_free.push_back(stage);
+                        } else {
+                            sh.comm->bytes_peer_stored += cnt * 4 * (size_t)(sh.world - 1);
+                        }
+                        for (int q = q0; q < q1; ++q) {
+                            const int k = k0 + q;
+                            const uint32_t* src[8];
+                            uint32_t* dst[8];
+                            for (int t = 0; t < sh.world; ++t) {
+                                if (packed && use_ipc)  // the column's shards already sit in their owners' buffers
+                                    src[t] = peer_ptr(sh.comm, t, local) + (size_t)k * rl;
+                                else if (packed)
+                                    src[t] = (t == sh.rank ? local + (size_t)a * rl : pack + (size_t)t * (b - a) * rl) + (size_t)(k - a) * rl;
+                                else
+                                    src[t] = own + (size_t)(k - a) * out_stride + (size_t)t * rl;
+                                if (use_ipc)
+                                    dst[t] = peer_ptr(sh.comm, t, rq.dst) + (size_t)q * rl;
+                                else
+                                    dst[t] = (t == sh.rank ? rq.dst + (size_t)q * rl : stage + (size_t)t * cnt + (size_t)(q - q0) * rl);
+                            }
+                            ck(shifted_prev_column(dst, sh.world, src, sh.world, rq.domain_log, L, st), "shifted column");
+                        }
+                        if (!use_ipc)
+                            for (int t = 0; t < sh.world; ++t)
+                                if (t != sh.rank) xs.push_back({stage + (size_t)t * cnt, nullptr, cnt, t, true});
+                    }
+                }
+            return local;
+        };
         auto commit_tree = [&](CommitTree& tree, const std::vector<AuxReq>* aux = nullptr) {
             // evaluate every polynomial on CanonicCoset(log + blowup), Merkle-commit, mix the root.  Sharded: every rank
             // extends the columns it owns, one grouped exchange turns the column shards into row shards (rank r gets rows
@@ -1057,116 +1182,12 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                     }
                     continue;
                 }
-                if (L - sh.logw < 2) fail(LB_ERR_BAD_ARG, "prove (sharded): a committed column has fewer than 4 rows per rank");
-                int a, b;
-                own_range(tree, run, sh.rank, a, b);
+                uint32_t* local = shard_run(tree, run, L, aux, xs, to_free);
                 const size_t rl = out_stride >> sh.logw;
-                uint32_t* local = use_ipc ? sym_alloc(sh.comm, rl * run.n) : arena.alloc<uint32_t>(rl * run.n);
-                // Large columns: the last pass of the transform (cfft_evaluate_scatter) writes every 4096-row tile straight
-                // to where it belongs.  Fused exchange (use_ipc): that is the owner rank's row-shard buffer itself, mapped over
-                // NVLink - no staging, no message, the transfer overlaps the butterflies tile by tile.  Otherwise: a
-                // per-destination staging block, so the exchange is ONE contiguous NCCL message per peer and run, received in
-                // place (an owner's columns are contiguous in the run).  Small columns: plain transform, one message per column
-                // and peer.
-                const bool packed = L >= 16 && L - sh.logw >= 12 && sh.world <= 8;
-                uint32_t* own = nullptr;   // !packed: the owned columns, whole
-                uint32_t* pack = nullptr;  // packed: [peer][owned column][rl] (this rank's slot unused)
-                if (b > a) {
-                    own = arena.alloc<uint32_t>(out_stride * (b - a));
-                    to_free.push_back(own);
-                    if (packed) {
-                        uint32_t* peers[8];
-                        if (use_ipc) {
-                            for (int r = 0; r < sh.world; ++r) peers[r] = peer_ptr(sh.comm, r, local) + (size_t)a * rl;
-                            sh.comm->bytes_peer_stored += (size_t)(b - a) * rl * 4 * (size_t)(sh.world - 1);
-                        } else {
-                            pack = arena.alloc<uint32_t>(out_stride * (b - a));
-                            to_free.push_back(pack);
-                            for (int r = 0; r < sh.world; ++r)
-                                peers[r] = r == sh.rank ? local + (size_t)a * rl : pack + (size_t)r * (b - a) * rl;
-                        }
-                        ck(cfft_evaluate_scatter(&tw, tree.cols[run.first + a].coeffs, stride, lg, own, out_stride, L, b - a, peers,
-                                                 sh.world, 0, ctx->sm_count, st),
-                           "LDE evaluate + scatter (own columns)");
-                        if (!use_ipc)
-                            for (int r = 0; r < sh.world; ++r)
-                                if (r != sh.rank) xs.push_back({peers[r], nullptr, (size_t)(b - a) * rl, r, true});
-                    } else {
-                        ck(cfft_evaluate(&tw, tree.cols[run.first + a].coeffs, stride, lg, own, out_stride, L, b - a, ctx->sm_count, st),
-                           "LDE evaluate (own columns)");
-                    }
-                }
-                if (packed && !use_ipc) {
-                    for (int r = 0; r < sh.world; ++r) {
-                        if (r == sh.rank) continue;
-                        int ra, rb;
-                        own_range(tree, run, r, ra, rb);
-                        if (rb > ra) xs.push_back({nullptr, local + (size_t)ra * rl, (size_t)(rb - ra) * rl, r, false});
-                    }
-                }
                 for (int k = 0; k < run.n; ++k) {
-                    PolyCol& pc = tree.cols[run.first + k];
-                    uint32_t* mine = local + (size_t)k * rl;
-                    if (!packed) {
-                        if (pc.owner == sh.rank) {
-                            const uint32_t* full = own + (size_t)(k - a) * out_stride;
-                            for (int r = 0; r < sh.world; ++r) xs.push_back({full + (size_t)r * rl, r == sh.rank ? mine : nullptr, rl, r, true});
-                        } else {
-                            xs.push_back({nullptr, mine, rl, pc.owner, false});
-                        }
-                    }
-                    pc.lde = mine;
-                    refs.push_back({mine, L - sh.logw});
+                    tree.cols[run.first + k].lde = local + (size_t)k * rl;
+                    refs.push_back({tree.cols[run.first + k].lde, L - sh.logw});
                 }
-                if (aux)
-                    for (const AuxReq& rq : *aux) {
-                        if (rq.col < run.first || rq.col >= run.first + (size_t)run.n) continue;
-                        // the four columns may have different owners; each owner's share is contiguous: one message per
-                        // owner and peer, written by the shift kernel straight into per-destination staging blocks
-                        const int k0 = (int)(rq.col - run.first);
-                        for (int r = 0; r < sh.world; ++r) {
-                            int q0 = 4, q1 = 0;  // columns k0 + q0 .. k0 + q1 - 1 are owned by rank r
-                            for (int q = 0; q < 4; ++q)
-                                if (tree.cols[rq.col + q].owner == r) {
-                                    q0 = std::min(q0, q);
-                                    q1 = std::max(q1, q + 1);
-                                }
-                            if (q1 <= q0) continue;
-                            const size_t cnt = (size_t)(q1 - q0) * rl;
-                            if (r != sh.rank) {
-                                if (!use_ipc) xs.push_back({nullptr, rq.dst + (size_t)q0 * rl, cnt, r, false});
-                                continue;
-                            }
-                            uint32_t* stage = nullptr;  // [peer][owned shifted column][rl]; fused exchange: not needed
-                            if (!use_ipc) {
-                                stage = arena.alloc<uint32_t>(cnt * sh.world);
-                                to_free.push_back(stage);
-                            } else {
-                                sh.comm->bytes_peer_stored += cnt * 4 * (size_t)(sh.world - 1);
-                            }
-                            for (int q = q0; q < q1; ++q) {
-                                const int k = k0 + q;
-                                const uint32_t* src[8];
-                                uint32_t* dst[8];
-                                for (int t = 0; t < sh.world; ++t) {
-                                    if (packed && use_ipc)  // the column's shards already sit in their owners' buffers
-                                        src[t] = peer_ptr(sh.comm, t, local) + (size_t)k * rl;
-                                    else if (packed)
-                                        src[t] = (t == sh.rank ? local + (size_t)a * rl : pack + (size_t)t * (b - a) * rl) + (size_t)(k - a) * rl;
-                                    else
-                                        src[t] = own + (size_t)(k - a) * out_stride + (size_t)t * rl;
-                                    if (use_ipc)
-                                        dst[t] = peer_ptr(sh.comm, t, rq.dst) + (size_t)q * rl;
-                                    else
-                                        dst[t] = (t == sh.rank ? rq.dst + (size_t)q * rl : stage + (size_t)t * cnt + (size_t)(q - q0) * rl);
-                                }
-                                ck(shifted_prev_column(dst, sh.world, src, sh.world, rq.domain_log, L, st), "shifted column");
-                            }
-                            if (!use_ipc)
-                                for (int t = 0; t < sh.world; ++t)
-                                    if (t != sh.rank) xs.push_back({stage + (size_t)t * cnt, nullptr, cnt, t, true});
-                        }
-                    }
             }
             if (sh.on()) {
                 if (!xs.empty()) run_exchange(ctx, sh, xs);
@@ -1348,12 +1369,13 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                     }
                     // the [-1] mask of the last LogUp column reads a predecessor row that lives in another rank's row shard:
                     // the column's owner ships a shifted copy with the exchange of this tree
-                    if (c.eval_log != c.log + blowup)
-                        fail(LB_ERR_BAD_ARG, "prove (sharded): a component evaluated on a domain other than its committed one "
-                                             "(lookup table larger than its consumer's trace) is not supported yet");
-                    size_t rl = ((size_t)1 << (c.log + blowup)) >> sh.logw;
-                    c.inter_prev = use_ipc ? sym_alloc(sh.comm, 4 * rl) : arena.alloc<uint32_t>(4 * rl);
-                    inter_aux.push_back({c.inter_loc + (size_t)(n_ic - 4), c.log, c.inter_prev});
+                    // (a component evaluated on another domain - lookup table larger than its trace, blow-up other than 2 -
+                    // gets its shifted copy when its columns are re-sharded on that domain, see the constraint loop)
+                    if (c.eval_log == c.log + blowup) {
+                        size_t rl = ((size_t)1 << (c.log + blowup)) >> sh.logw;
+                        c.inter_prev = use_ipc ? sym_alloc(sh.comm, 4 * rl) : arena.alloc<uint32_t>(4 * rl);
+                        inter_aux.push_back({c.inter_loc + (size_t)(n_ic - 4), c.log, c.inter_prev});
+                    }
                 }
                 c.main_loc = main_next;  // span in slot order (equals the pie-order location when the pie is slot-ordered)
                 main_next += shp.n_main;
@@ -1420,9 +1442,26 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                 // constraint-framework `need_to_extend`: columns not committed on the evaluation domain are
                 // re-evaluated there from their polynomials
                 std::vector<uint32_t*> scratch;
-                auto on_eval_domain = [&](CommitTree& tree, size_t first, int n_cols) -> const uint32_t* {
+                const size_t ne_local = ne >> sh.logw;  // rows of the evaluation domain this rank holds
+                std::vector<Xfer> ext_xs;            // sharded: the re-evaluated columns go column shards -> row shards like a tree
+                std::vector<uint32_t*> ext_free;
+                uint32_t* ext_prev = nullptr;
+                bool extended = false;
+                auto on_eval_domain = [&](CommitTree& tree, size_t first, int n_cols, bool with_shifted = false) -> const uint32_t* {
                     if (tree.cols[first].log + blowup == eval_log) return tree.cols[first].lde;
-                    if (sh.on()) fail(LB_ERR_BAD_ARG, "prove (sharded): evaluation-domain extension is not supported yet");
+                    if (sh.on()) {
+                        const ColRun* run = nullptr;
+                        for (const ColRun& r : tree.runs)
+                            if (r.first == first && r.n == n_cols) run = &r;
+                        if (!run) fail(LB_ERR_BAD_ARG, "internal: component columns are not one run");
+                        std::vector<AuxReq> one;
+                        if (with_shifted) {
+                            ext_prev = use_ipc ? sym_alloc(sh.comm, 4 * ne_local) : arena.alloc<uint32_t>(4 * ne_local);
+                            one.push_back({first + (size_t)(n_cols - 4), c.log, ext_prev});
+                        }
+                        extended = true;
+                        return shard_run(tree, *run, eval_log, with_shifted ? &one : nullptr, ext_xs, ext_free);
+                    }
                     uint32_t* ext = arena.alloc<uint32_t>(ne * n_cols);
                     scratch.push_back(ext);
                     int lg = tree.cols[first].log;
@@ -1430,16 +1469,21 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                        "extend to evaluation domain");
                     return ext;
                 };
-                const size_t ne_local = ne >> sh.logw;  // rows of the evaluation domain this rank holds
                 p.main = on_eval_domain(trees[1], c.main_loc, shp.n_main);
                 p.main_stride = ne_local;
-                p.inter = on_eval_domain(trees[2], c.inter_loc, 4 * shp.n_fracs);
+                p.inter = on_eval_domain(trees[2], c.inter_loc, 4 * shp.n_fracs, /*with_shifted=*/true);
                 p.inter_stride = ne_local;
                 for (int q = 0; q < shp.n_pre; ++q) p.pre.p[q] = on_eval_domain(trees[0], (size_t)c.pre_idx[q], 1);
                 if (sh.on()) {
+                    if (extended) {
+                        if (!ext_xs.empty()) run_exchange(ctx, sh, ext_xs);
+                        if (use_ipc) shard_barrier(ctx, sh, d_barrier);
+                        for (uint32_t* f : ext_free) arena.release(f);
+                    }
                     p.row0 = (uint32_t)(ne_local * sh.rank);
                     p.n_rows = (uint32_t)ne_local;
-                    p.inter_prev = c.inter_prev;
+                    p.inter_prev = ext_prev ? ext_prev : c.inter_prev;
+                    if (!p.inter_prev) fail(LB_ERR_BAD_ARG, "internal: no shifted LogUp column for a row-sharded component");
                 }
                 bool fresh = acc.find(eval_log) == acc.end();
                 if (fresh) acc[eval_log] = arena.alloc<uint32_t>(4 * ne_local);

@@ -66,17 +66,23 @@ if "--all-components" in sys.argv:
     # non-default PcsConfig and the "v2" channel: sharded bytes == single-GPU bytes
     from luminair_b200.prover import PcsConfig
     from oracle import pie as opie
-    pie, pre = opie.all_components_graph(n=1 << 16, seed=3)  # lookup tables (2^8 .. 2^15) no larger than their consumers
-    ok3 = True
-    for cfg, variant in ((None, "legacy"), (PcsConfig(7, 1, 1, 9), "v2")):  # blow-up 2 (the reference's): see DESIGN section 6
-        single = prove(pie, backend=be, preprocessed=pre, config=cfg, channel_variant=variant)
-        dist.barrier()
-        sharded = prove(pie, backend=be, preprocessed=pre, config=cfg, channel_variant=variant, comm=comm)
-        ok3 = ok3 and sharded == single
+    ok3, shapes = True, {}
+    # 2^16 elements: lookup tables (2^8 .. 2^15) no larger than their consumers; 2^11 elements: tables LARGER than the consumers'
+    # traces and a blow-up of 4 - the constraint-framework `need_to_extend` path (columns re-sharded on the evaluation domain)
+    for n_el, cases in ((1 << 16, ((None, "legacy"), (PcsConfig(7, 1, 1, 9), "v2"))),
+                        (1 << 11, ((None, "legacy"), (PcsConfig(6, 2, 1, 5), "v2")))):
+        pie, pre = opie.all_components_graph(n=n_el, seed=3)
+        shapes[str(n_el)] = {k: list(v.shape) for k, v in pie}
+        for cfg, variant in cases:
+            single = prove(pie, backend=be, preprocessed=pre, config=cfg, channel_variant=variant)
+            dist.barrier()
+            sharded = prove(pie, backend=be, preprocessed=pre, config=cfg, channel_variant=variant, comm=comm)
+            ok3 = ok3 and sharded == single
     flag = torch.tensor([1 if ok3 else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    out["all_components"] = {"proof_equals_single_device": bool(flag[0]), "tables": {k: list(v.shape) for k, v in pie},
-                             "configs": ["default / legacy channel", "pow 7, last-layer bound 2, 9 queries / v2 channel"]}
+    out["all_components"] = {"proof_equals_single_device": bool(flag[0]), "tables": shapes,
+                             "configs": ["2^16 elements: default / legacy channel; pow 7, last-layer bound 2, 9 queries / v2 channel",
+                                         "2^11 elements (lookup tables larger than the traces): default; blow-up 4, pow 6, 5 queries / v2"]}
     ok2 = ok2 and bool(flag[0])
 if rank == 0:
     print(json.dumps(out), flush=True)
