@@ -313,6 +313,8 @@ def run_gpu(args):
     prove_info = None
     if not args.no_prove:
         prove_info = bench_prove(be, torch, args)
+        if not distributed:
+            prove_info["concurrent"] = bench_concurrent_prove(args, prove_info["_proof_bytes"])
 
     # ---- N > 1: the column-sharded commit of BASELINE cfg 5 (the one place the path has a real exchange)
     sharded_info = None
@@ -755,6 +757,57 @@ def bench_prove(be, torch, args):
         "published_reference_add_32x32_prove_ms": 13.05,
         "published_note": "GitHub Actions ubuntu-latest CPU, Criterion; other hardware, context only",
     }
+
+
+def bench_concurrent_prove(args, expect_proof):
+    """Throughput of K independent provers on ONE GPU: K contexts (own stream, own pool), one host thread each, every thread
+    proving the same cfg-3 workload from its own device-resident tables.  A single proof is a dependent chain (Fiat-Shamir) with
+    latency-bound stretches and ~12 host synchronisations; a second proof in flight fills them."""
+    import threading
+    from luminair_b200.backend import CudaBackend
+    from luminair_b200.prover import prove
+    from luminair_b200.trace import DeviceGraphTrace
+    from luminair_b200.workloads import build_add_graph, synthetic_add_graph_inputs
+    a_raw, b_raw = synthetic_add_graph_inputs(args.prove_log, seed=42)
+    out = {}
+    for k in (2, 3):
+        bes = [CudaBackend(0) for _ in range(k)]
+        try:
+            recs = [build_add_graph(DeviceGraphTrace(b), a_raw, b_raw) for b in bes]
+            work = [r.finish() for r in recs]
+            reps = max(4, min(args.steps, 10))
+            for b, (meta, dev, _) in zip(bes, work):
+                if prove(meta, backend=b, device_tables=dev) != expect_proof:
+                    raise SystemExit("bench: a concurrent context produced different proof bytes")
+            gate = threading.Barrier(k + 1)
+            bad = []
+
+            def worker(b, meta, dev):
+                gate.wait()
+                for _ in range(reps):
+                    if len(prove(meta, backend=b, device_tables=dev)) != len(expect_proof):
+                        bad.append(1)
+                gate.wait()
+
+            th = [threading.Thread(target=worker, args=(b, w[0], w[1])) for b, w in zip(bes, work)]
+            for t in th:
+                t.start()
+            gate.wait()
+            t0 = time.perf_counter()
+            gate.wait()
+            dt = time.perf_counter() - t0
+            for t in th:
+                t.join()
+            if bad:
+                raise SystemExit("bench: concurrent proofs differ in size")
+            out[f"contexts_{k}"] = {"proofs_per_s": k * reps / dt, "ms_per_proof_amortised": dt * 1e3 / (k * reps), "proofs": k * reps}
+        finally:
+            for b in bes:
+                b.close()
+    out["how"] = ("K contexts on cuda:0, one host thread each (ctypes releases the GIL inside lb_prove), device-resident tables, "
+                  "wall clock from a common start barrier to the last proof; every context's proof checked against the "
+                  "single-context bytes first")
+    return out
 
 
 def main():

@@ -917,6 +917,124 @@ struct StageTimer {
     }
 };
 
+// Grind: the smallest-index nonce found by the device search whose mix leaves pow_bits trailing zero bits (stwo
+// prover/backend/simd/grind.rs semantics: any valid nonce verifies; the search order makes it the lowest one).
+uint64_t grind_nonce(const Channel& channel, const lb_prove_config& cfg, Arena& arena, cudaStream_t st) {
+    unsigned long long* d_found = arena.alloc<unsigned long long>(1);
+    uint32_t dg[8];
+    channel.digest_words(dg);
+    uint64_t base = 0;
+    // a nonce works with probability 2^-pow_bits: the first launch tries 2^(pow_bits + 7) of them (it misses with
+    // probability e^-128), later ones grow 16-fold up to 2^24
+    uint64_t chunk = (uint64_t)1 << std::min<uint32_t>(24, cfg.pow_bits + 7);
+    for (;;) {
+        ck(cudaMemsetAsync(d_found, 0xFF, 8, st), "grind memset");
+        ck(grind_range(dg, cfg.channel_variant, cfg.pow_bits, base, chunk, d_found, st), "grind");
+        unsigned long long found;
+        ck(cudaMemcpyAsync(&found, d_found, 8, cudaMemcpyDeviceToHost, st), "grind d2h");
+        ck(cudaStreamSynchronize(st), "grind sync");
+        if (found != ~0ull) return found;
+        base += chunk;
+        chunk = std::min<uint64_t>(chunk << 4, (uint64_t)1 << 24);
+    }
+}
+
+using SampledValues = std::vector<std::vector<std::vector<QM31>>>;  // [tree][column][sample]
+
+// The check stwo::prover::prove ends with: the composition polynomial at the OODS point, rebuilt from its four
+// coordinate samples, equals the constraints evaluated on the sampled mask values.
+void check_oods(const std::vector<Component>& comps, const SampledValues& sampled, const Relations& rels, QM31 random_coeff,
+                QPt oods) {
+    QM31 e[4] = {sampled[3][0][0], sampled[3][1][0], sampled[3][2][0], sampled[3][3][0]};
+    QM31 composition_oods = q_from_partial_evals(e);
+    QM31 accv = q_zero();
+    for (const Component& c : comps) {
+        PointEval pe;
+        pe.main = &sampled[1];
+        pe.inter = &sampled[2];
+        pe.pre = &sampled[0];
+        pe.pre_idx[0] = c.pre_idx[0];
+        pe.pre_idx[1] = c.pre_idx[1];
+        pe.mc = c.main_loc;
+        pe.ic = c.inter_loc;
+        pe.random_coeff = random_coeff;
+        pe.denom_inverse = q_inv(coset_vanishing_q(c.log, oods));
+        pe.acc = &accv;
+        pe.cumsum_shift = q_mul_m(c.claimed_sum, m_inv((uint32_t)(((uint64_t)1 << c.log) % P)));
+        eval_component(c.kind, pe, rels);
+    }
+    if (!q_eq(composition_oods, accv)) fail(LB_ERR_CONSTRAINTS, "ConstraintsNotSatisfied");
+}
+
+// Everything LuminairProof holds (crates/air/src/lib.rs:21-27), by reference; `Gatherer` carries the queried words.
+struct ProofParts {
+    const std::vector<int>& claim;
+    const std::vector<Component>& comps;
+    const std::vector<CommitTree>& trees;
+    const SampledValues& sampled;
+    const std::vector<DecommitIdx>& tree_dec;
+    uint64_t nonce;
+    const FriLayerOut& first_layer;
+    const std::vector<FriLayerOut>& inner_layers;
+    const std::vector<QM31>& last_layer_poly;
+};
+
+// bincode 1.x (fixed-width little-endian integers, u64 lengths) of LuminairProof { claim, interaction_claim, proof }
+void write_proof(std::vector<uint8_t>& out, const lb_prove_config& cfg, const ProofParts& p, const Gatherer& g) {
+    out.clear();
+    Writer w{out};
+    for (int s = 0; s < cfg.n_slots; ++s) {
+        if (p.claim[s] < 0)
+            w.u8(0);
+        else {
+            w.u8(1);
+            w.u32((uint32_t)p.claim[s]);
+        }
+    }
+    {
+        std::vector<const Component*> slot_comp(cfg.n_slots, nullptr);
+        for (const Component& c : p.comps) slot_comp[c.slot] = &c;
+        for (int s = 0; s < cfg.n_slots; ++s) {
+            if (!slot_comp[s])
+                w.u8(0);
+            else {
+                w.u8(1);
+                w.qm31(slot_comp[s]->claimed_sum);
+            }
+        }
+    }
+    w.u32(cfg.pow_bits);
+    w.u32(cfg.log_blowup_factor);
+    w.u32(cfg.log_last_layer_degree_bound);
+    w.u64(cfg.n_queries);
+    w.u64(4);
+    for (int t = 0; t < 4; ++t) w.hash(p.trees[t].merkle.root);
+    w.u64(4);
+    for (int t = 0; t < 4; ++t) {
+        w.u64(p.sampled[t].size());
+        for (auto& col : p.sampled[t]) {
+            w.u64(col.size());
+            for (QM31 v : col) w.qm31(v);
+        }
+    }
+    w.u64(4);
+    for (int t = 0; t < 4; ++t) write_decommit(w, p.tree_dec[t], g);
+    w.u64(4);
+    for (int t = 0; t < 4; ++t) {
+        w.u64(p.tree_dec[t].queried_values.size());
+        for (size_t i : p.tree_dec[t].queried_values) w.u32(g.values[i]);
+    }
+    w.u64(p.nonce);
+    write_fri_layer(w, p.first_layer, g);
+    w.u64(p.inner_layers.size());
+    for (auto& l : p.inner_layers) write_fri_layer(w, l, g);
+    w.u64(p.last_layer_poly.size());
+    for (QM31 v : p.last_layer_poly) w.qm31(v);
+    uint32_t lg = 0;
+    while (((size_t)1 << lg) < p.last_layer_poly.size()) ++lg;
+    w.u32(lg);
+}
+
 }  // namespace
 
 // ======================================================================================
@@ -2017,30 +2135,8 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
         timer.lap();  // stage 5: FRI commit
 
         // ---- proof of work --------------------------------------------------------------------------
-        uint64_t nonce = 0;
-        {
-            unsigned long long* d_found = arena.alloc<unsigned long long>(1);
-            uint32_t dg[8];
-            channel.digest_words(dg);
-            uint64_t base = 0;
-            // a nonce works with probability 2^-pow_bits: the first launch tries 2^(pow_bits + 7) of them (it misses with
-            // probability e^-128), later ones grow 16-fold up to 2^24
-            uint64_t chunk = (uint64_t)1 << std::min<uint32_t>(24, cfg.pow_bits + 7);
-            for (;;) {
-                ck(cudaMemsetAsync(d_found, 0xFF, 8, st), "grind memset");
-                ck(grind_range(dg, cfg.channel_variant, cfg.pow_bits, base, chunk, d_found, st), "grind");
-                unsigned long long found;
-                ck(cudaMemcpyAsync(&found, d_found, 8, cudaMemcpyDeviceToHost, st), "grind d2h");
-                ck(cudaStreamSynchronize(st), "grind sync");
-                if (found != ~0ull) {
-                    nonce = found;
-                    break;
-                }
-                base += chunk;
-                chunk = std::min<uint64_t>(chunk << 4, (uint64_t)1 << 24);
-            }
-            channel.mix_u64(nonce);
-        }
+        const uint64_t nonce = grind_nonce(channel, cfg, arena, st);
+        channel.mix_u64(nonce);
 
         // ---- queries + decommitment plan ---------------------------------------------------------------
         Gatherer g;
@@ -2100,83 +2196,11 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
         timer.lap();  // stage 6: grind + queries + decommitment
 
         // ---- OODS check (prove() returns ConstraintsNotSatisfied otherwise) ------------------------------
-        {
-            QM31 e[4] = {sampled[3][0][0], sampled[3][1][0], sampled[3][2][0], sampled[3][3][0]};
-            QM31 composition_oods = q_from_partial_evals(e);
-            QM31 accv = q_zero();
-            for (const Component& c : comps) {
-                PointEval pe;
-                pe.main = &sampled[1];
-                pe.inter = &sampled[2];
-                pe.pre = &sampled[0];
-                pe.pre_idx[0] = c.pre_idx[0];
-                pe.pre_idx[1] = c.pre_idx[1];
-                pe.mc = c.main_loc;
-                pe.ic = c.inter_loc;
-                pe.random_coeff = random_coeff;
-                pe.denom_inverse = q_inv(coset_vanishing_q(c.log, oods));
-                pe.acc = &accv;
-                pe.cumsum_shift = q_mul_m(c.claimed_sum, m_inv((uint32_t)(((uint64_t)1 << c.log) % P)));
-                eval_component(c.kind, pe, rels);
-            }
-            if (!q_eq(composition_oods, accv)) fail(LB_ERR_CONSTRAINTS, "ConstraintsNotSatisfied");
-        }
+        check_oods(comps, sampled, rels, random_coeff, oods);
 
         // ---- bincode -----------------------------------------------------------------------------------------
-        out.clear();
-        Writer w{out};
-        for (int s = 0; s < cfg.n_slots; ++s) {
-            if (claim[s] < 0)
-                w.u8(0);
-            else {
-                w.u8(1);
-                w.u32((uint32_t)claim[s]);
-            }
-        }
-        {
-            std::vector<const Component*> slot_comp(cfg.n_slots, nullptr);
-            for (const Component& c : comps) slot_comp[c.slot] = &c;
-            for (int s = 0; s < cfg.n_slots; ++s) {
-                if (!slot_comp[s])
-                    w.u8(0);
-                else {
-                    w.u8(1);
-                    w.qm31(slot_comp[s]->claimed_sum);
-                }
-            }
-        }
-        w.u32(cfg.pow_bits);
-        w.u32(cfg.log_blowup_factor);
-        w.u32(cfg.log_last_layer_degree_bound);
-        w.u64(cfg.n_queries);
-        w.u64(4);
-        for (int t = 0; t < 4; ++t) w.hash(trees[t].merkle.root);
-        w.u64(4);
-        for (int t = 0; t < 4; ++t) {
-            w.u64(sampled[t].size());
-            for (auto& col : sampled[t]) {
-                w.u64(col.size());
-                for (QM31 v : col) w.qm31(v);
-            }
-        }
-        w.u64(4);
-        for (int t = 0; t < 4; ++t) write_decommit(w, tree_dec[t], g);
-        w.u64(4);
-        for (int t = 0; t < 4; ++t) {
-            w.u64(tree_dec[t].queried_values.size());
-            for (size_t i : tree_dec[t].queried_values) w.u32(g.values[i]);
-        }
-        w.u64(nonce);
-        write_fri_layer(w, first_out, g);
-        w.u64(inner_out.size());
-        for (auto& l : inner_out) write_fri_layer(w, l, g);
-        w.u64(last_layer_poly.size());
-        for (QM31 v : last_layer_poly) w.qm31(v);
-        {
-            uint32_t lg = 0;
-            while (((size_t)1 << lg) < last_layer_poly.size()) ++lg;
-            w.u32(lg);
-        }
+        ProofParts parts{claim, comps, trees, sampled, tree_dec, nonce, first_out, inner_out, last_layer_poly};
+        write_proof(out, cfg, parts, g);
         timer.lap();  // stage 7: OODS check + serialisation
         return LB_OK;
     } catch (const ProveError& e) {

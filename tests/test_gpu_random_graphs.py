@@ -34,10 +34,10 @@ class _Both:
         return call
 
 
-def random_graph(seed: int, builder=None):
+def random_graph(seed: int, builder=None, n_range=(5, 90)):
     rng = np.random.Generator(np.random.PCG64(seed))
     g = builder or piemod.GraphTrace()
-    n = int(rng.integers(5, 90))
+    n = int(rng.integers(*n_range))
     pos = [g.input(piemod.to_fixed(rng.uniform(0.3, 3.0, n)))]   # strictly positive tensors (recip, sqrt, log2, rem divisor)
     any_ = [g.input(piemod.to_fixed(rng.uniform(-2.0, 2.0, n)))]  # any sign
     for _ in range(int(rng.integers(3, 10))):
@@ -103,3 +103,17 @@ def test_random_graph_device_gen_trace(be, seed):
     host_pie, host_pre, meta, dev = _compare(be, hg, dg)
     assert prove(meta, backend=be, device_tables=dev, preprocessed=dg.preprocessed) == \
         prove(host_pie, backend=be, preprocessed=host_pre)
+
+
+@pytest.mark.parametrize("seed,n_range", [(301, (1 << 10, 1 << 12)), (302, (1 << 12, 1 << 14)), (303, (1 << 14, 1 << 16)),
+                                          (304, (1 << 15, 1 << 17)), (305, (1 << 16, 1 << 18)), (306, (1 << 13, 1 << 17))])
+def test_random_graph_at_size_equals_cpu_prover(be, seed, n_range):
+    """Mid-size random graphs (ragged tensor lengths up to 2^18, tables up to 2^20 rows): too large for the numpy oracle inside a
+    test, so the checker is the compiled CPU prover (oracle/c/cpu_prover, pinned to the numpy oracle and the reference's committed
+    proof by tests/test_cpu_prover.py)."""
+    from luminair_b200.prover import prove
+    from oracle import cpu_prover as cp
+    pie, pre = random_graph(seed, n_range=n_range)
+    want = cp.prove(pie, preprocessed=pre)
+    got = prove(pie, backend=be, preprocessed=pre)
+    assert got == want
