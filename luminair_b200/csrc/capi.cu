@@ -61,12 +61,24 @@ int lb_ctx_create(int device, lb_ctx** out) {
         return LB_ERR_CUDA;
     }
     {
-        // keep stream-ordered allocations cached between prove() calls
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            unsigned long long thr = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        // a pool per context, its memory cached between prove() calls
+        cudaMemPoolProps pp = {};
+        pp.allocType = cudaMemAllocationTypePinned;
+        pp.handleTypes = cudaMemHandleTypeNone;
+        pp.location.type = cudaMemLocationTypeDevice;
+        pp.location.id = device;
+        if (cudaMemPoolCreate(&ctx->pool, &pp) != cudaSuccess) {
+            cudaGetLastError();
+            ctx->pool = nullptr;
+            if (cudaDeviceGetDefaultMemPool(&ctx->pool, device) != cudaSuccess) {
+                cudaStreamDestroy(ctx->stream);
+                delete ctx;
+                return LB_ERR_CUDA;
+            }
+            ctx->pool_is_default = true;
         }
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->total_mem = prop.totalGlobalMem;
@@ -91,6 +103,8 @@ void lb_ctx_destroy(lb_ctx* ctx) {
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
+    // blocks still held by the caller (lb_alloc_pooled) keep the pool alive until they are freed
+    if (ctx->pool && !ctx->pool_is_default) cudaMemPoolDestroy(ctx->pool);
     delete ctx;
 }
 
@@ -122,14 +136,14 @@ int lb_free(lb_ctx* ctx, uint32_t* d_ptr) {
     return LB_OK;
 }
 
-// stream-ordered variants (cudaMallocAsync on the context's stream, memory kept in the device pool): no device-wide
+// stream-ordered variants (cudaMallocFromPoolAsync on the context's stream, memory kept in the context's pool): no device-wide
 // synchronisation, for short-lived buffers such as the tensors and tables of a device-side gen_trace.  Not for lb_ipc_export.
 int lb_alloc_pooled(lb_ctx* ctx, size_t n_u32, uint32_t** d_out) {
     lb::DeviceGuard _dg(ctx);
     if (!ctx || !d_out) return LB_ERR_BAD_ARG;
     cudaSetDevice(ctx->device);
     void* p = nullptr;
-    CK(cudaMallocAsync(&p, (n_u32 ? n_u32 : 1) * sizeof(uint32_t), ctx->stream), "alloc_pooled");
+    CK(cudaMallocFromPoolAsync(&p, (n_u32 ? n_u32 : 1) * sizeof(uint32_t), ctx->pool, ctx->stream), "alloc_pooled");
     *d_out = (uint32_t*)p;
     return LB_OK;
 }

@@ -12,6 +12,10 @@ struct lb_comm;
 struct lb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    // stream-ordered allocations of this context come from its own pool: blocks freed by one context's stream are never handed
+    // to another context's stream (the device default pool would make the second stream wait for the first one's free point)
+    cudaMemPool_t pool = nullptr;
+    bool pool_is_default = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 0;
     size_t total_mem = 0;

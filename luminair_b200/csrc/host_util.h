@@ -26,14 +26,14 @@ inline void ck(cudaError_t e, const char* what) {
 // ------------------------------------------------------------------------------------
 class Arena {
    public:
-    explicit Arena(cudaStream_t s) : stream_(s) {}
+    Arena(cudaMemPool_t pool, cudaStream_t s) : pool_(pool), stream_(s) {}
     ~Arena() {
         for (void* p : ptrs_) cudaFreeAsync(p, stream_);
     }
     template <class T>
     T* alloc(size_t n) {
         void* p = nullptr;
-        ck(cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), stream_), "device alloc");
+        ck(cudaMallocFromPoolAsync(&p, (n ? n : 1) * sizeof(T), pool_, stream_), "device alloc");
         ptrs_.push_back(p);
         return (T*)p;
     }
@@ -54,6 +54,7 @@ class Arena {
     }
 
    private:
+    cudaMemPool_t pool_;
     cudaStream_t stream_;
     std::vector<void*> ptrs_;
 };

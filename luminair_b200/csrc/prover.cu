@@ -1083,7 +1083,7 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
         ctx->transcript.clear();
         ctx->stage_ms.clear();
         StageTimer timer(ctx);
-        Arena arena(st);
+        Arena arena(ctx->pool, st);
         Channel channel(cfg.channel_variant, &ctx->transcript);
         std::vector<CommitTree> trees(4);
 
@@ -2263,7 +2263,7 @@ int eval_at_point_impl(lb_ctx* ctx, const uint32_t* const* h_cols, int n_cols, i
                        uint32_t* h_out) {
     return guarded(ctx, [&] {
         ensure_kernels(ctx);
-        Arena arena(ctx->stream);
+        Arena arena(ctx->pool, ctx->stream);
         std::vector<const uint32_t*> cols(h_cols, h_cols + n_cols);
         QPt pt{q_from_words(point), q_from_words(point + 4)};
         QM31* d_out = arena.alloc<QM31>(n_cols);
@@ -2278,7 +2278,7 @@ int accumulate_quotients_impl(lb_ctx* ctx, int log, const uint32_t* const* h_col
                               const uint32_t random_coeff[4], uint32_t* const d_out[4]) {
     return guarded(ctx, [&] {
         ensure_kernels(ctx);
-        Arena arena(ctx->stream);
+        Arena arena(ctx->pool, ctx->stream);
         std::vector<const uint32_t*> cols(h_cols, h_cols + n_cols);
         std::vector<HostBatch> hb(n_batches);
         for (int b = 0; b < n_batches; ++b) {
@@ -2315,7 +2315,7 @@ int grind_impl(lb_ctx* ctx, const uint32_t digest[8], int variant, uint32_t pow_
     return guarded(ctx, [&] {
         ensure_kernels(ctx);
         if (pow_bits > 64) fail(LB_ERR_BAD_ARG, "grind: pow_bits > 64");
-        Arena arena(ctx->stream);
+        Arena arena(ctx->pool, ctx->stream);
         unsigned long long* d_found = arena.alloc<unsigned long long>(1);
         uint64_t base = 0;
         const uint64_t chunk = (uint64_t)1 << 24;
@@ -2354,7 +2354,7 @@ int logup_impl(lb_ctx* ctx, int kind, const uint32_t* d_main, size_t main_stride
             if (!d_lut || !d_lut[q]) fail(LB_ERR_BAD_ARG, "logup: component needs its LUT columns");
             pc.p[q] = d_lut[q];
         }
-        Arena arena(ctx->stream);
+        Arena arena(ctx->pool, ctx->stream);
         size_t n = (size_t)1 << log;
         uint32_t* scan_tmp = arena.alloc<uint32_t>(4 * n);
         uint32_t* block_sums = arena.alloc<uint32_t>(4 * (n / 1024 + 1));
@@ -2402,7 +2402,7 @@ int constraint_quotients_impl(lb_ctx* ctx, int kind, const uint32_t* d_main, siz
             Pt pt = host_index_to_point(init + step * bit_reverse(i, log_expand));
             dinv[i] = m_inv(coset_vanishing_m(log_size, pt));
         }
-        Arena arena(ctx->stream);
+        Arena arena(ctx->pool, ctx->stream);
         p.denom_inv = arena.upload(dinv);
         ck(constraint_quotients(kind, p, ctx->stream), "constraint quotients");
         ck(cudaStreamSynchronize(ctx->stream), "constraints sync");  // arena scratch is released on return

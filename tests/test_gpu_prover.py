@@ -467,3 +467,39 @@ def test_two_contexts_interleave(be):
         assert torch.cuda.current_device() == before  # the calls left the caller's device alone
     finally:
         other.close()
+
+
+def test_concurrent_contexts_prove_in_threads(be):
+    """Two contexts on one GPU (own stream, own memory pool), one host thread each, proving different graphs at the same time:
+    every proof equals the one the same context produces alone."""
+    import threading
+    from luminair_b200.backend import CudaBackend
+    from luminair_b200.prover import prove
+    from oracle import pie as piemod
+    pies = [piemod.synthetic_add_graph_pie(log, seed=7 + log) for log in (9, 12, 14)]
+    want = [prove(p, backend=be) for p in pies]
+    others = [CudaBackend(0), CudaBackend(0)]
+    got = [[None] * len(pies) for _ in others]
+    errs = []
+
+    def worker(k):
+        try:
+            for rep in range(3):
+                for i, p in enumerate(pies[::-1] if k else pies):
+                    j = len(pies) - 1 - i if k else i
+                    got[k][j] = prove(p, backend=others[k])
+        except Exception as e:  # surfaced below: an exception in a thread would otherwise pass silently
+            errs.append(e)
+
+    try:
+        th = [threading.Thread(target=worker, args=(k,)) for k in range(len(others))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert not errs, errs
+        for k in range(len(others)):
+            assert got[k] == want
+    finally:
+        for o in others:
+            o.close()
