@@ -939,6 +939,40 @@ uint64_t grind_nonce(const Channel& channel, const lb_prove_config& cfg, Arena& 
     }
 }
 
+// FriProver::commit_last_layer: the last line evaluation (4 coordinate columns of 2^line_log values, bit-reversed order as
+// stored on the device) interpolated on the host over LineDomain(half_odds(line_log)); the coefficients above the degree
+// bound must vanish, the ones below are the proof's last_layer_poly.
+std::vector<QM31> interpolate_last_layer(const std::vector<uint32_t>& hv, int line_log, uint32_t log_degree_bound) {
+    const size_t n = (size_t)1 << line_log;
+    std::vector<QM31> vals(n);
+    for (size_t i = 0; i < n; ++i) {
+        size_t s = bit_reverse((uint32_t)i, line_log);  // natural order
+        vals[i] = q_make(hv[s], hv[n + s], hv[2 * n + s], hv[3 * n + s]);
+    }
+    uint32_t d_init = subgroup_gen(line_log + 2), d_step = subgroup_gen(line_log);
+    size_t size = n;
+    while (size > 1) {
+        for (size_t start = 0; start < n; start += size)
+            for (size_t i = 0; i < size / 2; ++i) {
+                uint32_t x = host_index_to_point(d_init + d_step * (uint32_t)i).x;
+                uint32_t xinv = m_inv(x);
+                QM31 l = vals[start + i], r = vals[start + size / 2 + i];
+                vals[start + i] = q_add(l, r);
+                vals[start + size / 2 + i] = q_mul_m(q_sub(l, r), xinv);
+            }
+        d_init = (d_init * 2) & CIRCLE_ORDER_MASK;
+        d_step = (d_step * 2) & CIRCLE_ORDER_MASK;
+        size /= 2;
+    }
+    uint32_t inv_n = m_inv((uint32_t)(n % P));
+    std::vector<QM31> coeffs(n);
+    for (size_t i = 0; i < n; ++i) coeffs[i] = q_mul_m(vals[bit_reverse((uint32_t)i, line_log)], inv_n);
+    size_t bound = (size_t)1 << log_degree_bound;
+    for (size_t i = bound; i < n; ++i)
+        if (!q_is_zero(coeffs[i])) fail(LB_ERR_CONSTRAINTS, "fri: invalid last-layer degree (ConstraintsNotSatisfied)");
+    return std::vector<QM31>(coeffs.begin(), coeffs.begin() + bound);
+}
+
 using SampledValues = std::vector<std::vector<std::vector<QM31>>>;  // [tree][column][sample]
 
 // The check stwo::prover::prove ends with: the composition polynomial at the OODS point, rebuilt from its four
@@ -1035,58 +1069,148 @@ void write_proof(std::vector<uint8_t>& out, const lb_prove_config& cfg, const Pr
     w.u32(lg);
 }
 
-}  // namespace
 
-// ======================================================================================
-int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_preprocessed_column* pre_in, int n_pre,
-               const lb_prove_config* cfg_in, std::vector<uint8_t>& out, lb_comm* comm) {
-    try {
-        Shard sh;
-        if (comm && comm->world > 1) {
-            if (comm->ctx != ctx) fail(LB_ERR_BAD_ARG, "prove: the communicator belongs to another context");
-            sh.comm = comm;
-            sh.rank = comm->rank;
-            sh.world = comm->world;
-            sh.logw = comm->log_world;
-            comm->bytes_sent = comm->bytes_received = 0;
-            comm->n_collectives = 0;
-        }
-        lb_prove_config cfg;
-        if (cfg_in)
-            cfg = *cfg_in;
-        else {
-            cfg.pow_bits = 5;  // PcsConfig::default() (prover.rs:36)
-            cfg.log_blowup_factor = 1;
-            cfg.log_last_layer_degree_bound = 0;
-            cfg.n_queries = 3;
-            cfg.channel_variant = 0;
-            cfg.n_slots = 17;
-            cfg.air_era = 0;
-            cfg.draw_lookup_elements = 1;
-        }
-        if (n_tables < 1 || !tables) fail(LB_ERR_BAD_ARG, "prove: no trace tables");
-        if (cfg.n_slots < 2 || cfg.n_slots > 64) fail(LB_ERR_BAD_ARG, "prove: bad n_slots");
-        if (cfg.log_blowup_factor < 1 || cfg.log_blowup_factor > 4) fail(LB_ERR_BAD_ARG, "prove: bad blow-up");
-        // the grind loop below ends only when a nonce exists: a 64-bit nonce cannot be asked for more than 64 zero bits, and
-        // anything near that never finishes; stwo's own configurations stay below 32
-        if (cfg.pow_bits > 40) fail(LB_ERR_BAD_ARG, "prove: pow_bits > 40");
-        if (cfg.channel_variant != 0 && cfg.channel_variant != 1) fail(LB_ERR_BAD_ARG, "prove: unknown channel variant");
-        if (cfg.log_last_layer_degree_bound > 16 || cfg.n_queries < 1 || cfg.n_queries > 4096)
-            fail(LB_ERR_BAD_ARG, "prove: bad FRI configuration");
-        const int blowup = (int)cfg.log_blowup_factor;
-        cudaStream_t st = ctx->stream;
-        ck(cudaSetDevice(ctx->device), "set device");
-        if (!ctx->kernels_ready) {
-            ck(kernels_init(st), "kernels init");
-            ctx->kernels_ready = true;
-        }
-        ctx->transcript.clear();
-        ctx->stage_ms.clear();
-        StageTimer timer(ctx);
-        Arena arena(ctx->pool, st);
-        Channel channel(cfg.channel_variant, &ctx->transcript);
-        std::vector<CommitTree> trees(4);
+// non-committed columns shipped with a tree's exchange (sharded prover): the [-1]-shifted copies of the 4 coordinate columns
+// col .. col + 3 (the last LogUp column of a component)
+struct AuxReq {
+    size_t col;
+    int domain_log;
+    uint32_t* dst;  // this rank's row shards of them: 4 x rl, contiguous
+};
 
+// one DEEP-quotient column (a size class of compute_fri_quotients)
+struct QuotCol {
+    int log;               // of the whole column
+    uint32_t* coords[4];   // sharded: this rank's rows [rank * 2^(log - logw), ...)
+    uint32_t* full[4];     // sharded: the whole column once it was all-gathered for the replicated FRI layers (else null)
+};
+
+// one inner FRI layer (line evaluation + its Merkle tree)
+struct FriLayer {
+    int log;               // of the whole layer
+    uint32_t* coords[4];   // row shard when logw > 0
+    MerkleTree tree;
+    int logw = 0;
+};
+
+// PcsConfig::default() when the caller passes none (prover.rs:36); rejects what the protocol loops cannot handle
+lb_prove_config checked_config(const lb_prove_config* cfg_in) {
+    lb_prove_config cfg;
+    if (cfg_in)
+        cfg = *cfg_in;
+    else {
+        cfg.pow_bits = 5;
+        cfg.log_blowup_factor = 1;
+        cfg.log_last_layer_degree_bound = 0;
+        cfg.n_queries = 3;
+        cfg.channel_variant = 0;
+        cfg.n_slots = 17;
+        cfg.air_era = 0;
+        cfg.draw_lookup_elements = 1;
+    }
+    if (cfg.n_slots < 2 || cfg.n_slots > 64) fail(LB_ERR_BAD_ARG, "prove: bad n_slots");
+    if (cfg.log_blowup_factor < 1 || cfg.log_blowup_factor > 4) fail(LB_ERR_BAD_ARG, "prove: bad blow-up");
+    // the grind loop ends only when a nonce exists: a 64-bit nonce cannot be asked for more than 64 zero bits, and anything
+    // near that never finishes; stwo's own configurations stay below 32
+    if (cfg.pow_bits > 40) fail(LB_ERR_BAD_ARG, "prove: pow_bits > 40");
+    if (cfg.channel_variant != 0 && cfg.channel_variant != 1) fail(LB_ERR_BAD_ARG, "prove: unknown channel variant");
+    if (cfg.log_last_layer_degree_bound > 16 || cfg.n_queries < 1 || cfg.n_queries > 4096)
+        fail(LB_ERR_BAD_ARG, "prove: bad FRI configuration");
+    return cfg;
+}
+
+Shard make_shard(lb_ctx* ctx, lb_comm* comm) {
+    Shard sh;
+    if (comm && comm->world > 1) {
+        if (comm->ctx != ctx) fail(LB_ERR_BAD_ARG, "prove: the communicator belongs to another context");
+        sh.comm = comm;
+        sh.rank = comm->rank;
+        sh.world = comm->world;
+        sh.logw = comm->log_world;
+        comm->bytes_sent = comm->bytes_received = 0;
+        comm->n_collectives = 0;
+    }
+    return sh;
+}
+
+// One luminair_prover::prover::prove call (crates/prover/src/prover.rs:28-319 followed by stwo::prover::prove): the state the
+// phases hand to each other, one method per phase.  `sh` is the row/column shard of this rank when the proof is produced by
+// several GPUs together (lb_prove_sharded); with one GPU every sharded branch is skipped.
+class ProveJob {
+   public:
+    ProveJob(lb_ctx* ctx_, const lb_trace_table* tables_, int n_tables_, const lb_preprocessed_column* pre_in_, int n_pre_,
+             const lb_prove_config& cfg_, lb_comm* comm)
+        : ctx(ctx_), tables(tables_), n_tables(n_tables_), pre_in(pre_in_), n_pre(n_pre_), cfg(cfg_), sh(make_shard(ctx_, comm)),
+          blowup((int)cfg_.log_blowup_factor), st(ctx_->stream), tw(ctx_->tw), timer(ctx_), arena(ctx_->pool, ctx_->stream),
+          channel(cfg_.channel_variant, &ctx_->transcript), trees(4), lut_log(REL_COUNT, -1) {}
+
+    void run(std::vector<uint8_t>& out) {
+        setup();
+        commit_preprocessed();
+        commit_main_trace();
+        timer.lap();  // stage 0: upload + interpolate + LDE + Merkle of the main trace
+        commit_interaction_trace();
+        timer.lap();  // stage 1: LogUp + interpolate + LDE + Merkle of the interaction trace
+        commit_composition();
+        timer.lap();  // stage 2: constraint quotients + composition commit
+        sample_at_oods();
+        timer.lap();  // stage 3: OODS sampling
+        deep_quotients();
+        timer.lap();  // stage 4: DEEP quotients
+        fri_commit();
+        timer.lap();  // stage 5: FRI commit
+        nonce = grind_nonce(channel, cfg, arena, st);
+        channel.mix_u64(nonce);
+        decommit();
+        timer.lap();  // stage 6: grind + queries + decommitment
+        // prove() returns ConstraintsNotSatisfied otherwise
+        check_oods(comps, sampled, rels, random_coeff, oods);
+        ProofParts parts{claim, comps, trees, sampled, tree_dec, nonce, first_out, inner_out, last_layer_poly};
+        write_proof(out, cfg, parts, g);
+        timer.lap();  // stage 7: OODS check + serialisation
+    }
+
+   private:
+    // ---- the call
+    lb_ctx* ctx;
+    const lb_trace_table* tables;
+    int n_tables;
+    const lb_preprocessed_column* pre_in;
+    int n_pre;
+    const lb_prove_config cfg;
+    Shard sh;
+    const int blowup;
+    cudaStream_t st;
+    const Twiddles& tw;
+    StageTimer timer;
+    Arena arena;
+    Channel channel;
+    std::vector<CommitTree> trees;  // preprocessed, main, interaction, composition
+    bool use_ipc = false;           // fused exchange: LDE tiles stored straight into the owner rank's row-shard buffer (NVLink)
+    uint32_t* d_barrier = nullptr;
+    // ---- what the phases hand on
+    std::vector<PreCol> pre_cols;
+    std::vector<int> lut_log;
+    std::vector<int> claim;
+    std::vector<Component> by_slot;
+    Relations rels{};
+    std::vector<Component> comps;  // slot order = LuminairComponents order
+    std::vector<AuxReq> inter_aux;
+    QM31 random_coeff;
+    QPt oods;
+    std::vector<std::vector<std::vector<QPt>>> sample_points;  // [tree][col] = list of points
+    SampledValues sampled;
+    std::vector<QuotCol> quotients;
+    MerkleTree fri_first_tree;
+    std::vector<FriLayer> inner;
+    std::vector<QM31> last_layer_poly;
+    uint64_t nonce = 0;
+    Gatherer g;
+    FriLayerOut first_out;
+    std::vector<FriLayerOut> inner_out;
+    std::vector<DecommitIdx> tree_dec;
+
+    void setup() {
         // ---- sizes, twiddles -------------------------------------------------------------
         int max_log = 0;
         for (int t = 0; t < n_tables; ++t) {
@@ -1106,12 +1230,8 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
         }
         {
             int r = lb_twiddles_ensure(ctx, max_log + 1 + blowup);
-            if (r) return r;
+            if (r) fail(r, ctx->err);
         }
-        const Twiddles& tw = ctx->tw;
-
-        bool use_ipc = false;  // fused exchange: LDE tiles stored straight into the owner rank's row-shard buffer (NVLink)
-        uint32_t* d_barrier = nullptr;
         if (sh.on()) {
             if (!nccl_api().load()) fail(LB_ERR_NCCL, nccl_api().error);
             // symmetric heap: the row shards of every committed column + the shifted LogUp copies, the same layout on all ranks
@@ -1145,185 +1265,183 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             // no rank may store into a peer's heap before that peer is done with the previous proof
             if (use_ipc) shard_barrier(ctx, sh, d_barrier);
         }
-        struct AuxReq {  // non-committed columns shipped with a tree's exchange: the [-1]-shifted copies of the 4 coordinate
-            size_t col;  // columns col .. col + 3 (the last LogUp column of a component)
-            int domain_log;
-            uint32_t* dst;  // this rank's row shards of them: 4 x rl, contiguous
-        };
-        auto push_run = [&](CommitTree& tree, uint32_t* coeffs, int n, int lg) {
-            // n columns of 2^lg coefficients, contiguous; returns this rank's sub-range [a, b) of them
-            std::vector<int> owner = split_run(sh, n);
-            ColRun run{tree.cols.size(), n, lg};
-            for (int k = 0; k < n; ++k) {
-                PolyCol pc{coeffs ? coeffs + ((size_t)k << lg) : nullptr, nullptr, lg};
-                pc.owner = owner[k];
-                tree.cols.push_back(pc);
-            }
-            tree.runs.push_back(run);
-            return run;
-        };
-        // Sharded: evaluate the polynomials of one run (each on its owner rank) on CanonicCoset(L) and leave every rank with
-        // its row shard [rank R/W, (rank+1) R/W) of ALL of them (run.n columns at stride R/W; returned).  Transfers that need
-        // NCCL are appended to `xs` (the caller runs ONE grouped exchange for everything it shards), temporaries to `to_free`.
-        // `aux`: [-1]-shifted copies of columns of this run to ship along (constraint evaluation on row shards).
-        auto shard_run = [&](CommitTree& tree, const ColRun& run, int L, const std::vector<AuxReq>* aux, std::vector<Xfer>& xs,
-                             std::vector<uint32_t*>& to_free) -> uint32_t* {
-            const int lg = run.log;
-            const size_t stride = (size_t)1 << lg, out_stride = (size_t)1 << L;
-            if (L - sh.logw < 2) fail(LB_ERR_BAD_ARG, "prove (sharded): a committed column has fewer than 4 rows per rank");
-            int a, b;
-            own_range(tree, run, sh.rank, a, b);
-            const size_t rl = out_stride >> sh.logw;
-            uint32_t* local = use_ipc ? sym_alloc(sh.comm, rl * run.n) : arena.alloc<uint32_t>(rl * run.n);
-            // Large columns: the last pass of the transform (cfft_evaluate_scatter) writes every 4096-row tile straight
-            // to where it belongs.  Fused exchange (use_ipc): that is the owner rank's row-shard buffer itself, mapped over
-            // NVLink - no staging, no message, the transfer overlaps the butterflies tile by tile.  Otherwise: a
-            // per-destination staging block, so the exchange is ONE contiguous NCCL message per peer and run, received in
-            // place (an owner's columns are contiguous in the run).  Small columns: plain transform, one message per column
-            // and peer.
-            const bool packed = L >= 16 && L - sh.logw >= 12 && sh.world <= 8;
-            uint32_t* own = nullptr;   // !packed: the owned columns, whole
-            uint32_t* pack = nullptr;  // packed: [peer][owned column][rl] (this rank's slot unused)
-            if (b > a) {
-                own = arena.alloc<uint32_t>(out_stride * (b - a));
-                to_free.push_back(own);
-                if (packed) {
-                    uint32_t* peers[8];
-                    if (use_ipc) {
-                        for (int r = 0; r < sh.world; ++r) peers[r] = peer_ptr(sh.comm, r, local) + (size_t)a * rl;
-                        sh.comm->bytes_peer_stored += (size_t)(b - a) * rl * 4 * (size_t)(sh.world - 1);
-                    } else {
-                        pack = arena.alloc<uint32_t>(out_stride * (b - a));
-                        to_free.push_back(pack);
-                        for (int r = 0; r < sh.world; ++r)
-                            peers[r] = r == sh.rank ? local + (size_t)a * rl : pack + (size_t)r * (b - a) * rl;
-                    }
-                    ck(cfft_evaluate_scatter(&tw, tree.cols[run.first + a].coeffs, stride, lg, own, out_stride, L, b - a, peers,
-                                             sh.world, 0, ctx->sm_count, st),
-                       "LDE evaluate + scatter (own columns)");
-                    if (!use_ipc)
-                        for (int r = 0; r < sh.world; ++r)
-                            if (r != sh.rank) xs.push_back({peers[r], nullptr, (size_t)(b - a) * rl, r, true});
-                } else {
-                    ck(cfft_evaluate(&tw, tree.cols[run.first + a].coeffs, stride, lg, own, out_stride, L, b - a, ctx->sm_count, st),
-                       "LDE evaluate (own columns)");
-                }
-            }
-            if (packed && !use_ipc) {
-                for (int r = 0; r < sh.world; ++r) {
-                    if (r == sh.rank) continue;
-                    int ra, rb;
-                    own_range(tree, run, r, ra, rb);
-                    if (rb > ra) xs.push_back({nullptr, local + (size_t)ra * rl, (size_t)(rb - ra) * rl, r, false});
-                }
-            }
-            for (int k = 0; k < run.n; ++k) {
-                const PolyCol& pc = tree.cols[run.first + k];
-                uint32_t* mine = local + (size_t)k * rl;
-                if (!packed) {
-                    if (pc.owner == sh.rank) {
-                        const uint32_t* full = own + (size_t)(k - a) * out_stride;
-                        for (int r = 0; r < sh.world; ++r) xs.push_back({full + (size_t)r * rl, r == sh.rank ? mine : nullptr, rl, r, true});
-                    } else {
-                        xs.push_back({nullptr, mine, rl, pc.owner, false});
-                    }
-                }
-            }
-            if (aux)
-                for (const AuxReq& rq : *aux) {
-                    if (rq.col < run.first || rq.col >= run.first + (size_t)run.n) continue;
-                    // the four columns may have different owners; each owner's share is contiguous: one message per
-                    // owner and peer, written by the shift kernel straight into per-destination staging blocks
-                    const int k0 = (int)(rq.col - run.first);
-                    for (int r = 0; r < sh.world; ++r) {
-                        int q0 = 4, q1 = 0;  // columns k0 + q0 .. k0 + q1 - 1 are owned by rank r
-                        for (int q = 0; q < 4; ++q)
-                            if (tree.cols[rq.col + q].owner == r) {
-                                q0 = std::min(q0, q);
-                                q1 = std::max(q1, q + 1);
-                            }
-                        if (q1 <= q0) continue;
-                        const size_t cnt = (size_t)(q1 - q0) * rl;
-                        if (r != sh.rank) {
-                            if (!use_ipc) xs.push_back({nullptr, rq.dst + (size_t)q0 * rl, cnt, r, false});
-                            continue;
-                        }
-                        uint32_t* stage = nullptr;  // [peer][owned shifted column][rl]; fused exchange: not needed
-                        if (!use_ipc) {
-                            stage = arena.alloc<uint32_t>(cnt * sh.world);
-                            to_free.push_back(stage);
-                        } else {
-                            sh.comm->bytes_peer_stored += cnt * 4 * (size_t)(sh.world - 1);
-                        }
-                        for (int q = q0; q < q1; ++q) {
-                            const int k = k0 + q;
-                            const uint32_t* src[8];
-                            uint32_t* dst[8];
-                            for (int t = 0; t < sh.world; ++t) {
-                                if (packed && use_ipc)  // the column's shards already sit in their owners' buffers
-                                    src[t] = peer_ptr(sh.comm, t, local) + (size_t)k * rl;
-                                else if (packed)
-                                    src[t] = (t == sh.rank ? local + (size_t)a * rl : pack + (size_t)t * (b - a) * rl) + (size_t)(k - a) * rl;
-                                else
-                                    src[t] = own + (size_t)(k - a) * out_stride + (size_t)t * rl;
-                                if (use_ipc)
-                                    dst[t] = peer_ptr(sh.comm, t, rq.dst) + (size_t)q * rl;
-                                else
-                                    dst[t] = (t == sh.rank ? rq.dst + (size_t)q * rl : stage + (size_t)t * cnt + (size_t)(q - q0) * rl);
-                            }
-                            ck(shifted_prev_column(dst, sh.world, src, sh.world, rq.domain_log, L, st), "shifted column");
-                        }
-                        if (!use_ipc)
-                            for (int t = 0; t < sh.world; ++t)
-                                if (t != sh.rank) xs.push_back({stage + (size_t)t * cnt, nullptr, cnt, t, true});
-                    }
-                }
-            return local;
-        };
-        auto commit_tree = [&](CommitTree& tree, const std::vector<AuxReq>* aux = nullptr) {
-            // evaluate every polynomial on CanonicCoset(log + blowup), Merkle-commit, mix the root.  Sharded: every rank
-            // extends the columns it owns, one grouped exchange turns the column shards into row shards (rank r gets rows
-            // [r R/W, (r+1) R/W) of EVERY column), each rank hashes the sub-tree over its rows, the roots are all-gathered.
-            std::vector<ColRef> refs;
-            std::vector<Xfer> xs;
-            std::vector<uint32_t*> to_free;
-            for (const ColRun& run : tree.runs) {
-                const int lg = run.log, L = lg + blowup;
-                const size_t stride = (size_t)1 << lg, out_stride = (size_t)1 << L;
-                if (!sh.on()) {
-                    uint32_t* lde = arena.alloc<uint32_t>(out_stride * run.n);
-                    ck(cfft_evaluate(&tw, tree.cols[run.first].coeffs, stride, lg, lde, out_stride, L, run.n, ctx->sm_count, st),
-                       "LDE evaluate");
-                    for (int k = 0; k < run.n; ++k) {
-                        tree.cols[run.first + k].lde = lde + (size_t)k * out_stride;
-                        refs.push_back({tree.cols[run.first + k].lde, L});
-                    }
-                    continue;
-                }
-                uint32_t* local = shard_run(tree, run, L, aux, xs, to_free);
-                const size_t rl = out_stride >> sh.logw;
-                for (int k = 0; k < run.n; ++k) {
-                    tree.cols[run.first + k].lde = local + (size_t)k * rl;
-                    refs.push_back({tree.cols[run.first + k].lde, L - sh.logw});
-                }
-            }
-            if (sh.on()) {
-                if (!xs.empty()) run_exchange(ctx, sh, xs);
-                // fused exchange: my rows are complete once EVERY rank's kernels have run - a stream-ordered barrier
-                if (use_ipc) shard_barrier(ctx, sh, d_barrier);
-                for (uint32_t* f : to_free) arena.release(f);  // stream-ordered: freed after the sends have read them
-            }
-            merkle_commit(ctx, arena, refs, tree.merkle, /*fetch_root=*/!sh.on());
-            if (sh.on() && !tree.merkle.empty) finish_sharded_root(ctx, arena, sh, tree.merkle);
-            channel.mix_root(tree.merkle.root);
-        };
+    }
 
+    ColRun push_run(CommitTree& tree, uint32_t* coeffs, int n, int lg) {
+        // n columns of 2^lg coefficients, contiguous; returns this rank's sub-range [a, b) of them
+        std::vector<int> owner = split_run(sh, n);
+        ColRun run{tree.cols.size(), n, lg};
+        for (int k = 0; k < n; ++k) {
+            PolyCol pc{coeffs ? coeffs + ((size_t)k << lg) : nullptr, nullptr, lg};
+            pc.owner = owner[k];
+            tree.cols.push_back(pc);
+        }
+        tree.runs.push_back(run);
+        return run;
+    }
+
+    // Sharded: evaluate the polynomials of one run (each on its owner rank) on CanonicCoset(L) and leave every rank with
+    // its row shard [rank R/W, (rank+1) R/W) of ALL of them (run.n columns at stride R/W; returned).  Transfers that need
+    // NCCL are appended to `xs` (the caller runs ONE grouped exchange for everything it shards), temporaries to `to_free`.
+    // `aux`: [-1]-shifted copies of columns of this run to ship along (constraint evaluation on row shards).
+    uint32_t* shard_run(CommitTree& tree, const ColRun& run, int L, const std::vector<AuxReq>* aux, std::vector<Xfer>& xs,
+                        std::vector<uint32_t*>& to_free) {
+        const int lg = run.log;
+        const size_t stride = (size_t)1 << lg, out_stride = (size_t)1 << L;
+        if (L - sh.logw < 2) fail(LB_ERR_BAD_ARG, "prove (sharded): a committed column has fewer than 4 rows per rank");
+        int a, b;
+        own_range(tree, run, sh.rank, a, b);
+        const size_t rl = out_stride >> sh.logw;
+        uint32_t* local = use_ipc ? sym_alloc(sh.comm, rl * run.n) : arena.alloc<uint32_t>(rl * run.n);
+        // Large columns: the last pass of the transform (cfft_evaluate_scatter) writes every 4096-row tile straight
+        // to where it belongs.  Fused exchange (use_ipc): that is the owner rank's row-shard buffer itself, mapped over
+        // NVLink - no staging, no message, the transfer overlaps the butterflies tile by tile.  Otherwise: a
+        // per-destination staging block, so the exchange is ONE contiguous NCCL message per peer and run, received in
+        // place (an owner's columns are contiguous in the run).  Small columns: plain transform, one message per column
+        // and peer.
+        const bool packed = L >= 16 && L - sh.logw >= 12 && sh.world <= 8;
+        uint32_t* own = nullptr;   // !packed: the owned columns, whole
+        uint32_t* pack = nullptr;  // packed: [peer][owned column][rl] (this rank's slot unused)
+        if (b > a) {
+            own = arena.alloc<uint32_t>(out_stride * (b - a));
+            to_free.push_back(own);
+            if (packed) {
+                uint32_t* peers[8];
+                if (use_ipc) {
+                    for (int r = 0; r < sh.world; ++r) peers[r] = peer_ptr(sh.comm, r, local) + (size_t)a * rl;
+                    sh.comm->bytes_peer_stored += (size_t)(b - a) * rl * 4 * (size_t)(sh.world - 1);
+                } else {
+                    pack = arena.alloc<uint32_t>(out_stride * (b - a));
+                    to_free.push_back(pack);
+                    for (int r = 0; r < sh.world; ++r)
+                        peers[r] = r == sh.rank ? local + (size_t)a * rl : pack + (size_t)r * (b - a) * rl;
+                }
+                ck(cfft_evaluate_scatter(&tw, tree.cols[run.first + a].coeffs, stride, lg, own, out_stride, L, b - a, peers,
+                                         sh.world, 0, ctx->sm_count, st),
+                   "LDE evaluate + scatter (own columns)");
+                if (!use_ipc)
+                    for (int r = 0; r < sh.world; ++r)
+                        if (r != sh.rank) xs.push_back({peers[r], nullptr, (size_t)(b - a) * rl, r, true});
+            } else {
+                ck(cfft_evaluate(&tw, tree.cols[run.first + a].coeffs, stride, lg, own, out_stride, L, b - a, ctx->sm_count, st),
+                   "LDE evaluate (own columns)");
+            }
+        }
+        if (packed && !use_ipc) {
+            for (int r = 0; r < sh.world; ++r) {
+                if (r == sh.rank) continue;
+                int ra, rb;
+                own_range(tree, run, r, ra, rb);
+                if (rb > ra) xs.push_back({nullptr, local + (size_t)ra * rl, (size_t)(rb - ra) * rl, r, false});
+            }
+        }
+        for (int k = 0; k < run.n; ++k) {
+            const PolyCol& pc = tree.cols[run.first + k];
+            uint32_t* mine = local + (size_t)k * rl;
+            if (!packed) {
+                if (pc.owner == sh.rank) {
+                    const uint32_t* full = own + (size_t)(k - a) * out_stride;
+                    for (int r = 0; r < sh.world; ++r) xs.push_back({full + (size_t)r * rl, r == sh.rank ? mine : nullptr, rl, r, true});
+                } else {
+                    xs.push_back({nullptr, mine, rl, pc.owner, false});
+                }
+            }
+        }
+        if (aux)
+            for (const AuxReq& rq : *aux) {
+                if (rq.col < run.first || rq.col >= run.first + (size_t)run.n) continue;
+                // the four columns may have different owners; each owner's share is contiguous: one message per
+                // owner and peer, written by the shift kernel straight into per-destination staging blocks
+                const int k0 = (int)(rq.col - run.first);
+                for (int r = 0; r < sh.world; ++r) {
+                    int q0 = 4, q1 = 0;  // columns k0 + q0 .. k0 + q1 - 1 are owned by rank r
+                    for (int q = 0; q < 4; ++q)
+                        if (tree.cols[rq.col + q].owner == r) {
+                            q0 = std::min(q0, q);
+                            q1 = std::max(q1, q + 1);
+                        }
+                    if (q1 <= q0) continue;
+                    const size_t cnt = (size_t)(q1 - q0) * rl;
+                    if (r != sh.rank) {
+                        if (!use_ipc) xs.push_back({nullptr, rq.dst + (size_t)q0 * rl, cnt, r, false});
+                        continue;
+                    }
+                    uint32_t* stage = nullptr;  // [peer][owned shifted column][rl]; fused exchange: not needed
+                    if (!use_ipc) {
+                        stage = arena.alloc<uint32_t>(cnt * sh.world);
+                        to_free.push_back(stage);
+                    } else {
+                        sh.comm->bytes_peer_stored += cnt * 4 * (size_t)(sh.world - 1);
+                    }
+                    for (int q = q0; q < q1; ++q) {
+                        const int k = k0 + q;
+                        const uint32_t* src[8];
+                        uint32_t* dst[8];
+                        for (int t = 0; t < sh.world; ++t) {
+                            if (packed && use_ipc)  // the column's shards already sit in their owners' buffers
+                                src[t] = peer_ptr(sh.comm, t, local) + (size_t)k * rl;
+                            else if (packed)
+                                src[t] = (t == sh.rank ? local + (size_t)a * rl : pack + (size_t)t * (b - a) * rl) + (size_t)(k - a) * rl;
+                            else
+                                src[t] = own + (size_t)(k - a) * out_stride + (size_t)t * rl;
+                            if (use_ipc)
+                                dst[t] = peer_ptr(sh.comm, t, rq.dst) + (size_t)q * rl;
+                            else
+                                dst[t] = (t == sh.rank ? rq.dst + (size_t)q * rl : stage + (size_t)t * cnt + (size_t)(q - q0) * rl);
+                        }
+                        ck(shifted_prev_column(dst, sh.world, src, sh.world, rq.domain_log, L, st), "shifted column");
+                    }
+                    if (!use_ipc)
+                        for (int t = 0; t < sh.world; ++t)
+                            if (t != sh.rank) xs.push_back({stage + (size_t)t * cnt, nullptr, cnt, t, true});
+                }
+            }
+        return local;
+    }
+
+    void commit_tree(CommitTree& tree, const std::vector<AuxReq>* aux = nullptr) {
+        // evaluate every polynomial on CanonicCoset(log + blowup), Merkle-commit, mix the root.  Sharded: every rank
+        // extends the columns it owns, one grouped exchange turns the column shards into row shards (rank r gets rows
+        // [r R/W, (r+1) R/W) of EVERY column), each rank hashes the sub-tree over its rows, the roots are all-gathered.
+        std::vector<ColRef> refs;
+        std::vector<Xfer> xs;
+        std::vector<uint32_t*> to_free;
+        for (const ColRun& run : tree.runs) {
+            const int lg = run.log, L = lg + blowup;
+            const size_t stride = (size_t)1 << lg, out_stride = (size_t)1 << L;
+            if (!sh.on()) {
+                uint32_t* lde = arena.alloc<uint32_t>(out_stride * run.n);
+                ck(cfft_evaluate(&tw, tree.cols[run.first].coeffs, stride, lg, lde, out_stride, L, run.n, ctx->sm_count, st),
+                   "LDE evaluate");
+                for (int k = 0; k < run.n; ++k) {
+                    tree.cols[run.first + k].lde = lde + (size_t)k * out_stride;
+                    refs.push_back({tree.cols[run.first + k].lde, L});
+                }
+                continue;
+            }
+            uint32_t* local = shard_run(tree, run, L, aux, xs, to_free);
+            const size_t rl = out_stride >> sh.logw;
+            for (int k = 0; k < run.n; ++k) {
+                tree.cols[run.first + k].lde = local + (size_t)k * rl;
+                refs.push_back({tree.cols[run.first + k].lde, L - sh.logw});
+            }
+        }
+        if (sh.on()) {
+            if (!xs.empty()) run_exchange(ctx, sh, xs);
+            // fused exchange: my rows are complete once EVERY rank's kernels have run - a stream-ordered barrier
+            if (use_ipc) shard_barrier(ctx, sh, d_barrier);
+            for (uint32_t* f : to_free) arena.release(f);  // stream-ordered: freed after the sends have read them
+        }
+        merkle_commit(ctx, arena, refs, tree.merkle, /*fetch_root=*/!sh.on());
+        if (sh.on() && !tree.merkle.empty) finish_sharded_root(ctx, arena, sh, tree.merkle);
+        channel.mix_root(tree.merkle.root);
+    }
+
+    void commit_preprocessed() {
         // ---- phase 0: preprocessed trace (prover.rs:52-59) -----------------------------------------
         // lookups_to_preprocessed_column order from the caller, PreProcessedTrace::new sorts it (stable) by
         // log_size, descending (preprocessed.rs:152-155).  The LUT values themselves are the caller's
         // (host libm, preprocessed.rs:351-383); the path only interpolates and commits them.
-        std::vector<PreCol> pre_cols;
-        std::vector<int> lut_log(REL_COUNT, -1);
         {
             std::vector<int> order(n_pre);
             for (int k = 0; k < n_pre; ++k) order[k] = k;
@@ -1347,10 +1465,12 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             if (n_pre) ck(cudaStreamSynchronize(st), "LUT upload sync");  // host columns may be pageable
         }
         commit_tree(trees[0]);
+    }
 
+    void commit_main_trace() {
         // ---- phase 1: main trace (prover.rs:66-179) ------------------------------------------
-        std::vector<int> claim(cfg.n_slots, -1);
-        std::vector<Component> by_slot(cfg.n_slots);
+        claim.assign(cfg.n_slots, -1);
+        by_slot.assign(cfg.n_slots, Component{});
         for (int t = 0; t < n_tables; ++t) {
             const lb_trace_table& tb = tables[t];
             if (tb.slot < 0 || tb.slot >= cfg.n_slots) fail(LB_ERR_BAD_ARG, "prove: slot out of range");
@@ -1418,11 +1538,11 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
         for (int s = 0; s < cfg.n_slots; ++s)
             if (claim[s] >= 0) channel.mix_u64((uint64_t)claim[s]);  // LuminairClaim::mix_into
         commit_tree(trees[1]);
-        timer.lap();  // stage 0: upload + interpolate + LDE + Merkle of the main trace
+    }
 
+    void commit_interaction_trace() {
         // ---- phase 2: interaction trace (prover.rs:181-298) -----------------------------------
         // LuminairInteractionElements::draw (components/mod.rs:227-235): node, then sin, exp2, log2, range_check
-        Relations rels{};
         {
             std::vector<QM31> el = channel.draw_secure_felts(2);
             rels.r[REL_NODE] = Relation2{el[0], el[1]};
@@ -1434,8 +1554,6 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
         }
         if (!cfg.draw_lookup_elements && n_pre) fail(LB_ERR_BAD_ARG, "prove: LUT columns need draw_lookup_elements");
 
-        std::vector<Component> comps;  // slot order = LuminairComponents order
-        std::vector<AuxReq> inter_aux;
         {
             // TraceLocationAllocator hands out spans in component (slot) order
             size_t main_next = 0;
@@ -1521,10 +1639,11 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
         }
         for (const Component& c : comps) channel.mix_felts({c.claimed_sum});  // LuminairInteractionClaim::mix_into
         commit_tree(trees[2], sh.on() ? &inter_aux : nullptr);
-        timer.lap();  // stage 1: LogUp + interpolate + LDE + Merkle of the interaction trace
+    }
 
+    void commit_composition() {
         // ---- stwo::prover::prove -------------------------------------------------------------
-        QM31 random_coeff = channel.draw_secure_felt();
+        random_coeff = channel.draw_secure_felt();
         // constraint counts from the AIR itself
         std::vector<int> n_constraints;
         int total_constraints = 0;
@@ -1704,10 +1823,10 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             trees[3].runs.push_back(run);
         }
         commit_tree(trees[3]);
-        timer.lap();  // stage 2: constraint quotients + composition commit
+    }
 
+    void sample_at_oods() {
         // ---- OODS point and mask points ---------------------------------------------------------
-        QPt oods;
         {
             QM31 t = channel.draw_secure_felt();
             QM31 t2 = q_mul(t, t);
@@ -1715,8 +1834,7 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             oods.x = q_mul(q_sub(q_one(), t2), inv);
             oods.y = q_mul(q_add(t, t), inv);
         }
-        // sample_points[tree][col] = list of points
-        std::vector<std::vector<std::vector<QPt>>> sample_points(4);
+        sample_points.assign(4, {});
         sample_points[0].resize(trees[0].cols.size());  // only the columns a component reads are sampled
         sample_points[1].resize(trees[1].cols.size());
         sample_points[2].resize(trees[2].cols.size());
@@ -1736,7 +1854,7 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
         sample_points[3].assign(4, {oods});
 
         // ---- prove_values: sample every polynomial -----------------------------------------------
-        std::vector<std::vector<std::vector<QM31>>> sampled(4);
+        sampled.assign(4, {});
         for (int t = 0; t < 4; ++t) {
             sampled[t].resize(trees[t].cols.size());
             for (size_t c = 0; c < trees[t].cols.size(); ++c) sampled[t][c].resize(sample_points[t][c].size());
@@ -1816,16 +1934,11 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                     for (QM31 v : col) flat.push_back(v);
             channel.mix_felts(flat);
         }
-        timer.lap();  // stage 3: OODS sampling
-        QM31 rc_q = channel.draw_secure_felt();
+    }
 
+    void deep_quotients() {
         // ---- DEEP quotients (compute_fri_quotients) -----------------------------------------------
-        struct QuotCol {
-            int log;               // of the whole column
-            uint32_t* coords[4];   // sharded: this rank's rows [rank * 2^(log - logw), ...)
-            uint32_t* full[4];     // sharded: the whole column once it was all-gathered for the replicated FRI layers (else null)
-        };
-        std::vector<QuotCol> quotients;
+        const QM31 rc_q = channel.draw_secure_felt();
         {
             struct FlatCol {
                 const uint32_t* lde;
@@ -1872,16 +1985,10 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                 quotients.push_back(qc);
             }
         }
-        timer.lap();  // stage 4: DEEP quotients
+    }
 
+    void fri_commit() {
         // ---- FRI commit (FriProver::commit) ----------------------------------------------------------
-        struct FriLayer {
-            int log;               // of the whole layer
-            uint32_t* coords[4];   // row shard when logw > 0
-            MerkleTree tree;
-            int logw = 0;
-        };
-        MerkleTree fri_first_tree;
         {
             std::vector<ColRef> refs;
             for (auto& q : quotients)
@@ -1890,8 +1997,6 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             if (sh.on()) finish_sharded_root(ctx, arena, sh, fri_first_tree);
             channel.mix_root(fri_first_tree.root);
         }
-        std::vector<FriLayer> inner;
-        std::vector<QM31> last_layer_poly;
         {
             QM31 folding_alpha = channel.draw_secure_felt();
             int line_log = quotients[0].log - 1;
@@ -2102,50 +2207,18 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             std::vector<uint32_t> hv(4 * n);
             ck(cudaMemcpyAsync(hv.data(), cur, 4 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "last layer d2h");
             ck(cudaStreamSynchronize(st), "last layer sync");
-            std::vector<QM31> vals(n);
-            for (size_t i = 0; i < n; ++i) {
-                size_t s = bit_reverse((uint32_t)i, line_log);  // natural order
-                vals[i] = q_make(hv[s], hv[n + s], hv[2 * n + s], hv[3 * n + s]);
-            }
-            // LineEvaluation::interpolate on LineDomain(half_odds(line_log))
-            uint32_t d_init = subgroup_gen(line_log + 2), d_step = subgroup_gen(line_log);
-            size_t size = n;
-            while (size > 1) {
-                for (size_t start = 0; start < n; start += size)
-                    for (size_t i = 0; i < size / 2; ++i) {
-                        uint32_t x = host_index_to_point(d_init + d_step * (uint32_t)i).x;
-                        uint32_t xinv = m_inv(x);
-                        QM31 l = vals[start + i], r = vals[start + size / 2 + i];
-                        vals[start + i] = q_add(l, r);
-                        vals[start + size / 2 + i] = q_mul_m(q_sub(l, r), xinv);
-                    }
-                d_init = (d_init * 2) & CIRCLE_ORDER_MASK;
-                d_step = (d_step * 2) & CIRCLE_ORDER_MASK;
-                size /= 2;
-            }
-            uint32_t inv_n = m_inv((uint32_t)(n % P));
-            std::vector<QM31> coeffs(n);
-            for (size_t i = 0; i < n; ++i) coeffs[i] = q_mul_m(vals[bit_reverse((uint32_t)i, line_log)], inv_n);
-            size_t bound = (size_t)1 << cfg.log_last_layer_degree_bound;
-            for (size_t i = bound; i < n; ++i)
-                if (!q_is_zero(coeffs[i])) fail(LB_ERR_CONSTRAINTS, "fri: invalid last-layer degree (ConstraintsNotSatisfied)");
-            last_layer_poly.assign(coeffs.begin(), coeffs.begin() + bound);
+            last_layer_poly = interpolate_last_layer(hv, line_log, cfg.log_last_layer_degree_bound);
             channel.mix_felts(last_layer_poly);
         }
-        timer.lap();  // stage 5: FRI commit
+    }
 
-        // ---- proof of work --------------------------------------------------------------------------
-        const uint64_t nonce = grind_nonce(channel, cfg, arena, st);
-        channel.mix_u64(nonce);
-
+    void decommit() {
         // ---- queries + decommitment plan ---------------------------------------------------------------
-        Gatherer g;
         int max_lde_log = quotients[0].log;
         std::vector<uint32_t> queries = generate_queries(channel, max_lde_log, cfg.n_queries);
         std::map<int, std::vector<uint32_t>> qpos;
         for (auto& q : quotients) qpos[q.log] = fold_queries(queries, max_lde_log - q.log);
 
-        FriLayerOut first_out;
         first_out.commitment = fri_first_tree.root;
         {
             std::map<int, std::vector<uint32_t>> pos_by_size;
@@ -2158,7 +2231,7 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             merkle_decommit_plan(fri_first_tree, pos_by_size, g, first_out.decommit, sh.rank);
             first_out.decommit.queried_values.clear();
         }
-        std::vector<FriLayerOut> inner_out(inner.size());
+        inner_out.assign(inner.size(), FriLayerOut{});
         {
             std::vector<uint32_t> lq = fold_queries(queries, 1);
             for (size_t li = 0; li < inner.size(); ++li) {
@@ -2173,7 +2246,7 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
                 lq = fold_queries(lq, 1);
             }
         }
-        std::vector<DecommitIdx> tree_dec(4);
+        tree_dec.assign(4, DecommitIdx{});
         for (int t = 0; t < 4; ++t) merkle_decommit_plan(trees[t].merkle, qpos, g, tree_dec[t], sh.rank);
 
         // one gather for everything
@@ -2193,15 +2266,26 @@ int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb
             ck(cudaStreamSynchronize(st), "gather sync");
             for (auto& kv : g.consts) g.values[kv.first] = kv.second;
         }
-        timer.lap();  // stage 6: grind + queries + decommitment
+    }
+};
 
-        // ---- OODS check (prove() returns ConstraintsNotSatisfied otherwise) ------------------------------
-        check_oods(comps, sampled, rels, random_coeff, oods);
+}  // namespace
 
-        // ---- bincode -----------------------------------------------------------------------------------------
-        ProofParts parts{claim, comps, trees, sampled, tree_dec, nonce, first_out, inner_out, last_layer_poly};
-        write_proof(out, cfg, parts, g);
-        timer.lap();  // stage 7: OODS check + serialisation
+// ======================================================================================
+int prove_impl(lb_ctx* ctx, const lb_trace_table* tables, int n_tables, const lb_preprocessed_column* pre_in, int n_pre,
+               const lb_prove_config* cfg_in, std::vector<uint8_t>& out, lb_comm* comm) {
+    try {
+        const lb_prove_config cfg = checked_config(cfg_in);
+        if (n_tables < 1 || !tables) fail(LB_ERR_BAD_ARG, "prove: no trace tables");
+        ck(cudaSetDevice(ctx->device), "set device");
+        if (!ctx->kernels_ready) {
+            ck(kernels_init(ctx->stream), "kernels init");
+            ctx->kernels_ready = true;
+        }
+        ctx->transcript.clear();
+        ctx->stage_ms.clear();
+        ProveJob job(ctx, tables, n_tables, pre_in, n_pre, cfg, comm);
+        job.run(out);
         return LB_OK;
     } catch (const ProveError& e) {
         cudaStreamSynchronize(ctx->stream);
