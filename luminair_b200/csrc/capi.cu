@@ -80,6 +80,18 @@ int lb_ctx_create(int device, lb_ctx** out) {
         unsigned long long thr = ~0ull;
         cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
+    {
+        void* hp = nullptr;
+        const size_t bytes = (size_t)2 << 20;
+        if (cudaHostAlloc(&hp, bytes, cudaHostAllocDefault) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->ev_stage, cudaEventDisableTiming) == cudaSuccess) {
+            ctx->h_stage = (uint8_t*)hp;
+            ctx->h_stage_bytes = bytes;
+        } else {  // uploads fall back to pageable copies
+            cudaGetLastError();
+            if (hp) cudaFreeHost(hp);
+        }
+    }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->total_mem = prop.totalGlobalMem;
     *out = ctx;
@@ -102,6 +114,8 @@ void lb_ctx_destroy(lb_ctx* ctx) {
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_stage) cudaEventDestroy(ctx->ev_stage);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     cudaStreamDestroy(ctx->stream);
     // blocks still held by the caller (lb_alloc_pooled) keep the pool alive until they are freed
     if (ctx->pool && !ctx->pool_is_default) cudaMemPoolDestroy(ctx->pool);

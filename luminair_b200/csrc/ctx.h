@@ -16,6 +16,13 @@ struct lb_ctx {
     // to another context's stream (the device default pool would make the second stream wait for the first one's free point)
     cudaMemPool_t pool = nullptr;
     bool pool_is_default = false;
+    // pinned staging for the small host->device uploads of a call (pointer tables, batch descriptors, channel state): a copy
+    // from pageable memory drains the stream before it starts, a copy from here is asynchronous.  One user at a time
+    // (host_util.h::Arena), handed on through `ev_stage`.
+    uint8_t* h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+    cudaEvent_t ev_stage = nullptr;
+    bool stage_in_flight = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 0;
     size_t total_mem = 0;

@@ -1141,7 +1141,7 @@ class ProveJob {
     ProveJob(lb_ctx* ctx_, const lb_trace_table* tables_, int n_tables_, const lb_preprocessed_column* pre_in_, int n_pre_,
              const lb_prove_config& cfg_, lb_comm* comm)
         : ctx(ctx_), tables(tables_), n_tables(n_tables_), pre_in(pre_in_), n_pre(n_pre_), cfg(cfg_), sh(make_shard(ctx_, comm)),
-          blowup((int)cfg_.log_blowup_factor), st(ctx_->stream), tw(ctx_->tw), timer(ctx_), arena(ctx_->pool, ctx_->stream),
+          blowup((int)cfg_.log_blowup_factor), st(ctx_->stream), tw(ctx_->tw), timer(ctx_), arena(ctx_),
           channel(cfg_.channel_variant, &ctx_->transcript), trees(4), lut_log(REL_COUNT, -1) {}
 
     void run(std::vector<uint8_t>& out) {
@@ -2012,9 +2012,8 @@ class ProveJob {
             DevChannel* d_ch = arena.alloc<DevChannel>(1);
             QM31* d_alphas = arena.alloc<QM31>(n_layers + 1);
             uint32_t* d_digests = arena.alloc<uint32_t>(8 * (size_t)std::max(n_layers, 1));
-            ck(cudaMemcpyAsync(d_ch, &h_ch, sizeof(h_ch), cudaMemcpyHostToDevice, st), "channel h2d");
-            ck(cudaMemcpyAsync(d_alphas, &folding_alpha, sizeof(QM31), cudaMemcpyHostToDevice, st), "alpha h2d");
-            ck(cudaStreamSynchronize(st), "channel h2d sync");  // h_ch / folding_alpha are stack objects
+            arena.upload_to(d_ch, &h_ch, sizeof(h_ch));
+            arena.upload_to(d_alphas, &folding_alpha, sizeof(QM31));
             int li = 0;
             uint32_t* gathered = nullptr;  // sharded: the first replicated layer, all-gathered from the row shards
             const size_t top_words = 8 * (((size_t)2 << sh.logw) - 1);
@@ -2347,7 +2346,7 @@ int eval_at_point_impl(lb_ctx* ctx, const uint32_t* const* h_cols, int n_cols, i
                        uint32_t* h_out) {
     return guarded(ctx, [&] {
         ensure_kernels(ctx);
-        Arena arena(ctx->pool, ctx->stream);
+        Arena arena(ctx);
         std::vector<const uint32_t*> cols(h_cols, h_cols + n_cols);
         QPt pt{q_from_words(point), q_from_words(point + 4)};
         QM31* d_out = arena.alloc<QM31>(n_cols);
@@ -2362,7 +2361,7 @@ int accumulate_quotients_impl(lb_ctx* ctx, int log, const uint32_t* const* h_col
                               const uint32_t random_coeff[4], uint32_t* const d_out[4]) {
     return guarded(ctx, [&] {
         ensure_kernels(ctx);
-        Arena arena(ctx->pool, ctx->stream);
+        Arena arena(ctx);
         std::vector<const uint32_t*> cols(h_cols, h_cols + n_cols);
         std::vector<HostBatch> hb(n_batches);
         for (int b = 0; b < n_batches; ++b) {
@@ -2399,7 +2398,7 @@ int grind_impl(lb_ctx* ctx, const uint32_t digest[8], int variant, uint32_t pow_
     return guarded(ctx, [&] {
         ensure_kernels(ctx);
         if (pow_bits > 64) fail(LB_ERR_BAD_ARG, "grind: pow_bits > 64");
-        Arena arena(ctx->pool, ctx->stream);
+        Arena arena(ctx);
         unsigned long long* d_found = arena.alloc<unsigned long long>(1);
         uint64_t base = 0;
         const uint64_t chunk = (uint64_t)1 << 24;
@@ -2438,7 +2437,7 @@ int logup_impl(lb_ctx* ctx, int kind, const uint32_t* d_main, size_t main_stride
             if (!d_lut || !d_lut[q]) fail(LB_ERR_BAD_ARG, "logup: component needs its LUT columns");
             pc.p[q] = d_lut[q];
         }
-        Arena arena(ctx->pool, ctx->stream);
+        Arena arena(ctx);
         size_t n = (size_t)1 << log;
         uint32_t* scan_tmp = arena.alloc<uint32_t>(4 * n);
         uint32_t* block_sums = arena.alloc<uint32_t>(4 * (n / 1024 + 1));
@@ -2486,7 +2485,7 @@ int constraint_quotients_impl(lb_ctx* ctx, int kind, const uint32_t* d_main, siz
             Pt pt = host_index_to_point(init + step * bit_reverse(i, log_expand));
             dinv[i] = m_inv(coset_vanishing_m(log_size, pt));
         }
-        Arena arena(ctx->pool, ctx->stream);
+        Arena arena(ctx);
         p.denom_inv = arena.upload(dinv);
         ck(constraint_quotients(kind, p, ctx->stream), "constraint quotients");
         ck(cudaStreamSynchronize(ctx->stream), "constraints sync");  // arena scratch is released on return
