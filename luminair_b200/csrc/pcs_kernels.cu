@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(256) eval_partial_kernel(const uint32_t* const
     const int nc = min(EVAL_CPB, n_cols - c0);
     const uint32_t elems = 1u << m;  // 4096 on this path
     const uint32_t tid = threadIdx.x;
+    __shared__ QM31 s_w[EVAL_CPB][8];
     // thread t owns elements 4 * (t + 256 i) + q, i < 4, q < 4
     uint4 bs[16];
 #pragma unroll
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(256) eval_partial_kernel(const uint32_t* const
                 a1 += cq * b.y;
                 a2 += cq * b.z;
                 a3 += cq * b.w;
-                if (q & 1) {  // products < 2^62: fold before a third could overflow
+                if (q == 3) {  // canonical operands: four products (< 2^64 - 2^34) plus a folded sum (< 2^33 + 2^31) fit 64 bits
                     a0 = (a0 & P) + (a0 >> 31);
                     a1 = (a1 & P) + (a1 >> 31);
                     a2 = (a2 & P) + (a2 >> 31);
@@ -137,9 +138,17 @@ __global__ void __launch_bounds__(256) eval_partial_kernel(const uint32_t* const
                 }
             }
         }
-        QM31 s = q_make(fold64(a0), fold64(a1), fold64(a2), fold64(a3));
-        s = block_sum_q(s);
-        if (tid == 0) partials[(size_t)(c0 + c) * n_chunks + chunk] = q_mul(s, hi);
+        // per-warp sums go to shared memory; the block-wide reduction happens once, after the last column (no barrier between
+        // columns: the next column's loads are not held back by this one's reduction)
+        QM31 s = warp_sum_q(q_make(fold64(a0), fold64(a1), fold64(a2), fold64(a3)));
+        if ((tid & 31) == 0) s_w[c][tid >> 5] = s;
+    }
+    __syncthreads();
+    if ((int)tid < nc) {
+        QM31 r = q_zero();
+#pragma unroll
+        for (int w = 0; w < 8; ++w) r = q_add(r, s_w[tid][w]);
+        partials[(size_t)(c0 + tid) * n_chunks + chunk] = q_mul(r, hi);
     }
     (void)elems;
 }
@@ -158,7 +167,7 @@ __global__ void __launch_bounds__(256) eval_partial_small_kernel(const uint32_t*
         a1 += c * b.y;
         a2 += c * b.z;
         a3 += c * b.w;
-        if (++pending == 2) {
+        if (++pending == 4) {  // see eval_partial_kernel
             a0 = (a0 & P) + (a0 >> 31);
             a1 = (a1 & P) + (a1 >> 31);
             a2 = (a2 & P) + (a2 >> 31);
