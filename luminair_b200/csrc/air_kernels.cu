@@ -10,6 +10,7 @@
 // Both are one thread per row over column-major data (coalesced 128-byte warp reads, each input
 // byte read once); the LogUp prefix sum runs in canonic-coset order over the bit-reversed
 // storage as a three-phase scan.
+#include "launch.cuh"
 #include "kernels.cuh"
 
 namespace lb {
@@ -22,6 +23,7 @@ template <int KIND>
 __global__ void __launch_bounds__(256) logup_fracs_kernel(const uint32_t* __restrict__ main, size_t main_stride, const PreCols pre_cols,
                                                           uint32_t* __restrict__ inter, size_t inter_stride, uint32_t n,
                                                           const __grid_constant__ Relations rels) {
+    pdl_wait();
     constexpr int NF = component_shape(KIND).n_fracs;
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
@@ -81,6 +83,7 @@ constexpr int SCAN_BLOCK = 1024;  // elements per CTA (256 threads x 4)
 __global__ void __launch_bounds__(256) logup_scan_local_kernel(const uint32_t* __restrict__ col, size_t coord_stride,
                                                                uint32_t* __restrict__ tmp, uint32_t* __restrict__ block_sums,
                                                                int log) {
+    pdl_wait();
     __shared__ uint32_t s_warp[8];
     const uint32_t n = 1u << log;
     const int coord = blockIdx.y;
@@ -116,6 +119,8 @@ __global__ void __launch_bounds__(256) logup_scan_local_kernel(const uint32_t* _
 // phase 2: exclusive scan of the CTA totals (<= 2^24 / 1024 entries per coordinate); total -> claimed.
 // One CTA per coordinate: every thread scans a contiguous chunk, the 256 chunk totals are scanned in shared memory.
 __global__ void __launch_bounds__(256) logup_scan_sums_kernel(uint32_t* block_sums, uint32_t n_blocks, uint32_t* claimed) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ uint32_t s_tot[256];
     const int coord = blockIdx.x;
     uint32_t* s = block_sums + (size_t)coord * n_blocks;
@@ -148,6 +153,7 @@ __global__ void __launch_bounds__(256) logup_scan_apply_kernel(uint32_t* __restr
                                                                const uint32_t* __restrict__ tmp,
                                                                const uint32_t* __restrict__ block_sums,
                                                                const uint32_t* __restrict__ claimed, int log, uint32_t inv_n) {
+    pdl_wait();
     const uint32_t n = 1u << log;
     const int coord = blockIdx.y;
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -173,7 +179,7 @@ struct LogupLaunch {
     void operator()() {
         // the artifact-era Mul shares the LogUp terms of Mul
         constexpr int K = KIND == COMP_MUL_ARTIFACT ? COMP_MUL : KIND;
-        logup_fracs_kernel<K><<<(n + 255) / 256, 256, 0, stream>>>(main, main_stride, pre, inter, inter_stride, n, rels);
+        launch_k(logup_fracs_kernel<K>, (n + 255) / 256, 256, 0, stream, main, main_stride, pre, inter, inter_stride, n, rels);
     }
 };
 }  // namespace
@@ -190,10 +196,10 @@ cudaError_t logup_interaction_trace(int kind, const uint32_t* main, size_t main_
     if (!dispatch_kind(kind, launch)) return cudaErrorInvalidValue;
     uint32_t* last = inter + (size_t)(4 * (nf - 1)) * inter_stride;
     uint32_t n_blocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    logup_scan_local_kernel<<<dim3(n_blocks, 4), 256, 0, stream>>>(last, inter_stride, d_scan_tmp, d_block_sums, log);
-    logup_scan_sums_kernel<<<4, 256, 0, stream>>>(d_block_sums, n_blocks, d_claimed);
+    launch_k(logup_scan_local_kernel, dim3(n_blocks, 4), 256, 0, stream, last, inter_stride, d_scan_tmp, d_block_sums, log);
+    launch_k(logup_scan_sums_kernel, 4, 256, 0, stream, d_block_sums, n_blocks, d_claimed);
     uint32_t inv_n = m_inv(n % P);
-    logup_scan_apply_kernel<<<dim3(blocks, 4), 256, 0, stream>>>(last, inter_stride, d_scan_tmp, d_block_sums, d_claimed, log,
+    launch_k(logup_scan_apply_kernel, dim3(blocks, 4), 256, 0, stream, last, inter_stride, d_scan_tmp, d_block_sums, d_claimed, log,
                                                                  inv_n);
     return cudaGetLastError();
 }
@@ -264,6 +270,7 @@ __device__ __forceinline__ uint32_t prev_row_index(uint32_t j, int domain_log, i
 
 template <int KIND>
 __global__ void __launch_bounds__(256) constraint_quotients_kernel(const __grid_constant__ ConstraintParams p) {
+    pdl_wait();
     uint32_t n = p.n_rows ? p.n_rows : (1u << p.eval_log);
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;  // local row; the global row is row0 + j
     if (j >= n) return;
@@ -284,7 +291,7 @@ struct ConstraintLaunch {
     template <int KIND>
     void operator()() {
         uint32_t n = p.n_rows ? p.n_rows : (1u << p.eval_log);
-        constraint_quotients_kernel<KIND><<<(n + 255) / 256, 256, 0, stream>>>(p);
+        launch_k(constraint_quotients_kernel<KIND>, (n + 255) / 256, 256, 0, stream, p);
     }
 };
 }  // namespace
@@ -299,6 +306,7 @@ struct ShardOut {
 };
 __global__ void __launch_bounds__(256) shifted_prev_kernel(ShardOut out, ShardPtrs col, int src_shard_log, int dst_shard_log,
                                                            int domain_log, int eval_log) {
+    pdl_wait();
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= (1u << eval_log)) return;
     uint32_t q = prev_row_index(j, domain_log, eval_log);
@@ -319,7 +327,7 @@ cudaError_t shifted_prev_column(uint32_t* const out_shards[8], int n_out, const 
     for (int k = 0; k < n_src; ++k) sp.p[k] = src_shards[k];
     for (int k = 0; k < n_out; ++k) so.p[k] = out_shards[k];
     uint32_t n = 1u << eval_log;
-    shifted_prev_kernel<<<(n + 255) / 256, 256, 0, stream>>>(so, sp, eval_log - lg(n_src), eval_log - lg(n_out), domain_log, eval_log);
+    launch_k(shifted_prev_kernel, (n + 255) / 256, 256, 0, stream, so, sp, eval_log - lg(n_src), eval_log - lg(n_out), domain_log, eval_log);
     return cudaGetLastError();
 }
 

@@ -17,6 +17,7 @@
 // Inside a tile the m layers run as rounds of <= 4 layers on 16 register-resident elements per
 // thread; rounds exchange through shared memory.  Butterflies are lazy: values live in
 // [0, 2^32) and are folded only where the next operation needs it (see m31.cuh).
+#include "launch.cuh"
 #include "cfft.cuh"
 
 #include <algorithm>
@@ -52,6 +53,7 @@ __device__ __forceinline__ Pt point_of_index(uint32_t idx) {
 // X[k][h] = x(half_odds(k).at(bitrev(h, k-1))), h < 2^(k-1)      (line layers)
 // Y[k][h] = y(half_odds(k).at(bitrev(h, k))),   h < 2^k          (circle layer)
 __global__ void gen_twiddles_kernel(uint2* fwd, uint2* inv, int k, int is_y) {
+    pdl_wait();
     uint32_t bits = is_y ? k : k - 1;
     uint32_t n = 1u << bits;
     uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
@@ -97,11 +99,11 @@ cudaError_t twiddles_create(Twiddles* tw, int max_log, cudaStream_t stream) {
     for (int k = 0; k <= K; ++k) {
         size_t yo = nx + ((size_t)1 << k);
         uint32_t cy = 1u << k;
-        gen_twiddles_kernel<<<(cy + 255) / 256, 256, 0, stream>>>(tw->fwd + yo, tw->inv + yo, k, 1);
+        launch_k(gen_twiddles_kernel, (cy + 255) / 256, 256, 0, stream, tw->fwd + yo, tw->inv + yo, k, 1);
         if (k == 0) continue;
         size_t xo = ((size_t)1 << (k - 1));
         uint32_t cx = 1u << (k - 1);
-        gen_twiddles_kernel<<<(cx + 255) / 256, 256, 0, stream>>>(tw->fwd + xo, tw->inv + xo, k, 0);
+        launch_k(gen_twiddles_kernel, (cx + 255) / 256, 256, 0, stream, tw->fwd + xo, tw->inv + xo, k, 0);
     }
     return cudaGetLastError();
 }
@@ -254,6 +256,7 @@ __device__ __forceinline__ void run_round(uint32_t* sm, const PassParams& p, int
 // grid: x = tile, y = column group.  Each block loops over its columns.
 template <bool FWD, int W>
 __global__ void __launch_bounds__(256) cfft_pass_kernel(PassParams p, int cols_per_block) {
+    pdl_wait();
     extern __shared__ uint32_t sm[];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int tile_elems = 1 << p.ts;
@@ -578,6 +581,7 @@ __device__ __forceinline__ void low_round(uint32_t* sm, const PassParams& p, uin
 // twiddle load and index computation is shared by NC butterflies and each warp has NC x the independent work.
 template <bool FWD, int M, int NC>
 __global__ void __launch_bounds__(256, NC == 1 ? LB_LOW_MINB : LB_LOW_MINB2) cfft_low_fast(PassParams p, int cols_per_block) {
+    pdl_wait();
     extern __shared__ __align__(16) uint32_t sm[];  // NC * LOW_SMEM_WORDS
     constexpr int NR = (M + 3) / 4;
     const uint32_t tile = blockIdx.x;
@@ -698,6 +702,7 @@ struct HighGeom {
 template <bool FWD, int M, int ILO, int ZEXT, int NC>
 __global__ void __launch_bounds__(HighGeom<M>::THREADS, NC == 1 ? HighGeom<M>::MIN_BLOCKS : ((M <= 8) ? LB_HIGH_MINB2 : 1))
     cfft_high_fast(PassParams p, int cols_per_block) {
+    pdl_wait();
     constexpr int W = HighGeom<M>::W;
     constexpr int NR = (M + 3) / 4;
     extern __shared__ __align__(16) uint32_t smh[];
@@ -837,6 +842,7 @@ __device__ __forceinline__ void high_round_vec(uint32_t* sm, const PassParams& p
 
 template <bool FWD, int M, int ILO, int ZEXT, int VW>
 __global__ void __launch_bounds__((1 << (M - 4)) * 16, M == 8 ? (VW == 4 ? 2 : 4) : (M == 9 && VW == 2 ? 2 : 1)) cfft_high_vec(PassParams p) {
+    pdl_wait();
     static_assert(M >= 8 && M <= 10, "two or three rounds of up to four layers");
     extern __shared__ __align__(16) uint32_t smv[];
     constexpr uint32_t W = 16 * VW;
@@ -878,7 +884,7 @@ static cudaError_t launch_high_vec(const PassParams& p, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
     }
     dim3 grid((unsigned)tiles, (unsigned)p.n_cols);
-    k<<<grid, (1 << (M - 4)) * 16, smem, stream>>>(p);
+    launch_k(k, grid, (1 << (M - 4)) * 16, smem, stream, p);
     return cudaGetLastError();
 }
 
@@ -951,7 +957,7 @@ static cudaError_t launch_generic(const PassParams& p, int sm_count, cudaStream_
     int cpb = pick_cols_per_block(tiles, p.n_cols, sm_count);
     dim3 grid((unsigned)tiles, (unsigned)((p.n_cols + cpb - 1) / cpb));
     if (grid.y > 65535) return cudaErrorInvalidValue;
-    cfft_pass_kernel<FWD, 1><<<grid, 256, smem, stream>>>(p, cpb);
+    launch_k(cfft_pass_kernel<FWD, 1>, grid, 256, smem, stream, p, cpb);
     return cudaGetLastError();
 }
 
@@ -968,7 +974,7 @@ static cudaError_t launch_low_nc(const PassParams& p, int sm_count, cudaStream_t
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k<<<grid, 256, smem, stream>>>(p, cpb);
+    launch_k(k, grid, 256, smem, stream, p, cpb);
     return cudaGetLastError();
 }
 
@@ -1022,7 +1028,7 @@ static cudaError_t launch_high_nc(const PassParams& p, int sm_count, cudaStream_
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k<<<grid, HighGeom<M>::THREADS, smem, stream>>>(p, cpb);
+    launch_k(k, grid, HighGeom<M>::THREADS, smem, stream, p, cpb);
     return cudaGetLastError();
 }
 
@@ -1247,6 +1253,7 @@ static cudaError_t cfft_evaluate_scatter_all(const Twiddles* tw, const uint32_t*
 // stwo-format twiddle tree of a root half coset half_odds(root_log): per layer, x of the first
 // half of the k-times doubled coset, bit-reversed; concatenated; padded with 1.
 __global__ void export_stwo_twiddles_kernel(const uint2* fwd_x_base, uint32_t* out, int root_log) {
+    pdl_wait();
     // layer k (0-based) = X[root_log - k], size 2^(root_log-k-1), at out offset sum of previous sizes
     size_t total = ((size_t)1 << root_log);
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -1267,7 +1274,7 @@ __global__ void export_stwo_twiddles_kernel(const uint2* fwd_x_base, uint32_t* o
 cudaError_t twiddles_export_stwo(const Twiddles* tw, int root_log, uint32_t* d_out, cudaStream_t stream) {
     if (root_log < 1 || root_log > tw->max_log - 1) return cudaErrorInvalidValue;
     size_t total = (size_t)1 << root_log;
-    export_stwo_twiddles_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(tw->fwd, d_out, root_log);
+    launch_k(export_stwo_twiddles_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, tw->fwd, d_out, root_log);
     return cudaGetLastError();
 }
 

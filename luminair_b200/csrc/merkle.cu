@@ -8,6 +8,7 @@
 // (children absent on the deepest layer).  One thread hashes one node; columns are read
 // column-major so a warp reads 128 contiguous bytes per column; digests are stored as 8 u32
 // per node so the next layer reads its two children as one 64-byte segment.
+#include "launch.cuh"
 #include "merkle.cuh"
 
 #include "blake2s.cuh"
@@ -84,6 +85,7 @@ __device__ __forceinline__ void hash_node(uint32_t h[8], const uint32_t* prev, c
 __global__ void __launch_bounds__(256) merkle_layer_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ prev,
                                                            const uint32_t* const* __restrict__ cols, int n_cols,
                                                            uint32_t n_nodes, uint32_t one) {
+    pdl_wait();
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     uint32_t h[8];
@@ -98,7 +100,7 @@ cudaError_t merkle_commit_layer(uint32_t* out, const uint32_t* prev, const uint3
     uint32_t n = 1u << log_size;
     // (two nodes per thread, as in merkle_layer_small_kernel<2>, was measured slower here: the pointer-table loads and 96
     // registers cost more than the second chain gains - 12.53 vs 12.23 ms on the 61-column proof)
-    merkle_layer_kernel<<<(n + 255) / 256, 256, 0, stream>>>(out, prev, d_cols, n_cols, n, 1u);
+    launch_k(merkle_layer_kernel, (n + 255) / 256, 256, 0, stream, out, prev, d_cols, n_cols, n, 1u);
     return cudaGetLastError();
 }
 
@@ -112,6 +114,7 @@ __global__ void __launch_bounds__(256, NH == 1 ? 4 : 2) merkle_layer_small_kerne
                                                                                   const uint32_t* __restrict__ prev,
                                                                                   const __grid_constant__ MerkleColsArg cols,
                                                                                   int n_cols, uint32_t n_nodes, uint32_t one) {
+    pdl_wait();
     const uint32_t i0 = blockIdx.x * (256 * NH) + threadIdx.x;
     if (i0 >= n_nodes) return;  // NH > 1 is only launched for n_nodes that are multiples of 256 * NH
     uint32_t h[NH][8], m[NH][16];
@@ -158,9 +161,9 @@ cudaError_t merkle_commit_layer_small(uint32_t* out, const uint32_t* prev, const
     uint32_t n = 1u << log_size;
     // two nodes per thread once the layer still fills the machine that way (148 SMs x 2 CTAs x 512 nodes)
     if (LB_MERKLE_NH == 2 && log_size >= 18)
-        merkle_layer_small_kernel<2><<<n / 512, 256, 0, stream>>>(out, prev, cols, n_cols, n, 1u);
+        launch_k(merkle_layer_small_kernel<2>, n / 512, 256, 0, stream, out, prev, cols, n_cols, n, 1u);
     else
-        merkle_layer_small_kernel<1><<<(n + 255) / 256, 256, 0, stream>>>(out, prev, cols, n_cols, n, 1u);
+        launch_k(merkle_layer_small_kernel<1>, (n + 255) / 256, 256, 0, stream, out, prev, cols, n_cols, n, 1u);
     return cudaGetLastError();
 }
 
@@ -177,6 +180,8 @@ __device__ __forceinline__ void hash_children_latency(uint32_t h[8], const uint4
 }
 
 __global__ void __launch_bounds__(512) merkle_top_kernel(MerkleTopArgs a, uint32_t one) {
+    pdl_wait();
+    pdl_launch_dependents();
     (void)one;
     __shared__ uint4 sm[2 * 512];  // digest i of the level just hashed: sm[2 * i], sm[2 * i + 1]
     const uint32_t tid = threadIdx.x;
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(512) merkle_top_kernel(MerkleTopArgs a, uint32
 
 cudaError_t merkle_commit_top(const MerkleTopArgs& args, cudaStream_t stream) {
     if (args.from_log < 1 || args.from_log > MERKLE_TOP_MAX_LOG) return cudaErrorInvalidValue;
-    merkle_top_kernel<<<1, 512, 0, stream>>>(args, 1u);
+    launch_k(merkle_top_kernel, 1, 512, 0, stream, args, 1u);
     return cudaGetLastError();
 }
 
@@ -217,6 +222,7 @@ cudaError_t merkle_commit_top(const MerkleTopArgs& args, cudaStream_t stream) {
 // their S/2 parents, ... for `depth` levels.  Each level is written to its global buffer (the tree is kept for
 // decommitment) and read back by the same CTA after a block barrier.
 __global__ void __launch_bounds__(256, 2) merkle_subtree_kernel(const __grid_constant__ MerkleSubtreeArgs a, uint32_t one) {
+    pdl_wait();
     const uint32_t n_top = 1u << a.log_top;
     const uint32_t S = min(512u, n_top);  // nodes of layer log_top per CTA
     const uint32_t base = blockIdx.x * S;
@@ -289,12 +295,13 @@ cudaError_t merkle_commit_subtree(const MerkleSubtreeArgs& args, cudaStream_t st
         return cudaErrorInvalidValue;
     uint32_t n_top = 1u << args.log_top;
     uint32_t S = n_top < 512u ? n_top : 512u;
-    merkle_subtree_kernel<<<n_top / S, 256, 0, stream>>>(args, 1u);
+    launch_k(merkle_subtree_kernel, n_top / S, 256, 0, stream, args, 1u);
     return cudaGetLastError();
 }
 
 // out[k*n_cols + c] = cols[c][idx[k]]
 __global__ void gather_rows_kernel(uint32_t* out, const uint32_t* const* cols, int n_cols, const uint32_t* idx, int n_idx) {
+    pdl_wait();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_cols * n_idx) return;
     int k = t / n_cols, c = t % n_cols;
@@ -305,7 +312,7 @@ cudaError_t gather_rows(uint32_t* d_out, const uint32_t* const* d_cols, int n_co
                         cudaStream_t stream) {
     int total = n_cols * n_idx;
     if (total == 0) return cudaSuccess;
-    gather_rows_kernel<<<(total + 255) / 256, 256, 0, stream>>>(d_out, d_cols, n_cols, d_idx, n_idx);
+    launch_k(gather_rows_kernel, (total + 255) / 256, 256, 0, stream, d_out, d_cols, n_cols, d_idx, n_idx);
     return cudaGetLastError();
 }
 

@@ -9,6 +9,7 @@
 // All of them are one-pass, HBM-bound kernels over column-major u32 data: a warp reads 128
 // contiguous bytes per column, every input byte is read once, no shared-memory staging is
 // needed except for the block reductions of eval_at_point.
+#include "launch.cuh"
 #include "kernels.cuh"
 
 #include "blake2s.cuh"
@@ -45,6 +46,8 @@ __device__ __forceinline__ Pt k_point_of_index(uint32_t idx) {
 // Traffic: 4 B per coefficient (+ the 64 KiB basis table, L1/L2 resident).
 // ------------------------------------------------------------------------------------
 __global__ void eval_basis_kernel(QM31* basis, const QM31* mappings, int m) {
+    pdl_wait();
+    pdl_launch_dependents();
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= (1u << m)) return;
     QM31 r = q_from_m(1);
@@ -96,6 +99,7 @@ constexpr int EVAL_CPB = 8;
 __global__ void __launch_bounds__(256) eval_partial_kernel(const uint32_t* const* __restrict__ cols, int n_cols, int log, int m,
                                                            const QM31* __restrict__ basis,
                                                            const QM31* __restrict__ mappings, QM31* __restrict__ partials) {
+    pdl_wait();
     const uint32_t chunk = blockIdx.x;
     const uint32_t n_chunks = gridDim.x;
     const int c0 = blockIdx.y * EVAL_CPB;
@@ -156,6 +160,7 @@ __global__ void __launch_bounds__(256) eval_partial_kernel(const uint32_t* const
 // columns of fewer than 4096 coefficients: one CTA per column, scalar loads
 __global__ void __launch_bounds__(256) eval_partial_small_kernel(const uint32_t* const* __restrict__ cols, int log, int m,
                                                                  const QM31* __restrict__ basis, QM31* __restrict__ partials) {
+    pdl_wait();
     const uint32_t* col = cols[blockIdx.y];
     const uint32_t elems = 1u << m;
     uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
@@ -182,6 +187,8 @@ __global__ void __launch_bounds__(256) eval_partial_small_kernel(const uint32_t*
 }
 
 __global__ void __launch_bounds__(256) eval_sum_kernel(const QM31* __restrict__ partials, uint32_t n_chunks, QM31* out) {
+    pdl_wait();
+    pdl_launch_dependents();
     const QM31* p = partials + (size_t)blockIdx.x * n_chunks;
     QM31 v = q_zero();
     for (uint32_t i = threadIdx.x; i < n_chunks; i += 256) v = q_add(v, p[i]);
@@ -195,15 +202,15 @@ cudaError_t eval_at_point(const uint32_t* const* d_cols, int n_cols, int log, co
     int m = log < 12 ? log : 12;
     uint32_t n_chunks = 1u << (log - m);
     uint32_t nb = 1u << m;
-    eval_basis_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(d_basis, d_mappings, m);
+    launch_k(eval_basis_kernel, (nb + 255) / 256, 256, 0, stream, d_basis, d_mappings, m);
     if (m == 12) {
         dim3 grid(n_chunks, (n_cols + EVAL_CPB - 1) / EVAL_CPB);
-        eval_partial_kernel<<<grid, 256, 0, stream>>>(d_cols, n_cols, log, m, d_basis, d_mappings, d_partials);
+        launch_k(eval_partial_kernel, grid, 256, 0, stream, d_cols, n_cols, log, m, d_basis, d_mappings, d_partials);
     } else {
         dim3 grid(1, n_cols);
-        eval_partial_small_kernel<<<grid, 256, 0, stream>>>(d_cols, log, m, d_basis, d_partials);
+        launch_k(eval_partial_small_kernel, grid, 256, 0, stream, d_cols, log, m, d_basis, d_partials);
     }
-    eval_sum_kernel<<<n_cols, 256, 0, stream>>>(d_partials, n_chunks, d_out);
+    launch_k(eval_sum_kernel, n_cols, 256, 0, stream, d_partials, n_chunks, d_out);
     return cudaGetLastError();
 }
 
@@ -232,6 +239,7 @@ __global__ void __launch_bounds__(256, LB_Q_MINBLOCKS) quotients_kernel(uint32_t
                                                         const __grid_constant__ QuotientParams qp,
                                                         const uint2* __restrict__ tw_x, const uint2* __restrict__ tw_y,
                                                         uint32_t n, uint32_t row0) {
+    pdl_wait();
     // rows [row0, row0 + n) of the domain: the columns and the outputs are this row range (the whole domain on one GPU;
     // a rank's row shard in the sharded prover), the domain points are those of the global rows
     const uint32_t j0 = blockIdx.x * (256 * QROWS) + threadIdx.x;
@@ -353,7 +361,7 @@ cudaError_t accumulate_quotients(uint32_t* const out[4], const uint32_t* const* 
     const uint2* tw_y = tw->fwd + tw->y_off + ((size_t)1 << (log - 1));  // Y[log-1]
     unsigned blocks = (n + 256 * QROWS - 1) / (256 * QROWS);
 #define LB_Q_LAUNCH(NB) \
-    quotients_kernel<NB><<<blocks, 256, 0, stream>>>(out[0], out[1], out[2], out[3], d_cols, d_entries, qp, tw_x, tw_y, n, row0)
+    launch_k(quotients_kernel<NB>, blocks, 256, 0, stream, out[0], out[1], out[2], out[3], d_cols, d_entries, qp, tw_x, tw_y, n, row0)
     switch (qp.n_batches) {
         case 1: LB_Q_LAUNCH(1); break;
         case 2: LB_Q_LAUNCH(2); break;
@@ -377,6 +385,7 @@ struct CCoords4 {
 template <bool CIRCLE>
 __global__ void __launch_bounds__(256) fold_kernel(Coords4 dst, CCoords4 src, const uint2* __restrict__ itw, uint32_t n_out,
                                                    QM31 alpha, QM31 alpha_sq) {
+    pdl_wait();
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_out) return;
     uint32_t a[4], b[4];
@@ -410,7 +419,7 @@ cudaError_t fold_circle_into_line(uint32_t* const dst[4], const uint32_t* const 
         s.p[c] = src[c];
     }
     uint32_t n_out = 1u << (log - 1);
-    fold_kernel<true><<<(n_out + 255) / 256, 256, 0, stream>>>(d, s, itw, n_out, alpha, q_mul(alpha, alpha));
+    launch_k(fold_kernel<true>, (n_out + 255) / 256, 256, 0, stream, d, s, itw, n_out, alpha, q_mul(alpha, alpha));
     return cudaGetLastError();
 }
 
@@ -423,7 +432,7 @@ cudaError_t fold_line(uint32_t* const dst[4], const uint32_t* const src[4], cons
         s.p[c] = src[c];
     }
     uint32_t n_out = 1u << (log - 1);
-    fold_kernel<false><<<(n_out + 255) / 256, 256, 0, stream>>>(d, s, itw, n_out, alpha, q_zero());
+    launch_k(fold_kernel<false>, (n_out + 255) / 256, 256, 0, stream, d, s, itw, n_out, alpha, q_zero());
     return cudaGetLastError();
 }
 
@@ -431,6 +440,7 @@ cudaError_t fold_line(uint32_t* const dst[4], const uint32_t* const src[4], cons
 template <bool CIRCLE>
 __global__ void __launch_bounds__(256) fold_kernel_dev_alpha(Coords4 dst, CCoords4 src, const uint2* __restrict__ itw,
                                                              uint32_t n_out, const QM31* __restrict__ alpha_ptr) {
+    pdl_wait();
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_out) return;
     const QM31 alpha = *alpha_ptr;
@@ -465,7 +475,7 @@ cudaError_t fold_circle_into_line_dev(uint32_t* const dst[4], const uint32_t* co
         s.p[c] = src[c];
     }
     uint32_t n_out = 1u << (log - 1);
-    fold_kernel_dev_alpha<true><<<(n_out + 255) / 256, 256, 0, stream>>>(d, s, itw, n_out, d_alpha);
+    launch_k(fold_kernel_dev_alpha<true>, (n_out + 255) / 256, 256, 0, stream, d, s, itw, n_out, d_alpha);
     return cudaGetLastError();
 }
 
@@ -478,7 +488,7 @@ cudaError_t fold_line_dev(uint32_t* const dst[4], const uint32_t* const src[4], 
         s.p[c] = src[c];
     }
     uint32_t n_out = 1u << (log - 1);
-    fold_kernel_dev_alpha<false><<<(n_out + 255) / 256, 256, 0, stream>>>(d, s, itw, n_out, d_alpha);
+    launch_k(fold_kernel_dev_alpha<false>, (n_out + 255) / 256, 256, 0, stream, d, s, itw, n_out, d_alpha);
     return cudaGetLastError();
 }
 
@@ -536,6 +546,8 @@ __device__ void channel_mix_root_draw_dev(DevChannel* ch, const uint32_t* root, 
 
 __global__ void channel_mix_root_draw_kernel(DevChannel* ch, const uint32_t* root, int variant, QM31* alpha_out,
                                              uint32_t* digest_log) {
+    pdl_wait();
+    pdl_launch_dependents();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     channel_mix_root_draw_dev(ch, root, variant, alpha_out, digest_log);
 }
@@ -545,6 +557,8 @@ __global__ void channel_mix_root_draw_kernel(DevChannel* ch, const uint32_t* roo
 // receives every level: level k (2^k digests) at word 8 * (2^k - 1), level logw = the gathered roots themselves.
 __global__ void channel_mix_sharded_root_draw_kernel(DevChannel* ch, const uint32_t* roots, int logw, int variant,
                                                      QM31* alpha_out, uint32_t* digest_log, uint32_t* top_out) {
+    pdl_wait();
+    pdl_launch_dependents();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int w = 1 << logw;
     for (int i = 0; i < 8 * w; ++i) top_out[8 * (w - 1) + i] = roots[i];
@@ -564,7 +578,7 @@ __global__ void channel_mix_sharded_root_draw_kernel(DevChannel* ch, const uint3
 cudaError_t channel_mix_sharded_root_draw(DevChannel* d_ch, const uint32_t* d_roots, int logw, int variant, QM31* d_alpha_out,
                                           uint32_t* d_digest_log, uint32_t* d_top_out, cudaStream_t stream) {
     if (logw < 1 || logw > 6) return cudaErrorInvalidValue;
-    channel_mix_sharded_root_draw_kernel<<<1, 32, 0, stream>>>(d_ch, d_roots, logw, variant, d_alpha_out, d_digest_log, d_top_out);
+    launch_k(channel_mix_sharded_root_draw_kernel, 1, 32, 0, stream, d_ch, d_roots, logw, variant, d_alpha_out, d_digest_log, d_top_out);
     return cudaGetLastError();
 }
 
@@ -577,6 +591,8 @@ cudaError_t channel_mix_sharded_root_draw(DevChannel* d_ch, const uint32_t* d_ro
 // path uses (the decommitment reads them later).
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) fri_tail_kernel(const __grid_constant__ FriTailArgs a) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ QM31 s_alpha;
     __shared__ uint4 s_dig[2 * 1024];  // digest i of the tree level just hashed: s_dig[2 * i], s_dig[2 * i + 1]
     const uint32_t tid = threadIdx.x;
@@ -654,13 +670,13 @@ __global__ void __launch_bounds__(1024) fri_tail_kernel(const __grid_constant__ 
 
 cudaError_t fri_tail(const FriTailArgs& a, cudaStream_t stream) {
     if (a.from_log > FRI_TAIL_MAX_LOG || a.last_log < 0 || a.from_log <= a.last_log) return cudaErrorInvalidValue;
-    fri_tail_kernel<<<1, 1024, 0, stream>>>(a);
+    launch_k(fri_tail_kernel, 1, 1024, 0, stream, a);
     return cudaGetLastError();
 }
 
 cudaError_t channel_mix_root_draw(DevChannel* d_ch, const uint32_t* d_root, int variant, QM31* d_alpha_out, uint32_t* d_digest_log,
                                   cudaStream_t stream) {
-    channel_mix_root_draw_kernel<<<1, 32, 0, stream>>>(d_ch, d_root, variant, d_alpha_out, d_digest_log);
+    launch_k(channel_mix_root_draw_kernel, 1, 32, 0, stream, d_ch, d_root, variant, d_alpha_out, d_digest_log);
     return cudaGetLastError();
 }
 
@@ -673,6 +689,7 @@ struct Digest8 {
 
 __global__ void __launch_bounds__(256) grind_kernel(Digest8 dg, int variant, uint32_t pow_bits, uint64_t base,
                                                     uint64_t count, unsigned long long* found) {
+    pdl_wait();
     uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (t >= count) return;
     uint64_t nonce = base + t;
@@ -713,7 +730,7 @@ cudaError_t grind_range(const uint32_t digest[8], int variant, uint32_t pow_bits
     Digest8 dg;
     for (int i = 0; i < 8; ++i) dg.w[i] = digest[i];
     uint64_t blocks = (count + 255) / 256;
-    grind_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dg, variant, pow_bits, base, count, d_found);
+    launch_k(grind_kernel, (unsigned)blocks, 256, 0, stream, dg, variant, pow_bits, base, count, d_found);
     return cudaGetLastError();
 }
 
@@ -721,12 +738,13 @@ cudaError_t grind_range(const uint32_t digest[8], int variant, uint32_t pow_bits
 // column utilities
 // ------------------------------------------------------------------------------------
 __global__ void add_inplace_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t n) {
+    pdl_wait();
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i < n) dst[i] = m_add(dst[i], src[i]);
 }
 cudaError_t add_inplace(uint32_t* dst, const uint32_t* src, size_t n, cudaStream_t stream) {
     if (!n) return cudaSuccess;
-    add_inplace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dst, src, n);
+    launch_k(add_inplace_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, dst, src, n);
     return cudaGetLastError();
 }
 
@@ -735,6 +753,7 @@ cudaError_t add_inplace(uint32_t* dst, const uint32_t* src, size_t n, cudaStream
 // FieldOps::batch_inverse for BaseField and SecureField columns).
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bit_reverse_kernel(uint32_t* __restrict__ col, int log) {
+    pdl_wait();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >> log) return;
     const uint32_t j = log ? __brev(i) >> (32 - log) : 0;
@@ -746,7 +765,7 @@ __global__ void __launch_bounds__(256) bit_reverse_kernel(uint32_t* __restrict__
 }
 cudaError_t bit_reverse(uint32_t* col, int log, cudaStream_t stream) {
     const uint32_t n = 1u << log;
-    bit_reverse_kernel<<<(n + 255) / 256, 256, 0, stream>>>(col, log);
+    launch_k(bit_reverse_kernel, (n + 255) / 256, 256, 0, stream, col, log);
     return cudaGetLastError();
 }
 
@@ -754,6 +773,7 @@ cudaError_t bit_reverse(uint32_t* col, int log, cudaStream_t stream) {
 // (CircleEvaluation::new_canonical_ordered: coset point k is circle-domain point k/2 for even k, n/2 + (n-1-k)/2 for odd k)
 __global__ void __launch_bounds__(256) canonical_to_storage_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ in,
                                                                    int log) {
+    pdl_wait();
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >> log) return;
     const uint32_t n = 1u << log;
@@ -762,12 +782,13 @@ __global__ void __launch_bounds__(256) canonical_to_storage_kernel(uint32_t* __r
 }
 cudaError_t canonical_to_storage(uint32_t* out, const uint32_t* in, int log, cudaStream_t stream) {
     const uint32_t n = 1u << log;
-    canonical_to_storage_kernel<<<(n + 255) / 256, 256, 0, stream>>>(out, in, log);
+    launch_k(canonical_to_storage_kernel, (n + 255) / 256, 256, 0, stream, out, in, log);
     return cudaGetLastError();
 }
 
 // four consecutive elements per thread share one field inversion (Montgomery's trick); a zero input raises *flag
 __global__ void __launch_bounds__(256) batch_inverse_m31_kernel(uint32_t* out, const uint32_t* in, size_t n, int* flag) {
+    pdl_wait();
     const size_t i0 = 4 * (blockIdx.x * (size_t)blockDim.x + threadIdx.x);
     if (i0 >= n) return;
     uint32_t x[4], pre[4];
@@ -790,6 +811,7 @@ __global__ void __launch_bounds__(256) batch_inverse_m31_kernel(uint32_t* out, c
     }
 }
 __global__ void __launch_bounds__(256) batch_inverse_qm31_kernel(Coords4 out, CCoords4 in, size_t n, int* flag) {
+    pdl_wait();
     const size_t i0 = 4 * (blockIdx.x * (size_t)blockDim.x + threadIdx.x);
     if (i0 >= n) return;
     QM31 x[4], pre[4];
@@ -819,7 +841,7 @@ __global__ void __launch_bounds__(256) batch_inverse_qm31_kernel(Coords4 out, CC
 }
 cudaError_t batch_inverse_m31(uint32_t* out, const uint32_t* in, size_t n, int* d_flag, cudaStream_t stream) {
     if (!n) return cudaSuccess;
-    batch_inverse_m31_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, stream>>>(out, in, n, d_flag);
+    launch_k(batch_inverse_m31_kernel, (unsigned)((n + 1023) / 1024), 256, 0, stream, out, in, n, d_flag);
     return cudaGetLastError();
 }
 cudaError_t batch_inverse_qm31(uint32_t* const out[4], const uint32_t* const in[4], size_t n, int* d_flag, cudaStream_t stream) {
@@ -830,17 +852,18 @@ cudaError_t batch_inverse_qm31(uint32_t* const out[4], const uint32_t* const in[
         o.p[c] = out[c];
         s.p[c] = in[c];
     }
-    batch_inverse_qm31_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, stream>>>(o, s, n, d_flag);
+    launch_k(batch_inverse_qm31_kernel, (unsigned)((n + 1023) / 1024), 256, 0, stream, o, s, n, d_flag);
     return cudaGetLastError();
 }
 
 __global__ void gather_words_kernel(uint32_t* out, const uint32_t* const* addrs, int n) {
+    pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = addrs[i] ? *addrs[i] : 0u;  // a null address = a word another rank owns (sharded prover)
 }
 cudaError_t gather_words(uint32_t* d_out, const uint32_t* const* d_addrs, int n, cudaStream_t stream) {
     if (!n) return cudaSuccess;
-    gather_words_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_out, d_addrs, n);
+    launch_k(gather_words_kernel, (n + 255) / 256, 256, 0, stream, d_out, d_addrs, n);
     return cudaGetLastError();
 }
 
@@ -854,6 +877,7 @@ constexpr int TP_ROWS = 256;
 __global__ void __launch_bounds__(TP_ROWS) transpose_pad_kernel(uint32_t* __restrict__ cols, size_t stride,
                                                                 const uint32_t* __restrict__ rows, uint64_t n_rows, int n_cols,
                                                                 uint64_t n_padded, const PadRow pad) {
+    pdl_wait();
     extern __shared__ uint32_t tp_sm[];
     const int ncp = n_cols | 1;
     const uint64_t r0 = (uint64_t)blockIdx.x * TP_ROWS;
@@ -899,7 +923,7 @@ cudaError_t transpose_pad(uint32_t* d_cols, size_t stride, const uint32_t* d_row
     for (int c = 0; c < n_cols; ++c) pad.v[c] = padding_value(kind, c);
     uint64_t n = (uint64_t)1 << log;
     size_t smem = (size_t)TP_ROWS * (n_cols | 1) * sizeof(uint32_t);
-    transpose_pad_kernel<<<(unsigned)((n + TP_ROWS - 1) / TP_ROWS), TP_ROWS, smem, stream>>>(d_cols, stride, d_rows, n_rows, n_cols, n, pad);
+    launch_k(transpose_pad_kernel, (unsigned)((n + TP_ROWS - 1) / TP_ROWS), TP_ROWS, smem, stream, d_cols, stride, d_rows, n_rows, n_cols, n, pad);
     return cudaGetLastError();
 }
 

@@ -16,6 +16,7 @@
 // - bit-identical to the reference's f64 path by construction - and the entry's multiplicity counter is bumped with one
 // atomic (the *_lookup table's only column).  LessThan bumps the 8-bit range-check counters of its four limbs through a
 // per-CTA shared-memory histogram.
+#include "launch.cuh"
 #include "kernels.cuh"
 
 namespace lb {
@@ -63,6 +64,7 @@ __host__ __device__ constexpr int op_cols() {  // columns of the component's *Tr
 // shared memory (odd pitch: conflict-free) and the CTA copies the run out with 128-bit, fully coalesced stores.
 template <int OP>
 __global__ void __launch_bounds__(256) trace_rows_kernel(const TraceOp p) {
+    pdl_wait();
     constexpr int NC = op_cols<OP>(), NCP = NC | 1;
     __shared__ uint32_t stage[256 * NCP];
     __shared__ uint32_t hist[OP == LB_OP_LESS_THAN ? 256 : 1];
@@ -188,6 +190,7 @@ __global__ void __launch_bounds__(256) trace_rows_kernel(const TraceOp p) {
 // contiguous run, parked in shared memory and stored coalesced like trace_rows_kernel does.
 template <bool MAX, bool STAGED>
 __global__ void __launch_bounds__(256) trace_reduce_kernel(const TraceOp p) {
+    pdl_wait();
     extern __shared__ uint32_t rstage[];
     constexpr int NC = MAX ? 15 : 14;
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -247,6 +250,7 @@ __global__ void __launch_bounds__(256) trace_reduce_kernel(const TraceOp p) {
 }
 
 __global__ void __launch_bounds__(256) count_uses_kernel(uint32_t* __restrict__ uses, const uint32_t* __restrict__ idx, uint64_t n) {
+    pdl_wait();
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i < n) atomicAdd(&uses[idx ? (uint64_t)idx[i] : i], 1u);
 }
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(256) count_uses_kernel(uint32_t* __restrict__ 
 
 cudaError_t trace_count_uses(uint32_t* uses, const uint32_t* idx, uint64_t n, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    count_uses_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(uses, idx, n);
+    launch_k(count_uses_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, uses, idx, n);
     return cudaGetLastError();
 }
 
@@ -263,7 +267,7 @@ cudaError_t trace_op(const TraceOp& p, cudaStream_t stream) {
     if (p.n == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((p.n + 255) / 256);
 #define LB_TRACE_CASE(K) \
-    case K: trace_rows_kernel<K><<<blocks, 256, 0, stream>>>(p); break;
+    case K: launch_k(trace_rows_kernel<K>, blocks, 256, 0, stream, p); break;
     switch (p.op) {
         LB_TRACE_CASE(LB_OP_ADD) LB_TRACE_CASE(LB_OP_MUL) LB_TRACE_CASE(LB_OP_REM) LB_TRACE_CASE(LB_OP_LESS_THAN)
         LB_TRACE_CASE(LB_OP_RECIP) LB_TRACE_CASE(LB_OP_SQRT) LB_TRACE_CASE(LB_OP_SIN) LB_TRACE_CASE(LB_OP_EXP2)
@@ -273,11 +277,11 @@ cudaError_t trace_op(const TraceOp& p, cudaStream_t stream) {
             const bool mx = p.op == LB_OP_MAX_REDUCE;
             const size_t smem = 256 * (size_t)((p.group * (mx ? 15 : 14)) | 1) * sizeof(uint32_t);
             if (p.group <= 3 && smem <= 48 * 1024) {
-                if (mx) trace_reduce_kernel<true, true><<<blocks, 256, smem, stream>>>(p);
-                else trace_reduce_kernel<false, true><<<blocks, 256, smem, stream>>>(p);
+                if (mx) launch_k(trace_reduce_kernel<true, true>, blocks, 256, smem, stream, p);
+                else launch_k(trace_reduce_kernel<false, true>, blocks, 256, smem, stream, p);
             } else {
-                if (mx) trace_reduce_kernel<true, false><<<blocks, 256, 0, stream>>>(p);
-                else trace_reduce_kernel<false, false><<<blocks, 256, 0, stream>>>(p);
+                if (mx) launch_k(trace_reduce_kernel<true, false>, blocks, 256, 0, stream, p);
+                else launch_k(trace_reduce_kernel<false, false>, blocks, 256, 0, stream, p);
             }
             break;
         }
