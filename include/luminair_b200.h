@@ -37,7 +37,10 @@ typedef struct lb_ctx lb_ctx;
 
 /* ---- context / memory ---------------------------------------------------------------- */
 int lb_version(void);
-/* one context per GPU; owns a stream, scratch and the twiddle tables */
+/* A context belongs to one GPU and owns a stream, the twiddle tables, a memory pool for its stream-ordered allocations and a
+ * pinned staging buffer.  Calls on one context are serial (one stream); several contexts - on different GPUs or on the same
+ * one - can be driven from different host threads at the same time and do not wait on each other.  Every entry point makes
+ * the context's device current for the call and restores the caller's. */
 int lb_ctx_create(int device, lb_ctx** out);
 void lb_ctx_destroy(lb_ctx* ctx);
 const char* lb_last_error(lb_ctx* ctx);
