@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) eval_partial_kernel(const uint32_t* const
     const int nc = min(EVAL_CPB, n_cols - c0);
     const uint32_t elems = 1u << m;  // 4096 on this path
     const uint32_t tid = threadIdx.x;
-    __shared__ QM31 s_w[EVAL_CPB][8];
+    __shared__ uint4 s_part[EVAL_CPB][256];  // 32 KiB
     // thread t owns elements 4 * (t + 256 i) + q, i < 4, q < 4
     uint4 bs[16];
 #pragma unroll
@@ -117,11 +117,18 @@ __global__ void __launch_bounds__(256) eval_partial_kernel(const uint32_t* const
     QM31 hi = q_from_m(1);
     for (int b = 0; m + b < log; ++b)
         if ((chunk >> b) & 1) hi = q_mul(hi, mappings[m + b]);
-    for (int c = 0; c < nc; ++c) {
-        const uint4* col = reinterpret_cast<const uint4*>(cols[c0 + c] + ((size_t)chunk << m));
-        uint4 v[4];
+    uint4 v[4], nv[4];
+    {
+        const uint4* col = reinterpret_cast<const uint4*>(cols[c0] + ((size_t)chunk << m));
 #pragma unroll
         for (int i = 0; i < 4; ++i) v[i] = col[tid + 256 * i];
+    }
+    for (int c = 0; c < nc; ++c) {
+        if (c + 1 < nc) {  // the next column's loads are in flight while this one is multiplied
+            const uint4* col = reinterpret_cast<const uint4*>(cols[c0 + c + 1] + ((size_t)chunk << m));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) nv[i] = col[tid + 256 * i];
+        }
         uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -142,17 +149,26 @@ __global__ void __launch_bounds__(256) eval_partial_kernel(const uint32_t* const
                 }
             }
         }
-        // per-warp sums go to shared memory; the block-wide reduction happens once, after the last column (no barrier between
-        // columns: the next column's loads are not held back by this one's reduction)
-        QM31 s = warp_sum_q(q_make(fold64(a0), fold64(a1), fold64(a2), fold64(a3)));
-        if ((tid & 31) == 0) s_w[c][tid >> 5] = s;
+        // every thread parks its sum in shared memory; the block-wide reduction happens once, after the last column (no barrier
+        // and no shuffle tree per column: the next column's loads are not held back by this one's reduction)
+        s_part[c][tid] = make_uint4(fold64(a0), fold64(a1), fold64(a2), fold64(a3));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = nv[i];
     }
     __syncthreads();
-    if ((int)tid < nc) {
-        QM31 r = q_zero();
+    {
+        // warp w reduces column w: 8 entries per lane, then one shuffle tree
+        const int w = tid >> 5, lane = tid & 31;
+        if (w < nc) {
+            QM31 r = q_zero();
 #pragma unroll
-        for (int w = 0; w < 8; ++w) r = q_add(r, s_w[tid][w]);
-        partials[(size_t)(c0 + tid) * n_chunks + chunk] = q_mul(r, hi);
+            for (int k = 0; k < 8; ++k) {
+                const uint4 v = s_part[w][lane + 32 * k];
+                r = q_add(r, q_make(v.x, v.y, v.z, v.w));
+            }
+            r = warp_sum_q(r);
+            if (lane == 0) partials[(size_t)(c0 + w) * n_chunks + chunk] = q_mul(r, hi);
+        }
     }
     (void)elems;
 }
