@@ -7,6 +7,14 @@
 
 namespace lb {
 
+// eval_at_point works on chunks of 2^EVAL_CHUNK_LOG coefficients (one CTA each, basis entries in registers).  Measured on B200
+// (OODS stage of the cfg-3 / wide proof): 12 -> 0.271 / 0.398 ms at 116 registers; 11 -> 0.294 / 0.436 ms at 63 registers
+// (more CTAs per SM, but twice the per-chunk reductions and basis loads)
+#ifndef LB_EVAL_M
+#define LB_EVAL_M 12
+#endif
+constexpr int EVAL_CHUNK_LOG = LB_EVAL_M;
+
 cudaError_t kernels_init(cudaStream_t stream);  // constant tables (call once per context)
 
 // ---- PolyOps::eval_at_point ------------------------------------------------------------------

@@ -104,34 +104,35 @@ __global__ void __launch_bounds__(256) eval_partial_kernel(const uint32_t* const
     const uint32_t n_chunks = gridDim.x;
     const int c0 = blockIdx.y * EVAL_CPB;
     const int nc = min(EVAL_CPB, n_cols - c0);
-    const uint32_t elems = 1u << m;  // 4096 on this path
+    const uint32_t elems = 1u << m;  // 2^EVAL_CHUNK_LOG on this path
     const uint32_t tid = threadIdx.x;
     __shared__ uint4 s_part[EVAL_CPB][256];  // 32 KiB
-    // thread t owns elements 4 * (t + 256 i) + q, i < 4, q < 4
-    uint4 bs[16];
+    // thread t owns elements 4 * (t + 256 i) + q, i < NI, q < 4
+    constexpr int NI = (1 << EVAL_CHUNK_LOG) / 1024;
+    uint4 bs[4 * NI];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < NI; ++i)
 #pragma unroll
         for (int q = 0; q < 4; ++q) bs[4 * i + q] = *reinterpret_cast<const uint4*>(&basis[4 * (tid + 256 * i) + q]);
     // the chunk's high-bit factor (the same for every column)
     QM31 hi = q_from_m(1);
     for (int b = 0; m + b < log; ++b)
         if ((chunk >> b) & 1) hi = q_mul(hi, mappings[m + b]);
-    uint4 v[4], nv[4];
+    uint4 v[NI], nv[NI];
     {
         const uint4* col = reinterpret_cast<const uint4*>(cols[c0] + ((size_t)chunk << m));
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = col[tid + 256 * i];
+        for (int i = 0; i < NI; ++i) v[i] = col[tid + 256 * i];
     }
     for (int c = 0; c < nc; ++c) {
         if (c + 1 < nc) {  // the next column's loads are in flight while this one is multiplied
             const uint4* col = reinterpret_cast<const uint4*>(cols[c0 + c + 1] + ((size_t)chunk << m));
 #pragma unroll
-            for (int i = 0; i < 4; ++i) nv[i] = col[tid + 256 * i];
+            for (int i = 0; i < NI; ++i) nv[i] = col[tid + 256 * i];
         }
         uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < NI; ++i) {
             const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(256) eval_partial_kernel(const uint32_t* const
         // and no shuffle tree per column: the next column's loads are not held back by this one's reduction)
         s_part[c][tid] = make_uint4(fold64(a0), fold64(a1), fold64(a2), fold64(a3));
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = nv[i];
+        for (int i = 0; i < NI; ++i) v[i] = nv[i];
     }
     __syncthreads();
     {
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(256) eval_partial_kernel(const uint32_t* const
     (void)elems;
 }
 
-// columns of fewer than 4096 coefficients: one CTA per column, scalar loads
+// columns of fewer than 2^EVAL_CHUNK_LOG coefficients: one CTA per column, scalar loads
 __global__ void __launch_bounds__(256) eval_partial_small_kernel(const uint32_t* const* __restrict__ cols, int log, int m,
                                                                  const QM31* __restrict__ basis, QM31* __restrict__ partials) {
     pdl_wait();
@@ -215,11 +216,11 @@ __global__ void __launch_bounds__(256) eval_sum_kernel(const QM31* __restrict__ 
 cudaError_t eval_at_point(const uint32_t* const* d_cols, int n_cols, int log, const QM31* d_mappings, QM31* d_basis,
                           QM31* d_partials, QM31* d_out, cudaStream_t stream) {
     if (n_cols == 0) return cudaSuccess;
-    int m = log < 12 ? log : 12;
+    int m = log < EVAL_CHUNK_LOG ? log : EVAL_CHUNK_LOG;
     uint32_t n_chunks = 1u << (log - m);
     uint32_t nb = 1u << m;
     launch_k(eval_basis_kernel, (nb + 255) / 256, 256, 0, stream, d_basis, d_mappings, m);
-    if (m == 12) {
+    if (m == EVAL_CHUNK_LOG) {
         dim3 grid(n_chunks, (n_cols + EVAL_CPB - 1) / EVAL_CPB);
         launch_k(eval_partial_kernel, grid, 256, 0, stream, d_cols, n_cols, log, m, d_basis, d_mappings, d_partials);
     } else {

@@ -605,7 +605,7 @@ void launch_eval_jobs(lb_ctx* ctx, Arena& arena, const std::vector<EvalJob>& job
     uint8_t* d_blob = arena.upload(blob);
     for (size_t j = 0; j < jobs.size(); ++j) {
         const EvalJob& job = jobs[j];
-        int m = std::min(job.log, 12);
+        int m = std::min(job.log, EVAL_CHUNK_LOG);
         QM31* d_basis = arena.alloc<QM31>((size_t)1 << m);
         QM31* d_part = arena.alloc<QM31>(job.cols.size() << (job.log - m));
         ck(eval_at_point((const uint32_t* const*)(d_blob + off_cols[j]), (int)job.cols.size(), job.log, (const QM31*)(d_blob + off_map[j]),
