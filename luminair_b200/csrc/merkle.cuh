@@ -23,6 +23,7 @@ cudaError_t merkle_commit_top(const MerkleTopArgs& args, cudaStream_t stream);
 // latency-bound kernels: level 0 = layer `log_top` (children `prev` and / or <= MERKLE_SMALL_COLS columns), then `depth - 1`
 // column-less layers above it.  One CTA owns 512 adjacent nodes of layer log_top and what they reduce to.
 constexpr int MERKLE_SUBTREE_MAX_DEPTH = 10;
+// (threshold re-measured with dependent launch on, cfg-3 proof: 16 -> 7.91 ms, 17 -> 7.81, 18 -> 7.89, 19 -> 8.00)
 #ifndef LB_MERKLE_SUBTREE_MAX_LOG
 #define LB_MERKLE_SUBTREE_MAX_LOG 17
 #endif
