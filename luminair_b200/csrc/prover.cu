@@ -1462,7 +1462,9 @@ class ProveJob {
                 if (lut_log[pc.lut] >= 0 && lut_log[pc.lut] != pc.log_size) fail(LB_ERR_BAD_ARG, "prove: LUT columns of one table differ in size");
                 lut_log[pc.lut] = pc.log_size;
             }
-            if (n_pre) ck(cudaStreamSynchronize(st), "LUT upload sync");  // host columns may be pageable
+            bool any_host = false;
+            for (int k = 0; k < n_pre; ++k) any_host = any_host || !pre_in[k].on_device;
+            if (any_host) ck(cudaStreamSynchronize(st), "LUT upload sync");  // host columns may be pageable
         }
         commit_tree(trees[0]);
     }
@@ -1743,10 +1745,7 @@ class ProveJob {
                 }
                 p.denom_inv = arena.upload(dinv);
                 ck(constraint_quotients(c.kind, p, st), "constraint quotients");
-                if (!scratch.empty()) {
-                    ck(cudaStreamSynchronize(st), "extension sync");
-                    for (uint32_t* e : scratch) arena.release(e);
-                }
+                for (uint32_t* e : scratch) arena.release(e);  // stream-ordered: freed once the constraint kernel has read them
             }
         }
         // finalize: lift smaller accumulators into larger ones, interpolate -> composition coefficients
